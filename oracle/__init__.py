@@ -1,0 +1,31 @@
+"""CPU oracle for the PVO VO hot path -- TEST INFRASTRUCTURE ONLY.
+
+Everything under ``oracle/`` is a CPU restatement of the reference's algorithm
+(zju3dv/PVO @ c67a15f4, ``VO_Module``).  It exists to *check* the CUDA product
+path in ``pvo_b200/``; it is never the thing that is shipped or measured.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import from here.  Nothing in ``pvo_b200/`` imports
+``oracle`` (enforced by ``tests/test_no_oracle_in_product.py``).
+
+Pinning status (see DESIGN.md section "Oracle"):
+  * SE3 ops ............ pinned by lietorch's own property tests
+                          (thirdparty/lietorch/lietorch/run_tests.py:16-52), restated
+                          in tests/test_oracle_se3.py, and against the reference's
+                          Python geometry (geom/projective_ops.py, geom/ba.py) imported
+                          from /root/reference in this container -> tests/golden/.
+  * update operator ..... pinned against the reference's own DynamicUpdateModule /
+                          ConvGRU / GraphAgg classes imported from /root/reference
+                          (tests/golden/make_golden.py) -> tests/golden/update_op.npz.
+  * Python BA ........... pinned against reference geom/ba.py BA()/MoBA() run here
+                          on the shimmed lietorch -> tests/golden/ba_python.npz.
+  * corr_index lookup ... the reference has no CPU kernel and no test vectors; the
+                          restatement (oracle/corr_ref.c) is validated on the GPU box
+                          against the reference's own correlation_kernels.cu compiled
+                          into oracle/_ref/ (tests/test_corr_gpu.py).  Without a GPU:
+                          PARITY UNPINNED.
+  * droid_backends.ba ... reference cannot be built (vendored Eigen lacks Eigen/Core);
+                          restatement is cross-checked against the reference's *Python*
+                          BA where the two semantics coincide.  PARITY UNPINNED against
+                          the CUDA kernel itself.
+"""

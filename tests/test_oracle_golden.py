@@ -1,0 +1,68 @@
+"""The CPU oracle against the golden vectors produced by the REFERENCE's own code
+(tests/golden/make_golden.py) -- this is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geom, se3, step as ostep, update_op as oupd
+from tests.golden import cases
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _load(name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, name)).items()}
+
+
+def test_update_op_matches_reference_module():
+    gold = _load('update_op.npz')
+    sd = oupd.init_params(0)
+    net, inp, corr, flow = cases.update_inputs(E=3, h=12, w=16, seed=0)
+    with torch.no_grad():
+        o_net, o_delta, o_weight, o_eta, o_up, o_dm = oupd.update_op(sd, net, inp, corr, flow, gold['ii'])
+    for name, val in (('net', o_net), ('delta', o_delta), ('weight', o_weight), ('eta', o_eta),
+                      ('upmask', o_up[:, :, ::16]), ('delta_m', o_dm)):
+        assert torch.allclose(val, gold[name], atol=1e-6, rtol=1e-6), name
+
+
+def test_geometry_and_python_ba_match_reference():
+    gold = _load('geom.npz')
+    c = cases.graph_case(F=5, radius=2, h=12, w=16, seed=3, fdtype=torch.float32)
+    ii, jj = c['ii'], c['jj']
+    poses, disps, intr = c['poses'][None], c['disps'][None], c['intrinsics'][None]
+    x1, valid, (Ji, Jj, Jz) = geom.projective_transform(poses, disps, intr, ii, jj, jacobian=True)
+    for name, val in (('coords', x1), ('valid', valid), ('Ji', Ji), ('Jj', Jj), ('Jz', Jz)):
+        assert torch.allclose(val, gold[name], atol=1e-6, rtol=1e-6), name
+    p1, d1 = geom.BA(gold['target'], gold['weight'], gold['eta'], poses, disps, intr, ii, jj, fixedp=2)
+    p2, d2 = geom.BA(gold['target'], gold['weight'], gold['eta'], p1, d1, intr, ii, jj, fixedp=2)
+    pm = geom.MoBA(gold['target'], gold['weight'], gold['eta'], poses, disps, intr, ii, jj, fixedp=1)
+    assert torch.allclose(p1, gold['ba1_poses'], atol=1e-6)
+    assert torch.allclose(d1, gold['ba1_disps'], atol=1e-6)
+    assert torch.allclose(p2, gold['ba2_poses'], atol=1e-6)
+    assert torch.allclose(d2, gold['ba2_disps'], atol=1e-6)
+    assert torch.allclose(pm, gold['moba_poses'], atol=1e-6)
+
+
+def test_graph_step_matches_reference_factor_graph():
+    gold = _load('graph_step.npz')
+    c = cases.graph_case(F=5, radius=2, h=16, w=24, seed=4, with_segm=True)
+    sd = oupd.init_params(0)
+    st = ostep.make_state(c)
+    with torch.no_grad():
+        for it in range(2):
+            ostep.graph_update(sd, st, segm_filter=True, thresh=0.45)
+            F_ = c['F']
+            tag = str(it)
+            assert torch.allclose(st['poses'][:F_], gold['poses' + tag], atol=1e-6), it
+            assert torch.allclose(st['disps'][:F_], gold['disps' + tag], atol=1e-6), it
+            assert torch.allclose(st['target_cam'], gold['target' + tag], atol=1e-5), it
+            assert torch.allclose(st['weight'], gold['weight' + tag], atol=1e-6), it
+            assert torch.allclose(st['delta_dy'], gold['delta_dy' + tag], atol=1e-6), it
+            assert torch.allclose(st['raw_mask'], gold['raw_mask' + tag], atol=1e-6), it
+            assert torch.allclose(st['full_flow'], gold['full_flow' + tag], atol=1e-5), it
+            assert torch.allclose(st['net'][:, :, ::8], gold['net' + tag], atol=1e-6), it
+            assert torch.allclose(st['damping'][:F_], gold['damping' + tag], atol=1e-7), it
+    # the segment filter must actually have fired on this case, otherwise the test pins nothing
+    assert (st['delta_dy'] != 0).any() and (st['weight'] > 0.999).any()
