@@ -1,0 +1,142 @@
+/* pvo_b200 -- C ABI of libpvo_b200.so (B200 / sm_100a CUDA implementation of PVO's VO_Module hot path).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point replaces one
+ * function of the reference's pybind module `droid_backends` (VO_Module/src/droid.cpp:234-247) or one of the
+ * library calls the reference's Python makes around it; the reference interface is cited at each declaration.
+ * The Python module pvo_b200/droid_backends.py binds these with ctypes under the reference's own names, so
+ * VO_Module/droid_slam runs on it unchanged.
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers to contiguous row-major data; the library never allocates,
+ *     frees or retains caller memory (scratch comes from a caller-provided workspace);
+ *   - `stream` is a cudaStream_t (as void*); nothing synchronises the host, so every call can be captured in
+ *     a CUDA graph;
+ *   - return value: 0 ok, 1 invalid argument, 2 CUDA launch error, 3 unsupported, 4 workspace too small
+ *     (the Python shim raises RuntimeError, mirroring TORCH_CHECK in droid.cpp:83-84);
+ *   - dtype: 0 = float32, 1 = float16;
+ *   - index tensors ii/jj are int64 (torch.long), exactly what the reference passes.
+ */
+#ifndef PVO_B200_H_
+#define PVO_B200_H_
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVO_DTYPE_F32 0
+#define PVO_DTYPE_F16 1
+
+int pvo_version(void);
+
+/* ---- correlation ------------------------------------------------------------------------------------------- */
+
+/* droid_backends.corr_index_forward(volume, coords, radius) -> [corr]
+ *   src/droid.cpp:238, src/correlation_kernels.cu:19-70,126-155.   Bit-exact with the reference kernel.
+ *   volume (N,h1,w1,h2,w2), coords (N,2,h1,w1) float32, out (N,2r+1,2r+1,h1,w1) (written, need not be zeroed).
+ *   flags bit0: use 2-byte tap loads instead of the vectorised row fetch (for A/B measurement only). */
+int pvo_corr_index_forward(const void* volume, const float* coords, void* out, int N, int h1, int w1, int h2, int w2,
+                           int radius, int dtype, int flags, void* stream);
+
+/* droid_backends.corr_index_backward(volume, coords, grad, radius) -> [grad_volume]
+ *   src/droid.cpp:239, src/correlation_kernels.cu:73-124,157-185.  grad_volume must be zero-initialised. */
+int pvo_corr_index_backward(const float* coords, const void* corr_grad, void* volume_grad, int N, int h1, int w1,
+                            int h2, int w2, int radius, int dtype, void* stream);
+
+/* CorrBlock.__call__ fused over all pyramid levels (droid_slam/modules/corr.py:40-50): one launch instead of
+ *   4 x (CorrSampler + torch.zeros) + torch.cat.
+ *   levels[l]: (E,h,w,level_h[l],level_w[l]); coords (E,h,w,2) float32 (NOT permuted; level l uses coords/2^l);
+ *   layout 0: out (E, L*49, h, w) -- the reference's layout;
+ *   layout 1: out (E*h*w, out_cstride) pixel-major, channel = l*49 + xoff*7 + yoff, pad channels zero-filled. */
+int pvo_corr_lookup_pyramid(const void* const* levels, const int* level_h, const int* level_w, int num_levels,
+                            const float* coords, void* out, int E, int h, int w, int radius, int dtype, int layout,
+                            int out_cstride, int flags, void* stream);
+
+/* CorrBlock.__init__: all-pairs correlation + 3x avg_pool2d pyramid (droid_slam/modules/corr.py:23-38,63-71).
+ *   fmap1/fmap2: (E, h*w, 128) pixel-major float16 (the reference's (1,E,128,h,w) transposed), already the
+ *   per-edge gather fmaps[ii] / fmaps[jj];  out level l: (E,h,w,h>>l,w>>l) float16.
+ *   tcgen05 GEMM (fp32 accumulate in TMEM) with the 1/16 scale, the half rounding and all three pooling levels
+ *   fused into the epilogue. */
+/* same contraction on CUDA cores for any dtype (float32 volumes of the training path; fallback): fmaps (E,h*w,C) */
+int pvo_corr_volume(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w, int C,
+                    int num_levels, int dtype, void* stream);
+int pvo_corr_volume_f16(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w,
+                        int num_levels, void* stream);
+
+/* droid_backends.altcorr_forward(fmap1, fmap2, coords, radius) -> [corr]
+ *   src/droid.cpp:240, src/altcorr_kernel.cu:27-149,290-319.
+ *   fmap1 (B,H1,W1,C), fmap2 (B,H2,W2,C) float32, coords (B,S,H1,W1,2), out (B,S,(2r+1)^2,H1,W1). */
+int pvo_altcorr_forward(const float* fmap1, const float* fmap2, const float* coords, float* out, int B, int S, int H1,
+                        int W1, int H2, int W2, int C, int radius, void* stream);
+
+/* ---- geometry ---------------------------------------------------------------------------------------------- */
+
+/* DepthVideo.reproject(ii, jj) (droid_slam/depth_video.py:154-163 -> geom/projective_ops.py:102-130, lietorch
+ *   SE3 mul/inv/act4) fused with the motion-feature construction of FactorGraph.update (factor_graph.py:231-237).
+ *   poses (F,7), disps (F,ht,wd), intrinsics (F,4); coords out (E,ht,wd,2); valid out (E,ht,wd) or NULL;
+ *   motn out (E*ht*wd, 8) in motn_dtype or NULL; when motn != NULL target/delta_dy/raw_mask are (E,ht,wd,2). */
+int pvo_reproject(const float* poses, const float* disps, const float* intrinsics, const long* ii, const long* jj,
+                  float* coords, float* valid, const float* target, const float* delta_dy, const float* raw_mask,
+                  void* motn, int motn_dtype, int E, int ht, int wd, void* stream);
+
+/* droid_backends.frame_distance(poses, disps, intrinsics, ii, jj, beta) -> dist
+ *   src/droid.cpp:236, src/droid_kernels.cu:497-636.  intrinsics (4,). */
+int pvo_frame_distance(const float* poses, const float* disps, const float* intrinsics, const long* ii,
+                       const long* jj, float* dist, int n, int ht, int wd, float beta, void* stream);
+
+/* ---- dense bundle adjustment ------------------------------------------------------------------------------- */
+
+/* droid_backends.ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep,
+ *                   motion_only) -> [dx, dz]       src/droid.cpp:87-114,235, src/droid_kernels.cu:1293-1410.
+ *   In place on poses (nframes,7) / disps (nframes,ht,wd).  intrinsics (4,).  targets/weights (E,2,ht,wd)
+ *   [interleaved = 0, the reference layout] or (E,ht,wd,2) [interleaved = 1].  eta (K,ht,wd),
+ *   K = |unique(arange(t0,t1) U ii)|.  dx_out (t1-t0,6) / dz_out (K,ht*wd) may be NULL.
+ *   workspace >= pvo_ba_workspace_bytes(...).  flags bit0: reuse the edge plan already in the workspace. */
+long pvo_ba_workspace_bytes(int E, int nframes, int P, int K, int HW);
+int pvo_ba(float* poses, float* disps, const float* intrinsics, const float* targets, const float* weights,
+           const float* eta, const long* ii, const long* jj, int E, int nframes, int ht, int wd, int t0, int t1, int K,
+           int iterations, float lm, float ep, int motion_only, int interleaved, float* dx_out, float* dz_out,
+           void* workspace, long workspace_bytes, int flags, void* stream);
+/* copies {K seen on the device, error flag, max out-degree} to the host (synchronises; debugging only) */
+int pvo_ba_read_meta(const void* workspace, int E, int nframes, int P, int K, int HW, int* meta_host3);
+/* DepthVideo.ba's trailing disps.clamp_(min=0.001), depth_video.py:214 */
+int pvo_clamp_min(float* x, long n, float lo, void* stream);
+
+/* ---- update operator building blocks ----------------------------------------------------------------------- */
+
+/* nn.Conv2d (+ fused torch.cat of inputs, bias, activation, ConvGRU gate arithmetic) on CUDA cores, fp32
+ *   accumulate; droid_slam/droid_net.py:167-225, modules/gru.py:6-32.  See pvo_b200/csrc/conv_simt.cu. */
+int pvo_conv2d(const void* const* seg_ptr, const int* seg_channels, const int* seg_stride, int nseg, const float* W,
+               int wstride, const float* bias, int Cout, int KH, int KW, int pad, int nimg, int H, int Wd, int dtype,
+               int epilogue, void* out, int ostride, int ooff, void* out2, const void* aux0, int aux_stride,
+               const float* aux1, void* stream);
+/* the same contraction on tcgen05 tensor cores (float16 operands via TMA, fp32 accumulate in TMEM), 3x3 / 1x1 /
+ *   7x1 kernels with Cin % 16 == 0 and Cout % 64 == 0.  See pvo_b200/csrc/conv_tc.cu. */
+int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels, const int* seg_stride, int nseg, const void* Wh,
+                  const float* bias, int Cout, int KH, int KW, int nimg, int H, int Wd, int epilogue, void* out,
+                  int ostride, int ooff, void* out2, const void* aux0, int aux_stride, const float* aux1, void* stream);
+/* grouped 3x3 convolution with <= 2 outputs per group: the four 128->2 heads and GraphAgg's eta head */
+int pvo_conv3x3_small(const void* in, int istride, int cin_g, const float* W, const float* bias, float* out,
+                      int ostride, int G, int CG, int nimg, int H, int Wd, int dtype, int post, void* stream);
+int pvo_colmean(const void* in, float* out, int E, int HW, int C, int dtype, void* stream);           /* gru.py:26 */
+int pvo_glo_matvec(const float* glo, const float* W, const float* b, float* out, int E, void* stream); /* gru.py:28-30 */
+/* torch_scatter.scatter_mean over edges sharing ii (droid_net.py:83-88); ptr/idx/meta from pvo_group_edges */
+int pvo_segment_mean(const void* in, int istride, int ioff, void* out, const int* ptr, const int* idx, const int* meta,
+                     int Kmax, int HW, int C, int dtype, void* stream);
+/* torch.unique(ii, return_inverse) + grouping, on the device: kx[Kcap], ptr[Kcap+1], idx[E], meta[3], frame2k[nframes] */
+int pvo_group_edges(const long* ii, int E, int nframes, int t0, int t1, int Kcap, int* frame2k, int* kx, int* ptr,
+                    int* idx, int* meta, void* stream);
+int pvo_nchw_to_nhwc(const void* src, int sdtype, void* dst, int ddtype, int N, int C, int HW, int dstride, int doff,
+                     void* stream);
+int pvo_nhwc_to_nchw(const void* src, int sdtype, int sstride, int soff, void* dst, int ddtype, int N, int C, int HW,
+                     void* stream);
+
+/* FactorGraph.update post-processing (factor_graph.py:250-283): target_cam, raw_mask, bin_mask, panoptic segment
+ *   filter (:256-276, integer counting on the device instead of numpy on the host), delta_dy, sigmoid weights. */
+long pvo_update_post_workspace_ints(int E);
+int pvo_update_post(const float* coords1, const float* head_out /*(M,8)*/, const int* segm /*(E,ht,wd) or NULL*/,
+                    double thresh, float* target, float* weight, float* raw_mask, float* delta_dy, float* full_flow,
+                    int* seg_workspace, long seg_workspace_ints, int E, int ht, int wd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVO_B200_H_ */

@@ -1,0 +1,107 @@
+"""ctypes binding of libpvo_b200.so (include/pvo_b200.h).  There is NO fallback: if the CUDA library is
+missing or a call fails, a RuntimeError is raised (the reference raises from TORCH_CHECK, droid.cpp:83-84)."""
+import ctypes
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libpvo_b200.so')
+
+F32, F16 = 0, 1
+_ERR = {1: 'invalid argument', 2: 'CUDA launch error', 3: 'unsupported configuration', 4: 'workspace too small'}
+
+c_int, c_long, c_float, c_double, c_void_p = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
+
+_SIGS = {
+    'pvo_version': (c_int, []),
+    'pvo_corr_index_forward': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    'pvo_corr_index_backward': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    'pvo_corr_lookup_pyramid': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    'pvo_corr_volume': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    'pvo_corr_volume_f16': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    'pvo_altcorr_forward': (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
+    'pvo_reproject': (c_int, [c_void_p] * 11 + [c_int] * 4 + [c_void_p]),
+    'pvo_frame_distance': (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_float, c_void_p]),
+    'pvo_ba_workspace_bytes': (c_long, [c_int] * 5),
+    'pvo_ba': (c_int, [c_void_p] * 8 + [c_int] * 8 + [c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                                     c_long, c_int, c_void_p]),
+    'pvo_ba_read_meta': (c_int, [c_void_p] + [c_int] * 5 + [c_void_p]),
+    'pvo_clamp_min': (c_int, [c_void_p, c_long, c_float, c_void_p]),
+    'pvo_conv2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 9 +
+                   [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    'pvo_conv2d_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 7 +
+                      [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    'pvo_conv3x3_small': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    'pvo_colmean': (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    'pvo_glo_matvec': (c_int, [c_void_p] * 4 + [c_int, c_void_p]),
+    'pvo_segment_mean': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    'pvo_group_edges': (c_int, [c_void_p] + [c_int] * 5 + [c_void_p] * 6),
+    'pvo_nchw_to_nhwc': (c_int, [c_void_p, c_int, c_void_p, c_int] + [c_int] * 5 + [c_void_p]),
+    'pvo_nhwc_to_nchw': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int] + [c_int] * 3 + [c_void_p]),
+    'pvo_update_post_workspace_ints': (c_long, [c_int]),
+    'pvo_update_post': (c_int, [c_void_p, c_void_p, c_void_p, c_double] + [c_void_p] * 6 + [c_long] + [c_int] * 3 + [c_void_p]),
+}
+
+_lib = None
+
+
+def symbols():
+    return sorted(_SIGS)
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('pvo_b200: %s is missing -- run `python -m pvo_b200.build` (no CPU fallback exists)'
+                               % LIB_PATH)
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError('pvo_b200.%s failed: %s' % (what, _ERR.get(status, 'status %d' % status)))
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float16:
+        return F16
+    raise RuntimeError('pvo_b200: unsupported dtype %s (float32 / float16 only)' % t.dtype)
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError('pvo_b200: expected a CUDA tensor (there is no CPU path)')
+        if not t.is_contiguous():
+            raise RuntimeError('pvo_b200: tensor must be contiguous')   # droid.cpp:83-84 CHECK_CONTIGUOUS
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (for `const void* const*` parameters)."""
+    arr = (c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def int_array(vals):
+    return (c_int * len(vals))(*vals)

@@ -1,0 +1,557 @@
+// Dense bundle adjustment (Gauss-Newton / LM step on poses + per-pixel inverse depth via Schur complement),
+// entirely on the device.
+//
+// Replaces droid_backends.ba -> ba_cuda (VO_Module/src/droid.cpp:87-114, VO_Module/src/droid_kernels.cu:1293-1410)
+// and the kernels / host code it drives:
+//   projective_transform_kernel :177-403   accum_kernel + accum_cuda (host CSR, D2H/H2D) :833-853,927-977
+//   EEt6x6 / Ev6x1 / EvT6x1     :980-1094  SparseBlock (Eigen SimplicialLLT on the CPU, float64) :1096-1198
+//   schur_block (host O(P^2 deg^2) loops) :1201-1290   pose_retr / disp_retr :856-925
+// Semantics kept (SURVEY.md section 8(a) addendum): MIN_DEPTH 0.25 gating of weight and 1/Z; quaternions used as
+// stored; Q = 1/(C + eta); LM damping applied to the SCHUR COMPLEMENT diag += ep + lm*diag; failed factorisation
+// => dx = 0; EvT's "pose index <= 0 contributes nothing to dz" quirk (:1084); in-place update of poses/disps.
+// Deviation: expSE3 reads xi[5] where the reference reads the out-of-bounds xi[45] (:154, undefined behaviour).
+//
+// B200 design.  The reference launches one block per EDGE (36 blocks on 148 SMs), materialises Eii/Eij/Cii/bz for
+// every edge, then bounces through the host >= 6 times per iteration (argsort CSR, Eigen triplets, sparse LLT).
+// Here work is organised by SOURCE FRAME: block (k, s) owns 256 pixels of depth frame kx[k] and walks that frame's
+// out-edges, so C, w and the self-row Ei are complete in registers without any cross-block accumulation, the
+// per-edge 12x12 Hessian is reduced with warp shuffles, and the grid is K * ceil(HW/256) blocks (152 at config 2).
+// The reduced camera system (6P x 6P) is accumulated in float64 with atomics straight into one dense matrix, the
+// Schur products are formed per frame from an smem tile, and a single-block float64 Cholesky solves it on the
+// device.  No host synchronisation anywhere: the whole call is CUDA-graph capturable.
+// Algorithmic HBM bytes per GN iteration: 76 B * HW * E -> latency-bound at config 2.
+#include "se3.cuh"
+
+namespace {
+
+constexpr float kMinDepth = 0.25f;
+constexpr int kPix = 256;       // pixels (= threads) per block
+
+struct Plan {          // lives in the integer part of the workspace
+  int* frame2k;        // [nframes] frame index -> row in kx, or -1
+  int* kx;             // [Kcap]    sorted unique(ts U ii)
+  int* src_ptr;        // [Kcap+1]  CSR over edges grouped by source frame (rows follow kx)
+  int* src_idx;        // [E]       edge ids, ascending within a row
+  int* meta;           // [0]=K on device, [1]=error flag, [2]=max out-degree
+};
+
+struct Bufs {
+  float* Eij;          // [E][6][HW]
+  float* Ei;           // [K][6][HW]
+  float* Q;            // [K][HW]
+  float* w;            // [K][HW]
+  double* H;           // [n][n]  reduced camera system, n = 6P
+  double* b;           // [n]
+  float* dx;           // [P][6]
+};
+
+// ---------------------------------------------------------------------------------------------------
+// plan: kx = unique(arange(t0,t1) U ii), edges grouped by source frame.  One block.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) ba_plan_kernel(const long* __restrict__ ii, int E, int nframes, int t0, int t1,
+                                                       int Kcap, Plan pl, double* H, double* b, int n) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int tid = threadIdx.x;
+  for (int f = tid; f < nframes; f += blockDim.x) pl.frame2k[f] = (f >= t0 && f < t1) ? 1 : 0;
+  __syncthreads();
+  for (int e = tid; e < E; e += blockDim.x) {
+    const long f = ii[e];
+    if (f >= 0 && f < nframes) pl.frame2k[f] = 1;
+  }
+  __syncthreads();
+  // block-wide exclusive scan over nframes flags, chunked per thread
+  const int chunk = (nframes + blockDim.x - 1) / blockDim.x;
+  const int lo = min(tid * chunk, nframes), hi = min(lo + chunk, nframes);
+  int cnt = 0;
+  for (int f = lo; f < hi; f++) cnt += pl.frame2k[f];
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((tid & 31) >= o) inc += v;
+  }
+  if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+  __syncthreads();
+  if (tid < 32) {
+    int v = (tid < (int)(blockDim.x >> 5)) ? s_warp[tid] : 0;
+    int w = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, w, o);
+      if (tid >= o) w += u;
+    }
+    s_warp[tid] = w - v;
+    if (tid == 31) s_total = w;
+  }
+  __syncthreads();
+  int base = s_warp[tid >> 5] + inc - cnt;
+  for (int f = lo; f < hi; f++) {
+    if (pl.frame2k[f]) {
+      if (base < Kcap) pl.kx[base] = f;
+      pl.frame2k[f] = base++;
+    } else {
+      pl.frame2k[f] = -1;
+    }
+  }
+  __syncthreads();
+  const int K = s_total;
+  if (tid == 0) {
+    pl.meta[0] = K;
+    pl.meta[1] = (K > Kcap) ? 1 : 0;
+    pl.meta[2] = 0;
+  }
+  __syncthreads();
+  // CSR rows: thread per source frame, edges kept in ascending id order (deterministic accumulation order)
+  const int Kc = min(K, Kcap);
+  for (int k = tid; k < Kc; k += blockDim.x) {
+    int c = 0;
+    const int f = pl.kx[k];
+    for (int e = 0; e < E; e++) c += (ii[e] == f);
+    pl.src_ptr[k + 1] = c;                       // counts first, scanned below
+    atomicMax(&pl.meta[2], c);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    pl.src_ptr[0] = 0;
+    for (int k = 0; k < Kc; k++) pl.src_ptr[k + 1] += pl.src_ptr[k];
+  }
+  __syncthreads();
+  for (int k = tid; k < Kc; k += blockDim.x) {
+    int o = pl.src_ptr[k];
+    const int f = pl.kx[k];
+    for (int e = 0; e < E; e++)
+      if (ii[e] == f) pl.src_idx[o++] = e;
+  }
+  for (long i = tid; i < (long)n * n; i += blockDim.x) H[i] = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) b[i] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pass 1: residuals, Jacobians, per-edge Hessian blocks, per-frame C / w / Ei, per-edge Eij
+// ---------------------------------------------------------------------------------------------------
+struct EdgeJac {
+  float Ju[12], Jv[12];     // [Ji | Jj] for the x and y residual rows
+  float Jzu, Jzv, wu, wv, ru, rv;
+};
+
+__device__ __forceinline__ void edge_jacobian(const float* Pi, const float* Pj, float fx, float fy, float cx, float cy,
+                                              float u, float v, float disp, float tu, float tv, float wgu, float wgv,
+                                              EdgeJac& J) {
+  Vec3 tij; Quat qij;
+  dk_rel_pose(Pi, Pj, tij, qij);
+  const Vec3 X0{(u - cx) / fx, (v - cy) / fy, 1.0f};
+  const Vec3 r = q_rot(qij, X0);
+  const float x = r.x + disp * tij.x, y = r.y + disp * tij.y, z = r.z + disp * tij.z, h = disp;
+  const bool bad = z < kMinDepth;
+  const float d = bad ? 0.0f : 1.0f / z;
+  const float d2 = d * d;
+  J.wu = bad ? 0.0f : .001f * wgu;
+  J.wv = bad ? 0.0f : .001f * wgv;
+  J.ru = tu - (fx * d * x + cx);
+  J.rv = tv - (fy * d * y + cy);
+  float* Jj = &J.Ju[6];
+  Jj[0] = fx * (h * d); Jj[1] = fx * 0; Jj[2] = fx * (-x * h * d2);
+  Jj[3] = fx * (-x * y * d2); Jj[4] = fx * (1 + x * x * d2); Jj[5] = fx * (-y * d);
+  J.Jzu = fx * (tij.x * d - tij.z * (x * d2));
+  dk_adj(tij, qij, Jj, &J.Ju[0]);
+#pragma unroll
+  for (int n = 0; n < 6; n++) J.Ju[n] = -J.Ju[n];
+  Jj = &J.Jv[6];
+  Jj[0] = fy * 0; Jj[1] = fy * (h * d); Jj[2] = fy * (-y * h * d2);
+  Jj[3] = fy * (-1 - y * y * d2); Jj[4] = fy * (x * y * d2); Jj[5] = fy * (x * d);
+  J.Jzv = fy * (tij.y * d - tij.z * (y * d2));
+  dk_adj(tij, qij, Jj, &J.Jv[0]);
+#pragma unroll
+  for (int n = 0; n < 6; n++) J.Jv[n] = -J.Jv[n];
+}
+
+__global__ void __launch_bounds__(kPix) ba_pass1_kernel(
+    const float* __restrict__ poses, const float* __restrict__ disps, const float* __restrict__ intrinsics,
+    const float* __restrict__ targets, const float* __restrict__ weights, const float* __restrict__ eta,
+    const long* __restrict__ ii, const long* __restrict__ jj, Plan pl, Bufs bf, int E, int HW, int wd, int t0, int P,
+    int interleaved, int motion_only) {
+  const int K = pl.meta[0];
+  const int k = blockIdx.y;
+  if (k >= K) return;
+  const int f = pl.kx[k];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pix = blockIdx.x * kPix + tid;
+  const bool active = pix < HW;
+  const float fx = intrinsics[0], fy = intrinsics[1], cx = intrinsics[2], cy = intrinsics[3];
+  const int i = active ? pix / wd : 0, j = active ? pix - i * wd : 0;
+  const float disp = active ? disps[(long)f * HW + pix] : 1.0f;
+  float Ei[6] = {0, 0, 0, 0, 0, 0};
+  float C = 0.f, wacc = 0.f;
+  __shared__ float red[kPix / 32][90];
+  const int n = 6 * P;
+  for (int it = pl.src_ptr[k]; it < pl.src_ptr[k + 1]; it++) {
+    const int e = pl.src_idx[it];
+    const int jx = (int)jj[e];
+    float tu = 0, tv = 0, wgu = 0, wgv = 0;
+    if (active) {
+      if (interleaved) {
+        const float2 t = reinterpret_cast<const float2*>(targets)[(long)e * HW + pix];
+        const float2 w = reinterpret_cast<const float2*>(weights)[(long)e * HW + pix];
+        tu = t.x; tv = t.y; wgu = w.x; wgv = w.y;
+      } else {
+        tu = targets[((long)e * 2 + 0) * HW + pix]; tv = targets[((long)e * 2 + 1) * HW + pix];
+        wgu = weights[((long)e * 2 + 0) * HW + pix]; wgv = weights[((long)e * 2 + 1) * HW + pix];
+      }
+    }
+    EdgeJac J;
+    edge_jacobian(poses + 7 * f, poses + 7 * jx, fx, fy, cx, cy, (float)j, (float)i, disp, tu, tv, wgu, wgv, J);
+    if (!active) { J.wu = 0.f; J.wv = 0.f; }
+    if (!motion_only) {
+      const float au = J.wu * J.Jzu, av = J.wv * J.Jzv;
+      if (active) {
+#pragma unroll
+        for (int m = 0; m < 6; m++) bf.Eij[((long)e * 6 + m) * HW + pix] = au * J.Ju[6 + m] + av * J.Jv[6 + m];
+      }
+#pragma unroll
+      for (int m = 0; m < 6; m++) Ei[m] += au * J.Ju[m] + av * J.Jv[m];
+      C += au * J.Jzu + av * J.Jzv;
+      wacc += au * J.ru + av * J.rv;
+    }
+    // 12x12 lower triangle (78) + vi, vj (12): warp-shuffle reduce, then 8 warps through smem
+    {
+      int l = 0;
+#pragma unroll
+      for (int a = 0; a < 12; a++) {
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+          const float v = warp_sum(J.wu * J.Ju[a] * J.Ju[b] + J.wv * J.Jv[a] * J.Jv[b]);
+          if (lane == 0) red[warp][l] = v;
+          l++;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 12; a++) {
+        const float v = warp_sum(J.wu * J.ru * J.Ju[a] + J.wv * J.rv * J.Jv[a]);
+        if (lane == 0) red[warp][78 + a] = v;
+      }
+    }
+    __syncthreads();
+    if (tid < 90) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kPix / 32; w++) s += (double)red[w][tid];
+      const int pi = f - t0, pj = jx - t0;
+      if (tid < 78) {
+        int a = 0, rem = tid;                      // invert l = a(a+1)/2 + b
+        while (rem > a) { rem -= a + 1; a++; }
+        const int bcol = rem;
+        const int pa = a < 6 ? pi : pj, pb = bcol < 6 ? pi : pj;
+        if (pa >= 0 && pa < P && pb >= 0 && pb < P) {
+          const int row = 6 * pa + (a % 6), col = 6 * pb + (bcol % 6);
+          atomicAdd(&bf.H[(long)row * n + col], s);
+          if (row != col) atomicAdd(&bf.H[(long)col * n + row], s);
+        }
+      } else {
+        const int a = tid - 78;
+        const int pa = a < 6 ? pi : pj;
+        if (pa >= 0 && pa < P) atomicAdd(&bf.b[6 * pa + (a % 6)], s);
+      }
+    }
+    __syncthreads();
+  }
+  if (active && !motion_only) {
+#pragma unroll
+    for (int m = 0; m < 6; m++) bf.Ei[((long)k * 6 + m) * HW + pix] = Ei[m];
+    bf.Q[(long)k * HW + pix] = 1.0f / (C + eta[(long)k * HW + pix]);
+    bf.w[(long)k * HW + pix] = wacc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pass 2: Schur complement.  For depth frame k the E-rows are: the frame's own pose (Ei) and the target pose of
+// every out-edge (Eij), restricted to poses inside [t0,t1).  S += sum_pix Erow_a Q Erow_b^T for ALL row pairs
+// (exactly the pair enumeration of schur_block :1236-1251), b -= sum_pix Q w Erow.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__ jj, Plan pl, Bufs bf, int HW, int t0,
+                                                        int P, int smem_floats) {
+  extern __shared__ float sm[];
+  const int K = pl.meta[0];
+  const int k = blockIdx.y;
+  if (k >= K) return;
+  const int f = pl.kx[k];
+  const int tid = threadIdx.x;
+  const int deg = pl.src_ptr[k + 1] - pl.src_ptr[k];
+  const int R = deg + 1, R6 = 6 * R;                 // row 0 = self, rows 1.. = out-edges (CSR order)
+  // smem: rowpose[R] ints | Qs[PC] | QWs[PC] | tile[PC][R6]
+  int* rowpose = reinterpret_cast<int*>(sm);
+  const int hdr = (R + 3) & ~3;
+  int PC = (smem_floats - hdr) / (R6 + 2);
+  PC = min(kPix, PC & ~31);
+  if (PC <= 0) { if (tid == 0) pl.meta[1] = 2; return; }
+  float* Qs = sm + hdr;
+  float* QWs = Qs + PC;
+  float* tile = QWs + PC;
+  for (int r = tid; r < R; r += kPix) {
+    const int pose = (r == 0) ? f - t0 : (int)jj[pl.src_idx[pl.src_ptr[k] + r - 1]] - t0;
+    rowpose[r] = (pose >= 0 && pose < P) ? pose : -1;
+  }
+  const int n = 6 * P;
+  const int pix0 = blockIdx.x * kPix;
+  for (int c0 = 0; c0 < kPix; c0 += PC) {
+    __syncthreads();
+    const int np = min(PC, HW - pix0 - c0);
+    if (np <= 0) break;
+    // load tile (coalesced along pixels), rows outside the window are zero
+    for (int idx = tid; idx < R6 * PC; idx += kPix) {
+      const int row = idx / PC, p = idx - row * PC;
+      const int r = row / 6, m = row - 6 * r;
+      float v = 0.f;
+      if (p < np && rowpose[r] >= 0) {
+        const long px = pix0 + c0 + p;
+        v = (r == 0) ? bf.Ei[((long)k * 6 + m) * HW + px]
+                     : bf.Eij[((long)pl.src_idx[pl.src_ptr[k] + r - 1] * 6 + m) * HW + px];
+      }
+      tile[p * R6 + row] = v;
+    }
+    for (int p = tid; p < PC; p += kPix) {
+      const bool ok = p < np;
+      const float q = ok ? bf.Q[(long)k * HW + pix0 + c0 + p] : 0.f;
+      Qs[p] = q;
+      QWs[p] = ok ? q * bf.w[(long)k * HW + pix0 + c0 + p] : 0.f;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < R6 * R6; idx += kPix) {
+      const int a = idx / R6, b = idx - a * R6;
+      const int pa = rowpose[a / 6], pb = rowpose[b / 6];
+      if (pa < 0 || pb < 0) continue;
+      float s = 0.f;
+      for (int p = 0; p < np; p++) s += tile[p * R6 + a] * Qs[p] * tile[p * R6 + b];
+      atomicAdd(&bf.H[(long)(6 * pa + a % 6) * n + (6 * pb + b % 6)], -(double)s);
+    }
+    for (int a = tid; a < R6; a += kPix) {
+      const int pa = rowpose[a / 6];
+      if (pa < 0) continue;
+      float s = 0.f;
+      for (int p = 0; p < np; p++) s += QWs[p] * tile[p * R6 + a];
+      atomicAdd(&bf.b[6 * pa + a % 6], -(double)s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// solve: LM damping on the diagonal, dense Cholesky + two triangular solves in float64, one block.
+// ---------------------------------------------------------------------------------------------------
+template <bool IN_SMEM>
+__global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm, float ep) {
+  extern __shared__ double smd[];
+  __shared__ int s_fail;
+  const int n = 6 * P;
+  const int tid = threadIdx.x, T = blockDim.x;
+  double* A = IN_SMEM ? smd : bf.H;
+  double* y = IN_SMEM ? smd + (long)n * n : nullptr;
+  if (IN_SMEM) {
+    for (long i = tid; i < (long)n * n; i += T) A[i] = bf.H[i];
+    for (int i = tid; i < n; i += T) y[i] = bf.b[i];
+  } else {
+    y = bf.b;
+  }
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += T) A[(long)i * n + i] += (double)ep + (double)lm * A[(long)i * n + i];
+  __syncthreads();
+  for (int j = 0; j < n; j++) {
+    if (tid == 0) {
+      const double d = A[(long)j * n + j];
+      if (!(d > 0.0)) s_fail = 1;
+      A[(long)j * n + j] = sqrt(d > 0.0 ? d : 1.0);
+    }
+    __syncthreads();
+    if (s_fail) break;
+    const double inv = 1.0 / A[(long)j * n + j];
+    for (int i = j + 1 + tid; i < n; i += T) A[(long)i * n + j] *= inv;
+    __syncthreads();
+    const int m = n - j - 1;
+    for (int idx = tid; idx < m * m; idx += T) {
+      const int i = j + 1 + idx / m, c = j + 1 + idx % m;
+      if (c <= i) A[(long)i * n + c] -= A[(long)i * n + j] * A[(long)c * n + j];
+    }
+    __syncthreads();
+  }
+  const bool fail = s_fail != 0;
+  if (!fail) {
+    // L z = b
+    for (int j = 0; j < n; j++) {
+      if (tid == 0) y[j] /= A[(long)j * n + j];
+      __syncthreads();
+      const double yj = y[j];
+      for (int i = j + 1 + tid; i < n; i += T) y[i] -= A[(long)i * n + j] * yj;
+      __syncthreads();
+    }
+    // L^T x = z
+    for (int j = n - 1; j >= 0; j--) {
+      if (tid == 0) y[j] /= A[(long)j * n + j];
+      __syncthreads();
+      const double yj = y[j];
+      for (int i = tid; i < j; i += T) y[i] -= A[(long)j * n + i] * yj;
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += T) bf.dx[i] = fail ? 0.0f : (float)y[i];
+  __syncthreads();
+  // leave the system zeroed for the next iteration / next call
+  for (long i = tid; i < (long)n * n; i += T) bf.H[i] = 0.0;
+  for (int i = tid; i < n; i += T) bf.b[i] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pass 3: dz = Q (w - sum_rows E^T dx) [rows with pose index <= 0 skipped, EvT6x1_kernel :1084], disps += dz,
+// poses <- Exp(dx) * poses
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPix) ba_pass3_kernel(float* __restrict__ poses, float* __restrict__ disps,
+                                                        const long* __restrict__ jj, Plan pl, Bufs bf,
+                                                        float* __restrict__ dz_out, int HW, int t0, int P,
+                                                        int motion_only) {
+  const int K = pl.meta[0];
+  const int k = blockIdx.y;
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0 && k == 0) {
+    for (int p = tid; p < P; p += kPix) {
+      float xi[6], T[7];
+#pragma unroll
+      for (int m = 0; m < 6; m++) xi[m] = bf.dx[6 * p + m];
+#pragma unroll
+      for (int m = 0; m < 7; m++) T[m] = poses[7 * (t0 + p) + m];
+      dk_retr(xi, T);
+#pragma unroll
+      for (int m = 0; m < 7; m++) poses[7 * (t0 + p) + m] = T[m];
+    }
+  }
+  if (motion_only || k >= K) return;
+  const int f = pl.kx[k];
+  const int pix = blockIdx.x * kPix + tid;
+  if (pix >= HW) return;
+  float acc = 0.f;
+  {
+    const int p = f - t0;
+    if (p > 0 && p < P) {
+#pragma unroll
+      for (int m = 0; m < 6; m++) acc += bf.Ei[((long)k * 6 + m) * HW + pix] * bf.dx[6 * p + m];
+    }
+  }
+  for (int it = pl.src_ptr[k]; it < pl.src_ptr[k + 1]; it++) {
+    const int e = pl.src_idx[it];
+    const int p = (int)jj[e] - t0;
+    if (p > 0 && p < P) {
+      float dw = 0.f;
+#pragma unroll
+      for (int m = 0; m < 6; m++) dw += bf.Eij[((long)e * 6 + m) * HW + pix] * bf.dx[6 * p + m];
+      acc += dw;
+    }
+  }
+  const float dz = bf.Q[(long)k * HW + pix] * (bf.w[(long)k * HW + pix] - acc);
+  disps[(long)f * HW + pix] += dz;
+  if (dz_out) dz_out[(long)k * HW + pix] = dz;
+}
+
+__global__ void clamp_min_kernel(float* x, long n, float lo) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = fmaxf(x[i], lo);
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Layout {
+  size_t off_frame2k, off_kx, off_ptr, off_idx, off_meta, off_Eij, off_Ei, off_Q, off_w, off_H, off_b, off_dx, total;
+};
+
+Layout make_layout(int E, int nframes, int P, int K, int HW) {
+  Layout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  L.off_frame2k = take(sizeof(int) * (size_t)nframes);
+  L.off_kx = take(sizeof(int) * (size_t)K);
+  L.off_ptr = take(sizeof(int) * (size_t)(K + 1));
+  L.off_idx = take(sizeof(int) * (size_t)(E > 0 ? E : 1));
+  L.off_meta = take(sizeof(int) * 8);
+  L.off_Eij = take(sizeof(float) * 6 * (size_t)E * HW);
+  L.off_Ei = take(sizeof(float) * 6 * (size_t)K * HW);
+  L.off_Q = take(sizeof(float) * (size_t)K * HW);
+  L.off_w = take(sizeof(float) * (size_t)K * HW);
+  L.off_H = take(sizeof(double) * 36 * (size_t)P * P);
+  L.off_b = take(sizeof(double) * 6 * (size_t)P);
+  L.off_dx = take(sizeof(float) * 6 * (size_t)P);
+  L.total = o;
+  return L;
+}
+
+}  // namespace
+
+extern "C" long pvo_ba_workspace_bytes(int E, int nframes, int P, int K, int HW) {
+  if (E < 0 || nframes <= 0 || P <= 0 || K <= 0 || HW <= 0) return -1;
+  return (long)make_layout(E, nframes, P, K, HW).total;
+}
+
+// poses (nframes,7) and disps (nframes,ht,wd) are updated IN PLACE.  targets/weights: (E,2,ht,wd) when
+// interleaved == 0 (the reference's layout, factor_graph.py:297-300) or (E,ht,wd,2) when interleaved == 1.
+// eta: (K,ht,wd) with K = |unique(arange(t0,t1) U ii)|, rows ordered by frame index.  dx_out (P,6), dz_out (K,HW)
+// may be null.  flags bit0: skip the plan kernel (workspace already holds the plan for this ii/jj/t0/t1).
+extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const float* targets, const float* weights,
+                      const float* eta, const long* ii, const long* jj, int E, int nframes, int ht, int wd, int t0,
+                      int t1, int K, int iterations, float lm, float ep, int motion_only, int interleaved,
+                      float* dx_out, float* dz_out, void* workspace, long workspace_bytes, int flags, void* stream) {
+  const int P = t1 - t0, HW = ht * wd;
+  if (E <= 0 || P <= 0 || K <= 0 || nframes <= 0 || t0 < 0 || t1 > nframes || HW <= 0) return PVO_ERR_INVALID;
+  const Layout L = make_layout(E, nframes, P, K, HW);
+  if (!workspace || workspace_bytes < (long)L.total) return PVO_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  Plan pl{(int*)(ws + L.off_frame2k), (int*)(ws + L.off_kx), (int*)(ws + L.off_ptr), (int*)(ws + L.off_idx),
+          (int*)(ws + L.off_meta)};
+  Bufs bf{(float*)(ws + L.off_Eij), (float*)(ws + L.off_Ei), (float*)(ws + L.off_Q), (float*)(ws + L.off_w),
+          (double*)(ws + L.off_H), (double*)(ws + L.off_b), (float*)(ws + L.off_dx)};
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = 6 * P;
+  if (!(flags & 1)) ba_plan_kernel<<<1, 1024, 0, s>>>(ii, E, nframes, t0, t1, K, pl, bf.H, bf.b, n);
+  const dim3 grid(ceil_div(HW, kPix), K);
+  static bool attr_set = false;
+  const int pass2_smem = 160 * 1024;
+  const size_t solve_smem = sizeof(double) * ((size_t)n * n + n);
+  const bool solve_in_smem = solve_smem <= 200 * 1024;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ba_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pass2_smem);
+    cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  for (int it = 0; it < iterations; it++) {
+    ba_pass1_kernel<<<grid, kPix, 0, s>>>(poses, disps, intrinsics, targets, weights, eta, ii, jj, pl, bf, E, HW, wd,
+                                          t0, P, interleaved, motion_only);
+    if (!motion_only)
+      ba_pass2_kernel<<<grid, kPix, pass2_smem, s>>>(jj, pl, bf, HW, t0, P, pass2_smem / 4);
+    if (solve_in_smem)
+      ba_solve_kernel<true><<<1, 512, solve_smem, s>>>(bf, P, lm, ep);
+    else
+      ba_solve_kernel<false><<<1, 512, 0, s>>>(bf, P, lm, ep);
+    const bool last = it == iterations - 1;
+    if (last && dx_out)
+      cudaMemcpyAsync(dx_out, bf.dx, sizeof(float) * n, cudaMemcpyDeviceToDevice, s);
+    ba_pass3_kernel<<<grid, kPix, 0, s>>>(poses, disps, jj, pl, bf, last ? dz_out : nullptr, HW, t0, P, motion_only);
+  }
+  return pvo_check_launch();
+}
+
+// torch.unique(ii) + grouping of edges by source frame, for GraphAgg's scatter_mean (droid_net.py:83-88)
+extern "C" int pvo_group_edges(const long* ii, int E, int nframes, int t0, int t1, int Kcap, int* frame2k, int* kx,
+                               int* ptr, int* idx, int* meta, void* stream) {
+  if (E < 0 || nframes <= 0 || Kcap <= 0) return PVO_ERR_INVALID;
+  Plan pl{frame2k, kx, ptr, idx, meta};
+  ba_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ii, E, nframes, t0, t1, Kcap, pl, nullptr, nullptr, 0);
+  return pvo_check_launch();
+}
+
+// DepthVideo.ba's trailing disps.clamp_(min=0.001) (depth_video.py:214)
+extern "C" int pvo_clamp_min(float* x, long n, float lo, void* stream) {
+  if (n <= 0) return PVO_OK;
+  clamp_min_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, lo);
+  return pvo_check_launch();
+}
+
+extern "C" int pvo_ba_read_meta(const void* workspace, int E, int nframes, int P, int K, int HW, int* meta_host3) {
+  const Layout L = make_layout(E, nframes, P, K, HW);
+  return cudaMemcpy(meta_host3, (const char*)workspace + L.off_meta, 3 * sizeof(int), cudaMemcpyDeviceToHost) ==
+                 cudaSuccess ? PVO_OK : PVO_ERR_CUDA;
+}

@@ -1,0 +1,538 @@
+// Implicit-GEMM convolution on CUDA cores (FP32 accumulate) with fused epilogues, pixel-major (NHWC) activations.
+//
+// This is the float32 PARITY path of the update operator -- every nn.Conv2d of DynamicUpdateModule / ConvGRU /
+// GraphAgg (VO_Module/droid_slam/droid_net.py:167-225,64-95; modules/gru.py:6-32) -- and the path for the small or
+// oddly shaped layers in half mode.  The dense 3x3 layers in half mode run on tcgen05 (conv_tc.cu).
+// The reference calls cuDNN once per conv and then separate elementwise kernels for bias/ReLU/sigmoid/tanh, the
+// torch.cat of the GRU inputs and the gate arithmetic; here the concatenation is virtual (input = up to 4 channel
+// segments with their own strides) and the gate arithmetic is the epilogue.
+//
+//   GEMM view: M = pixels (all edges), N = Cout, K = KH*KW*Cin, k = tap*Cin + c.
+//   Tile 128 x BN x 16, 256 threads, 8 x (BN/16) outputs per thread, double-buffered smem.
+#include "common.cuh"
+
+namespace {
+
+struct Seg {
+  const void* ptr;   // element (m, c) at ptr[m*stride + c]
+  int channels;
+  int stride;
+};
+
+struct ConvP {
+  Seg seg[4];
+  int nseg;
+  int Cin;           // sum of segment channels
+  const float* W;    // [KH*KW*Cin][Wstride], Wstride % 4 == 0, zero padded
+  int Wstride;
+  int Cout;
+  int KH, KW, pad;
+  int H, Wd;         // spatial size; M = nimg * H * Wd
+  long M;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+// ------------------------------------------------------------------------------------------------ epilogues
+// store<V>(m, n, acc): V consecutive output channels n..n+V-1 of pixel m.
+template <typename TO>
+struct EpiBias {      // out = act(acc + bias)
+  const float* bias; TO* out; int ostride; int ooff; int Cout; int relu;
+  template <int V> __device__ __forceinline__ void store(long m, int n, const float* a) const {
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+      if (n + j < Cout) {
+        float v = a[j] + bias[n + j];
+        if (relu) v = fmaxf(v, 0.0f);
+        stf(out + m * ostride + ooff + n + j, v);
+      }
+    }
+  }
+};
+
+template <typename TO>
+struct EpiGlo {       // gru.py:25: sigmoid(w(net)) * net       (the spatial mean is taken by colmean_kernel)
+  const float* bias; const TO* net; int nstride; TO* out; int Cout;
+  template <int V> __device__ __forceinline__ void store(long m, int n, const float* a) const {
+#pragma unroll
+    for (int j = 0; j < V; j++)
+      if (n + j < Cout) stf(out + m * Cout + n + j, sigmoidf_(a[j] + bias[n + j]) * ldf(net + m * nstride + n + j));
+  }
+};
+
+template <typename TO>
+struct EpiZR {        // gru.py:28-29: z | r = sigmoid(conv([net,inp]) + conv_glo(glo)); also emits r*net
+  const float* bias; const float* glo /*[E][384] = gz|gr|gq*/; const TO* net; int nstride; TO* z; TO* rnet; int HW;
+  template <int V> __device__ __forceinline__ void store(long m, int n, const float* a) const {
+    const long e = m / HW;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+      const int c = n + j;
+      if (c >= 256) continue;
+      const float s = sigmoidf_(a[j] + bias[c] + glo[e * 384 + c]);
+      if (c < 128) stf(z + m * 128 + c, s);
+      else stf(rnet + m * 128 + (c - 128), s * ldf(net + m * nstride + (c - 128)));
+    }
+  }
+};
+
+template <typename TO>
+struct EpiQ {         // gru.py:30-32: q = tanh(conv([r*net,inp]) + glo); net = (1-z)*net + z*q   (in place)
+  const float* bias; const float* glo; const TO* z; TO* net; int nstride; int HW;
+  template <int V> __device__ __forceinline__ void store(long m, int n, const float* a) const {
+    const long e = m / HW;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+      const int c = n + j;
+      if (c >= 128) continue;
+      const float q = tanhf(a[j] + bias[c] + glo[e * 384 + 256 + c]);
+      const float zz = ldf(z + m * 128 + c);
+      const float h = ldf(net + m * nstride + c);
+      stf(net + m * nstride + c, (1.0f - zz) * h + zz * q);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ main kernel
+template <typename TI, int BN, bool VEC, typename Epi>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ ConvP p, const Epi epi) {
+  constexpr int BM = 128, BK = 16, TN = BN / 16;
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const long m0 = (long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int Ktot = p.KH * p.KW * p.Cin;
+  const int HW = p.H * p.Wd;
+  // A-tile ownership: pixel row am, 8 consecutive k starting at ak
+  const int am = tid >> 1, ak = (tid & 1) * 8;
+  const long m = m0 + am;
+  const bool mvalid = m < p.M;
+  const long img = mvalid ? m / HW : 0;
+  const int rem = mvalid ? (int)(m - img * HW) : 0;
+  const int py = rem / p.Wd, px = rem - py * p.Wd;
+
+  float ra[8];
+  float4 rb[(BK * BN / 4 + 255) / 256];
+
+  auto fetch = [&](int k0) {
+    // ---- A
+    if (VEC) {
+      const int kb = k0 + ak;
+      bool ok = mvalid && kb < Ktot;
+      const int tap = kb / p.Cin;
+      int c = kb - tap * p.Cin;
+      const int dy = tap / p.KW, dxx = tap - dy * p.KW;
+      const int iy = py + dy - p.pad, ix = px + dxx - p.pad;
+      ok = ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.Wd;
+      if (ok) {
+        int s = 0;
+        while (s < p.nseg - 1 && c >= p.seg[s].channels) { c -= p.seg[s].channels; s++; }
+        const long pm = img * HW + (long)iy * p.Wd + ix;
+        const TI* src = reinterpret_cast<const TI*>(p.seg[s].ptr) + pm * p.seg[s].stride + c;
+        if (sizeof(TI) == 4) {
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          ra[0] = v0.x; ra[1] = v0.y; ra[2] = v0.z; ra[3] = v0.w;
+          ra[4] = v1.x; ra[5] = v1.y; ra[6] = v1.z; ra[7] = v1.w;
+        } else {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+          const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const float2 f = __half22float2(h[q]);
+            ra[2 * q] = f.x; ra[2 * q + 1] = f.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) ra[q] = 0.0f;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int k = k0 + ak + q;
+        float v = 0.0f;
+        if (mvalid && k < Ktot) {
+          const int tap = k / p.Cin;
+          int c = k - tap * p.Cin;
+          const int dy = tap / p.KW, dxx = tap - dy * p.KW;
+          const int iy = py + dy - p.pad, ix = px + dxx - p.pad;
+          if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.Wd) {
+            int s = 0;
+            while (s < p.nseg - 1 && c >= p.seg[s].channels) { c -= p.seg[s].channels; s++; }
+            const long pm = img * HW + (long)iy * p.Wd + ix;
+            v = ldf(reinterpret_cast<const TI*>(p.seg[s].ptr) + pm * p.seg[s].stride + c);
+          }
+        }
+        ra[q] = v;
+      }
+    }
+    // ---- B
+#pragma unroll
+    for (int i = 0; i < (BK * BN / 4 + 255) / 256; i++) {
+      const int idx = tid + i * 256;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < BK * BN / 4) {
+        const int bk = idx / (BN / 4), bn = (idx - bk * (BN / 4)) * 4;
+        const int k = k0 + bk;
+        if (k < Ktot && n0 + bn < p.Wstride) v = __ldg(reinterpret_cast<const float4*>(p.W + (long)k * p.Wstride + n0 + bn));
+      }
+      rb[i] = v;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) As[buf][ak + q][am] = ra[q];
+#pragma unroll
+    for (int i = 0; i < (BK * BN / 4 + 255) / 256; i++) {
+      const int idx = tid + i * 256;
+      if (idx < BK * BN / 4) {
+        const int bk = idx / (BN / 4), bn = (idx - bk * (BN / 4)) * 4;
+        *reinterpret_cast<float4*>(&Bs[buf][bk][bn]) = rb[i];
+      }
+    }
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j] = 0.0f;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  const int nk = (Ktot + BK - 1) / BK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int t = 0; t < nk; t++) {
+    const int buf = t & 1;
+    if (t + 1 < nk) fetch((t + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      float a[8], b[TN];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      if (TN == 8) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][BN / 2 + tx * 4]);
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+        b[4 % TN] = b1.x; b[5 % TN] = b1.y; b[6 % TN] = b1.z; b[7 % TN] = b1.w;
+      } else if (TN == 4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+        b[0] = b0.x; b[1 % TN] = b0.y; b[2 % TN] = b0.z; b[3 % TN] = b0.w;
+      } else {
+        const float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][kk][tx * 2]);
+        b[0] = b0.x; b[1 % TN] = b0.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (t + 1 < nk) stash(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const long mo = m0 + ty * 8 + i;
+    if (mo >= p.M) continue;
+    if (TN == 8) {
+      epi.template store<4>(mo, n0 + tx * 4, &acc[i][0]);
+      epi.template store<4>(mo, n0 + BN / 2 + tx * 4, &acc[i][4 % TN]);
+    } else {
+      epi.template store<TN>(mo, n0 + tx * TN, &acc[i][0]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small-N grouped 3x3
+// out[m][g*CG + o] = post(bias + sum_{tap,c} in[m@tap][g*Cg_in + c] * W[g][tap][c][o]),  CG <= 2, used for the four
+// 128->2 head convolutions (droid_net.py:189-214, one group per head) and GraphAgg's 128->1 eta head (:72-75).
+// post: 0 none, 1 = 0.01 * softplus (droid_net.py:95 with nn.Softplus defaults beta=1, threshold=20)
+template <typename TI, int CG>
+__global__ void __launch_bounds__(128) conv3x3_small_kernel(const TI* __restrict__ in, int istride, int cin_g,
+                                                            const float* __restrict__ W, const float* __restrict__ bias,
+                                                            float* __restrict__ out, int ostride, int G, int H, int Wd,
+                                                            long M, int post) {
+  extern __shared__ float wsm[];                       // [G][9][cin_g][CG]
+  const int nW = G * 9 * cin_g * CG;
+  for (int i = threadIdx.x; i < nW; i += blockDim.x) wsm[i] = W[i];
+  __syncthreads();
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long m = t / G;
+  const int g = (int)(t - m * G);
+  if (m >= M) return;
+  const int HW = H * Wd;
+  const long img = m / HW;
+  const int rem = (int)(m - img * HW);
+  const int py = rem / Wd, px = rem - py * Wd;
+  float acc[CG];
+#pragma unroll
+  for (int o = 0; o < CG; o++) acc[o] = 0.0f;
+  for (int tap = 0; tap < 9; tap++) {
+    const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= Wd) continue;
+    const TI* src = in + (img * HW + (long)iy * Wd + ix) * istride + g * cin_g;
+    const float* w = wsm + ((g * 9 + tap) * cin_g) * CG;
+    for (int c = 0; c < cin_g; c += 8) {
+      float v[8];
+      if (sizeof(TI) == 4) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + c));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + c) + 1);
+        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+      } else {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c));
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const float2 f = __half22float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+#pragma unroll
+        for (int o = 0; o < CG; o++) acc[o] = fmaf(v[q], w[(c + q) * CG + o], acc[o]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < CG; o++) {
+    float v = acc[o] + bias[g * CG + o];
+    if (post == 1) v = 0.01f * ((v > 20.0f) ? v : log1pf(expf(v)));
+    out[m * ostride + g * CG + o] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small helpers
+// mean over the HW pixels of each image: in [E][HW][C] -> out [E][C]   (gru.py:26)
+template <typename TI>
+__global__ void __launch_bounds__(256) colmean_kernel(const TI* __restrict__ in, float* __restrict__ out, int HW, int C) {
+  const int e = blockIdx.x;
+  const int c = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int part = threadIdx.x >> 5;                   // 8 pixel partitions
+  __shared__ float red[8][32];
+  float s = 0.0f;
+  if (c < C)
+    for (int p = part; p < HW; p += 8) s += ldf(in + ((long)e * HW + p) * C + c);
+  red[part][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (part == 0 && c < C) {
+    float t = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) t += red[q][threadIdx.x];
+    out[(long)e * C + c] = t / (float)HW;
+  }
+}
+
+// the three 1x1 "glo" convolutions on the pooled vector (gru.py:28-30): out[e][g*128+o] = b_g[o] + W_g[o][:] . glo[e]
+__global__ void __launch_bounds__(384) glo_matvec_kernel(const float* __restrict__ glo, const float* __restrict__ W /*[3][128][128] (o,c)*/,
+                                                         const float* __restrict__ b /*[3][128]*/, float* __restrict__ out) {
+  const int e = blockIdx.x;
+  __shared__ float g[128];
+  if (threadIdx.x < 128) g[threadIdx.x] = glo[(long)e * 128 + threadIdx.x];
+  __syncthreads();
+  const int row = threadIdx.x;                          // 0..383
+  const float* w = W + (long)row * 128;
+  float s = b[row];
+  for (int c = 0; c < 128; c++) s = fmaf(w[c], g[c], s);
+  out[(long)e * 384 + row] = s;
+}
+
+// scatter_mean over edges sharing a source frame (droid_net.py:83-88): out[k][pix][c] = mean_{e in row k} in[e][pix][c]
+template <typename T>
+__global__ void __launch_bounds__(256) segment_mean_kernel(const T* __restrict__ in, int istride, int ioff,
+                                                           T* __restrict__ out, const int* __restrict__ ptr,
+                                                           const int* __restrict__ idx, const int* __restrict__ meta,
+                                                           int HW, int C) {
+  const int k = blockIdx.y;
+  if (k >= meta[0]) return;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)HW * C) return;
+  const long pix = i / C;
+  const int c = (int)(i - pix * C);
+  float s = 0.0f;
+  const int b = ptr[k], e_ = ptr[k + 1];
+  for (int it = b; it < e_; it++) s += ldf(in + ((long)idx[it] * HW + pix) * istride + ioff + c);
+  const int cnt = e_ - b;
+  stf(out + ((long)k * HW + pix) * C + c, s / (float)(cnt > 0 ? cnt : 1));
+}
+
+// layout / dtype conversion between the reference's planar (N,C,H,W) tensors and pixel-major (N,HW,Cs) buffers
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int C, int HW,
+                                                           int dstride, int doff, long total) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    tile[r][tx] = (c < C && p < HW) ? ldf(src + ((long)n * C + c) * HW + p) : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    if (c < C && p < HW) stf(dst + ((long)n * HW + p) * dstride + doff + c, tile[tx][r]);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const TS* __restrict__ src, int sstride, int soff, TD* __restrict__ dst,
+                                                           int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    tile[r][tx] = (c < C && p < HW) ? ldf(src + ((long)n * HW + p) * sstride + soff + c) : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    if (c < C && p < HW) stf(dst + ((long)n * C + c) * HW + p, tile[tx][r]);
+  }
+}
+
+template <typename TI, typename Epi>
+int launch_conv(const ConvP& p, const Epi& epi, bool vec, cudaStream_t s) {
+  const int gm = ceil_div(p.M, 128);
+  if (p.Cout > 64) {
+    dim3 grid(gm, ceil_div(p.Cout, 128));
+    if (vec) conv_simt_kernel<TI, 128, true, Epi><<<grid, 256, 0, s>>>(p, epi);
+    else conv_simt_kernel<TI, 128, false, Epi><<<grid, 256, 0, s>>>(p, epi);
+  } else if (p.Cout > 32) {
+    dim3 grid(gm, 1);
+    if (vec) conv_simt_kernel<TI, 64, true, Epi><<<grid, 256, 0, s>>>(p, epi);
+    else conv_simt_kernel<TI, 64, false, Epi><<<grid, 256, 0, s>>>(p, epi);
+  } else {
+    dim3 grid(gm, 1);
+    if (vec) conv_simt_kernel<TI, 32, true, Epi><<<grid, 256, 0, s>>>(p, epi);
+    else conv_simt_kernel<TI, 32, false, Epi><<<grid, 256, 0, s>>>(p, epi);
+  }
+  return pvo_check_launch();
+}
+
+}  // namespace
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+// Generic convolution.  Activations are pixel-major: element (pixel m, channel c) of input segment s lives at
+// seg_ptr[s][m*seg_stride[s] + c]; the concatenation of the segments is the conv input (replaces torch.cat,
+// gru.py:20-21,30).  Weights are pre-packed [KH*KW*Cin][wstride] float32 (pack_conv_weight in pvo_b200/nn.py).
+// epilogue: 0 bias, 1 bias+ReLU, 2 sigmoid(.)*net ("glo" gate), 3 GRU z|r, 4 GRU q + state update.
+// aux pointers by epilogue:  2: aux0 = net (stride aux_stride)        3: aux0 = net, aux1 = glo[E][384], out = z, out2 = r*net
+//                            4: aux0 = z, aux1 = glo[E][384], out = net (in place, stride ostride)
+extern "C" int pvo_conv2d(const void* const* seg_ptr, const int* seg_channels, const int* seg_stride, int nseg,
+                          const float* W, int wstride, const float* bias, int Cout, int KH, int KW, int pad, int nimg,
+                          int H, int Wd, int dtype, int epilogue, void* out, int ostride, int ooff, void* out2,
+                          const void* aux0, int aux_stride, const float* aux1, void* stream) {
+  if (nseg < 1 || nseg > 4 || Cout < 1 || wstride % 4 || nimg < 0) return PVO_ERR_INVALID;
+  if (nimg == 0) return PVO_OK;
+  ConvP p;
+  p.nseg = nseg;
+  p.Cin = 0;
+  const size_t esz = dtype == PVO_DTYPE_F32 ? 4 : 2;
+  bool vec = true;
+  for (int s = 0; s < nseg; s++) {
+    p.seg[s] = Seg{seg_ptr[s], seg_channels[s], seg_stride[s]};
+    p.Cin += seg_channels[s];
+    if (seg_channels[s] % 8) vec = false;
+    if ((seg_stride[s] * esz) % 16 || ((uintptr_t)seg_ptr[s]) % 16) vec = false;
+  }
+  for (int s = nseg; s < 4; s++) p.seg[s] = Seg{nullptr, 0, 0};
+  p.W = W; p.Wstride = wstride; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad; p.H = H; p.Wd = Wd;
+  p.M = (long)nimg * H * Wd;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int HW = H * Wd;
+#define DISPATCH(TI)                                                                                               \
+  switch (epilogue) {                                                                                              \
+    case 0: case 1: return launch_conv<TI>(p, EpiBias<TI>{bias, (TI*)out, ostride, ooff, Cout, epilogue}, vec, s); \
+    case 2: return launch_conv<TI>(p, EpiGlo<TI>{bias, (const TI*)aux0, aux_stride, (TI*)out, Cout}, vec, s);      \
+    case 3: return launch_conv<TI>(p, EpiZR<TI>{bias, aux1, (const TI*)aux0, aux_stride, (TI*)out, (TI*)out2, HW}, vec, s); \
+    case 4: return launch_conv<TI>(p, EpiQ<TI>{bias, aux1, (const TI*)aux0, (TI*)out, ostride, HW}, vec, s);       \
+    default: return PVO_ERR_UNSUPPORTED;                                                                           \
+  }
+  if (dtype == PVO_DTYPE_F32) { DISPATCH(float) }
+  else if (dtype == PVO_DTYPE_F16) { DISPATCH(__half) }
+#undef DISPATCH
+  return PVO_ERR_UNSUPPORTED;
+}
+
+extern "C" int pvo_conv3x3_small(const void* in, int istride, int cin_g, const float* W, const float* bias, float* out,
+                                 int ostride, int G, int CG, int nimg, int H, int Wd, int dtype, int post, void* stream) {
+  if (cin_g % 8 || (CG != 1 && CG != 2) || G < 1) return PVO_ERR_INVALID;
+  if (nimg == 0) return PVO_OK;
+  const long M = (long)nimg * H * Wd;
+  const size_t smem = sizeof(float) * G * 9 * cin_g * CG;
+  const int grid = ceil_div(M * G, 128);
+  cudaStream_t s = (cudaStream_t)stream;
+#define L(TI, CGV)                                                                                                  \
+  {                                                                                                                 \
+    cudaFuncSetAttribute(conv3x3_small_kernel<TI, CGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    conv3x3_small_kernel<TI, CGV><<<grid, 128, smem, s>>>((const TI*)in, istride, cin_g, W, bias, out, ostride, G, H, Wd, M, post); \
+  }
+  if (dtype == PVO_DTYPE_F32) { if (CG == 1) L(float, 1) else L(float, 2) }
+  else if (dtype == PVO_DTYPE_F16) { if (CG == 1) L(__half, 1) else L(__half, 2) }
+  else return PVO_ERR_UNSUPPORTED;
+#undef L
+  return pvo_check_launch();
+}
+
+extern "C" int pvo_colmean(const void* in, float* out, int E, int HW, int C, int dtype, void* stream) {
+  if (E == 0) return PVO_OK;
+  dim3 grid(E, ceil_div(C, 32));
+  if (dtype == PVO_DTYPE_F32) colmean_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, out, HW, C);
+  else colmean_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)in, out, HW, C);
+  return pvo_check_launch();
+}
+
+extern "C" int pvo_glo_matvec(const float* glo, const float* W, const float* b, float* out, int E, void* stream) {
+  if (E == 0) return PVO_OK;
+  glo_matvec_kernel<<<E, 384, 0, (cudaStream_t)stream>>>(glo, W, b, out);
+  return pvo_check_launch();
+}
+
+extern "C" int pvo_segment_mean(const void* in, int istride, int ioff, void* out, const int* ptr, const int* idx,
+                                const int* meta, int Kmax, int HW, int C, int dtype, void* stream) {
+  if (Kmax == 0) return PVO_OK;
+  dim3 grid(ceil_div((long)HW * C, 256), Kmax);
+  if (dtype == PVO_DTYPE_F32)
+    segment_mean_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, istride, ioff, (float*)out, ptr, idx, meta, HW, C);
+  else
+    segment_mean_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)in, istride, ioff, (__half*)out, ptr, idx, meta, HW, C);
+  return pvo_check_launch();
+}
+
+// src (N,C,H,W) -> dst pixel-major with channel stride/offset; sdtype/ddtype independently f32/f16
+extern "C" int pvo_nchw_to_nhwc(const void* src, int sdtype, void* dst, int ddtype, int N, int C, int HW, int dstride,
+                                int doff, void* stream) {
+  if (N == 0) return PVO_OK;
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long total = (long)N * C * HW;
+  if (sdtype == 0 && ddtype == 0) nchw_to_nhwc_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, (float*)dst, C, HW, dstride, doff, total);
+  else if (sdtype == 0 && ddtype == 1) nchw_to_nhwc_kernel<float, __half><<<grid, 256, 0, s>>>((const float*)src, (__half*)dst, C, HW, dstride, doff, total);
+  else if (sdtype == 1 && ddtype == 0) nchw_to_nhwc_kernel<__half, float><<<grid, 256, 0, s>>>((const __half*)src, (float*)dst, C, HW, dstride, doff, total);
+  else nchw_to_nhwc_kernel<__half, __half><<<grid, 256, 0, s>>>((const __half*)src, (__half*)dst, C, HW, dstride, doff, total);
+  return pvo_check_launch();
+}
+
+extern "C" int pvo_nhwc_to_nchw(const void* src, int sdtype, int sstride, int soff, void* dst, int ddtype, int N, int C,
+                                int HW, void* stream) {
+  if (N == 0) return PVO_OK;
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (sdtype == 0 && ddtype == 0) nhwc_to_nchw_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, sstride, soff, (float*)dst, C, HW);
+  else if (sdtype == 0 && ddtype == 1) nhwc_to_nchw_kernel<float, __half><<<grid, 256, 0, s>>>((const float*)src, sstride, soff, (__half*)dst, C, HW);
+  else if (sdtype == 1 && ddtype == 0) nhwc_to_nchw_kernel<__half, float><<<grid, 256, 0, s>>>((const __half*)src, sstride, soff, (float*)dst, C, HW);
+  else nhwc_to_nchw_kernel<__half, __half><<<grid, 256, 0, s>>>((const __half*)src, sstride, soff, (__half*)dst, C, HW);
+  return pvo_check_launch();
+}

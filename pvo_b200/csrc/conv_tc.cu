@@ -1,0 +1,323 @@
+// Implicit-GEMM convolution on 5th-generation tensor cores: TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue.
+//
+// The dense convolutions of the update operator in half precision (what the reference's inference autocasts to,
+// VO_Module/droid_slam/factor_graph.py:227,242): ConvGRU's three 448->128 3x3 convs (modules/gru.py:10-12, 59% of
+// the operator's FLOPs), the encoders' 3x3 layers and the heads' first layers (droid_net.py:172-214).  The reference
+// runs each as a cuDNN call followed by separate bias / activation / gate kernels; here bias, ReLU and the GRU gate
+// arithmetic are the epilogue, and torch.cat of the GRU input is virtual (one TMA tensor map per input segment).
+//
+// GEMM view  D[pixel, cout] = sum_{tap, c} X[pixel + tap, c] * W[cout, tap, c]
+//   M tile  = 128 pixels = an 8 x 16 patch of one image (TMA box {64 ch, 16, 8, 1}; out-of-image taps and rows are
+//             zero-filled by TMA, which is the convolution's zero padding)
+//   N tile  = BN output channels (64 / 128 / 256), K block = 64 channels of one tap (128-byte swizzled rows)
+//   UMMA 128 x BN x 16, fp16 operands, fp32 accumulators in TMEM, double-buffered (2 x BN columns)
+// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2-5 = epilogue (one TMEM lane quarter each).  smem ring of kStages {A 16 KB, B BN*128 B} stages.
+// Roofline: tensor pipe; with single-CTA tiles the operand stream (48 KB per 512 MMA cycles at BN=256) makes L2 the
+// practical bound -- see DESIGN.md for the measured fraction and the 2-CTA / halo-reuse follow-ups.
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kBM = 128, kBK = 64, kTileW = 16, kTileH = 8;
+constexpr int kThreads = 192;
+constexpr int kMaxSeg = 4;
+
+struct TcParams {
+  CUtensorMap tmA[kMaxSeg];
+  CUtensorMap tmB;
+  int seg_blocks[kMaxSeg];   // 64-channel blocks per segment
+  int nseg;
+  int blocks_per_tap;        // sum of seg_blocks
+  int taps, KW, padH, padW;
+  int H, W, nimg;
+  int tiles_x, tiles_y, n_tiles, total_tiles;
+  int Cout;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// ---- epilogues: store16(m, e, n, v): 16 consecutive output channels n.. of pixel m (image/edge e) -------------
+struct EpBias {          // out = act(acc + bias)
+  const float* bias; __half* out; int ostride; int ooff; int Cout; int relu;
+  __device__ __forceinline__ void store16(long m, long, int n, const float* v) const {
+    if (n >= Cout) return;
+    __align__(16) __half h[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      float x = v[j] + ((n + j < Cout) ? __ldg(bias + n + j) : 0.0f);
+      if (relu) x = fmaxf(x, 0.0f);
+      h[j] = __float2half_rn(x);
+    }
+    __half* o = out + m * ostride + ooff + n;
+    if (n + 16 <= Cout) {
+      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&h[0]);
+      *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+    } else {
+      for (int j = 0; n + j < Cout; j++) o[j] = h[j];
+    }
+  }
+};
+
+struct EpZR {            // gru.py:28-29 (see conv_simt.cu EpiZR)
+  const float* bias; const float* glo; const __half* net; int nstride; __half* z; __half* rnet;
+  __device__ __forceinline__ void store16(long m, long e, int n, const float* v) const {
+    if (n >= 256) return;
+    __align__(16) __half h[16];
+    __align__(16) __half hn[16];
+    const bool isr = n >= 128;
+    const int c0 = isr ? n - 128 : n;
+    if (isr) {
+      *reinterpret_cast<uint4*>(&hn[0]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + c0));
+      *reinterpret_cast<uint4*>(&hn[8]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + c0 + 8));
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      float s = sigmoidf_(v[j] + __ldg(bias + n + j) + __ldg(glo + e * 384 + n + j));
+      if (isr) s *= __half2float(hn[j]);
+      h[j] = __float2half_rn(s);
+    }
+    __half* o = (isr ? rnet : z) + m * 128 + c0;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&h[0]);
+    *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+  }
+};
+
+struct EpQ {             // gru.py:30-32, state update in place
+  const float* bias; const float* glo; const __half* z; __half* net; int nstride;
+  __device__ __forceinline__ void store16(long m, long e, int n, const float* v) const {
+    if (n >= 128) return;
+    __align__(16) __half hz[16];
+    __align__(16) __half hn[16];
+    __align__(16) __half h[16];
+    *reinterpret_cast<uint4*>(&hz[0]) = __ldg(reinterpret_cast<const uint4*>(z + m * 128 + n));
+    *reinterpret_cast<uint4*>(&hz[8]) = __ldg(reinterpret_cast<const uint4*>(z + m * 128 + n + 8));
+    *reinterpret_cast<uint4*>(&hn[0]) = *reinterpret_cast<const uint4*>(net + m * nstride + n);
+    *reinterpret_cast<uint4*>(&hn[8]) = *reinterpret_cast<const uint4*>(net + m * nstride + n + 8);
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const float q = tanhf(v[j] + __ldg(bias + n + j) + __ldg(glo + e * 384 + 256 + n + j));
+      const float zz = __half2float(hz[j]);
+      h[j] = __float2half_rn((1.0f - zz) * __half2float(hn[j]) + zz * q);
+    }
+    __half* o = net + m * nstride + n;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&h[0]);
+    *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+  }
+};
+
+template <int BN> struct Cfg {
+  static constexpr int kStageA = kBM * kBK * 2;                 // 16 KB
+  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN; // 128 / 256 / 512: powers of two
+  static constexpr int kSmem = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, typename Epi>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p, const Epi epi) {
+  using C = Cfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B)
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + C::kStages * C::kStage);
+  uint64_t* full = bars;                       // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + C::kStages;         // [kStages]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * C::kStages;     // [2]        MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = p.taps * p.blocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; s++) prefetch_tmap(&p.tmA[s]);
+    prefetch_tmap(&p.tmB);
+    for (int s = 0; s < C::kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = tile / p.n_tiles;
+        const int img = mt / (p.tiles_x * p.tiles_y);
+        const int r = mt - img * (p.tiles_x * p.tiles_y);
+        const int y0 = (r / p.tiles_x) * kTileH, x0 = (r % p.tiles_x) * kTileW;
+        for (int tap = 0; tap < p.taps; tap++) {
+          const int dy = tap / p.KW - p.padH, dx = tap % p.KW - p.padW;
+          int kb = tap * p.blocks_per_tap;
+          for (int s = 0; s < p.nseg; s++) {
+            for (int cb = 0; cb < p.seg_blocks[s]; cb++, kb++) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              unsigned char* sa = ring + stage * C::kStage;
+              mbar_arrive_expect_tx(&full[stage], C::kStage);
+              tma_load_4d(&p.tmA[s], &full[stage], sa, cb * kBK, x0 + dx, y0 + dy, img);
+              tma_load_2d(&p.tmB, &full[stage], sa + C::kStageA, kb * kBK, nt * BN);
+              if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = idesc_f16(kBM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      fence_after_sync();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < nkb; kb++) {
+        mbar_wait(&full[stage], phase);
+        fence_after_sync();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(ring + stage * C::kStage);
+          const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + C::kStageA);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; k++)         // advance 32 B (= 16 halves) inside the swizzle atom: +2 in >>4 units
+            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);                // frees the smem stage when these MMAs retire
+          if (kb == nkb - 1) umma_commit(&tfull[as]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      const int img = mt / (p.tiles_x * p.tiles_y);
+      const int r = mt - img * (p.tiles_x * p.tiles_y);
+      const int row = q * 32 + lane;                 // accumulator row = pixel within the 8x16 patch
+      const int y = (r / p.tiles_x) * kTileH + row / kTileW, x = (r % p.tiles_x) * kTileW + row % kTileW;
+      const bool ok = y < p.H && x < p.W;
+      const long m = ((long)img * p.H + y) * p.W + x;
+      mbar_wait(&tfull[as], aphase);
+      fence_after_sync();
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (ok) epi.store16(m, img, nt * BN + c, reinterpret_cast<const float*>(v));
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+template <int BN, typename Epi>
+int launch_tc(const TcParams& p, const Epi& epi, cudaStream_t s) {
+  using C = Cfg<BN>;
+  static bool set = false;
+  if (!set) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) != cudaSuccess)
+      return PVO_ERR_CUDA;
+    set = true;
+  }
+  const int grid = p.total_tiles < PVO_SM_COUNT ? p.total_tiles : PVO_SM_COUNT;
+  conv_tc_kernel<BN, Epi><<<grid, kThreads, C::kSmem, s>>>(p, epi);
+  return pvo_check_launch();
+}
+
+template <typename Epi>
+int dispatch_bn(const TcParams& p0, const Epi& epi, int bn, cudaStream_t s) {
+  TcParams p = p0;
+  p.n_tiles = (p.Cout + bn - 1) / bn;
+  p.total_tiles = p.nimg * p.tiles_x * p.tiles_y * p.n_tiles;
+  if (bn == 256) return launch_tc<256>(p, epi, s);
+  if (bn == 128) return launch_tc<128>(p, epi, s);
+  return launch_tc<64>(p, epi, s);
+}
+
+}  // namespace
+
+// Segments: pixel-major fp16 tensors (nimg*H*W, stride) whose channel slices are concatenated into the conv input;
+// seg_channels[s] need not be a multiple of 64 (the tail is zero-filled by TMA; the packed weights carry zeros there).
+// Wh: fp16 [Cout][taps * sum_s ceil64(seg_channels[s])], K ordered (tap, segment, channel) -- pack_conv_weight_tc.
+// epilogue: 0 bias, 1 bias+ReLU, 3 GRU z|r, 4 GRU q + state update (same meaning and aux pointers as pvo_conv2d).
+extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels, const int* seg_stride, int nseg,
+                             const void* Wh, const float* bias, int Cout, int KH, int KW, int nimg, int H, int Wd,
+                             int epilogue, void* out, int ostride, int ooff, void* out2, const void* aux0, int aux_stride,
+                             const float* aux1, void* stream) {
+  if (nseg < 1 || nseg > kMaxSeg || Cout < 1 || nimg < 0 || !(KH & 1) || !(KW & 1)) return PVO_ERR_INVALID;
+  if (nimg == 0) return PVO_OK;
+  TcParams p;
+  p.nseg = nseg;
+  p.blocks_per_tap = 0;
+  for (int s = 0; s < kMaxSeg; s++) p.seg_blocks[s] = 0;
+  for (int s = 0; s < nseg; s++) {
+    if (seg_channels[s] % 8 || (seg_stride[s] * 2) % 16 || ((uintptr_t)seg_ptr[s]) % 16) return PVO_ERR_INVALID;
+    p.seg_blocks[s] = (seg_channels[s] + kBK - 1) / kBK;
+    p.blocks_per_tap += p.seg_blocks[s];
+    const uint64_t dims[4] = {(uint64_t)seg_channels[s], (uint64_t)Wd, (uint64_t)H, (uint64_t)nimg};
+    const uint64_t strides[3] = {(uint64_t)seg_stride[s] * 2, (uint64_t)seg_stride[s] * 2 * Wd, (uint64_t)seg_stride[s] * 2 * Wd * H};
+    const uint32_t box[4] = {kBK, kTileW, kTileH, 1};
+    const int rc = make_tmap_f16(&p.tmA[s], seg_ptr[s], 4, dims, strides, box);
+    if (rc != PVO_OK) return rc;
+  }
+  for (int s = nseg; s < kMaxSeg; s++) p.tmA[s] = p.tmA[0];
+  p.taps = KH * KW; p.KW = KW; p.padH = KH / 2; p.padW = KW / 2;
+  p.H = H; p.W = Wd; p.nimg = nimg;
+  p.tiles_x = (Wd + kTileW - 1) / kTileW;
+  p.tiles_y = (H + kTileH - 1) / kTileH;
+  p.Cout = Cout;
+  const long Ktot = (long)p.taps * p.blocks_per_tap * kBK;
+  int bn = Cout >= 256 ? 256 : (Cout >= 128 ? 128 : 64);
+  // keep at least ~2 waves of tiles: prefer the narrower tile when the wide one leaves SMs idle
+  {
+    const long mt = (long)nimg * p.tiles_x * p.tiles_y;
+    while (bn > 64 && mt * ((Cout + bn - 1) / bn) < 2 * PVO_SM_COUNT) bn >>= 1;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Cout};
+    const uint64_t strides[1] = {(uint64_t)Ktot * 2};
+    const uint32_t box[2] = {kBK, (uint32_t)bn};
+    const int rc = make_tmap_f16(&p.tmB, Wh, 2, dims, strides, box);
+    if (rc != PVO_OK) return rc;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (epilogue) {
+    case 0: case 1:
+      if ((ostride * 2) % 16 || (ooff * 2) % 16) return PVO_ERR_INVALID;
+      return dispatch_bn(p, EpBias{bias, (__half*)out, ostride, ooff, Cout, epilogue}, bn, s);
+    case 3:
+      if (Cout != 256) return PVO_ERR_INVALID;
+      return dispatch_bn(p, EpZR{bias, aux1, (const __half*)aux0, aux_stride, (__half*)out, (__half*)out2}, bn, s);
+    case 4:
+      if (Cout != 128) return PVO_ERR_INVALID;
+      return dispatch_bn(p, EpQ{bias, aux1, (const __half*)aux0, (__half*)out, ostride}, bn, s);
+    default:
+      return PVO_ERR_UNSUPPORTED;
+  }
+}

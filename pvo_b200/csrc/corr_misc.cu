@@ -1,0 +1,128 @@
+// Remaining droid_backends correlation entry points: the lookup's backward pass and the on-the-fly ("alt")
+// correlation used by the global-BA path.
+//
+//   corr_index_backward : VO_Module/src/correlation_kernels.cu:73-124,157-185  (training only)
+//   altcorr_forward     : VO_Module/src/altcorr_kernel.cu:27-149,290-319      (FactorGraph.update_lowmem)
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ bool inb(int y, int x, int H, int W) { return y >= 0 && y < H && x >= 0 && x < W; }
+
+template <typename T> struct Ar;
+template <> struct Ar<float> {
+  static __device__ __forceinline__ float w(float v) { return v; }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float zero() { return 0.0f; }
+};
+template <> struct Ar<__half> {
+  static __device__ __forceinline__ __half w(float v) { return __float2half_rn(v); }
+  static __device__ __forceinline__ __half fma_(__half a, __half b, __half c) { return __hadd_rn(c, __hmul_rn(a, b)); }
+  static __device__ __forceinline__ __half add(__half a, __half b) { return __hadd_rn(a, b); }
+  static __device__ __forceinline__ __half zero() { return __float2half_rn(0.0f); }
+};
+
+// one thread per source pixel owns its (h2,w2) slice of volume_grad: g accumulates the <= 4 contributions in the
+// reference's order, then one += into the (zero-initialised) slice -- same arithmetic as the reference kernel.
+template <typename T>
+__global__ void __launch_bounds__(128) corr_index_bwd_kernel(const float* __restrict__ coords, const T* __restrict__ cg,
+                                                             T* __restrict__ vg, int N, int h1, int w1, int h2, int w2, int r) {
+  const long plane = (long)h1 * w1;
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long)N * plane) return;
+  const int n = (int)(p / plane);
+  const long pix = p - (long)n * plane;
+  const float x0 = coords[((long)n * 2 + 0) * plane + pix], y0 = coords[((long)n * 2 + 1) * plane + pix];
+  const float dx = x0 - floorf(x0), dy = y0 - floorf(y0);
+  const int fx = (int)fminf(fmaxf(floorf(x0), -16777216.f), 16777216.f), fy = (int)fminf(fmaxf(floorf(y0), -16777216.f), 16777216.f);
+  const int rd = 2 * r + 1;
+  const T* g = cg + (long)n * rd * rd * plane + pix;
+  T* v = vg + p * (long)h2 * w2;
+  const auto wDD = Ar<T>::w(dx * dy), wDN = Ar<T>::w(dx * (1.0f - dy)), wND = Ar<T>::w((1.0f - dx) * dy),
+             wNN = Ar<T>::w((1.0f - dx) * (1.0f - dy));
+  for (int i = 0; i < rd + 1; i++)
+    for (int j = 0; j < rd + 1; j++) {
+      const int x1 = fx - r + i, y1 = fy - r + j;
+      if (!inb(y1, x1, h2, w2)) continue;
+      T acc = Ar<T>::zero();
+      if (i > 0 && j > 0) acc = Ar<T>::fma_(g[(long)((i - 1) * rd + (j - 1)) * plane], wDD, acc);
+      if (i > 0 && j < rd) acc = Ar<T>::fma_(g[(long)((i - 1) * rd + j) * plane], wDN, acc);
+      if (i < rd && j > 0) acc = Ar<T>::fma_(g[(long)(i * rd + (j - 1)) * plane], wND, acc);
+      if (i < rd && j < rd) acc = Ar<T>::fma_(g[(long)(i * rd + j) * plane], wNN, acc);
+      v[(long)y1 * w2 + x1] = Ar<T>::add(v[(long)y1 * w2 + x1], acc);
+    }
+}
+
+// altcorr: one thread per (b, s, pixel); 8x8 taps, each a C-channel dot product (float4 loads), bilinear splat kept in
+// registers.  First version (SURVEY.md section 8(f) item 3 marks the tiled / tensor-core rewrite as "next").
+__global__ void __launch_bounds__(128) altcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+                                                          const float* __restrict__ coords, float* __restrict__ out,
+                                                          int B, int S, int H1, int W1, int H2, int W2, int C) {
+  const long plane = (long)H1 * W1;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)B * S * plane) return;
+  const long bs = t / plane;
+  const long pix = t - bs * plane;
+  const int b = (int)(bs / S);
+  const float x2 = coords[t * 2], y2 = coords[t * 2 + 1];
+  const float dx = x2 - floorf(x2), dy = y2 - floorf(y2);
+  const int fx = (int)fminf(fmaxf(floorf(x2), -16777216.f), 16777216.f), fy = (int)fminf(fmaxf(floorf(y2), -16777216.f), 16777216.f);
+  const float* a = f1 + ((long)b * plane + pix) * C;
+  float acc[49];
+#pragma unroll
+  for (int q = 0; q < 49; q++) acc[q] = 0.0f;
+#pragma unroll
+  for (int iy = 0; iy < 8; iy++) {
+#pragma unroll
+    for (int ix = 0; ix < 8; ix++) {
+      const int hh = fy - 3 + iy, ww = fx - 3 + ix;
+      float s = 0.0f;
+      if (inb(hh, ww, H2, W2)) {
+        const float* bb = f2 + (((long)b * H2 + hh) * W2 + ww) * C;
+        for (int c = 0; c < C; c += 4) {
+          const float4 u = __ldg(reinterpret_cast<const float4*>(a + c));
+          const float4 v = __ldg(reinterpret_cast<const float4*>(bb + c));
+          s = fmaf(u.x, v.x, s); s = fmaf(u.y, v.y, s); s = fmaf(u.z, v.z, s); s = fmaf(u.w, v.w, s);
+        }
+      }
+      if (iy > 0 && ix > 0) acc[(iy - 1) + 7 * (ix - 1)] += s * (dy * dx);
+      if (iy > 0 && ix < 7) acc[(iy - 1) + 7 * ix] += s * (dy * (1 - dx));
+      if (iy < 7 && ix > 0) acc[iy + 7 * (ix - 1)] += s * ((1 - dy) * dx);
+      if (iy < 7 && ix < 7) acc[iy + 7 * ix] += s * ((1 - dy) * (1 - dx));
+    }
+  }
+  float* o = out + bs * 49 * plane + pix;
+#pragma unroll
+  for (int q = 0; q < 49; q++) o[(long)q * plane] = acc[q];
+}
+
+}  // namespace
+
+extern "C" int pvo_version(void) { return 100; }
+
+extern "C" int pvo_corr_index_backward(const float* coords, const void* corr_grad, void* volume_grad, int N, int h1,
+                                       int w1, int h2, int w2, int radius, int dtype, void* stream) {
+  if (N < 0 || h1 <= 0 || w1 <= 0 || h2 <= 0 || w2 <= 0 || radius < 0) return PVO_ERR_INVALID;
+  if (N == 0) return PVO_OK;
+  const int grid = ceil_div((long)N * h1 * w1, 128);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == PVO_DTYPE_F32)
+    corr_index_bwd_kernel<float><<<grid, 128, 0, s>>>(coords, (const float*)corr_grad, (float*)volume_grad, N, h1, w1, h2, w2, radius);
+  else if (dtype == PVO_DTYPE_F16)
+    corr_index_bwd_kernel<__half><<<grid, 128, 0, s>>>(coords, (const __half*)corr_grad, (__half*)volume_grad, N, h1, w1, h2, w2, radius);
+  else
+    return PVO_ERR_UNSUPPORTED;
+  return pvo_check_launch();
+}
+
+extern "C" int pvo_altcorr_forward(const float* fmap1, const float* fmap2, const float* coords, float* out, int B, int S,
+                                   int H1, int W1, int H2, int W2, int C, int radius, void* stream) {
+  if (B < 0 || S < 0 || C % 4) return PVO_ERR_INVALID;
+  if (radius != 3) return PVO_ERR_UNSUPPORTED;
+  if (B == 0 || S == 0) return PVO_OK;
+  const int grid = ceil_div((long)B * S * H1 * W1, 128);
+  altcorr_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(fmap1, fmap2, coords, out, B, S, H1, W1, H2, W2, C);
+  return pvo_check_launch();
+}

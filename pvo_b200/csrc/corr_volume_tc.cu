@@ -1,0 +1,261 @@
+// All-pairs correlation volume + 4-level pooling pyramid on tcgen05 tensor cores, one pass.
+//
+// Replaces CorrBlock.__init__ (VO_Module/droid_slam/modules/corr.py:23-38,63-71): torch.matmul on (E,HW,128)x(E,128,HW)
+// half operands followed by three F.avg_pool2d passes that re-read and re-write the volume.  Here each edge's
+// C = F1 . F2^T is produced tile by tile in TMEM and the epilogue emits ALL FOUR levels from registers: level 0 is
+// written once and never re-read (61 MB/edge written, 0 read back -- the reference moves ~2x that).
+//
+//   work item = (edge, 128 source pixels);  A = F1 rows [128 x 128] loaded once per item (2 SW128 K blocks)
+//   chunk     = 2 rows of image 2 = N = 2*W columns (one UMMA N);  B = F2 rows [2W x 128], TMA ring of 3 stages
+//   accumulators: 2 x (2W) TMEM columns (double buffered) so the MMA of chunk c+1 overlaps the epilogue of chunk c
+//   epilogue thread = one source pixel (TMEM lane): rounds to half (level 0), pools 2x2 of the ROUNDED values in
+//   float in raster order and rounds again (levels 1..3), exactly the cascade avg_pool2d applies.
+// Inputs are pixel-major (E, HW, 128) fp16 ALREADY divided by 4 (the reference's `fmap / 4.0`, corr.py:66-67).
+// HBM-bound on the level-0 write: algorithmic bytes = 2 * (1 + 1/4 + 1/16 + 1/64) * HW^2 per edge.
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 192;
+constexpr int kStagesB = 3;
+
+struct VolParams {
+  CUtensorMap tmA, tmB;
+  __half* lvl[4];
+  int E, H, HW, mtiles, items, nchunks;
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+__device__ __forceinline__ __half pool4(__half a, __half b, __half c, __half d) {
+  float s = __half2float(a);
+  s += __half2float(b);
+  s += __half2float(c);
+  s += __half2float(d);
+  return __float2half_rn(s * 0.25f);
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __grid_constant__ VolParams p) {
+  constexpr int N = 2 * W;                       // UMMA N = two rows of image 2
+  constexpr int kA = 2 * 128 * 128;              // A: two K blocks of [128 rows][64 halves]
+  constexpr int kBblk = N * 128;                 // one K block of B
+  constexpr int kStage = 2 * kBblk;
+  constexpr int W1 = W / 2, W2 = W / 4, W3 = W / 8;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smA = base;
+  unsigned char* smB = base + kA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + kStagesB * kStage);
+  uint64_t* full = bars;                  // [3]
+  uint64_t* empty = bars + kStagesB;      // [3]
+  uint64_t* afull = empty + kStagesB;     // [1]
+  uint64_t* aempty = afull + 1;           // [1]
+  uint64_t* tfull = aempty + 1;           // [2]
+  uint64_t* tempty = tfull + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA);
+    prefetch_tmap(&p.tmB);
+    for (int s = 0; s < kStagesB; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(afull, 1);
+    mbar_init(aempty, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int kAcc = (N <= 256) ? 256 : 0;     // column offset of the second accumulator
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, aph = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int e = item / p.mtiles, mt = item - e * p.mtiles;
+        mbar_wait(aempty, aph ^ 1);
+        mbar_arrive_expect_tx(afull, kA);
+        tma_load_2d(&p.tmA, afull, smA, 0, e * p.HW + mt * 128);      // rows past this edge belong to the next one:
+        tma_load_2d(&p.tmA, afull, smA + kA / 2, 64, e * p.HW + mt * 128);   // harmless, those lanes are never stored
+        aph ^= 1;
+        for (int c = 0; c < p.nchunks; c++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* sb = smB + stage * kStage;
+          mbar_arrive_expect_tx(&full[stage], kStage);
+          tma_load_2d(&p.tmB, &full[stage], sb, 0, e * p.HW + c * N);
+          tma_load_2d(&p.tmB, &full[stage], sb + kBblk, 64, e * p.HW + c * N);
+          if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = idesc_f16(128, N);
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0, aph = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      mbar_wait(afull, aph);
+      aph ^= 1;
+      for (int c = 0; c < p.nchunks; c++) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        mbar_wait(&full[stage], phase);
+        fence_after_sync();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smA), sb = smem_u32(smB + stage * kStage);
+          const uint32_t tmem_d = tmem_base + as * kAcc;
+#pragma unroll
+          for (int kb = 0; kb < 2; kb++) {
+            const uint64_t da = smem_desc_sw128(sa + kb * (kA / 2)), db = smem_desc_sw128(sb + kb * kBblk);
+#pragma unroll
+            for (int k = 0; k < 4; k++) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          umma_commit(&tfull[as]);
+          if (c == p.nchunks - 1) umma_commit(aempty);
+        }
+        __syncwarp();
+        if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    const int H = p.H, H1 = H / 2, H2 = H1 / 2, H3 = H2 / 2;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int e = item / p.mtiles, mt = item - e * p.mtiles;
+      const int p1 = mt * 128 + q * 32 + lane;
+      const bool ok = p1 < p.HW;
+      const long rowi = (long)e * p.HW + p1;
+      __half* o0 = p.lvl[0] + rowi * ((long)H * W);
+      __half* o1 = p.lvl[1] + rowi * ((long)H1 * W1);
+      __half* o2 = p.lvl[2] + rowi * ((long)H2 * W2);
+      __half* o3 = p.lvl[3] + rowi * ((long)H3 * W3);
+      // pooled rows are kept packed (two halves per register); every loop below is fully unrolled so they stay in
+      // registers.  pair x of a level-k row = columns (2x, 2x+1).
+      __half2 l1prev[W1 / 2], l1cur[W1 / 2], l2prev[W2 / 2 + 1], l2cur[W2 / 2 + 1];
+      for (int c = 0; c < p.nchunks; c++) {
+        mbar_wait(&tfull[as], aphase);
+        fence_after_sync();
+        const uint32_t taddr = tmem_base + as * kAcc + ((uint32_t)(q * 32) << 16);
+        const bool row1 = 2 * c + 1 < H;
+#pragma unroll
+        for (int j = 0; j < W / 8; j++) {
+          uint32_t a[8], b[8];
+          tmem_ld8(taddr + j * 8, a);
+          tmem_ld8(taddr + W + j * 8, b);
+          tmem_ld_wait();
+          __half2 pa[4], pb[4];
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            pa[t] = __floats2half2_rn(__uint_as_float(a[2 * t]), __uint_as_float(a[2 * t + 1]));
+            pb[t] = __floats2half2_rn(__uint_as_float(b[2 * t]), __uint_as_float(b[2 * t + 1]));
+          }
+          if (ok) {
+            *reinterpret_cast<uint4*>(o0 + (long)(2 * c) * W + j * 8) = make_uint4(h2u(pa[0]), h2u(pa[1]), h2u(pa[2]), h2u(pa[3]));
+            if (row1)
+              *reinterpret_cast<uint4*>(o0 + (long)(2 * c + 1) * W + j * 8) = make_uint4(h2u(pb[0]), h2u(pb[1]), h2u(pb[2]), h2u(pb[3]));
+          }
+#pragma unroll
+          for (int t = 0; t < 2; t++)
+            l1cur[2 * j + t] = __halves2half2(pool4(__low2half(pa[2 * t]), __high2half(pa[2 * t]), __low2half(pb[2 * t]), __high2half(pb[2 * t])),
+                                              pool4(__low2half(pa[2 * t + 1]), __high2half(pa[2 * t + 1]), __low2half(pb[2 * t + 1]), __high2half(pb[2 * t + 1])));
+        }
+        // the accumulator is drained: hand it back before the (register-only) pooling tail
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (ok && c < H1) {
+#pragma unroll
+          for (int x = 0; x < W1 / 4; x++)
+            *reinterpret_cast<uint2*>(o1 + (long)c * W1 + 4 * x) = make_uint2(h2u(l1cur[2 * x]), h2u(l1cur[2 * x + 1]));
+        }
+        if (c & 1) {
+          const int r2 = c >> 1;
+#pragma unroll
+          for (int x = 0; x < W2 / 2; x++)
+            l2cur[x] = __halves2half2(pool4(__low2half(l1prev[2 * x]), __high2half(l1prev[2 * x]), __low2half(l1cur[2 * x]), __high2half(l1cur[2 * x])),
+                                      pool4(__low2half(l1prev[2 * x + 1]), __high2half(l1prev[2 * x + 1]), __low2half(l1cur[2 * x + 1]), __high2half(l1cur[2 * x + 1])));
+          if (ok && r2 < H2) {
+#pragma unroll
+            for (int x = 0; x < W2 / 2; x++) *reinterpret_cast<uint32_t*>(o2 + (long)r2 * W2 + 2 * x) = h2u(l2cur[x]);
+          }
+          if (r2 & 1) {
+            const int r3 = r2 >> 1;
+            if (ok && r3 < H3) {
+#pragma unroll
+              for (int x = 0; x < W3; x++)
+                o3[(long)r3 * W3 + x] = pool4(__low2half(l2prev[x]), __high2half(l2prev[x]), __low2half(l2cur[x]), __high2half(l2cur[x]));
+            }
+          } else {
+#pragma unroll
+            for (int x = 0; x < W2 / 2; x++) l2prev[x] = l2cur[x];
+          }
+        } else {
+#pragma unroll
+          for (int x = 0; x < W1 / 2; x++) l1prev[x] = l1cur[x];
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int W>
+int launch_vol(const VolParams& p, cudaStream_t s) {
+  constexpr int smem = 2 * 128 * 128 + kStagesB * 2 * (2 * W) * 128 + 1024 + 256;
+  static bool set = false;
+  if (!set) {
+    if (cudaFuncSetAttribute(corr_volume_tc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return PVO_ERR_CUDA;
+    set = true;
+  }
+  const int grid = p.items < PVO_SM_COUNT ? p.items : PVO_SM_COUNT;
+  corr_volume_tc_kernel<W><<<grid, kThreads, smem, s>>>(p);
+  return pvo_check_launch();
+}
+
+}  // namespace
+
+// fmap1, fmap2: (E, h*w, 128) fp16 pixel-major, pre-divided by 4.  levels_out[l]: (E, h, w, h>>l, w>>l) fp16.
+// Supported: num_levels == 4, w in {40, 80} (N = 2w must be a legal UMMA N and pooling stays register resident);
+// anything else returns PVO_ERR_UNSUPPORTED and the caller uses pvo_corr_volume.
+extern "C" int pvo_corr_volume_f16(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w,
+                                   int num_levels, void* stream) {
+  if (E < 0 || h <= 0 || w <= 0) return PVO_ERR_INVALID;
+  if (num_levels != 4 || (w != 80 && w != 40) || h < 8) return PVO_ERR_UNSUPPORTED;
+  if (E == 0) return PVO_OK;
+  VolParams p;
+  const int HW = h * w;
+  const uint64_t dims[2] = {128, (uint64_t)E * HW};
+  const uint64_t strides[1] = {256};
+  const uint32_t boxA[2] = {64, 128};
+  const uint32_t boxB[2] = {64, (uint32_t)(2 * w)};
+  int rc = tc::make_tmap_f16(&p.tmA, fmap1, 2, dims, strides, boxA);
+  if (rc != PVO_OK) return rc;
+  rc = tc::make_tmap_f16(&p.tmB, fmap2, 2, dims, strides, boxB);
+  if (rc != PVO_OK) return rc;
+  for (int l = 0; l < 4; l++) p.lvl[l] = (__half*)levels_out[l];
+  p.E = E; p.H = h; p.HW = HW;
+  p.mtiles = (HW + 127) / 128;
+  p.items = E * p.mtiles;
+  p.nchunks = (h + 1) / 2;
+  cudaStream_t s = (cudaStream_t)stream;
+  return w == 80 ? launch_vol<80>(p, s) : launch_vol<40>(p, s);
+}

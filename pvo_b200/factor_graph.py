@@ -1,0 +1,266 @@
+"""FactorGraph: edge bookkeeping + the hot loop body ``update()`` -- one "update-op iteration"
+(VO_Module/droid_slam/factor_graph.py:12-307), on the fused B200 path.
+
+update() does, with no host synchronisation and ~30 kernel launches (CUDA-graph capturable):
+    reproject + 8 motion channels          1 launch   (reference: ~30 torch kernels, factor_graph.py:231-237)
+    4-level correlation lookup             1 launch   (reference: 4 x (zeros + kernel) + cat, :240)
+    update operator                        ~14 launches (reference: ~20 cuDNN + ~12 elementwise, :242)
+    target / mask / segment filter / weights  1-3 launches (reference: host numpy round trip, :250-283)
+    dense BA, 2 Gauss-Newton iterations    9 launches (reference: >= 12 host round trips, :302)
+State that the reference keeps as (1,E,C,h,w) tensors (net, inp) lives pixel-major inside the update engine between
+iterations; the reference-layout views are materialised only when the edge set changes (add/rm factors).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import nn as pnn
+from ._lib import check, ptr, stream
+from .droid_net import DynamicUpdateModule
+from .modules.corr import CorrBlock, AltCorrBlock
+
+
+def coords_grid(ht, wd, device):
+    """geom/projective_ops.py:13-18"""
+    y, x = torch.meshgrid(torch.arange(ht, device=device).float(), torch.arange(wd, device=device).float(), indexing='ij')
+    return torch.stack([x, y], dim=-1)
+
+
+class FactorGraph:
+    def __init__(self, video, update_op, device='cuda:0', corr_impl='volume', max_factors=-1, precision='auto'):
+        self.video = video
+        self.update_op = update_op
+        self.device = device
+        self.max_factors = max_factors
+        self.corr_impl = corr_impl
+        self.precision = precision
+        self.ht = ht = video.ht // 8
+        self.wd = wd = video.wd // 8
+        self.dy_thresh = 0.5
+        self.mask_num = 2
+        self.coords0 = coords_grid(ht, wd, device)
+        lz = lambda: torch.as_tensor([], dtype=torch.long, device=device)
+        fz = lambda c=2: torch.zeros([1, 0, ht, wd, c], device=device, dtype=torch.float)
+        self.ii, self.jj, self.age = lz(), lz(), lz()
+        self.corr = None
+        self._net = self._inp = None          # reference-layout caches (1,E,128,h,w)
+        self._state_in_engine = False         # True: engine.X[:, :256] holds the authoritative net|inp
+        self.segm = None
+        self.damping = 1e-6 * torch.ones_like(self.video.disps)
+        self.target_cam, self.weight, self.delta_dy, self.full_flow = fz(), fz(), fz(), fz()
+        self.raw_mask = fz(self.mask_num)
+        self.ii_inac, self.jj_inac, self.ii_bad, self.jj_bad = lz(), lz(), lz(), lz()
+        self.target_cam_inac, self.weight_inac, self.delta_dy_inac = fz(), fz(), fz()
+        self.raw_mask_inac = fz(self.mask_num)
+        self._cache = None                    # per-edge-set constants (unique(ii), K, default t0, workspaces)
+
+    # ------------------------------------------------------------------ reference-layout state (lazy)
+    def _engine(self):
+        if not isinstance(self.update_op, DynamicUpdateModule):
+            raise RuntimeError('FactorGraph: update_op must be a pvo_b200.droid_net.DynamicUpdateModule')
+        prec = self.precision if self.precision != 'auto' else self.update_op.precision
+        mode = prec if prec in ('fp32', 'fp16') else 'fp16'       # the reference's update() is autocast (:227)
+        return self.update_op.engine(mode, self.device)
+
+    def _pull_state(self):
+        """engine (pixel-major) -> reference layout; called before the edge set is edited."""
+        if self._state_in_engine:
+            eng = self._engine()
+            E = self.ii.shape[0]
+            self._net = eng.store_nchw(eng.X, 448, 0, 128, E).view(1, E, 128, self.ht, self.wd)
+            self._state_in_engine = False
+
+    @property
+    def net(self):
+        self._pull_state()
+        return self._net
+
+    @net.setter
+    def net(self, v):
+        self._net = v
+        self._state_in_engine = False
+
+    @property
+    def inp(self):
+        return self._inp
+
+    @inp.setter
+    def inp(self, v):
+        self._inp = v
+        self._state_in_engine = False
+
+    # ------------------------------------------------------------------ edge bookkeeping (factor_graph.py:60-225)
+    def __filter_repeated_edges(self, ii, jj):
+        keep = torch.zeros(ii.shape[0], dtype=torch.bool, device=ii.device)
+        eset = set([(i.item(), j.item()) for i, j in zip(self.ii, self.jj)] +
+                   [(i.item(), j.item()) for i, j in zip(self.ii_inac, self.jj_inac)])
+        for k, (i, j) in enumerate(zip(ii, jj)):
+            keep[k] = (i.item(), j.item()) not in eset
+        return ii[keep], jj[keep]
+
+    def clear_edges(self):
+        self.rm_factors(self.ii >= 0)
+        self.net = None
+        self.inp = None
+
+    def add_factors(self, ii, jj, remove=False):
+        """add edges (factor_graph.py:106-161): volume pyramid for the new edges, hidden state from the video."""
+        ii = torch.as_tensor(ii, dtype=torch.long, device=self.device)
+        jj = torch.as_tensor(jj, dtype=torch.long, device=self.device)
+        ii, jj = self.__filter_repeated_edges(ii, jj)
+        if ii.shape[0] == 0:
+            return
+        if self.max_factors > 0 and self.ii.shape[0] + ii.shape[0] > self.max_factors and self.corr is not None and remove:
+            ix = torch.arange(len(self.age))[torch.argsort(self.age).cpu()]
+            self.rm_factors(ix >= self.max_factors - ii.shape[0], store=True)
+        self._pull_state()
+        net = self.video.nets[ii].to(self.device).unsqueeze(0)
+        if self.corr_impl == 'volume':
+            corr = CorrBlock(self.video.fmaps[ii].to(self.device).unsqueeze(0),
+                             self.video.fmaps[jj].to(self.device).unsqueeze(0))
+            self.corr = corr if self.corr is None else self.corr.cat(corr)
+            inp = self.video.inps[ii].to(self.device).unsqueeze(0)
+            self._inp = inp if self._inp is None else torch.cat([self._inp, inp], 1)
+        target, _ = self.video.reproject(ii, jj)
+        self.ii = torch.cat([self.ii, ii], 0)
+        self.jj = torch.cat([self.jj, jj], 0)
+        self.age = torch.cat([self.age, torch.zeros_like(ii)], 0)
+        self._net = net if self._net is None else torch.cat([self._net.to(net.dtype), net], 1)
+        self.target_cam = torch.cat([self.target_cam, target], 1)
+        self.weight = torch.cat([self.weight, torch.zeros_like(target)], 1)
+        self.raw_mask = torch.cat([self.raw_mask, torch.zeros_like(target)[..., 0:self.mask_num]], 1)
+        self.delta_dy = torch.cat([self.delta_dy, torch.zeros_like(target)], 1)
+        segm = self.video.segms[ii].to(self.device).unsqueeze(0)
+        self.segm = segm if self.segm is None else torch.cat([self.segm, segm], 1)
+        self._cache = None
+
+    def rm_factors(self, mask, store=False):
+        """drop edges (factor_graph.py:163-199)"""
+        mask = mask.to(self.device)
+        self._pull_state()
+        if store:
+            self.ii_inac = torch.cat([self.ii_inac, self.ii[mask]], 0)
+            self.jj_inac = torch.cat([self.jj_inac, self.jj[mask]], 0)
+            self.target_cam_inac = torch.cat([self.target_cam_inac, self.target_cam[:, mask]], 1)
+            self.weight_inac = torch.cat([self.weight_inac, self.weight[:, mask]], 1)
+            self.raw_mask_inac = torch.cat([self.raw_mask_inac, self.raw_mask[:, mask]], 1)
+            self.delta_dy_inac = torch.cat([self.delta_dy_inac, self.delta_dy[:, mask]], 1)
+        keep = ~mask
+        self.ii, self.jj, self.age = self.ii[keep], self.jj[keep], self.age[keep]
+        if self.corr_impl == 'volume' and self.corr is not None:
+            self.corr = self.corr[keep]
+        if self._net is not None:
+            self._net = self._net[:, keep]
+        if self._inp is not None:
+            self._inp = self._inp[:, keep]
+        if self.segm is not None:
+            self.segm = self.segm[:, keep]
+        self.target_cam = self.target_cam[:, keep]
+        self.weight = self.weight[:, keep]
+        self.raw_mask = self.raw_mask[:, keep]
+        self.delta_dy = self.delta_dy[:, keep]
+        self._cache = None
+
+    def rm_keyframe(self, ix):
+        """drop a keyframe and its edges (factor_graph.py:201-225)"""
+        with self.video.get_lock():
+            for buf in (self.video.poses, self.video.disps, self.video.intrinsics, self.video.nets, self.video.inps,
+                        self.video.fmaps):
+                buf[ix] = buf[ix + 1]
+            if self.video.segm_filter:
+                self.video.segms[ix] = self.video.segms[ix + 1]
+        m = (self.ii == ix) | (self.jj == ix)
+        self.ii[self.ii >= ix] -= 1
+        self.jj[self.jj >= ix] -= 1
+        self.ii_inac[self.ii_inac >= ix] -= 1
+        self.jj_inac[self.jj_inac >= ix] -= 1
+        self.rm_factors(m, store=False)
+
+    def add_neighborhood_factors(self, t0, t1, r=3):
+        """edges between all frames within distance r (factor_graph.py:362-370)"""
+        ii, jj = torch.meshgrid(torch.arange(t0, t1), torch.arange(t0, t1), indexing='ij')
+        ii, jj = ii.reshape(-1).to(self.device), jj.reshape(-1).to(self.device)
+        keep = ((ii - jj).abs() > 0) & ((ii - jj).abs() <= r)
+        self.add_factors(ii[keep], jj[keep])
+
+    # ------------------------------------------------------------------ the hot loop body
+    def _prepare(self):
+        """Per-edge-set constants.  The only host synchronisation of the hot path, paid when edges change."""
+        eng = self._engine()
+        E = self.ii.shape[0]
+        kx = torch.unique(self.ii)
+        K = int(kx.shape[0])
+        nframes = self.video.disps.shape[0]
+        eng.reserve(E, K, self.ht, self.wd, nframes)
+        if not self._state_in_engine:
+            eng.load_nchw(self._net.reshape(E, 128, self.ht, self.wd).contiguous(), eng.X, 448, 0)
+            eng.load_nchw(self._inp.reshape(E, 128, self.ht, self.wd).contiguous(), eng.X, 448, 128)
+            self._state_in_engine = True
+        eng.group(self.ii)
+        L = _lib.lib()
+        c = dict(E=E, K=K, kx=kx, t0_default=max(1, int(self.ii.min().item()) + 1),
+                 t1_default=int(max(self.ii.max().item(), self.jj.max().item())) + 1,
+                 head_dirty=True, ba_key=None)
+        c['coords1'] = torch.empty(1, E, self.ht, self.wd, 2, device=self.device)
+        c['seg_ws'] = torch.zeros(int(L.pvo_update_post_workspace_ints(E)), dtype=torch.int32, device=self.device)
+        c['segm'] = self.segm[0, :, 0].contiguous() if self.segm is not None else None
+        for name in ('target_cam', 'weight', 'raw_mask', 'delta_dy'):
+            setattr(self, name, getattr(self, name).contiguous())
+        self.full_flow = torch.empty_like(self.target_cam)
+        self._cache = c
+        return c
+
+    @torch.no_grad()
+    def update(self, t0=None, t1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
+        """run update operator on factor graph (factor_graph.py:227-307)"""
+        c = self._cache or self._prepare()
+        eng = self._engine()
+        L = _lib.lib()
+        E, K, ht, wd = c['E'], c['K'], self.ht, self.wd
+        v = self.video
+        coords1 = c['coords1']
+        # (1) reprojection + motion features, written straight into the flow encoder's input buffer
+        check(L.pvo_reproject(ptr(v.poses), ptr(v.disps), ptr(v.intrinsics), ptr(self.ii), ptr(self.jj), ptr(coords1),
+                              None, ptr(self.target_cam), ptr(self.delta_dy), ptr(self.raw_mask), ptr(eng.motn),
+                              eng.dcode, E, ht, wd, stream()), 'reproject')
+        # (2) correlation features, pixel-major into the corr encoder's input buffer
+        if self.corr.corr_pyramid[0].dtype == eng.tdtype:
+            self.corr(coords1, out=eng.corr, layout=1, out_cstride=pnn.CORR_STRIDE)
+        else:
+            self._lookup_mixed(coords1, eng)
+        # (3) update operator
+        eng.run(with_agg=True)
+        # (4) target, masks, segment filter, weights (in place on the graph's state tensors)
+        if t0 is None:
+            t0 = c['t0_default']
+        segm = c['segm'] if v.segm_filter else None
+        check(L.pvo_update_post(ptr(coords1), ptr(eng.head_out), ptr(segm), float(v.thresh), ptr(self.target_cam),
+                                ptr(self.weight), ptr(self.raw_mask), ptr(self.delta_dy), ptr(self.full_flow),
+                                ptr(c['seg_ws']), c['seg_ws'].numel(), E, ht, wd, stream()), 'update_post')
+        self.damping.index_copy_(0, c['kx'], eng.eta)
+        if use_inactive:
+            m = (self.ii_inac >= t0 - 3) & (self.jj_inac >= t0 - 3)
+            ii = torch.cat([self.ii_inac[m], self.ii], 0)
+            jj = torch.cat([self.jj_inac[m], self.jj], 0)
+            target_cam = torch.cat([self.target_cam_inac[:, m], self.target_cam], 1).contiguous()
+            weight = torch.cat([self.weight_inac[:, m], self.weight], 1).contiguous()
+            damping = (.2 * self.damping[torch.unique(ii)] + EP).contiguous()
+            reuse = False
+        else:
+            ii, jj, target_cam, weight = self.ii, self.jj, self.target_cam, self.weight
+            damping = .2 * self.damping.index_select(0, c['kx']) + EP
+            reuse = c['ba_key'] == (t0, t1, ii.shape[0])
+            c['ba_key'] = (t0, t1, ii.shape[0])
+        # (5) dense bundle adjustment, in place on video.poses / video.disps
+        if t1 is None:
+            t1 = c['t1_default'] if not use_inactive else None
+        v.ba(target_cam[0], weight[0], damping, ii, jj, t0, t1, itrs=itrs, lm=1e-4, ep=0.1, motion_only=motion_only,
+             interleaved=True, reuse_plan=reuse)
+        self.age += 1
+
+    def _lookup_mixed(self, coords1, eng):
+        """volume dtype != engine dtype (e.g. half volume feeding the float32 parity engine)"""
+        E = coords1.shape[1]
+        tmp = torch.empty(E * self.ht * self.wd, pnn.CORR_STRIDE, dtype=self.corr.corr_pyramid[0].dtype, device=self.device)
+        self.corr(coords1, out=tmp, layout=1, out_cstride=pnn.CORR_STRIDE)
+        eng.corr.copy_(tmp)

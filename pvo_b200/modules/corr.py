@@ -1,0 +1,172 @@
+"""CorrSampler / CorrBlock / CorrLayer / AltCorrBlock with the reference's interface
+(VO_Module/droid_slam/modules/corr.py), on the B200 kernels.
+
+Differences that are invisible to callers: the volume + pyramid of CorrBlock.__init__ is one fused launch
+(tcgen05 GEMM for half, CUDA cores for float32); __call__ looks up all four levels in one launch and writes the
+concatenated (B,E,196,h,w) tensor directly (no per-level zeros + cat)."""
+import torch
+
+from .. import _lib, droid_backends
+from .._lib import check, ptr, stream
+
+
+class CorrSampler(torch.autograd.Function):
+    """corr.py:6-20"""
+
+    @staticmethod
+    def forward(ctx, volume, coords, radius):
+        ctx.save_for_backward(volume, coords)
+        ctx.radius = radius
+        corr, = droid_backends.corr_index_forward(volume, coords, radius)
+        return corr
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        volume, coords = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        grad_volume, = droid_backends.corr_index_backward(volume, coords, grad_output, ctx.radius)
+        return grad_volume, None, None
+
+
+def to_pixel_major(x):
+    """(N,C,H,W) -> (N,H*W,C) contiguous, same dtype, through the transpose kernel."""
+    N, C, H, W = x.shape
+    out = torch.empty(N, H * W, C, dtype=x.dtype, device=x.device)
+    check(_lib.lib().pvo_nchw_to_nhwc(ptr(x), _lib.dtype_code(x), ptr(out), _lib.dtype_code(out), N, C, H * W, C, 0,
+                                      stream()), 'nchw_to_nhwc')
+    return out
+
+
+def build_pyramid(fmap1, fmap2, num_levels=4, use_tc=None):
+    """fmap1, fmap2: (N,C,h,w).  Returns [ (N,h,w,h>>l,w>>l) ] -- corr.py:23-38,63-71 in one call."""
+    _lib.require_cuda(fmap1, fmap2)
+    N, C, h, w = fmap1.shape
+    if use_tc is None:
+        use_tc = fmap1.dtype == torch.float16 and C == 128 and w in (40, 80) and h >= 8 and num_levels == 4
+    if use_tc:      # the tensor-core kernel takes the reference's `fmap / 4.0` (a half op, corr.py:66-67) as input
+        f1, f2 = to_pixel_major(fmap1 / 4.0), to_pixel_major(fmap2 / 4.0)
+    else:           # the CUDA-core kernel applies the same rounding while loading
+        f1, f2 = to_pixel_major(fmap1), to_pixel_major(fmap2)
+    levels = [torch.empty(N, h, w, h >> l, w >> l, dtype=fmap1.dtype, device=fmap1.device) for l in range(num_levels)]
+    arr = _lib.ptr_array(levels)
+    if use_tc:
+        check(_lib.lib().pvo_corr_volume_f16(ptr(f1), ptr(f2), arr, N, h, w, num_levels, stream()), 'corr_volume_f16')
+    else:
+        check(_lib.lib().pvo_corr_volume(ptr(f1), ptr(f2), arr, N, h, w, C, num_levels, _lib.dtype_code(fmap1),
+                                         stream()), 'corr_volume')
+    return levels
+
+
+class CorrBlock:
+    """corr.py:23-71"""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=3, use_tc=None):
+        self.num_levels = num_levels
+        self.radius = radius
+        batch, num, dim, ht, wd = fmap1.shape
+        if fmap1.dtype not in (torch.float16, torch.float32):
+            raise RuntimeError('CorrBlock: float16 / float32 feature maps only')
+        self.corr_pyramid = build_pyramid(fmap1.reshape(batch * num, dim, ht, wd).contiguous(),
+                                          fmap2.reshape(batch * num, dim, ht, wd).contiguous(), num_levels, use_tc)
+
+    def __call__(self, coords, out=None, layout=0, out_cstride=0):
+        """coords (B,E,h,w,2) float32 -> (B,E,L*49,h,w) in the volume's dtype (corr.py:40-50).
+        layout=1 writes pixel-major (B*E*h*w, out_cstride) into ``out`` for the fused update operator."""
+        batch, num, ht, wd, _ = coords.shape
+        coords = coords.contiguous().float()
+        if self.radius != 3 or coords.requires_grad or any(p.requires_grad for p in self.corr_pyramid):
+            return self._call_per_level(coords)
+        pyr = self.corr_pyramid
+        L = self.num_levels
+        if out is None:
+            out = torch.empty(batch, num, L * 49, ht, wd, dtype=pyr[0].dtype, device=coords.device)
+        check(_lib.lib().pvo_corr_lookup_pyramid(_lib.ptr_array(pyr), _lib.int_array([p.shape[3] for p in pyr]),
+                                                 _lib.int_array([p.shape[4] for p in pyr]), L, ptr(coords), ptr(out),
+                                                 batch * num, ht, wd, self.radius, _lib.dtype_code(pyr[0]), layout,
+                                                 out_cstride, 0, stream()), 'corr_lookup_pyramid')
+        return out
+
+    def _call_per_level(self, coords):
+        """The reference's literal per-level path (differentiable through CorrSampler)."""
+        out_pyramid = []
+        batch, num, ht, wd, _ = coords.shape
+        c = coords.permute(0, 1, 4, 2, 3).contiguous().view(batch * num, 2, ht, wd)
+        for i in range(self.num_levels):
+            corr = CorrSampler.apply(self.corr_pyramid[i], (c / 2 ** i).contiguous(), self.radius)
+            out_pyramid.append(corr.view(batch, num, -1, ht, wd))
+        return torch.cat(out_pyramid, dim=2)
+
+    def cat(self, other):
+        for i in range(self.num_levels):
+            self.corr_pyramid[i] = torch.cat([self.corr_pyramid[i], other.corr_pyramid[i]], 0)
+        return self
+
+    def __getitem__(self, index):
+        for i in range(self.num_levels):
+            self.corr_pyramid[i] = self.corr_pyramid[i][index].contiguous()
+        return self
+
+    @staticmethod
+    def corr(fmap1, fmap2):
+        """all-pairs correlation (corr.py:63-71): level 0 only, (B,E,h,w,h,w)."""
+        batch, num, dim, ht, wd = fmap1.shape
+        lv = build_pyramid(fmap1.reshape(batch * num, dim, ht, wd).contiguous(),
+                           fmap2.reshape(batch * num, dim, ht, wd).contiguous(), 1)
+        return lv[0].view(batch, num, ht, wd, ht, wd)
+
+
+class CorrLayer(torch.autograd.Function):
+    """corr.py:74-88"""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, coords, r):
+        ctx.r = r
+        ctx.save_for_backward(fmap1, fmap2, coords)
+        corr, = droid_backends.altcorr_forward(fmap1, fmap2, coords, ctx.r)
+        return corr
+
+    @staticmethod
+    def backward(ctx, grad_corr):
+        fmap1, fmap2, coords = ctx.saved_tensors
+        g1, g2, gc = droid_backends.altcorr_backward(fmap1, fmap2, coords, grad_corr.contiguous(), ctx.r)
+        return g1, g2, gc, None
+
+
+class AltCorrBlock:
+    """corr.py:91-139: correlation computed on the fly from the feature pyramid (global-BA path)."""
+
+    def __init__(self, fmaps, num_levels=4, radius=3):
+        self.num_levels = num_levels
+        self.radius = radius
+        B, N, C, H, W = fmaps.shape
+        fmaps = fmaps.view(B * N, C, H, W) / 4.0
+        self.pyramid = []
+        for i in range(self.num_levels):
+            sz = (B, N, H // 2 ** i, W // 2 ** i, C)
+            self.pyramid.append(fmaps.permute(0, 2, 3, 1).contiguous().view(*sz))
+            fmaps = torch.nn.functional.avg_pool2d(fmaps, 2, stride=2)
+
+    def corr_fn(self, coords, ii, jj):
+        B, N, H, W, S, _ = coords.shape
+        coords = coords.permute(0, 1, 4, 2, 3, 5)
+        corr_list = []
+        for i in range(self.num_levels):
+            fmap1_i = self.pyramid[0][:, ii]
+            fmap2_i = self.pyramid[i][:, jj]
+            coords_i = (coords / 2 ** i).reshape(B * N, S, H, W, 2).contiguous()
+            fmap1_i = fmap1_i.reshape((B * N,) + fmap1_i.shape[2:])
+            fmap2_i = fmap2_i.reshape((B * N,) + fmap2_i.shape[2:])
+            corr = CorrLayer.apply(fmap1_i.float().contiguous(), fmap2_i.float().contiguous(), coords_i, self.radius)
+            corr = corr.view(B, N, S, -1, H, W).permute(0, 1, 3, 4, 5, 2)
+            corr_list.append(corr)
+        return torch.cat(corr_list, dim=2)
+
+    def __call__(self, coords, ii, jj):
+        squeeze_output = False
+        if len(coords.shape) == 5:
+            coords = coords.unsqueeze(dim=-2)
+            squeeze_output = True
+        corr = self.corr_fn(coords, ii, jj)
+        if squeeze_output:
+            corr = corr.squeeze(dim=-1)
+        return corr.contiguous()

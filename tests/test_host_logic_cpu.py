@@ -1,0 +1,140 @@
+"""Host-side logic that needs no GPU: weight packing layouts, parameter names, oracle self-consistency
+(lietorch's own property tests restated, CUDA-BA restatement vs the reference's Python BA)."""
+import torch
+
+from oracle import ba_cuda, geom, se3, update_op as oupd, corr as ocorr
+from pvo_b200 import nn as pnn
+from pvo_b200.droid_net import DynamicUpdateModule
+from tests.golden import cases
+
+
+def test_pack_conv_weight_layouts():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(6, 5, 3, 3, generator=g)
+    W = pnn.pack_conv_weight(w, cin_pad=8)
+    assert W.shape == (9 * 8, 8)
+    for co in range(6):
+        for ci in range(5):
+            for kh in range(3):
+                for kw in range(3):
+                    assert W[(kh * 3 + kw) * 8 + ci, co] == w[co, ci, kh, kw]
+    assert W[:, 6:].abs().sum() == 0 and W.reshape(9, 8, 8)[:, 5:].abs().sum() == 0
+    w = torch.randn(4, 70 + 10, 1, 3, generator=g)
+    Wh = pnn.pack_conv_weight_tc(w, segs=[70, 10])
+    assert Wh.shape == (4, 3 * (128 + 64)) and Wh.dtype == torch.float16
+    Wr = Wh.reshape(4, 3, 192)
+    assert torch.equal(Wr[:, :, :70], w[:, :70].permute(0, 2, 3, 1).reshape(4, 3, 70).half())
+    assert torch.equal(Wr[:, :, 128:138], w[:, 70:].permute(0, 2, 3, 1).reshape(4, 3, 10).half())
+    assert Wr[:, :, 70:128].abs().sum() == 0 and Wr[:, :, 138:].abs().sum() == 0
+    ws = pnn.pack_small_weight([torch.randn(2, 128, 3, 3, generator=g) for _ in range(4)])
+    assert ws.shape == (4, 9, 128, 2)
+
+
+def test_module_state_dict_matches_reference_names():
+    """checkpoint-compatibility contract of DroidNet.update."""
+    m = DynamicUpdateModule()
+    shapes = oupd.param_shapes()
+    sd = m.state_dict()
+    assert sorted(sd) == sorted(shapes)
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+    assert sum(v.numel() for v in sd.values()) == 2881801
+
+
+# ---- lietorch/run_tests.py:16-52 restated on the oracle's SE3 (float64, atol 1e-8) ----------------------------
+def test_se3_exp_log():
+    a = .2 * torch.randn(2, 3, 4, 6, dtype=torch.float64)
+    assert torch.allclose(se3.se3_log(se3.se3_exp(a)), a, atol=1e-8)
+
+
+def test_se3_inverse():
+    X = se3.se3_exp(.1 * torch.randn(2, 3, 6, dtype=torch.float64))
+    a = se3.se3_log(se3.se3_mul(X, se3.se3_inv(X)))
+    assert torch.allclose(a, torch.zeros_like(a), atol=1e-8)
+
+
+def test_se3_adjoint():
+    X = se3.se3_exp(torch.randn(2, 3, 6, dtype=torch.float64))
+    a = torch.randn(2, 3, 6, dtype=torch.float64)
+    Y1 = se3.se3_mul(X, se3.se3_exp(a))
+    Y2 = se3.se3_mul(se3.se3_exp(se3.se3_adj(X, a)), X)
+    c = se3.se3_log(se3.se3_mul(Y1, se3.se3_inv(Y2)))
+    assert torch.allclose(c, torch.zeros_like(c), atol=1e-8)
+    # adjT is the transpose of adj
+    b = torch.randn(2, 3, 6, dtype=torch.float64)
+    assert torch.allclose((se3.se3_adj(X, a) * b).sum(-1), (a * se3.se3_adjT(X, b)).sum(-1), atol=1e-8)
+
+
+def test_se3_act_matches_matrix():
+    X = se3.se3_exp(torch.randn(5, 6, dtype=torch.float64))
+    p = torch.randn(5, 3, dtype=torch.float64)
+    ph = torch.cat([p, torch.ones(5, 1, dtype=torch.float64)], -1)
+    assert torch.allclose(se3.se3_act3(X, p), (se3.se3_matrix(X) @ ph[..., None])[..., :3, 0], atol=1e-8)
+
+
+def test_cuda_ba_restatement_agrees_with_python_ba_where_semantics_coincide():
+    """SURVEY.md 8(c) self-validation (2): same reduced system when all depths are > 0.25, eta shifted by 1e-7,
+    lm = 0 (the two implementations damp different matrices, 8(a) addendum)."""
+    c = cases.graph_case(F=5, radius=2, h=12, w=16, seed=7, fdtype=torch.float32)
+    g = torch.Generator().manual_seed(70)
+    ii, jj = c['ii'], c['jj']
+    poses, disps, intr = c['poses'], c['disps'].clamp(min=0.5), c['intrinsics']
+    tgt, _ = geom.projective_transform(poses[None], disps[None], intr[None], ii, jj)
+    tgt = tgt + 0.5 * torch.randn(tgt.shape, generator=g)
+    wgt = torch.rand(tgt.shape, generator=g)
+    eta = 0.01 * torch.rand(torch.unique(ii).shape[0], 12, 16, generator=g)
+    _, _, dbg = geom.BA(tgt, wgt, eta[None], poses[None], disps[None], intr[None], ii, jj, fixedp=2, return_debug=True)
+    rec = []
+    T = tgt[0].permute(0, 3, 1, 2).contiguous()
+    W = wgt[0].permute(0, 3, 1, 2).contiguous()
+    ba_cuda.ba(poses.clone(), disps.clone(), intr[0], T, W, eta + 1e-7, ii, jj, 2, 5, 1, 0.0, 0.1, False, debug=rec)
+    S_py = dbg['S'][0].double()
+    A_cu = rec[0]['A']
+    off = (S_py - A_cu) - torch.diag(torch.diagonal(S_py - A_cu))
+    assert off.abs().max() < 1e-6 * A_cu.abs().max()
+    assert (dbg['v'][0, :, 0].double() - rec[0]['b']).abs().max() < 1e-5 * rec[0]['b'].abs().max()
+
+
+def test_cuda_ba_restatement_jacobians_by_finite_differences():
+    """SURVEY.md 8(c) self-validation (3): K5's Jj / Jz against numeric derivatives of the projection."""
+    torch.manual_seed(3)
+    c = cases.graph_case(F=3, radius=1, h=6, w=8, seed=9, fdtype=torch.float32)
+    ii, jj = c['ii'][:1], c['jj'][:1]
+    poses, disps, intr = c['poses'].double(), c['disps'].double().clamp(min=0.5), c['intrinsics'][0].double()
+    z = torch.zeros(1, 2, 6, 8, dtype=torch.float64)
+
+    def proj(poses, disps):
+        b = ba_cuda.edge_blocks(poses.float(), disps.float(), intr.float(), z.float(), z.float() + 1, ii, jj)
+        return -b['ru'].double(), -b['rv'].double()   # target = 0 -> r = -(projection)
+
+    b0 = ba_cuda.edge_blocks(poses.float(), disps.float(), intr.float(), z.float(), z.float() + 1, ii, jj)
+    eps = 1e-3
+    d2 = disps.clone()
+    d2[ii[0]] += eps
+    u1, v1 = proj(poses, d2)
+    u0, v0 = proj(poses, disps)
+    assert torch.allclose((u1 - u0) / eps, b0['Jzu'].double(), atol=2e-2, rtol=2e-2)
+    assert torch.allclose((v1 - v0) / eps, b0['Jzv'].double(), atol=2e-2, rtol=2e-2)
+    for k in range(6):
+        xi = torch.zeros(6, dtype=torch.float64)
+        xi[k] = eps
+        p2 = poses.clone()
+        p2[jj[0]] = ba_cuda.retr_se3(xi.float()[None], poses[jj[0]].float()[None])[0].double()
+        u1, v1 = proj(p2, disps)
+        assert torch.allclose((u1 - u0) / eps, b0['Jju'][..., k].double(), atol=5e-2, rtol=5e-2), k
+        assert torch.allclose((v1 - v0) / eps, b0['Jjv'][..., k].double(), atol=5e-2, rtol=5e-2), k
+
+
+def test_oracle_lookup_half_matches_float_on_exact_inputs():
+    """With integer coordinates the bilinear weights are exactly 0/1, so the half and float models must agree."""
+    g = torch.Generator().manual_seed(1)
+    vol = torch.randint(-8, 8, (2, 5, 6, 9, 11), generator=g).float()
+    coords = torch.stack([torch.randint(-2, 13, (2, 5, 6), generator=g), torch.randint(-2, 11, (2, 5, 6), generator=g)], 1).float()
+    a = ocorr.corr_index_forward(vol, coords, 3)
+    b = ocorr.corr_index_forward(vol.half(), coords, 3)
+    assert torch.equal(a, b.float())
+    # window centre equals the volume value at the (in-bounds) coordinate
+    for n, y, x in ((0, 1, 2), (1, 4, 5)):
+        cx, cy = int(coords[n, 0, y, x]), int(coords[n, 1, y, x])
+        if 0 <= cx < 11 and 0 <= cy < 9:
+            assert a[n, 3, 3, y, x] == vol[n, y, x, cy, cx]
