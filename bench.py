@@ -1,0 +1,371 @@
+"""bench.py -- frame-graph update-op iterations/sec on B200 (BASELINE.json metric), with roofline + CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp16|fp32]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" = ONE pass of the hot path over one frame graph = FactorGraph.update (factor_graph.py:227-307):
+4-level correlation lookup for all edges + DynamicUpdateModule (incl. GraphAgg) + weight / mask post-processing +
+2 Gauss-Newton iterations of the dense BA.  Workload at N=1: BASELINE.json configs[1] -- 8 keyframes at 480x640
+(60x80 grid), neighbourhood radius 3 => 36 edges, r=3 correlation window, half-precision volume and update operator
+(what the reference's inference autocasts to), state fed back from step to step.  The volume build (per new edge,
+not per iteration) is reported separately as ``edge_add_ms``.  At N>1 each rank owns the out-edges of 8 keyframes of
+one 8N-keyframe graph (weak scaling) and the reduced camera system is all-reduced over NCCL once per BA iteration.
+
+JSON keys follow the driver contract: value = whole-job steps/s with the state resident in HBM; e2e = the same step
+driven through the public API with the mutable graph state arriving from / returning to pinned HOST buffers inside
+the timed region; roofline = the dominant kernel (tensor-core 448->256 GRU gate convolution) vs the measured bf16
+peak in MEASURED_PEAKS.json; cpu_baseline = the CPU oracle (a port of the reference's Python path) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'VO update-op iters/sec (480x640, 8 KF, r=3)'
+UNIT = 'iters/s'
+F_PER_GPU, RADIUS, HT, WD = 8, 3, 60, 80
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith('active'):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def make_case(nf, seed=1):
+    from tests.golden import cases
+    return cases.graph_case(F=nf, radius=RADIUS, h=HT, w=WD, seed=seed)
+
+
+def update_flops(E, K, hw):
+    """MACs*2 of DynamicUpdateModule as executed: per edge and per source frame."""
+    per_px_edge = (196 * 128 + 128 * 128 * 9 + 8 * 49 * 128 + 128 * 64 * 9 + 128 * 128 + 3 * 448 * 128 * 9 +
+                   5 * 128 * 128 * 9 + 4 * 128 * 2 * 9)
+    per_px_frame = 128 * 128 * 9 + 128 * 9
+    return 2.0 * hw * (E * per_px_edge + K * per_px_frame)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from pvo_b200 import _lib
+    from pvo_b200.depth_video import DepthVideo
+    from pvo_b200.droid_net import DynamicUpdateModule
+    from pvo_b200.factor_graph import FactorGraph
+    from oracle import update_op as oupd      # weights only (seeded init shared with the parity tests)
+
+    torch.cuda.set_device(local_rank)
+    dev = 'cuda:%d' % local_rank
+    nf = F_PER_GPU * world
+    c = make_case(nf)
+    ii, jj = c['ii'], c['jj']
+    if world > 1:                               # shard: this rank owns the out-edges of its 8 keyframes
+        own = (ii // F_PER_GPU) == rank
+        ii, jj = ii[own], jj[own]
+    E = ii.shape[0]
+    v = DepthVideo(image_size=(8 * HT, 8 * WD), buffer=max(nf + 8, 16), device=dev, store_images=False)
+    v.poses[:nf] = c['poses'].to(dev)
+    v.disps[:nf] = c['disps'].to(dev)
+    v.intrinsics[:] = c['intrinsics'][0].to(dev)
+    v.fmaps[:nf] = c['fmaps'].to(dev)
+    v.nets[:nf] = c['nets'].to(dev)
+    v.inps[:nf] = c['inps'].to(dev)
+    v.counter.value = nf
+    m = DynamicUpdateModule(precision=args.precision).to(dev)
+    m.load_state_dict(oupd.init_params(0))
+    fg = FactorGraph(v, m, device=dev, precision=args.precision)
+    if world > 1:
+        from pvo_b200 import dist as pdist
+        pdist.attach(fg, rank, world, F_PER_GPU)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- edge add (volume build), timed separately
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    ev0.record()
+    fg.add_factors(ii, jj)
+    ev1.record()
+    sync()
+    edge_add_ms = ev0.elapsed_time(ev1)
+    pose0, disp0 = v.poses.clone(), v.disps.clone()
+    state0 = None
+
+    def reset_state():
+        """keep the iteration numerically tame over many timed steps: restart from the initial graph state"""
+        v.poses.copy_(pose0)
+        v.disps.copy_(disp0)
+
+    def step():
+        fg.update(t0=1, t1=nf, itrs=2)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    # the per-step working set (volume 2.2 GB + activations ~0.9 GB) is far larger than L2, so consecutive steps
+    # cannot hit in L2; the explicit flush below is belt and braces and sits OUTSIDE the timed events.
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync()
+    times = []
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    for k in range(args.steps):
+        flush.zero_()
+        if k % 10 == 0:
+            reset_state()
+        sync()
+        ev0.record()
+        step()
+        ev1.record()
+        sync()
+        times.append(ev0.elapsed_time(ev1))
+    clocks.stop_flag = True
+    clocks.join(timeout=2)
+    total_ms = sum(times)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    units_per_step = (E * world) / 36.0 if world > 1 else 1.0       # 8-KF-graph equivalents processed per step
+    value = units_per_step * 1000.0 / ms_per_step
+
+    # ---- instrumented pass: per-launch CUDA events on the launching stream
+    eng = fg._engine()
+    kern = {}
+    eng.timers = kern
+    fg.timers = kern
+    for _ in range(min(args.steps, 10)):
+        step()
+    torch.cuda.synchronize()
+    eng.timers = None
+    fg.timers = None
+    kernel_ms = {k: sum(a.elapsed_time(b) for a, b in evs) / len(evs) for k, evs in kern.items()}
+    launches = getattr(fg, 'launch_count', None)
+
+    # ---- end to end through the public API with HOST state buffers
+    K = fg._cache['K']
+    host = {n: torch.empty_like(t_, device='cpu').pin_memory() for n, t_ in
+            (('poses', v.poses[:nf]), ('disps', v.disps[:nf]), ('target', fg.target_cam), ('weight', fg.weight),
+             ('raw_mask', fg.raw_mask), ('delta_dy', fg.delta_dy), ('net', eng.X[:, :128].contiguous()))}
+    host['poses'].copy_(pose0[:nf])
+    host['disps'].copy_(disp0[:nf])
+    for n, t_ in (('target', fg.target_cam), ('weight', fg.weight), ('raw_mask', fg.raw_mask), ('delta_dy', fg.delta_dy)):
+        host[n].copy_(t_)
+    host['net'].copy_(eng.X[:, :128])
+    out_host = {n: torch.empty_like(host[n]).pin_memory() for n in ('poses', 'disps', 'net')}
+    out_host['full_flow'] = torch.empty_like(host['target']).pin_memory()
+    h2d = sum(t_.numel() * t_.element_size() for t_ in host.values())
+    d2h = sum(t_.numel() * t_.element_size() for t_ in out_host.values())
+
+    def e2e_step():
+        v.poses[:nf].copy_(host['poses'], non_blocking=True)
+        v.disps[:nf].copy_(host['disps'], non_blocking=True)
+        fg.target_cam.copy_(host['target'], non_blocking=True)
+        fg.weight.copy_(host['weight'], non_blocking=True)
+        fg.raw_mask.copy_(host['raw_mask'], non_blocking=True)
+        fg.delta_dy.copy_(host['delta_dy'], non_blocking=True)
+        eng.X[:, :128].copy_(host['net'], non_blocking=True)
+        fg.update(t0=1, t1=nf, itrs=2)
+        out_host['poses'].copy_(v.poses[:nf], non_blocking=True)
+        out_host['disps'].copy_(v.disps[:nf], non_blocking=True)
+        out_host['full_flow'].copy_(fg.full_flow, non_blocking=True)
+        out_host['net'].copy_(eng.X[:, :128], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    sync()
+    n_e2e = max(3, min(args.steps, 20))
+    ev0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    ev1.record()
+    sync()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = units_per_step * 1000.0 * n_e2e / float(t.item())
+
+    if rank != 0:
+        return
+    pk = peaks()
+    hw = HT * WD
+    # dominant kernel: the 448->256 (z|r) 3x3 gate convolution on tensor cores
+    zr_flops = 2.0 * E * hw * 448 * 9 * 256
+    zr_ms = kernel_ms.get('conv_zr')
+    roof = None
+    if zr_ms:
+        ach = zr_flops / (zr_ms * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'kernel': 'conv_tc_kernel<256,EpZR> (GRU z|r gates, 448->256 3x3)', 'achieved': round(ach, 1),
+                'peak': pk['tf_burst'], 'unit': 'TFLOP/s', 'frac': round(ach / pk['tf_burst'], 4), 'traffic': None,
+                'peak_source': pk['src'] + ' (burst: kernel timed per launch)', 'ms_per_launch': round(zr_ms, 4),
+                'flops_per_launch': zr_flops}
+    look_ms = kernel_ms.get('corr_lookup')
+    secondary = {}
+    if look_ms:
+        lb = E * hw * (4 * 64 * 2 + 8 + 208 * 2)
+        secondary['corr_lookup'] = {'bound': 'hbm', 'achieved': round(lb / (look_ms * 1e-3) / 1e9, 1), 'peak': pk['hbm'], 'unit': 'GB/s',
+                                    'frac': round(lb / (look_ms * 1e-3) / 1e9 / pk['hbm'], 4), 'bytes_per_launch': lb}
+    ba_ms = sum(v_ for k_, v_ in kernel_ms.items() if k_.startswith('ba'))
+    upd_ms = sum(v_ for k_, v_ in kernel_ms.items() if k_.startswith('conv') or k_ in ('colmean', 'glo_matvec', 'heads2', 'segment_mean', 'eta'))
+    cpu = cpu_baseline_sample()
+    line = {
+        'metric': METRIC, 'value': round(value, 3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16' if args.precision == 'fp16' else 'f32', 'data': 'synthetic (seeded random features / random-init weights)',
+        'config': {'workload': 'BASELINE configs[1]: %d-keyframe 480x640 factor graph per GPU, r=3 corr, %d edges/GPU, 2 BA iters per update; '
+                               'update-op iterations feed back state' % (F_PER_GPU, E),
+                   'edges': E * world, 'keyframes': nf, 'grid': [HT, WD], 'precision': args.precision,
+                   'l2': 'per-step working set (2.2 GB volume + 0.9 GB activations) >> 126 MB L2; 256 MB flush between timed steps',
+                   'parallelism': 'edges sharded by source keyframe, NCCL all-reduce of the reduced camera system' if world > 1 else 'single GPU'},
+        'e2e': {'value': round(e2e_value, 3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'what': 'mutable graph state (poses, disps, target, weight, masks, hidden state) H2D from pinned host memory, '
+                        'FactorGraph.update, results (poses, disps, flow, hidden state) D2H, every step'},
+        'gpu_launches': launches,
+        'clocks': clocks.result(),
+        'roofline': roof, 'roofline_other': secondary,
+        'kernel_ms': {k: round(x, 4) for k, x in sorted(kernel_ms.items())},
+        'stage_ms': {'update_operator': round(upd_ms, 4), 'ba_2_iterations': round(ba_ms, 4), 'corr_lookup': look_ms,
+                     'edge_add_ms': round(edge_add_ms, 3)},
+        'update_op_tflops': round(update_flops(E, K, hw) / (upd_ms * 1e-3) / 1e12, 1) if upd_ms else None,
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def _oracle_step_time(nf, steps=1, warm=0, threads=None):
+    import torch
+    torch.set_grad_enabled(False)
+    if threads:
+        torch.set_num_threads(threads)
+    from oracle import step as ostep, update_op as oupd
+    c = make_case(nf)
+    sd = oupd.init_params(0)
+    st = ostep.make_state(c)
+    ts = []
+    for k in range(warm + steps):
+        t0 = time.perf_counter()
+        ostep.graph_update(sd, st, t0=1, t1=nf, itrs=2)
+        if k >= warm:
+            ts.append(time.perf_counter() - t0)
+    return sum(ts) / len(ts), c['E']
+
+
+def cpu_baseline_sample():
+    """Bounded sample of the same workload on the host cores (oracle = port of the reference's Python/CPU path)."""
+    import torch
+    cores = os.cpu_count() or 1
+    try:
+        t, E = _oracle_step_time(F_PER_GPU, steps=1, warm=0, threads=cores)
+        return {'value': round(1.0 / t, 4), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                'sample': '1 full update step of the config-2 graph (36 edges, 60x80) on the CPU oracle: %.2f s' % t}
+    except Exception as ex:       # the baseline must never take the GPU number down with it
+        return {'value': None, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU-capable path (its Python stack; droid_backends has no CPU kernels,
+    BASELINE.md section 3) as restated by the oracle, all host threads, same config/metric/unit."""
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    total = args.steps + args.warmup
+    t_full, E = _oracle_step_time(F_PER_GPU, steps=1, warm=0, threads=cores)
+    budget = 200.0
+    if t_full * total <= budget:
+        t, _ = _oracle_step_time(F_PER_GPU, steps=args.steps, warm=args.warmup, threads=cores)
+        sample = 'full config-2 step (36 edges) per step'
+        scale = 1.0
+    else:                       # bounded sample: a 4-keyframe graph (12 edges), cost extrapolated linearly in edges
+        t, Es = _oracle_step_time(4, steps=args.steps, warm=args.warmup, threads=cores)
+        scale = E / float(Es)
+        sample = '4-keyframe sub-graph (%d of %d edges) per step, time scaled by %.2f' % (Es, E, scale)
+    value = 1.0 / (t * scale)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': round(value, 4), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': round(t * scale * 1e3, 2), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (seeded random features / random-init weights)',
+            'config': {'workload': 'BASELINE configs[1]: 8-keyframe 480x640 factor graph, r=3 corr, 36 edges, 2 BA iters per update',
+                       'grid': [HT, WD], 'precision': 'fp32', 'parallelism': 'host cores'},
+            'cpu_baseline': {'value': round(value, 4), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+            'e2e': {'value': round(value, 4), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda:%d' % local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -95,6 +95,9 @@ int pvo_ba(float* poses, float* disps, const float* intrinsics, const float* tar
            const float* eta, const long* ii, const long* jj, int E, int nframes, int ht, int wd, int t0, int t1, int K,
            int iterations, float lm, float ep, int motion_only, int interleaved, float* dx_out, float* dz_out,
            void* workspace, long workspace_bytes, int flags, void* stream);
+/* byte range of {H, b} (float64) inside the workspace -- what pvo_b200/dist.py all-reduces between the two phases
+ *   (flags bits 1-2 of pvo_ba: 1 = assemble only, 2 = solve + update only) when edges are sharded over GPUs */
+int pvo_ba_system_range(int E, int nframes, int P, int K, int HW, long* offset, long* bytes);
 /* copies {K seen on the device, error flag, max out-degree} to the host (synchronises; debugging only) */
 int pvo_ba_read_meta(const void* workspace, int E, int nframes, int P, int K, int HW, int* meta_host3);
 /* DepthVideo.ba's trailing disps.clamp_(min=0.001), depth_video.py:214 */

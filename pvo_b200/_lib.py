@@ -26,6 +26,7 @@ _SIGS = {
     'pvo_ba_workspace_bytes': (c_long, [c_int] * 5),
     'pvo_ba': (c_int, [c_void_p] * 8 + [c_int] * 8 + [c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                                      c_long, c_int, c_void_p]),
+    'pvo_ba_system_range': (c_int, [c_int] * 5 + [c_void_p, c_void_p]),
     'pvo_ba_read_meta': (c_int, [c_void_p] + [c_int] * 5 + [c_void_p]),
     'pvo_clamp_min': (c_int, [c_void_p, c_long, c_float, c_void_p]),
     'pvo_conv2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 9 +
@@ -66,9 +67,32 @@ def lib():
     return _lib
 
 
-def check(status, what):
+LAUNCHES = [0]          # kernels launched through the C ABI since import (bench.py reports launches per step)
+
+
+def check(status, what, launches=1):
     if status != 0:
         raise RuntimeError('pvo_b200.%s failed: %s' % (what, _ERR.get(status, 'status %d' % status)))
+    LAUNCHES[0] += launches
+
+
+class timed:
+    """with timed(timers, name): ...  -- records a CUDA event pair on the current stream when timers is a dict."""
+
+    def __init__(self, timers, name):
+        self.timers, self.name = timers, name
+
+    def __enter__(self):
+        if self.timers is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.timers is not None:
+            self.b.record()
+            self.timers.setdefault(self.name, []).append((self.a, self.b))
+        return False
 
 
 def dtype_code(t):

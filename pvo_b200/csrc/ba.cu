@@ -517,11 +517,18 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
     cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
+  // flags bits 1-2 select a phase for the multi-GPU path (pvo_b200/dist.py): 0 = whole iteration(s),
+  // 1 = assemble only (pass 1 + Schur: the reduced camera system is left in the workspace for an all-reduce),
+  // 2 = solve + back-substitution + retraction only.
+  const int phase = (flags >> 1) & 3;
   for (int it = 0; it < iterations; it++) {
-    ba_pass1_kernel<<<grid, kPix, 0, s>>>(poses, disps, intrinsics, targets, weights, eta, ii, jj, pl, bf, E, HW, wd,
-                                          t0, P, interleaved, motion_only);
-    if (!motion_only)
-      ba_pass2_kernel<<<grid, kPix, pass2_smem, s>>>(jj, pl, bf, HW, t0, P, pass2_smem / 4);
+    if (phase != 2) {
+      ba_pass1_kernel<<<grid, kPix, 0, s>>>(poses, disps, intrinsics, targets, weights, eta, ii, jj, pl, bf, E, HW, wd,
+                                            t0, P, interleaved, motion_only);
+      if (!motion_only)
+        ba_pass2_kernel<<<grid, kPix, pass2_smem, s>>>(jj, pl, bf, HW, t0, P, pass2_smem / 4);
+    }
+    if (phase == 1) break;
     if (solve_in_smem)
       ba_solve_kernel<true><<<1, 512, solve_smem, s>>>(bf, P, lm, ep);
     else
@@ -530,6 +537,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
     if (last && dx_out)
       cudaMemcpyAsync(dx_out, bf.dx, sizeof(float) * n, cudaMemcpyDeviceToDevice, s);
     ba_pass3_kernel<<<grid, kPix, 0, s>>>(poses, disps, jj, pl, bf, last ? dz_out : nullptr, HW, t0, P, motion_only);
+    if (phase == 2) break;
   }
   return pvo_check_launch();
 }
@@ -548,6 +556,16 @@ extern "C" int pvo_clamp_min(float* x, long n, float lo, void* stream) {
   if (n <= 0) return PVO_OK;
   clamp_min_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, lo);
   return pvo_check_launch();
+}
+
+// byte range of the reduced camera system {H (6P x 6P doubles), b (6P doubles)} inside the workspace: the only data
+// exchanged between GPUs when edges are sharded by source keyframe
+extern "C" int pvo_ba_system_range(int E, int nframes, int P, int K, int HW, long* offset, long* bytes) {
+  if (E < 0 || nframes <= 0 || P <= 0 || K <= 0 || HW <= 0) return PVO_ERR_INVALID;
+  const Layout L = make_layout(E > 0 ? E : 1, nframes, P, K, HW);
+  *offset = (long)L.off_H;
+  *bytes = (long)(L.off_b + sizeof(double) * 6 * (size_t)P - L.off_H);
+  return PVO_OK;
 }
 
 extern "C" int pvo_ba_read_meta(const void* workspace, int E, int nframes, int P, int K, int HW, int* meta_host3) {

@@ -1,0 +1,87 @@
+"""Multi-GPU frame graphs: edges sharded by SOURCE keyframe, one all-reduce of the reduced camera system per
+Gauss-Newton iteration.
+
+Why this sharding: every per-iteration quantity is either per-edge (correlation lookup, update-operator convolutions,
+Jacobians) or a reduction over edges that share the same source frame ii -- GraphAgg's scatter_mean
+(droid_net.py:83-88), the depth blocks C / w / Ei (droid_kernels.cu:1374-1378) and the Schur products, which pair only
+rows of the same depth frame (droid_kernels.cu:1236-1251).  With all out-edges of a keyframe on one GPU everything is
+local except the pose system: each rank forms its partial  A_g - S_g  (6P x 6P) and  b_g  (6P) in float64, ONE
+all-reduce (sum) over NCCL / NVLink combines them (7 KB at P=7, 1.1 MB at P=63 -- latency bound, issued in-stream
+on the compute stream), every rank solves the identical system redundantly and applies dx to its pose replica and dz
+to the depth maps of the frames it owns.  Nothing else crosses GPUs per iteration.
+
+The reference has no multi-GPU inference path; this is new capability, validated against the single-GPU result
+(tests/test_dist_cpu.py for the host logic over gloo, tests/test_dist_gpu.py on 2 GPUs).
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, droid_backends
+from ._lib import check, ptr, stream
+
+
+def owner_of(frame, frames_per_rank):
+    return frame // frames_per_rank
+
+
+def shard_edges(ii, jj, rank, world, frames_per_rank):
+    """Edges whose SOURCE frame is owned by `rank` (contiguous blocks of frames_per_rank keyframes per rank)."""
+    own = (torch.div(ii, frames_per_rank, rounding_mode='floor') == rank) if world > 1 else torch.ones_like(ii, dtype=torch.bool)
+    return ii[own], jj[own], own
+
+
+def allreduce_system(buf, group=None):
+    """Sum the (H | b) float64 block across ranks; NCCL on the GPU box, gloo in the CPU tests."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf
+
+
+def system_view(ws, E, nframes, P, K, HW):
+    """float64 view of the reduced camera system inside a BA workspace (torch.uint8 tensor)."""
+    off, nb = ctypes.c_long(0), ctypes.c_long(0)
+    check(_lib.lib().pvo_ba_system_range(E, nframes, P, K, HW, ctypes.byref(off), ctypes.byref(nb)), 'ba_system_range', launches=0)
+    return ws[off.value:off.value + nb.value].view(torch.float64)
+
+
+def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only,
+               interleaved=False, group=None, workspace=None):
+    """droid_backends.ba for a rank's shard of the edges: assemble -> all-reduce -> solve + update, per iteration.
+    poses must be identical on all ranks on entry and are identical on exit."""
+    E = ii.shape[0]
+    nframes, ht, wd = disps.shape
+    K, P = eta.shape[0], t1 - t0
+    ws = workspace if workspace is not None else droid_backends.ba_workspace(E, nframes, P, K, ht * wd, poses.device)
+    sysbuf = system_view(ws, E, nframes, P, K, ht * wd)
+    dx = torch.empty(P, 6, dtype=torch.float32, device=poses.device)
+    dz = torch.empty(K, ht * wd, dtype=torch.float32, device=poses.device)
+    L = _lib.lib()
+
+    def call(phase, reuse):
+        flags = (1 if reuse else 0) | (phase << 1)
+        check(L.pvo_ba(ptr(poses), ptr(disps), ptr(intrinsics), ptr(targets), ptr(weights), ptr(eta), ptr(ii), ptr(jj), E,
+                       nframes, ht, wd, int(t0), int(t1), K, 1, float(lm), float(ep), 1 if motion_only else 0,
+                       1 if interleaved else 0, ptr(dx), ptr(dz), ptr(ws), ws.numel(), flags, stream()), 'ba',
+              launches=(0 if reuse else 1) + 2)
+    for it in range(int(iterations)):
+        call(1, it > 0)
+        allreduce_system(sysbuf, group)
+        call(2, True)
+    return [dx, dz]
+
+
+def attach(fg, rank, world, frames_per_rank, group=None):
+    """Make a FactorGraph's BA go through ba_sharded.  The caller adds only this rank's edges (shard_edges)."""
+    video = fg.video
+
+    def ba(target, weight, eta, ii, jj, t0=1, t1=None, itrs=2, lm=1e-4, ep=0.1, motion_only=False, interleaved=False,
+           reuse_plan=False):
+        out = ba_sharded(video.poses, video.disps, video.intrinsics[0].contiguous(), target, weight, eta, ii, jj, t0, t1,
+                         itrs, lm, ep, motion_only, interleaved=interleaved, group=group)
+        check(_lib.lib().pvo_clamp_min(ptr(video.disps), video.disps.numel(), 0.001, stream()), 'clamp_min')
+        return out
+    video.ba = ba
+    fg.rank, fg.world = rank, world
+    return fg

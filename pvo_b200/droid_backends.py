@@ -96,7 +96,8 @@ def ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iteratio
     check(_lib.lib().pvo_ba(ptr(poses), ptr(disps), ptr(intrinsics), ptr(targets), ptr(weights), ptr(eta), ptr(ii),
                             ptr(jj), E, nframes, ht, wd, int(t0), int(t1), K, int(iterations), float(lm), float(ep),
                             1 if motion_only else 0, 1 if interleaved else 0, ptr(dx), ptr(dz), ptr(ws), ws.numel(),
-                            1 if reuse_plan else 0, stream()), 'ba')
+                            1 if reuse_plan else 0, stream()), 'ba',
+          launches=(0 if reuse_plan else 1) + int(iterations) * (3 if motion_only else 4))
     return [dx, dz]
 
 

@@ -53,6 +53,8 @@ class FactorGraph:
         self.target_cam_inac, self.weight_inac, self.delta_dy_inac = fz(), fz(), fz()
         self.raw_mask_inac = fz(self.mask_num)
         self._cache = None                    # per-edge-set constants (unique(ii), K, default t0, workspaces)
+        self.timers = None                    # dict -> per-stage CUDA events (bench.py)
+        self.launch_count = None              # kernels launched by the last update()
 
     # ------------------------------------------------------------------ reference-layout state (lazy)
     def _engine(self):
@@ -200,7 +202,7 @@ class FactorGraph:
         L = _lib.lib()
         c = dict(E=E, K=K, kx=kx, t0_default=max(1, int(self.ii.min().item()) + 1),
                  t1_default=int(max(self.ii.max().item(), self.jj.max().item())) + 1,
-                 head_dirty=True, ba_key=None)
+                 ba_key=None, ba_kx={})
         c['coords1'] = torch.empty(1, E, self.ht, self.wd, 2, device=self.device)
         c['seg_ws'] = torch.zeros(int(L.pvo_update_post_workspace_ints(E)), dtype=torch.int32, device=self.device)
         c['segm'] = self.segm[0, :, 0].contiguous() if self.segm is not None else None
@@ -219,24 +221,30 @@ class FactorGraph:
         E, K, ht, wd = c['E'], c['K'], self.ht, self.wd
         v = self.video
         coords1 = c['coords1']
+        T = lambda name: _lib.timed(self.timers, name)
+        n0 = _lib.LAUNCHES[0]
         # (1) reprojection + motion features, written straight into the flow encoder's input buffer
-        check(L.pvo_reproject(ptr(v.poses), ptr(v.disps), ptr(v.intrinsics), ptr(self.ii), ptr(self.jj), ptr(coords1),
-                              None, ptr(self.target_cam), ptr(self.delta_dy), ptr(self.raw_mask), ptr(eng.motn),
-                              eng.dcode, E, ht, wd, stream()), 'reproject')
+        with T('reproject'):
+            check(L.pvo_reproject(ptr(v.poses), ptr(v.disps), ptr(v.intrinsics), ptr(self.ii), ptr(self.jj), ptr(coords1),
+                                  None, ptr(self.target_cam), ptr(self.delta_dy), ptr(self.raw_mask), ptr(eng.motn),
+                                  eng.dcode, E, ht, wd, stream()), 'reproject')
         # (2) correlation features, pixel-major into the corr encoder's input buffer
-        if self.corr.corr_pyramid[0].dtype == eng.tdtype:
-            self.corr(coords1, out=eng.corr, layout=1, out_cstride=pnn.CORR_STRIDE)
-        else:
-            self._lookup_mixed(coords1, eng)
+        with T('corr_lookup'):
+            if self.corr.corr_pyramid[0].dtype == eng.tdtype:
+                self.corr(coords1, out=eng.corr, layout=1, out_cstride=pnn.CORR_STRIDE)
+            else:
+                self._lookup_mixed(coords1, eng)
         # (3) update operator
         eng.run(with_agg=True)
         # (4) target, masks, segment filter, weights (in place on the graph's state tensors)
         if t0 is None:
             t0 = c['t0_default']
         segm = c['segm'] if v.segm_filter else None
-        check(L.pvo_update_post(ptr(coords1), ptr(eng.head_out), ptr(segm), float(v.thresh), ptr(self.target_cam),
-                                ptr(self.weight), ptr(self.raw_mask), ptr(self.delta_dy), ptr(self.full_flow),
-                                ptr(c['seg_ws']), c['seg_ws'].numel(), E, ht, wd, stream()), 'update_post')
+        with T('update_post'):
+            check(L.pvo_update_post(ptr(coords1), ptr(eng.head_out), ptr(segm), float(v.thresh), ptr(self.target_cam),
+                                    ptr(self.weight), ptr(self.raw_mask), ptr(self.delta_dy), ptr(self.full_flow),
+                                    ptr(c['seg_ws']), c['seg_ws'].numel(), E, ht, wd, stream()), 'update_post',
+                  launches=3 if segm is not None else 1)
         self.damping.index_copy_(0, c['kx'], eng.eta)
         if use_inactive:
             m = (self.ii_inac >= t0 - 3) & (self.jj_inac >= t0 - 3)
@@ -248,15 +256,22 @@ class FactorGraph:
             reuse = False
         else:
             ii, jj, target_cam, weight = self.ii, self.jj, self.target_cam, self.weight
-            damping = .2 * self.damping.index_select(0, c['kx']) + EP
+            if t1 is None:
+                t1 = c['t1_default']
+            # the BA's depth frames are unique(arange(t0,t1) U ii) (droid_kernels.cu:1311-1319); normally == unique(ii)
+            kx_ba = c['ba_kx'].get((t0, t1))
+            if kx_ba is None:
+                kx_ba = torch.unique(torch.cat([torch.arange(t0, t1, device=self.device), ii]))
+                c['ba_kx'][(t0, t1)] = kx_ba
+            damping = .2 * self.damping.index_select(0, kx_ba) + EP
             reuse = c['ba_key'] == (t0, t1, ii.shape[0])
             c['ba_key'] = (t0, t1, ii.shape[0])
         # (5) dense bundle adjustment, in place on video.poses / video.disps
-        if t1 is None:
-            t1 = c['t1_default'] if not use_inactive else None
-        v.ba(target_cam[0], weight[0], damping, ii, jj, t0, t1, itrs=itrs, lm=1e-4, ep=0.1, motion_only=motion_only,
-             interleaved=True, reuse_plan=reuse)
+        with T('ba_total'):
+            v.ba(target_cam[0], weight[0], damping, ii, jj, t0, t1, itrs=itrs, lm=1e-4, ep=0.1, motion_only=motion_only,
+                 interleaved=True, reuse_plan=reuse)
         self.age += 1
+        self.launch_count = _lib.LAUNCHES[0] - n0
 
     def _lookup_mixed(self, coords1, eng):
         """volume dtype != engine dtype (e.g. half volume feeding the float32 parity engine)"""

@@ -118,6 +118,7 @@ class UpdateEngine:
         self.eta_b = g('agg.eta.0.bias').float().contiguous()
         self.c_upmask = _Conv(g('agg.upmask_disp.0.weight'), g('agg.upmask_disp.0.bias'), tc=tc)
         self.E = self.K = self.H = self.W = 0
+        self.timers = None            # dict -> per-launch CUDA events (bench.py)
 
     # ------------------------------------------------------------------ buffers
     def reserve(self, E, K, H, W, nframes=None):
@@ -176,36 +177,51 @@ class UpdateEngine:
         """X[:, :256] (net|inp), corr, motn must be loaded.  Updates X[:, :128] (net) in place and fills head_out,
         eta (when with_agg).  ~14 launches, no host sync."""
         L = _lib.lib()
+        T = lambda name: _lib.timed(self.timers, name)
         E, K, H, W, dc, tc = self.E, self.K, self.H, self.W, self.dcode, self.use_tc
         HW = H * W
         X = self.X
         esz = X.element_size()
         # corr_encoder: 1x1 196(208)->128 + ReLU, 3x3 128->128 + ReLU  -> X[:,256:384]
-        conv2d(self.c_corr0, [(self.corr, CORR_STRIDE, CORR_STRIDE)], E, H, W, dc, self.c1, 128, 0, 1, use_tc=tc)
-        conv2d(self.c_corr2, [(self.c1, 128, 128)], E, H, W, dc, X, 448, 256, 1, use_tc=tc)
+        with T('conv_corr0'):
+            conv2d(self.c_corr0, [(self.corr, CORR_STRIDE, CORR_STRIDE)], E, H, W, dc, self.c1, 128, 0, 1, use_tc=tc)
+        with T('conv_corr2'):
+            conv2d(self.c_corr2, [(self.c1, 128, 128)], E, H, W, dc, X, 448, 256, 1, use_tc=tc)
         # flow_encoder: 7x7 8->128 + ReLU, 3x3 128->64 + ReLU  -> X[:,384:448]
-        conv2d(self.c_flow0, [(self.motn, 8, 8)], E, H, W, dc, self.f1, 128, 0, 1)
-        conv2d(self.c_flow2, [(self.f1, 128, 128)], E, H, W, dc, X, 448, 384, 1, use_tc=tc)
+        with T('conv_flow0'):
+            conv2d(self.c_flow0, [(self.motn, 8, 8)], E, H, W, dc, self.f1, 128, 0, 1)
+        with T('conv_flow2'):
+            conv2d(self.c_flow2, [(self.f1, 128, 128)], E, H, W, dc, X, 448, 384, 1, use_tc=tc)
         # global context: mean_HW(sigmoid(w(net)) * net) -> three 128x128 mat-vecs
-        conv2d(self.c_w, [(X, 128, 448)], E, H, W, dc, self.glo_tmp, 128, 0, 2, aux0=X, aux_stride=448)
-        check(L.pvo_colmean(ptr(self.glo_tmp), ptr(self.glo), E, HW, 128, dc, stream()), 'colmean')
-        check(L.pvo_glo_matvec(ptr(self.glo), ptr(self.glo_W), ptr(self.glo_b), ptr(self.glo3), E, stream()), 'glo_matvec')
+        with T('conv_glo'):
+            conv2d(self.c_w, [(X, 128, 448)], E, H, W, dc, self.glo_tmp, 128, 0, 2, aux0=X, aux_stride=448)
+        with T('colmean'):
+            check(L.pvo_colmean(ptr(self.glo_tmp), ptr(self.glo), E, HW, 128, dc, stream()), 'colmean')
+        with T('glo_matvec'):
+            check(L.pvo_glo_matvec(ptr(self.glo), ptr(self.glo_W), ptr(self.glo_b), ptr(self.glo3), E, stream()), 'glo_matvec')
         # z|r in one 448->256 conv; epilogue emits z and r*net
-        conv2d(self.c_zr, [(X, 448, 448)], E, H, W, dc, self.z, 128, 0, 3, out2=self.rnet, aux0=X, aux_stride=448,
-               aux1=self.glo3, use_tc=tc)
+        with T('conv_zr'):
+            conv2d(self.c_zr, [(X, 448, 448)], E, H, W, dc, self.z, 128, 0, 3, out2=self.rnet, aux0=X, aux_stride=448,
+                   aux1=self.glo3, use_tc=tc)
         # q on [r*net | inp | corr | flow]; epilogue applies net = (1-z) net + z q in place
-        conv2d(self.c_q, [(self.rnet, 128, 128), (X.data_ptr() + 128 * esz, 320, 448)], E, H, W, dc, X, 448, 0, 4,
-               aux0=self.z, aux1=self.glo3, use_tc=tc)
+        with T('conv_q'):
+            conv2d(self.c_q, [(self.rnet, 128, 128), (X.data_ptr() + 128 * esz, 320, 448)], E, H, W, dc, X, 448, 0, 4,
+                   aux0=self.z, aux1=self.glo3, use_tc=tc)
         # 4 heads' first conv + agg.conv1 as one 128->640 conv + ReLU
-        conv2d(self.c_heads1, [(X, 128, 448)], E, H, W, dc, self.Hb, 640, 0, 1, use_tc=tc)
-        check(L.pvo_conv3x3_small(ptr(self.Hb), 640, 128, ptr(self.heads2_W), ptr(self.heads2_b), ptr(self.head_out), 8,
-                                  4, 2, E, H, W, dc, 0, stream()), 'heads2')
+        with T('conv_heads1'):
+            conv2d(self.c_heads1, [(X, 128, 448)], E, H, W, dc, self.Hb, 640, 0, 1, use_tc=tc)
+        with T('heads2'):
+            check(L.pvo_conv3x3_small(ptr(self.Hb), 640, 128, ptr(self.heads2_W), ptr(self.heads2_b), ptr(self.head_out), 8,
+                                      4, 2, E, H, W, dc, 0, stream()), 'heads2')
         if with_agg:
-            check(L.pvo_segment_mean(ptr(self.Hb), 640, 512, ptr(self.A), ptr(self.g_ptr), ptr(self.g_idx),
-                                     ptr(self.g_meta), K, HW, 128, dc, stream()), 'segment_mean')
-            conv2d(self.c_agg2, [(self.A, 128, 128)], K, H, W, dc, self.a2, 128, 0, 1, use_tc=tc)
-            check(L.pvo_conv3x3_small(ptr(self.a2), 128, 128, ptr(self.eta_W), ptr(self.eta_b), ptr(self.eta), 1, 1, 1,
-                                      K, H, W, dc, 1, stream()), 'eta')
+            with T('segment_mean'):
+                check(L.pvo_segment_mean(ptr(self.Hb), 640, 512, ptr(self.A), ptr(self.g_ptr), ptr(self.g_idx),
+                                         ptr(self.g_meta), K, HW, 128, dc, stream()), 'segment_mean')
+            with T('conv_agg2'):
+                conv2d(self.c_agg2, [(self.A, 128, 128)], K, H, W, dc, self.a2, 128, 0, 1, use_tc=tc)
+            with T('eta'):
+                check(L.pvo_conv3x3_small(ptr(self.a2), 128, 128, ptr(self.eta_W), ptr(self.eta_b), ptr(self.eta), 1, 1, 1,
+                                          K, H, W, dc, 1, stream()), 'eta')
 
     def run_upmask(self):
         """GraphAgg.upmask_disp (droid_net.py:76-77,93): only DroidNet.forward consumes it; FactorGraph.update

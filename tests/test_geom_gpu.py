@@ -1,0 +1,179 @@
+"""GPU parity: reprojection, frame distance and the on-device dense BA against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ba_cuda, geom
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _video(c, buffer=None, segm=False):
+    from pvo_b200.depth_video import DepthVideo
+    F_, h, w = c['F'], c['h'], c['w']
+    v = DepthVideo(image_size=(8 * h, 8 * w), buffer=buffer or F_ + 3, device='cuda', segm_filter=segm, store_images=False)
+    v.poses[:F_] = c['poses'].cuda()
+    v.disps[:F_] = c['disps'].cuda()
+    v.intrinsics[:F_] = c['intrinsics'].cuda()
+    v.intrinsics[F_:] = c['intrinsics'][0].cuda()
+    v.counter.value = F_
+    return v
+
+
+def test_reproject_matches_oracle():
+    c = cases.graph_case(F=6, radius=3, h=24, w=32, seed=2, fdtype=torch.float32)
+    v = _video(c)
+    ref, refv = geom.projective_transform(c['poses'][None], c['disps'][None], c['intrinsics'][None], c['ii'], c['jj'])
+    out, val = v.reproject(c['ii'], c['jj'])
+    assert out.shape == ref.shape and val.shape == refv.shape
+    assert (out.cpu() - ref).abs().max() < 2e-4          # a few float32 ulps of an 80-pixel coordinate
+    assert torch.equal(val.cpu(), refv)
+
+
+def test_reproject_motion_features():
+    c = cases.graph_case(F=4, radius=2, h=16, w=24, seed=5, fdtype=torch.float32)
+    v = _video(c)
+    ii, jj = c['ii'], c['jj']
+    E = ii.shape[0]
+    g = torch.Generator().manual_seed(1)
+    coords1, _ = geom.projective_transform(c['poses'][None], c['disps'][None], c['intrinsics'][None], ii, jj)
+    tgt = coords1 + 30 * torch.randn(coords1.shape, generator=g)
+    dd = 40 * torch.randn(coords1.shape, generator=g)
+    rm = 3 * torch.randn(coords1.shape, generator=g)
+    coords0 = geom.coords_grid(16, 24)
+    ref = torch.cat([tgt - coords0, tgt - coords0 + dd, tgt - coords1, rm], -1).clamp(-64, 64)
+    for dt in (torch.float32, torch.float16):
+        mo = torch.empty(E * 16 * 24, 8, dtype=dt, device='cuda')
+        out, _ = v.reproject(ii, jj, motion=(tgt.cuda().contiguous(), dd.cuda().contiguous(), rm.cuda().contiguous(), mo))
+        tol = 2e-4 if dt == torch.float32 else 6e-2
+        assert (mo.float().cpu().view(1, E, 16, 24, 8) - ref).abs().max() < tol
+        assert (ref.abs() == 64).any()
+
+
+def _frame_distance_ref(poses, disps, intr, ii, jj, beta):
+    out = []
+    ht, wd = disps.shape[1:]
+    for i, j in zip(ii.tolist(), jj.tolist()):
+        tij, qij = ba_cuda._rel_se3(poses[i, :3], poses[i, 3:], poses[j, :3], poses[j, 3:])
+        v, u = torch.meshgrid(torch.arange(ht).float(), torch.arange(wd).float(), indexing='ij')
+        X0 = torch.stack([(u - intr[2]) / intr[0], (v - intr[3]) / intr[1], torch.ones_like(u)], -1)
+        d = disps[i]
+        acc = val = tot = 0.0
+        for full, wgt in ((True, beta), (False, 1 - beta)):
+            X = (ba_cuda._act_so3(qij, X0) if full else X0) + d[..., None] * tij
+            du = intr[0] * X[..., 0] / X[..., 2] + intr[2] - u
+            dv = intr[1] * X[..., 1] / X[..., 2] + intr[3] - v
+            m = X[..., 2] > 0.25
+            acc += (wgt * torch.sqrt(du * du + dv * dv)[m]).sum().item()
+            val += wgt * m.sum().item()
+            tot += wgt * m.numel()
+        out.append(1000.0 if val / (tot + 1e-8) < 0.75 else acc / val)
+    return torch.tensor(out)
+
+
+def test_frame_distance():
+    c = cases.graph_case(F=6, radius=5, h=24, w=32, seed=8, fdtype=torch.float32)
+    v = _video(c)
+    d = v.distance(c['ii'], c['jj'], beta=0.3, bidirectional=False)
+    ref = _frame_distance_ref(c['poses'], c['disps'], c['intrinsics'][0], c['ii'], c['jj'], 0.3)
+    assert torch.allclose(d.cpu(), ref, rtol=2e-4, atol=1e-4)
+    db = v.distance(c['ii'], c['jj'], beta=0.6, bidirectional=True)
+    refb = .5 * (_frame_distance_ref(c['poses'], c['disps'], c['intrinsics'][0], c['ii'], c['jj'], 0.6) +
+                 _frame_distance_ref(c['poses'], c['disps'], c['intrinsics'][0], c['jj'], c['ii'], 0.6))
+    assert torch.allclose(db.cpu(), refb, rtol=2e-4, atol=1e-4)
+
+
+def _ba_case(F, radius, h, w, seed, noise=0.5):
+    c = cases.graph_case(F=F, radius=radius, h=h, w=w, seed=seed, fdtype=torch.float32)
+    g = torch.Generator().manual_seed(seed + 100)
+    ii, jj = c['ii'], c['jj']
+    tgt, _ = geom.projective_transform(c['poses'][None], c['disps'][None], c['intrinsics'][None], ii, jj)
+    tgt = (tgt + noise * torch.randn(tgt.shape, generator=g))[0].permute(0, 3, 1, 2).contiguous()
+    wgt = torch.rand(tgt.shape, generator=g)
+    return c, tgt, wgt, g
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+@pytest.mark.parametrize('cfg', [dict(F=5, radius=2, h=16, w=24, t0=1), dict(F=8, radius=3, h=24, w=32, t0=1),
+                                 dict(F=7, radius=2, h=16, w=24, t0=3), dict(F=6, radius=5, h=12, w=16, t0=2)])
+@pytest.mark.parametrize('motion_only', [False, True])
+def test_ba_matches_oracle(cfg, motion_only):
+    """droid_backends.ba: in-place poses/disps, returned dx/dz, 2 Gauss-Newton iterations.  Tolerance 1e-4 relative
+    (BASELINE.json north_star): reduction order differs, the reduced system is solved in float64 on both sides."""
+    from pvo_b200 import droid_backends
+    c, tgt, wgt, g = _ba_case(cfg['F'], cfg['radius'], cfg['h'], cfg['w'], seed=40 + cfg['F'])
+    ii, jj, t0, t1 = c['ii'], c['jj'], cfg['t0'], cfg['F']
+    kx = torch.unique(torch.cat([torch.arange(t0, t1), ii]))
+    eta = 0.02 * torch.rand(kx.shape[0], cfg['h'], cfg['w'], generator=g) + 1e-7
+    p_ref, d_ref = c['poses'].clone(), c['disps'].clone()
+    dx_ref, dz_ref = ba_cuda.ba(p_ref, d_ref, c['intrinsics'][0], tgt, wgt, eta, ii, jj, t0, t1, 2, 1e-4, 0.1, motion_only)
+    v = _video(c, buffer=cfg['F'] + 5)
+    dx, dz = droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), tgt.cuda(), wgt.cuda(), eta.cuda(),
+                               ii.cuda(), jj.cuda(), t0, t1, 2, 1e-4, 0.1, motion_only)
+    F_ = cfg['F']
+    assert _rel(dx.cpu(), dx_ref) < 1e-4
+    assert _rel(v.poses[:F_].cpu(), p_ref) < 1e-4
+    assert torch.equal(v.poses[:t0].cpu(), c['poses'][:t0])            # frames before t0 are fixed
+    if not motion_only:
+        assert _rel(dz.cpu(), dz_ref) < 1e-4
+        assert _rel(v.disps[:F_].cpu(), d_ref) < 1e-4
+    else:
+        assert torch.equal(v.disps[:F_].cpu(), c['disps'])
+    assert torch.equal(v.disps[F_:].cpu(), torch.ones_like(v.disps[F_:].cpu()))
+
+
+def test_ba_interleaved_layout_and_plan_reuse():
+    from pvo_b200 import droid_backends
+    c, tgt, wgt, g = _ba_case(6, 2, 16, 24, seed=77)
+    ii, jj = c['ii'].cuda(), c['jj'].cuda()
+    eta = (0.02 * torch.rand(6, 16, 24, generator=g) + 1e-7).cuda()
+    outs = []
+    for inter in (False, True):
+        v = _video(c)
+        t = tgt.cuda().permute(0, 2, 3, 1).contiguous() if inter else tgt.cuda()
+        w = wgt.cuda().permute(0, 2, 3, 1).contiguous() if inter else wgt.cuda()
+        droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), t, w, eta, ii, jj, 1, 6, 1, 1e-4, 0.1, False, interleaved=inter)
+        droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), t, w, eta, ii, jj, 1, 6, 1, 1e-4, 0.1, False, interleaved=inter,
+                          reuse_plan=True)
+        outs.append((v.poses.clone(), v.disps.clone()))
+    assert torch.allclose(outs[0][0], outs[1][0], atol=1e-6) and torch.allclose(outs[0][1], outs[1][1], atol=1e-6)
+
+
+def test_ba_failed_factorisation_is_a_zero_update():
+    """droid_kernels.cu:1178-1189 / chol.py:9-17: Cholesky failure => dx = 0 (NaN weights poison the system)."""
+    from pvo_b200 import droid_backends
+    c, tgt, wgt, g = _ba_case(4, 1, 8, 8, seed=5)
+    v = _video(c)
+    wgt = wgt.clone()
+    wgt[0, 0, 0, 0] = float('nan')
+    eta = torch.full((4, 8, 8), 1e-3).cuda()
+    dx, dz = droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), tgt.cuda(), wgt.cuda(), eta, c['ii'].cuda(),
+                               c['jj'].cuda(), 1, 4, 1, 1e-4, 0.1, True)
+    assert (dx == 0).all()
+    assert torch.allclose(v.poses[:4].cpu(), c['poses'], atol=1e-6)
+
+
+def test_ba_full_size_consistency():
+    """Config-2 size (8 keyframes, 36 edges, 60x80): a noise-free target is a fixed point; a perturbed pose is
+    pulled back towards it (encode -> perturb -> solve round trip)."""
+    from pvo_b200 import droid_backends
+    c = cases.graph_case(F=8, radius=3, h=60, w=80, seed=1, fdtype=torch.float32)
+    ii, jj = c['ii'], c['jj']
+    tgt, _ = geom.projective_transform(c['poses'][None], c['disps'][None], c['intrinsics'][None], ii, jj)
+    tgt = tgt[0].permute(0, 3, 1, 2).contiguous().cuda()
+    wgt = torch.ones_like(tgt)
+    eta = torch.full((8, 60, 80), 1e-4).cuda()
+    v = _video(c)
+    dx, dz = droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), tgt, wgt, eta, ii.cuda(), jj.cuda(), 1, 8, 2, 1e-4, 0.1, False)
+    assert dx.abs().max() < 2e-4 and dz.abs().max() < 2e-3
+    v = _video(c)
+    v.poses[4, :3] += torch.tensor([0.03, -0.02, 0.01], device='cuda')
+    before = (v.poses[4, :3].cpu() - c['poses'][4, :3]).norm()
+    for _ in range(4):
+        droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), tgt, wgt, eta, ii.cuda(), jj.cuda(), 1, 8, 2, 1e-4, 0.1, True)
+    after = (v.poses[4, :3].cpu() - c['poses'][4, :3]).norm()
+    assert after < 0.2 * before
