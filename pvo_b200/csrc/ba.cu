@@ -42,6 +42,7 @@ struct Bufs {
   float* w;            // [K][HW]
   double* H;           // [n][n]  reduced camera system, n = 6P
   double* b;           // [n]
+  double* dA;          // [n]     diagonal of the pose block alone (Python-BA damping, chol.py:55-57)
   float* dx;           // [P][6]
 };
 
@@ -49,7 +50,7 @@ struct Bufs {
 // plan: kx = unique(arange(t0,t1) U ii), edges grouped by source frame.  One block.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) ba_plan_kernel(const long* __restrict__ ii, int E, int nframes, int t0, int t1,
-                                                       int Kcap, Plan pl, double* H, double* b, int n) {
+                                                       int Kcap, Plan pl, double* H, double* b, double* dA, int n) {
   __shared__ int s_warp[32];
   __shared__ int s_total;
   const int tid = threadIdx.x;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(1024) ba_plan_kernel(const long* __restrict__ 
       if (ii[e] == f) pl.src_idx[o++] = e;
   }
   for (long i = tid; i < (long)n * n; i += blockDim.x) H[i] = 0.0;
-  for (int i = tid; i < n; i += blockDim.x) b[i] = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) { b[i] = 0.0; dA[i] = 0.0; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -137,14 +138,16 @@ struct EdgeJac {
 
 __device__ __forceinline__ void edge_jacobian(const float* Pi, const float* Pj, float fx, float fy, float cx, float cy,
                                               float u, float v, float disp, float tu, float tv, float wgu, float wgv,
-                                              EdgeJac& J) {
+                                              int sem, EdgeJac& J) {
   Vec3 tij; Quat qij;
-  dk_rel_pose(Pi, Pj, tij, qij);
+  if (sem) lt_rel_pose(Pi, Pj, tij, qij); else dk_rel_pose(Pi, Pj, tij, qij);
   const Vec3 X0{(u - cx) / fx, (v - cy) / fy, 1.0f};
   const Vec3 r = q_rot(qij, X0);
   const float x = r.x + disp * tij.x, y = r.y + disp * tij.y, z = r.z + disp * tij.z, h = disp;
-  const bool bad = z < kMinDepth;
-  const float d = bad ? 0.0f : 1.0f / z;
+  // sem 0 (droid_kernels.cu:26,284-291): Z < 0.25 zeroes weight and 1/Z.
+  // sem 1 (geom/projective_ops.py:6,48,117): valid = Z > 0.2; Z < 0.1 -> 1 before the divide.
+  const bool bad = sem ? !(z > 0.2f) : (z < kMinDepth);
+  const float d = sem ? (1.0f / ((z < 0.1f) ? 1.0f : z)) : (bad ? 0.0f : 1.0f / z);
   const float d2 = d * d;
   J.wu = bad ? 0.0f : .001f * wgu;
   J.wv = bad ? 0.0f : .001f * wgv;
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kPix) ba_pass1_kernel(
     const float* __restrict__ poses, const float* __restrict__ disps, const float* __restrict__ intrinsics,
     const float* __restrict__ targets, const float* __restrict__ weights, const float* __restrict__ eta,
     const long* __restrict__ ii, const long* __restrict__ jj, Plan pl, Bufs bf, int E, int HW, int wd, int t0, int P,
-    int interleaved, int motion_only) {
+    int interleaved, int motion_only, int sem) {
   const int K = pl.meta[0];
   const int k = blockIdx.y;
   if (k >= K) return;
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(kPix) ba_pass1_kernel(
       }
     }
     EdgeJac J;
-    edge_jacobian(poses + 7 * f, poses + 7 * jx, fx, fy, cx, cy, (float)j, (float)i, disp, tu, tv, wgu, wgv, J);
+    edge_jacobian(poses + 7 * f, poses + 7 * jx, fx, fy, cx, cy, (float)j, (float)i, disp, tu, tv, wgu, wgv, sem, J);
     if (!active) { J.wu = 0.f; J.wv = 0.f; }
     if (!motion_only) {
       const float au = J.wu * J.Jzu, av = J.wv * J.Jzv;
@@ -246,6 +249,7 @@ __global__ void __launch_bounds__(kPix) ba_pass1_kernel(
           const int row = 6 * pa + (a % 6), col = 6 * pb + (bcol % 6);
           atomicAdd(&bf.H[(long)row * n + col], s);
           if (row != col) atomicAdd(&bf.H[(long)col * n + row], s);
+          else if (sem) atomicAdd(&bf.dA[row], s);
         }
       } else {
         const int a = tid - 78;
@@ -258,7 +262,8 @@ __global__ void __launch_bounds__(kPix) ba_pass1_kernel(
   if (active && !motion_only) {
 #pragma unroll
     for (int m = 0; m < 6; m++) bf.Ei[((long)k * 6 + m) * HW + pix] = Ei[m];
-    bf.Q[(long)k * HW + pix] = 1.0f / (C + eta[(long)k * HW + pix]);
+    bf.Q[(long)k * HW + pix] = sem ? 1.0f / (C + eta[(long)k * HW + pix] + 1e-7f)      // geom/ba.py:91
+                                   : 1.0f / (C + eta[(long)k * HW + pix]);             // droid_kernels.cu:1376
     bf.w[(long)k * HW + pix] = wacc;
   }
 }
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__
 // solve: LM damping on the diagonal, dense Cholesky + two triangular solves in float64, one block.
 // ---------------------------------------------------------------------------------------------------
 template <bool IN_SMEM>
-__global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm, float ep) {
+__global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem) {
   extern __shared__ double smd[];
   __shared__ int s_fail;
   const int n = 6 * P;
@@ -353,7 +358,8 @@ __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm,
   }
   if (tid == 0) s_fail = 0;
   __syncthreads();
-  for (int i = tid; i < n; i += T) A[(long)i * n + i] += (double)ep + (double)lm * A[(long)i * n + i];
+  // sem 0: damp the Schur complement (droid_kernels.cu:1175-1176); sem 1: damp H before subtracting E Q E^T (chol.py:55-62)
+  for (int i = tid; i < n; i += T) A[(long)i * n + i] += (double)ep + (double)lm * (sem ? bf.dA[i] : A[(long)i * n + i]);
   __syncthreads();
   for (int j = 0; j < n; j++) {
     if (tid == 0) {
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm,
   __syncthreads();
   // leave the system zeroed for the next iteration / next call
   for (long i = tid; i < (long)n * n; i += T) bf.H[i] = 0.0;
-  for (int i = tid; i < n; i += T) bf.b[i] = 0.0;
+  for (int i = tid; i < n; i += T) { bf.b[i] = 0.0; bf.dA[i] = 0.0; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -406,7 +412,7 @@ __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm,
 __global__ void __launch_bounds__(kPix) ba_pass3_kernel(float* __restrict__ poses, float* __restrict__ disps,
                                                         const long* __restrict__ jj, Plan pl, Bufs bf,
                                                         float* __restrict__ dz_out, int HW, int t0, int P,
-                                                        int motion_only) {
+                                                        int motion_only, int sem) {
   const int K = pl.meta[0];
   const int k = blockIdx.y;
   const int tid = threadIdx.x;
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(kPix) ba_pass3_kernel(float* __restrict__ pose
       for (int m = 0; m < 6; m++) xi[m] = bf.dx[6 * p + m];
 #pragma unroll
       for (int m = 0; m < 7; m++) T[m] = poses[7 * (t0 + p) + m];
-      dk_retr(xi, T);
+      if (sem) lt_retr(xi, T); else dk_retr(xi, T);
 #pragma unroll
       for (int m = 0; m < 7; m++) poses[7 * (t0 + p) + m] = T[m];
     }
@@ -427,9 +433,10 @@ __global__ void __launch_bounds__(kPix) ba_pass3_kernel(float* __restrict__ pose
   const int pix = blockIdx.x * kPix + tid;
   if (pix >= HW) return;
   float acc = 0.f;
+  const int pmin = sem ? 0 : 1;          // EvT6x1_kernel :1084 drops pose index <= 0; chol.py:69 uses every pose
   {
     const int p = f - t0;
-    if (p > 0 && p < P) {
+    if (p >= pmin && p < P) {
 #pragma unroll
       for (int m = 0; m < 6; m++) acc += bf.Ei[((long)k * 6 + m) * HW + pix] * bf.dx[6 * p + m];
     }
@@ -437,7 +444,7 @@ __global__ void __launch_bounds__(kPix) ba_pass3_kernel(float* __restrict__ pose
   for (int it = pl.src_ptr[k]; it < pl.src_ptr[k + 1]; it++) {
     const int e = pl.src_idx[it];
     const int p = (int)jj[e] - t0;
-    if (p > 0 && p < P) {
+    if (p >= pmin && p < P) {
       float dw = 0.f;
 #pragma unroll
       for (int m = 0; m < 6; m++) dw += bf.Eij[((long)e * 6 + m) * HW + pix] * bf.dx[6 * p + m];
@@ -445,7 +452,9 @@ __global__ void __launch_bounds__(kPix) ba_pass3_kernel(float* __restrict__ pose
     }
   }
   const float dz = bf.Q[(long)k * HW + pix] * (bf.w[(long)k * HW + pix] - acc);
-  disps[(long)f * HW + pix] += dz;
+  float dnew = disps[(long)f * HW + pix] + dz;
+  if (sem) { dnew = (dnew > 10.0f) ? 0.0f : dnew; dnew = fmaxf(dnew, 0.0f); }      // geom/ba.py:103-104
+  disps[(long)f * HW + pix] = dnew;
   if (dz_out) dz_out[(long)k * HW + pix] = dz;
 }
 
@@ -457,7 +466,7 @@ __global__ void clamp_min_kernel(float* x, long n, float lo) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
-  size_t off_frame2k, off_kx, off_ptr, off_idx, off_meta, off_Eij, off_Ei, off_Q, off_w, off_H, off_b, off_dx, total;
+  size_t off_frame2k, off_kx, off_ptr, off_idx, off_meta, off_Eij, off_Ei, off_Q, off_w, off_H, off_b, off_dA, off_dx, total;
 };
 
 Layout make_layout(int E, int nframes, int P, int K, int HW) {
@@ -475,6 +484,7 @@ Layout make_layout(int E, int nframes, int P, int K, int HW) {
   L.off_w = take(sizeof(float) * (size_t)K * HW);
   L.off_H = take(sizeof(double) * 36 * (size_t)P * P);
   L.off_b = take(sizeof(double) * 6 * (size_t)P);
+  L.off_dA = take(sizeof(double) * 6 * (size_t)P);
   L.off_dx = take(sizeof(float) * 6 * (size_t)P);
   L.total = o;
   return L;
@@ -503,10 +513,10 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
   Plan pl{(int*)(ws + L.off_frame2k), (int*)(ws + L.off_kx), (int*)(ws + L.off_ptr), (int*)(ws + L.off_idx),
           (int*)(ws + L.off_meta)};
   Bufs bf{(float*)(ws + L.off_Eij), (float*)(ws + L.off_Ei), (float*)(ws + L.off_Q), (float*)(ws + L.off_w),
-          (double*)(ws + L.off_H), (double*)(ws + L.off_b), (float*)(ws + L.off_dx)};
+          (double*)(ws + L.off_H), (double*)(ws + L.off_b), (double*)(ws + L.off_dA), (float*)(ws + L.off_dx)};
   cudaStream_t s = (cudaStream_t)stream;
   const int n = 6 * P;
-  if (!(flags & 1)) ba_plan_kernel<<<1, 1024, 0, s>>>(ii, E, nframes, t0, t1, K, pl, bf.H, bf.b, n);
+  if (!(flags & 1)) ba_plan_kernel<<<1, 1024, 0, s>>>(ii, E, nframes, t0, t1, K, pl, bf.H, bf.b, bf.dA, n);
   const dim3 grid(ceil_div(HW, kPix), K);
   static bool attr_set = false;
   const int pass2_smem = 160 * 1024;
@@ -521,22 +531,23 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
   // 1 = assemble only (pass 1 + Schur: the reduced camera system is left in the workspace for an all-reduce),
   // 2 = solve + back-substitution + retraction only.
   const int phase = (flags >> 1) & 3;
+  const int sem = (flags >> 3) & 1;      // 0: droid_backends.ba semantics, 1: geom/ba.py BA()/MoBA() semantics
   for (int it = 0; it < iterations; it++) {
     if (phase != 2) {
       ba_pass1_kernel<<<grid, kPix, 0, s>>>(poses, disps, intrinsics, targets, weights, eta, ii, jj, pl, bf, E, HW, wd,
-                                            t0, P, interleaved, motion_only);
+                                            t0, P, interleaved, motion_only, sem);
       if (!motion_only)
         ba_pass2_kernel<<<grid, kPix, pass2_smem, s>>>(jj, pl, bf, HW, t0, P, pass2_smem / 4);
     }
     if (phase == 1) break;
     if (solve_in_smem)
-      ba_solve_kernel<true><<<1, 512, solve_smem, s>>>(bf, P, lm, ep);
+      ba_solve_kernel<true><<<1, 512, solve_smem, s>>>(bf, P, lm, ep, sem);
     else
-      ba_solve_kernel<false><<<1, 512, 0, s>>>(bf, P, lm, ep);
+      ba_solve_kernel<false><<<1, 512, 0, s>>>(bf, P, lm, ep, sem);
     const bool last = it == iterations - 1;
     if (last && dx_out)
       cudaMemcpyAsync(dx_out, bf.dx, sizeof(float) * n, cudaMemcpyDeviceToDevice, s);
-    ba_pass3_kernel<<<grid, kPix, 0, s>>>(poses, disps, jj, pl, bf, last ? dz_out : nullptr, HW, t0, P, motion_only);
+    ba_pass3_kernel<<<grid, kPix, 0, s>>>(poses, disps, jj, pl, bf, last ? dz_out : nullptr, HW, t0, P, motion_only, sem);
     if (phase == 2) break;
   }
   return pvo_check_launch();
@@ -547,7 +558,7 @@ extern "C" int pvo_group_edges(const long* ii, int E, int nframes, int t0, int t
                                int* ptr, int* idx, int* meta, void* stream) {
   if (E < 0 || nframes <= 0 || Kcap <= 0) return PVO_ERR_INVALID;
   Plan pl{frame2k, kx, ptr, idx, meta};
-  ba_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ii, E, nframes, t0, t1, Kcap, pl, nullptr, nullptr, 0);
+  ba_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ii, E, nframes, t0, t1, Kcap, pl, nullptr, nullptr, nullptr, 0);
   return pvo_check_launch();
 }
 
@@ -564,7 +575,7 @@ extern "C" int pvo_ba_system_range(int E, int nframes, int P, int K, int HW, lon
   if (E < 0 || nframes <= 0 || P <= 0 || K <= 0 || HW <= 0) return PVO_ERR_INVALID;
   const Layout L = make_layout(E > 0 ? E : 1, nframes, P, K, HW);
   *offset = (long)L.off_H;
-  *bytes = (long)(L.off_b + sizeof(double) * 6 * (size_t)P - L.off_H);
+  *bytes = (long)(L.off_dA + sizeof(double) * 6 * (size_t)P - L.off_H);
   return PVO_OK;
 }
 

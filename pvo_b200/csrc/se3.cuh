@@ -107,3 +107,35 @@ __device__ __forceinline__ void dk_retr(const float xi[6], float P[7]) {
   P[0] = r.x + dt.x; P[1] = r.y + dt.y; P[2] = r.z + dt.z;
   P[3] = q1.x; P[4] = q1.y; P[5] = q1.z; P[6] = q1.w;
 }
+
+// lietorch retraction Exp(xi) * T (groups.py:153-156; so3.h:153-175 Exp, so3.h:177-196 left Jacobian, se3.h:134-142),
+// quaternion renormalised as every lietorch constructor does.
+__device__ __forceinline__ void lt_retr(const float xi[6], float P[7]) {
+  const float px = xi[3], py = xi[4], pz = xi[5];
+  const float theta2 = px * px + py * py + pz * pz;
+  const float theta = sqrtf(theta2);
+  float imag, real, c1, c2;
+  if (theta < 1e-6f) {
+    const float theta4 = theta2 * theta2;
+    imag = 0.5f - (1.0f / 48.0f) * theta2 + (1.0f / 3840.0f) * theta4;
+    real = 1.0f - (1.0f / 8.0f) * theta2 + (1.0f / 384.0f) * theta4;
+    c1 = 0.5f - (1.0f / 24.0f) * theta2;
+    c2 = 1.0f / 6.0f - (1.0f / 120.0f) * theta2;
+  } else {
+    imag = sinf(0.5f * theta) / theta;
+    real = cosf(0.5f * theta);
+    c1 = (1.0f - cosf(theta)) / theta2;
+    c2 = (theta - sinf(theta)) / (theta2 * theta);
+  }
+  const Quat dq = q_normalize(Quat{imag * px, imag * py, imag * pz, real});
+  // t = (I + c1 Phi + c2 Phi^2) tau
+  const Vec3 tau{xi[0], xi[1], xi[2]};
+  const Vec3 a{py * tau.z - pz * tau.y, pz * tau.x - px * tau.z, px * tau.y - py * tau.x};
+  const Vec3 b{py * a.z - pz * a.y, pz * a.x - px * a.z, px * a.y - py * a.x};
+  const Vec3 dt{tau.x + c1 * a.x + c2 * b.x, tau.y + c1 * a.y + c2 * b.y, tau.z + c1 * a.z + c2 * b.z};
+  const Quat q = q_normalize(Quat{P[3], P[4], P[5], P[6]});
+  const Quat q1 = q_normalize(q_mul(dq, q));
+  const Vec3 r = q_rot(dq, Vec3{P[0], P[1], P[2]});
+  P[0] = r.x + dt.x; P[1] = r.y + dt.y; P[2] = r.z + dt.z;
+  P[3] = q1.x; P[4] = q1.y; P[5] = q1.z; P[6] = q1.w;
+}

@@ -177,3 +177,27 @@ def test_ba_full_size_consistency():
         droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), tgt, wgt, eta, ii.cuda(), jj.cuda(), 1, 8, 2, 1e-4, 0.1, True)
     after = (v.poses[4, :3].cpu() - c['poses'][4, :3]).norm()
     assert after < 0.2 * before
+
+
+def test_python_ba_entry_point_matches_reference_golden():
+    """geom.ba.BA / MoBA (Python-BA semantics, pvo_ba flags bit 3) vs tests/golden/geom.npz, which was produced by the
+    reference's own geom/ba.py run on CPU."""
+    import os
+    from pvo_b200.geom.ba import BA, MoBA
+    from pvo_b200.geom import projective_ops as pops
+    from pvo_b200.lietorch import SE3
+    gold = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(os.path.dirname(__file__), 'golden', 'geom.npz')).items()}
+    c = cases.graph_case(F=5, radius=2, h=12, w=16, seed=3, fdtype=torch.float32)
+    ii, jj = c['ii'].cuda(), c['jj'].cuda()
+    Gs = SE3(c['poses'][None].cuda())
+    disps, intr = c['disps'][None].cuda(), c['intrinsics'][None].cuda()
+    x1, valid = pops.projective_transform(Gs, disps, intr, ii, jj)
+    assert (x1.cpu() - gold['coords']).abs().max() < 1e-4 and torch.equal(valid.cpu(), gold['valid'])
+    tgt, wgt, eta = gold['target'].cuda(), gold['weight'].cuda(), gold['eta'].cuda()
+    G1, d1 = BA(tgt, wgt, eta, Gs, disps, intr, ii, jj, fixedp=2)
+    assert _rel(G1.data.cpu(), gold['ba1_poses']) < 1e-4 and _rel(d1.cpu(), gold['ba1_disps']) < 1e-4
+    G2, d2 = BA(tgt, wgt, eta, G1, d1, intr, ii, jj, fixedp=2)
+    assert _rel(G2.data.cpu(), gold['ba2_poses']) < 1e-4 and _rel(d2.cpu(), gold['ba2_disps']) < 1e-4
+    Gm = MoBA(tgt, wgt, eta, Gs, disps, intr, ii, jj, fixedp=1)
+    assert _rel(Gm.data.cpu(), gold['moba_poses']) < 1e-4
+    assert torch.equal(Gs.data.cpu(), c['poses'][None])          # functional: inputs untouched
