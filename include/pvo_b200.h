@@ -119,7 +119,11 @@ int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels, const int
 /* grouped 3x3 convolution with <= 2 outputs per group: the four 128->2 heads and GraphAgg's eta head */
 int pvo_conv3x3_small(const void* in, int istride, int cin_g, const float* W, const float* bias, float* out,
                       int ostride, int G, int CG, int nimg, int H, int Wd, int dtype, int post, void* stream);
-int pvo_colmean(const void* in, float* out, int E, int HW, int C, int dtype, void* stream);           /* gru.py:26 */
+int pvo_colmean(const void* in, float* out, float* scratch /* E*32*C floats */, int E, int HW, int C, int dtype,
+                void* stream);                                                                    /* gru.py:26 */
+/* flow-encoder input for the tensor-core path: (M,8) half motion features -> (M,64) with channel dxi*8+c = feature c
+ *   of the pixel dxi-3 columns away, so the 7x7 conv (droid_net.py:179) runs as a 7x1 conv over 64 channels */
+int pvo_expand_x7(const void* motn, void* out, int nimg, int H, int Wd, void* stream);
 int pvo_glo_matvec(const float* glo, const float* W, const float* b, float* out, int E, void* stream); /* gru.py:28-30 */
 /* torch_scatter.scatter_mean over edges sharing ii (droid_net.py:83-88); ptr/idx/meta from pvo_group_edges */
 int pvo_segment_mean(const void* in, int istride, int ioff, void* out, const int* ptr, const int* idx, const int* meta,

@@ -321,13 +321,25 @@ __global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__
       QWs[p] = ok ? q * bf.w[(long)k * HW + pix0 + c0 + p] : 0.f;
     }
     __syncthreads();
-    for (int idx = tid; idx < R6 * R6; idx += kPix) {
-      const int a = idx / R6, b = idx - a * R6;
+    // S is symmetric: enumerate a <= b only (903 of 1764 entries at config 2) and mirror
+    for (int idx = tid; idx < R6 * (R6 + 1) / 2; idx += kPix) {
+      int a = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);          // idx = a(a+1)/2 + b, b <= a  (then swap roles)
+      while (a * (a + 1) / 2 > idx) a--;
+      while ((a + 1) * (a + 2) / 2 <= idx) a++;
+      const int b = idx - a * (a + 1) / 2;                               // b <= a
       const int pa = rowpose[a / 6], pb = rowpose[b / 6];
       if (pa < 0 || pb < 0) continue;
       float s = 0.f;
       for (int p = 0; p < np; p++) s += tile[p * R6 + a] * Qs[p] * tile[p * R6 + b];
-      atomicAdd(&bf.H[(long)(6 * pa + a % 6) * n + (6 * pb + b % 6)], -(double)s);
+      const long i = 6 * pa + a % 6, j = 6 * pb + b % 6;
+      if (a == b) {
+        atomicAdd(&bf.H[i * n + j], -(double)s);
+      } else if (i == j) {                                               // two rows of the same pose (duplicate edges)
+        atomicAdd(&bf.H[i * n + j], -2.0 * (double)s);
+      } else {
+        atomicAdd(&bf.H[i * n + j], -(double)s);
+        atomicAdd(&bf.H[j * n + i], -(double)s);
+      }
     }
     for (int a = tid; a < R6; a += kPix) {
       const int pa = rowpose[a / 6];
@@ -403,6 +415,56 @@ __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm,
   // leave the system zeroed for the next iteration / next call
   for (long i = tid; i < (long)n * n; i += T) bf.H[i] = 0.0;
   for (int i = tid; i < n; i += T) { bf.b[i] = 0.0; bf.dA[i] = 0.0; }
+}
+
+// n <= 64: one warp, left-looking Cholesky in shared memory with __syncwarp only (the block version above spends its
+// time in ~7n __syncthreads).  Same damping / failure semantics.
+__global__ void __launch_bounds__(32) ba_solve_warp_kernel(Bufs bf, int P, float lm, float ep, int sem) {
+  extern __shared__ double smw[];
+  const int n = 6 * P, ld = n + 1;
+  const int lane = threadIdx.x;
+  double* A = smw;
+  double* y = smw + (long)n * ld;
+  for (int i = lane; i < n * n; i += 32) A[(i / n) * ld + (i % n)] = bf.H[i];
+  for (int i = lane; i < n; i += 32) y[i] = bf.b[i];
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) A[i * ld + i] += (double)ep + (double)lm * (sem ? bf.dA[i] : A[i * ld + i]);
+  __syncwarp();
+  bool fail = false;
+  for (int j = 0; j < n; j++) {
+    double s = 0.0;
+    for (int k = lane; k < j; k += 32) s += A[j * ld + k] * A[j * ld + k];
+    s = warp_sum_d(s);
+    const double djj = A[j * ld + j] - s;
+    if (!(djj > 0.0)) { fail = true; break; }
+    const double d = sqrt(djj), inv = 1.0 / d;
+    for (int i = j + 1 + lane; i < n; i += 32) {
+      double t = A[i * ld + j];
+      for (int k = 0; k < j; k++) t -= A[i * ld + k] * A[j * ld + k];
+      A[i * ld + j] = t * inv;
+    }
+    if (lane == 0) A[j * ld + j] = d;
+    __syncwarp();
+  }
+  if (!fail) {
+    for (int j = 0; j < n; j++) {                      // L z = b
+      if (lane == 0) y[j] /= A[j * ld + j];
+      __syncwarp();
+      const double yj = y[j];
+      for (int i = j + 1 + lane; i < n; i += 32) y[i] -= A[i * ld + j] * yj;
+      __syncwarp();
+    }
+    for (int j = n - 1; j >= 0; j--) {                 // L^T x = z
+      if (lane == 0) y[j] /= A[j * ld + j];
+      __syncwarp();
+      const double yj = y[j];
+      for (int i = lane; i < j; i += 32) y[i] -= A[j * ld + i] * yj;
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < n; i += 32) bf.dx[i] = fail ? 0.0f : (float)y[i];
+  for (int i = lane; i < n * n; i += 32) bf.H[i] = 0.0;
+  for (int i = lane; i < n; i += 32) { bf.b[i] = 0.0; bf.dA[i] = 0.0; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -505,6 +567,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
                       const float* eta, const long* ii, const long* jj, int E, int nframes, int ht, int wd, int t0,
                       int t1, int K, int iterations, float lm, float ep, int motion_only, int interleaved,
                       float* dx_out, float* dz_out, void* workspace, long workspace_bytes, int flags, void* stream) {
+  // flags bits 8-19: optional hint = max out-degree of the graph (0 = unknown); only sizes pass 2's shared memory
   const int P = t1 - t0, HW = ht * wd;
   if (E <= 0 || P <= 0 || K <= 0 || nframes <= 0 || t0 < 0 || t1 > nframes || HW <= 0) return PVO_ERR_INVALID;
   const Layout L = make_layout(E, nframes, P, K, HW);
@@ -519,11 +582,18 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
   if (!(flags & 1)) ba_plan_kernel<<<1, 1024, 0, s>>>(ii, E, nframes, t0, t1, K, pl, bf.H, bf.b, bf.dA, n);
   const dim3 grid(ceil_div(HW, kPix), K);
   static bool attr_set = false;
-  const int pass2_smem = 160 * 1024;
+  const int deg_hint = (flags >> 8) & 0xFFF;
+  int pass2_smem = 160 * 1024;
+  if (deg_hint > 0) {        // tile [256][6(deg+1)] + Q + QW + row table; smaller request => several blocks per SM, one wave
+    const long need = 4L * (256L * (6 * (deg_hint + 1) + 2) + ((deg_hint + 1 + 3) & ~3)) + 64;
+    if (need < pass2_smem) pass2_smem = (int)need;
+  }
   const size_t solve_smem = sizeof(double) * ((size_t)n * n + n);
   const bool solve_in_smem = solve_smem <= 200 * 1024;
+  const size_t warp_smem = sizeof(double) * ((size_t)n * (n + 1) + n);
   if (!attr_set) {
-    cudaFuncSetAttribute(ba_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pass2_smem);
+    cudaFuncSetAttribute(ba_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(ba_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
@@ -540,7 +610,9 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
         ba_pass2_kernel<<<grid, kPix, pass2_smem, s>>>(jj, pl, bf, HW, t0, P, pass2_smem / 4);
     }
     if (phase == 1) break;
-    if (solve_in_smem)
+    if (n <= 64)
+      ba_solve_warp_kernel<<<1, 32, warp_smem, s>>>(bf, P, lm, ep, sem);
+    else if (solve_in_smem)
       ba_solve_kernel<true><<<1, 512, solve_smem, s>>>(bf, P, lm, ep, sem);
     else
       ba_solve_kernel<false><<<1, 512, 0, s>>>(bf, P, lm, ep, sem);

@@ -26,7 +26,7 @@ struct ConvP {
   const float* W;    // [KH*KW*Cin][Wstride], Wstride % 4 == 0, zero padded
   int Wstride;
   int Cout;
-  int KH, KW, pad;
+  int KH, KW, padH, padW;
   int H, Wd;         // spatial size; M = nimg * H * Wd
   long M;
 };
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ 
       const int tap = kb / p.Cin;
       int c = kb - tap * p.Cin;
       const int dy = tap / p.KW, dxx = tap - dy * p.KW;
-      const int iy = py + dy - p.pad, ix = px + dxx - p.pad;
+      const int iy = py + dy - p.padH, ix = px + dxx - p.padW;
       ok = ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.Wd;
       if (ok) {
         int s = 0;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ 
           const int tap = k / p.Cin;
           int c = k - tap * p.Cin;
           const int dy = tap / p.KW, dxx = tap - dy * p.KW;
-          const int iy = py + dy - p.pad, ix = px + dxx - p.pad;
+          const int iy = py + dy - p.padH, ix = px + dxx - p.padW;
           if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.Wd) {
             int s = 0;
             while (s < p.nseg - 1 && c >= p.seg[s].channels) { c -= p.seg[s].channels; s++; }
@@ -255,79 +255,126 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------ small-N grouped 3x3
-// out[m][g*CG + o] = post(bias + sum_{tap,c} in[m@tap][g*Cg_in + c] * W[g][tap][c][o]),  CG <= 2, used for the four
-// 128->2 head convolutions (droid_net.py:189-214, one group per head) and GraphAgg's 128->1 eta head (:72-75).
-// post: 0 none, 1 = 0.01 * softplus (droid_net.py:95 with nn.Softplus defaults beta=1, threshold=20)
+// out[m][g*CG + o] = post(bias + sum_{tap,c} in[m@tap][g*cin_g + c] * W[g][tap][c][o]),  CG <= 2: the four 128->2 head
+// convolutions (droid_net.py:189-214, one group per head) and GraphAgg's 128->1 eta head (:72-75).
+// post: 0 none, 1 = 0.01 * softplus (droid_net.py:95 with nn.Softplus defaults beta=1, threshold=20).
+// HBM-bound (each input read once): block = one 8x16 pixel patch of one group; the 10x18 halo patch is staged in
+// shared memory (pixel stride padded by 16 B so the per-pixel 16-byte reads are bank-conflict free), weights in smem.
 template <typename TI, int CG>
 __global__ void __launch_bounds__(128) conv3x3_small_kernel(const TI* __restrict__ in, int istride, int cin_g,
                                                             const float* __restrict__ W, const float* __restrict__ bias,
                                                             float* __restrict__ out, int ostride, int G, int H, int Wd,
-                                                            long M, int post) {
-  extern __shared__ float wsm[];                       // [G][9][cin_g][CG]
-  const int nW = G * 9 * cin_g * CG;
-  for (int i = threadIdx.x; i < nW; i += blockDim.x) wsm[i] = W[i];
+                                                            int tiles_x, int tiles_y, int post) {
+  constexpr int TH = 8, TW = 16, PH = TH + 2, PW = TW + 2;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int pstride = cin_g + 16 / (int)sizeof(TI);            // elements per patch pixel (+16 B pad)
+  TI* patch = reinterpret_cast<TI*>(sm_raw);
+  float* wsm = reinterpret_cast<float*>(sm_raw + (((size_t)PH * PW * pstride * sizeof(TI) + 15) & ~size_t(15)));
+  const int g = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int img = tile / (tiles_x * tiles_y);
+  const int r = tile - img * (tiles_x * tiles_y);
+  const int y0 = (r / tiles_x) * TH, x0 = (r % tiles_x) * TW;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 9 * cin_g * CG; i += 128) wsm[i] = W[(long)g * 9 * cin_g * CG + i];
+  // stage the halo patch: 16-byte chunks, consecutive threads -> consecutive chunks of one pixel
+  const int cpp = cin_g * (int)sizeof(TI) / 16;                 // chunks per pixel
+  for (int i = tid; i < PH * PW * cpp; i += 128) {
+    const int pp = i / cpp, ch = i - pp * cpp;
+    const int py = y0 - 1 + pp / PW, px = x0 - 1 + pp % PW;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (py >= 0 && py < H && px >= 0 && px < Wd)
+      v = __ldg(reinterpret_cast<const uint4*>(in + ((long)(img * H + py) * Wd + px) * istride + g * cin_g) + ch);
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(patch + (long)pp * pstride) + 16 * ch) = v;
+  }
   __syncthreads();
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long m = t / G;
-  const int g = (int)(t - m * G);
-  if (m >= M) return;
-  const int HW = H * Wd;
-  const long img = m / HW;
-  const int rem = (int)(m - img * HW);
-  const int py = rem / Wd, px = rem - py * Wd;
+  const int ty = tid / TW, tx = tid % TW;
+  const int y = y0 + ty, x = x0 + tx;
   float acc[CG];
 #pragma unroll
   for (int o = 0; o < CG; o++) acc[o] = 0.0f;
+#pragma unroll
   for (int tap = 0; tap < 9; tap++) {
-    const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= Wd) continue;
-    const TI* src = in + (img * HW + (long)iy * Wd + ix) * istride + g * cin_g;
-    const float* w = wsm + ((g * 9 + tap) * cin_g) * CG;
+    const TI* src = patch + (long)((ty + tap / 3) * PW + tx + tap % 3) * pstride;
+    const float* w = wsm + tap * cin_g * CG;
     for (int c = 0; c < cin_g; c += 8) {
       float v[8];
       if (sizeof(TI) == 4) {
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + c));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + c) + 1);
+        const float4 v0 = *reinterpret_cast<const float4*>(src + c);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + c + 4);
         v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
       } else {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c));
+        const uint4 u = *reinterpret_cast<const uint4*>(src + c);
         const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
         for (int q = 0; q < 4; q++) { const float2 f = __half22float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
       }
 #pragma unroll
-      for (int q = 0; q < 8; q++)
-#pragma unroll
-        for (int o = 0; o < CG; o++) acc[o] = fmaf(v[q], w[(c + q) * CG + o], acc[o]);
+      for (int q = 0; q < 8; q++) {
+        if (CG == 2) {
+          const float2 ww = *reinterpret_cast<const float2*>(w + (c + q) * 2);
+          acc[0] = fmaf(v[q], ww.x, acc[0]);
+          acc[CG - 1] = fmaf(v[q], ww.y, acc[CG - 1]);
+        } else {
+          acc[0] = fmaf(v[q], w[c + q], acc[0]);
+        }
+      }
     }
   }
+  if (y < H && x < Wd) {
+    const long m = (long)(img * H + y) * Wd + x;
 #pragma unroll
-  for (int o = 0; o < CG; o++) {
-    float v = acc[o] + bias[g * CG + o];
-    if (post == 1) v = 0.01f * ((v > 20.0f) ? v : log1pf(expf(v)));
-    out[m * ostride + g * CG + o] = v;
+    for (int o = 0; o < CG; o++) {
+      float v = acc[o] + bias[g * CG + o];
+      if (post == 1) v = 0.01f * ((v > 20.0f) ? v : log1pf(expf(v)));
+      out[m * ostride + g * CG + o] = v;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ small helpers
-// mean over the HW pixels of each image: in [E][HW][C] -> out [E][C]   (gru.py:26)
+// mean over the HW pixels of each image: in [E][HW][C] -> out [E][C]   (gru.py:26).  Two deterministic stages:
+// kColChunks partial sums per image (coalesced rows, 2 channels per thread), then a fixed-order final sum.
+constexpr int kColChunks = 32;
 template <typename TI>
-__global__ void __launch_bounds__(256) colmean_kernel(const TI* __restrict__ in, float* __restrict__ out, int HW, int C) {
-  const int e = blockIdx.x;
-  const int c = blockIdx.y * 32 + (threadIdx.x & 31);
-  const int part = threadIdx.x >> 5;                   // 8 pixel partitions
-  __shared__ float red[8][32];
-  float s = 0.0f;
-  if (c < C)
-    for (int p = part; p < HW; p += 8) s += ldf(in + ((long)e * HW + p) * C + c);
-  red[part][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (part == 0 && c < C) {
-    float t = 0.0f;
-#pragma unroll
-    for (int q = 0; q < 8; q++) t += red[q][threadIdx.x];
-    out[(long)e * C + c] = t / (float)HW;
+__global__ void __launch_bounds__(64) colsum_partial_kernel(const TI* __restrict__ in, float* __restrict__ part, int HW, int C) {
+  const int e = blockIdx.x, ch = blockIdx.y;
+  const int per = (HW + kColChunks - 1) / kColChunks;
+  const int p0 = ch * per, p1 = min(HW, p0 + per);
+  for (int c = 2 * threadIdx.x; c < C; c += 2 * blockDim.x) {
+    float s0 = 0.0f, s1 = 0.0f;
+    for (int p = p0; p < p1; p++) {
+      const TI* q = in + ((long)e * HW + p) * C + c;
+      s0 += ldf(q);
+      s1 += ldf(q + 1);
+    }
+    part[((long)e * kColChunks + ch) * C + c] = s0;
+    part[((long)e * kColChunks + ch) * C + c + 1] = s1;
   }
+}
+__global__ void __launch_bounds__(128) colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int HW, int C) {
+  const int e = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.0f;
+#pragma unroll 4
+    for (int k = 0; k < kColChunks; k++) s += part[((long)e * kColChunks + k) * C + c];
+    out[(long)e * C + c] = s / (float)HW;
+  }
+}
+
+// flow-encoder input for the tensor-core path: the 7x7 conv over 8 motion channels (droid_net.py:179) is run as a
+// 7x1 conv over 64 channels, where channel (dxi*8 + c) of pixel (y,x) holds motion channel c of pixel (y, x+dxi-3)
+// (zero outside the image) and channels 56..63 are zero.
+__global__ void __launch_bounds__(256) expand_x7_kernel(const __half* __restrict__ motn, __half* __restrict__ out, int Wd, long M) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long m = t >> 3;
+  const int k = (int)(t & 7);
+  if (m >= M) return;
+  const int x = (int)(m % Wd);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  const int xs = x + k - 3;
+  if (k < 7 && xs >= 0 && xs < Wd) v = __ldg(reinterpret_cast<const uint4*>(motn) + (m + k - 3));
+  reinterpret_cast<uint4*>(out)[m * 8 + k] = v;
 }
 
 // the three 1x1 "glo" convolutions on the pooled vector (gru.py:28-30): out[e][g*128+o] = b_g[o] + W_g[o][:] . glo[e]
@@ -448,7 +495,7 @@ extern "C" int pvo_conv2d(const void* const* seg_ptr, const int* seg_channels, c
     if ((seg_stride[s] * esz) % 16 || ((uintptr_t)seg_ptr[s]) % 16) vec = false;
   }
   for (int s = nseg; s < 4; s++) p.seg[s] = Seg{nullptr, 0, 0};
-  p.W = W; p.Wstride = wstride; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad; p.H = H; p.Wd = Wd;
+  p.W = W; p.Wstride = wstride; p.Cout = Cout; p.KH = KH; p.KW = KW; p.padH = KH / 2; p.padW = KW / 2; (void)pad;   /* 'same' padding is the only mode the path uses */ p.H = H; p.Wd = Wd;
   p.M = (long)nimg * H * Wd;
   cudaStream_t s = (cudaStream_t)stream;
   const int HW = H * Wd;
@@ -470,14 +517,18 @@ extern "C" int pvo_conv3x3_small(const void* in, int istride, int cin_g, const f
                                  int ostride, int G, int CG, int nimg, int H, int Wd, int dtype, int post, void* stream) {
   if (cin_g % 8 || (CG != 1 && CG != 2) || G < 1) return PVO_ERR_INVALID;
   if (nimg == 0) return PVO_OK;
-  const long M = (long)nimg * H * Wd;
-  const size_t smem = sizeof(float) * G * 9 * cin_g * CG;
-  const int grid = ceil_div(M * G, 128);
+  const size_t esz = dtype == PVO_DTYPE_F32 ? 4 : 2;
+  if ((istride * esz) % 16 || (cin_g * esz) % 16 || ((uintptr_t)in) % 16) return PVO_ERR_INVALID;
+  const int tiles_x = (Wd + 15) / 16, tiles_y = (H + 7) / 8;
+  const size_t patch = ((size_t)10 * 18 * (cin_g * esz + 16) + 15) & ~size_t(15);
+  const size_t smem = patch + sizeof(float) * 9 * cin_g * CG;
+  dim3 grid(nimg * tiles_x * tiles_y, G);
   cudaStream_t s = (cudaStream_t)stream;
 #define L(TI, CGV)                                                                                                  \
   {                                                                                                                 \
     cudaFuncSetAttribute(conv3x3_small_kernel<TI, CGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    conv3x3_small_kernel<TI, CGV><<<grid, 128, smem, s>>>((const TI*)in, istride, cin_g, W, bias, out, ostride, G, H, Wd, M, post); \
+    conv3x3_small_kernel<TI, CGV><<<grid, 128, smem, s>>>((const TI*)in, istride, cin_g, W, bias, out, ostride, G, H, Wd, \
+                                                          tiles_x, tiles_y, post);                                  \
   }
   if (dtype == PVO_DTYPE_F32) { if (CG == 1) L(float, 1) else L(float, 2) }
   else if (dtype == PVO_DTYPE_F16) { if (CG == 1) L(__half, 1) else L(__half, 2) }
@@ -486,11 +537,22 @@ extern "C" int pvo_conv3x3_small(const void* in, int istride, int cin_g, const f
   return pvo_check_launch();
 }
 
-extern "C" int pvo_colmean(const void* in, float* out, int E, int HW, int C, int dtype, void* stream) {
+// scratch: E * 32 * C floats
+extern "C" int pvo_colmean(const void* in, float* out, float* scratch, int E, int HW, int C, int dtype, void* stream) {
   if (E == 0) return PVO_OK;
-  dim3 grid(E, ceil_div(C, 32));
-  if (dtype == PVO_DTYPE_F32) colmean_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, out, HW, C);
-  else colmean_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)in, out, HW, C);
+  if (C % 2 || !scratch) return PVO_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(E, kColChunks);
+  if (dtype == PVO_DTYPE_F32) colsum_partial_kernel<float><<<grid, 64, 0, s>>>((const float*)in, scratch, HW, C);
+  else colsum_partial_kernel<__half><<<grid, 64, 0, s>>>((const __half*)in, scratch, HW, C);
+  colsum_final_kernel<<<E, 128, 0, s>>>(scratch, out, HW, C);
+  return pvo_check_launch();
+}
+
+extern "C" int pvo_expand_x7(const void* motn, void* out, int nimg, int H, int Wd, void* stream) {
+  if (nimg == 0) return PVO_OK;
+  const long M = (long)nimg * H * Wd;
+  expand_x7_kernel<<<ceil_div(M * 8, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)motn, (__half*)out, Wd, M);
   return pvo_check_launch();
 }
 

@@ -61,6 +61,22 @@ struct EpBias {          // out = act(acc + bias)
   }
 };
 
+struct EpGlo {           // gru.py:25: sigmoid(w(net)) * net  (spatial mean taken by colmean)
+  const float* bias; const __half* net; int nstride; __half* out; int Cout;
+  __device__ __forceinline__ void store16(long m, long, int n, const float* v) const {
+    if (n >= Cout) return;
+    __align__(16) __half hn[16];
+    __align__(16) __half h[16];
+    *reinterpret_cast<uint4*>(&hn[0]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + n));
+    *reinterpret_cast<uint4*>(&hn[8]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + n + 8));
+#pragma unroll
+    for (int j = 0; j < 16; j++) h[j] = __float2half_rn(sigmoidf_(v[j] + __ldg(bias + n + j)) * __half2float(hn[j]));
+    __half* o = out + m * Cout + n;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&h[0]);
+    *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+  }
+};
+
 struct EpZR {            // gru.py:28-29 (see conv_simt.cu EpiZR)
   const float* bias; const float* glo; const __half* net; int nstride; __half* z; __half* rnet;
   __device__ __forceinline__ void store16(long m, long e, int n, const float* v) const {
@@ -265,7 +281,7 @@ int dispatch_bn(const TcParams& p0, const Epi& epi, int bn, cudaStream_t s) {
 // Segments: pixel-major fp16 tensors (nimg*H*W, stride) whose channel slices are concatenated into the conv input;
 // seg_channels[s] need not be a multiple of 64 (the tail is zero-filled by TMA; the packed weights carry zeros there).
 // Wh: fp16 [Cout][taps * sum_s ceil64(seg_channels[s])], K ordered (tap, segment, channel) -- pack_conv_weight_tc.
-// epilogue: 0 bias, 1 bias+ReLU, 3 GRU z|r, 4 GRU q + state update (same meaning and aux pointers as pvo_conv2d).
+// epilogue: 0 bias, 1 bias+ReLU, 2 sigmoid(.)*net, 3 GRU z|r, 4 GRU q + state update (same meaning and aux pointers as pvo_conv2d).
 extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels, const int* seg_stride, int nseg,
                              const void* Wh, const float* bias, int Cout, int KH, int KW, int nimg, int H, int Wd,
                              int epilogue, void* out, int ostride, int ooff, void* out2, const void* aux0, int aux_stride,
@@ -311,6 +327,9 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
     case 0: case 1:
       if ((ostride * 2) % 16 || (ooff * 2) % 16) return PVO_ERR_INVALID;
       return dispatch_bn(p, EpBias{bias, (__half*)out, ostride, ooff, Cout, epilogue}, bn, s);
+    case 2:
+      if (Cout % 16) return PVO_ERR_INVALID;
+      return dispatch_bn(p, EpGlo{bias, (const __half*)aux0, aux_stride, (__half*)out, Cout}, bn, s);
     case 3:
       if (Cout != 256) return PVO_ERR_INVALID;
       return dispatch_bn(p, EpZR{bias, aux1, (const __half*)aux0, aux_stride, (__half*)out, (__half*)out2}, bn, s);

@@ -78,7 +78,7 @@ def ba_workspace(E, nframes, P, K, HW, device):
 
 
 def ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only,
-       interleaved=False, reuse_plan=False, workspace=None):
+       interleaved=False, reuse_plan=False, workspace=None, max_degree=0):
     """src/droid_kernels.cu:1293-1410.  Mutates poses (buf,7) and disps (buf,ht,wd) in place; returns [dx, dz].
 
     targets / weights: (E,2,ht,wd) as the reference passes them (factor_graph.py:297-300), or (E,ht,wd,2) with
@@ -96,7 +96,7 @@ def ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iteratio
     check(_lib.lib().pvo_ba(ptr(poses), ptr(disps), ptr(intrinsics), ptr(targets), ptr(weights), ptr(eta), ptr(ii),
                             ptr(jj), E, nframes, ht, wd, int(t0), int(t1), K, int(iterations), float(lm), float(ep),
                             1 if motion_only else 0, 1 if interleaved else 0, ptr(dx), ptr(dz), ptr(ws), ws.numel(),
-                            1 if reuse_plan else 0, stream()), 'ba',
+                            (1 if reuse_plan else 0) | ((int(max_degree) & 0xFFF) << 8), stream()), 'ba',
           launches=(0 if reuse_plan else 1) + int(iterations) * (3 if motion_only else 4))
     return [dx, dz]
 

@@ -27,13 +27,15 @@ def coords_grid(ht, wd, device):
 
 
 class FactorGraph:
-    def __init__(self, video, update_op, device='cuda:0', corr_impl='volume', max_factors=-1, precision='auto'):
+    def __init__(self, video, update_op, device='cuda:0', corr_impl='volume', max_factors=-1, precision='auto',
+                 use_cuda_graph=False):
         self.video = video
         self.update_op = update_op
         self.device = device
         self.max_factors = max_factors
         self.corr_impl = corr_impl
         self.precision = precision
+        self.use_cuda_graph = use_cuda_graph   # replay the whole iteration as one CUDA graph (no per-launch CPU cost)
         self.ht = ht = video.ht // 8
         self.wd = wd = video.wd // 8
         self.dy_thresh = 0.5
@@ -81,6 +83,7 @@ class FactorGraph:
     def net(self, v):
         self._net = v
         self._state_in_engine = False
+        self._cache = None
 
     @property
     def inp(self):
@@ -90,6 +93,7 @@ class FactorGraph:
     def inp(self, v):
         self._inp = v
         self._state_in_engine = False
+        self._cache = None
 
     # ------------------------------------------------------------------ edge bookkeeping (factor_graph.py:60-225)
     def __filter_repeated_edges(self, ii, jj):
@@ -202,7 +206,8 @@ class FactorGraph:
         L = _lib.lib()
         c = dict(E=E, K=K, kx=kx, t0_default=max(1, int(self.ii.min().item()) + 1),
                  t1_default=int(max(self.ii.max().item(), self.jj.max().item())) + 1,
-                 ba_key=None, ba_kx={})
+                 ba_key=None, ba_kx={}, graphs={},
+                 max_degree=int(torch.bincount(self.ii).max().item()))
         c['coords1'] = torch.empty(1, E, self.ht, self.wd, 2, device=self.device)
         c['seg_ws'] = torch.zeros(int(L.pvo_update_post_workspace_ints(E)), dtype=torch.int32, device=self.device)
         c['segm'] = self.segm[0, :, 0].contiguous() if self.segm is not None else None
@@ -215,6 +220,26 @@ class FactorGraph:
     @torch.no_grad()
     def update(self, t0=None, t1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
         """run update operator on factor graph (factor_graph.py:227-307)"""
+        if not (self.use_cuda_graph and self.timers is None and not use_inactive):
+            return self._update(t0, t1, itrs, use_inactive, EP, motion_only)
+        # CUDA-graph path: 1st call with a given signature runs eagerly (lazy initialisation, attribute setup),
+        # 2nd call captures, later calls replay.  Every launch of the iteration is capture-safe (no host sync).
+        c = self._cache or self._prepare()
+        key = (t0, t1, itrs, EP, motion_only)
+        entry = c['graphs'].get(key)
+        if entry is None:
+            c['graphs'][key] = 'warm'
+            return self._update(t0, t1, itrs, use_inactive, EP, motion_only)
+        if entry == 'warm':
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._update(t0, t1, itrs, use_inactive, EP, motion_only)
+            c['graphs'][key] = g
+            entry = g
+        entry.replay()
+
+    def _update(self, t0=None, t1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
         c = self._cache or self._prepare()
         eng = self._engine()
         L = _lib.lib()
@@ -234,8 +259,9 @@ class FactorGraph:
                 self.corr(coords1, out=eng.corr, layout=1, out_cstride=pnn.CORR_STRIDE)
             else:
                 self._lookup_mixed(coords1, eng)
-        # (3) update operator
+        # (3) update operator (hidden state advances in place inside the engine)
         eng.run(with_agg=True)
+        self._state_in_engine = True
         # (4) target, masks, segment filter, weights (in place on the graph's state tensors)
         if t0 is None:
             t0 = c['t0_default']
@@ -269,7 +295,7 @@ class FactorGraph:
         # (5) dense bundle adjustment, in place on video.poses / video.disps
         with T('ba_total'):
             v.ba(target_cam[0], weight[0], damping, ii, jj, t0, t1, itrs=itrs, lm=1e-4, ep=0.1, motion_only=motion_only,
-                 interleaved=True, reuse_plan=reuse)
+                 interleaved=True, reuse_plan=reuse, max_degree=0 if use_inactive else c['max_degree'])
         self.age += 1
         self.launch_count = _lib.LAUNCHES[0] - n0
 

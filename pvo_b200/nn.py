@@ -102,8 +102,14 @@ class UpdateEngine:
         self.c_corr0 = _Conv(g('corr_encoder.0.weight'), g('corr_encoder.0.bias'), cin_pad=CORR_STRIDE, tc=tc)
         self.c_corr2 = _Conv(g('corr_encoder.2.weight'), g('corr_encoder.2.bias'), tc=tc)
         self.c_flow0 = _Conv(g('flow_encoder.0.weight'), g('flow_encoder.0.bias'))
+        if tc:
+            # 7x7 over 8 channels == 7x1 over the x-expanded 64-channel input (pvo_expand_x7): W'[co][dxi*8+c][kh]
+            w7 = g('flow_encoder.0.weight')                                    # (128, 8, 7, 7) = (co, c, kh, kw)
+            wx = torch.zeros(128, 64, 7, 1, device=w7.device, dtype=w7.dtype)
+            wx[:, :56, :, 0] = w7.permute(0, 3, 1, 2).reshape(128, 56, 7)       # (co, kw, c, kh) -> (co, kw*8+c, kh)
+            self.c_flow0x = _Conv(wx, g('flow_encoder.0.bias'), tc=True)
         self.c_flow2 = _Conv(g('flow_encoder.2.weight'), g('flow_encoder.2.bias'), tc=tc)
-        self.c_w = _Conv(g('gru.w.weight'), g('gru.w.bias'))
+        self.c_w = _Conv(g('gru.w.weight'), g('gru.w.bias'), tc=tc)
         self.c_zr = _Conv(torch.cat([g('gru.convz.weight'), g('gru.convr.weight')], 0),
                           torch.cat([g('gru.convz.bias'), g('gru.convr.bias')], 0), tc=tc)
         self.c_q = _Conv(g('gru.convq.weight'), g('gru.convq.bias'), tc=tc, segs=[128, 320])
@@ -131,6 +137,8 @@ class UpdateEngine:
         self.X = z(M, 448)             # [net | inp | corr_enc | flow_enc]   (gru.py:20-21 channel order)
         self.corr = z(M, CORR_STRIDE)
         self.motn = z(M, 8)
+        self.motx = z(M, 64) if self.use_tc else None      # x-expanded motion features (tensor-core flow encoder)
+        self.col_scratch = z(E * 32 * 128, dtype=torch.float32)
         self.c1 = z(M, 128)
         self.f1 = z(M, 128)
         self.glo_tmp = z(M, 128)
@@ -188,15 +196,22 @@ class UpdateEngine:
         with T('conv_corr2'):
             conv2d(self.c_corr2, [(self.c1, 128, 128)], E, H, W, dc, X, 448, 256, 1, use_tc=tc)
         # flow_encoder: 7x7 8->128 + ReLU, 3x3 128->64 + ReLU  -> X[:,384:448]
-        with T('conv_flow0'):
-            conv2d(self.c_flow0, [(self.motn, 8, 8)], E, H, W, dc, self.f1, 128, 0, 1)
+        if tc:
+            with T('expand_x7'):
+                check(L.pvo_expand_x7(ptr(self.motn), ptr(self.motx), E, H, W, stream()), 'expand_x7')
+            with T('conv_flow0'):
+                conv2d(self.c_flow0x, [(self.motx, 64, 64)], E, H, W, dc, self.f1, 128, 0, 1, use_tc=True)
+        else:
+            with T('conv_flow0'):
+                conv2d(self.c_flow0, [(self.motn, 8, 8)], E, H, W, dc, self.f1, 128, 0, 1)
         with T('conv_flow2'):
             conv2d(self.c_flow2, [(self.f1, 128, 128)], E, H, W, dc, X, 448, 384, 1, use_tc=tc)
         # global context: mean_HW(sigmoid(w(net)) * net) -> three 128x128 mat-vecs
         with T('conv_glo'):
-            conv2d(self.c_w, [(X, 128, 448)], E, H, W, dc, self.glo_tmp, 128, 0, 2, aux0=X, aux_stride=448)
+            conv2d(self.c_w, [(X, 128, 448)], E, H, W, dc, self.glo_tmp, 128, 0, 2, aux0=X, aux_stride=448, use_tc=tc)
         with T('colmean'):
-            check(L.pvo_colmean(ptr(self.glo_tmp), ptr(self.glo), E, HW, 128, dc, stream()), 'colmean')
+            check(L.pvo_colmean(ptr(self.glo_tmp), ptr(self.glo), ptr(self.col_scratch), E, HW, 128, dc, stream()), 'colmean',
+                  launches=2)
         with T('glo_matvec'):
             check(L.pvo_glo_matvec(ptr(self.glo), ptr(self.glo_W), ptr(self.glo_b), ptr(self.glo3), E, stream()), 'glo_matvec')
         # z|r in one 448->256 conv; epilogue emits z and r*net
@@ -259,7 +274,8 @@ def gru_forward(sd, net, inp):
     z = torch.empty(M, 128, dtype=dt, device=dev)
     rnet = torch.empty(M, 128, dtype=dt, device=dev)
     conv2d(c_w, [(X, 128, 448)], N, H, W, dc, tmp, 128, 0, 2, aux0=X, aux_stride=448)
-    check(L.pvo_colmean(ptr(tmp), ptr(glo), N, HW, 128, dc, stream()), 'colmean')
+    scratch = torch.empty(N * 32 * 128, dtype=torch.float32, device=dev)
+    check(L.pvo_colmean(ptr(tmp), ptr(glo), ptr(scratch), N, HW, 128, dc, stream()), 'colmean', launches=2)
     check(L.pvo_glo_matvec(ptr(glo), ptr(glo_W), ptr(glo_b), ptr(glo3), N, stream()), 'glo_matvec')
     conv2d(c_zr, [(X, 448, 448)], N, H, W, dc, z, 128, 0, 3, out2=rnet, aux0=X, aux_stride=448, aux1=glo3)
     conv2d(c_q, [(rnet, 128, 128), (X.data_ptr() + 128 * X.element_size(), 320, 448)], N, H, W, dc, X, 448, 0, 4,

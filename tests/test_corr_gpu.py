@@ -154,11 +154,15 @@ def test_lookup_full_size_properties():
     centre = out[0, :, 3 * 7 + 3]                     # level 0, (xoff, yoff) = (0, 0)
     diag = vol0.reshape(E, h * w, h * w).diagonal(dim1=1, dim2=2).reshape(E, h, w)
     assert torch.equal(centre, diag)
-    # doubling the volume doubles the output exactly (power-of-two scaling commutes with every rounding)
+    # doubling the volume doubles the output: power-of-two scaling commutes with every rounding except in the
+    # subnormal range of half (fixed 2^-24 spacing), so compare exactly away from it and to one spacing inside it
     blk2 = CorrBlock(f1, f2)
     blk2.corr_pyramid = [p * 2 for p in blk.corr_pyramid]
     c = grid + 0.37
-    assert torch.equal(blk2(c), blk(c) * 2)
+    a, b = blk2(c).float(), blk(c).float() * 2
+    big = b.abs() > 2e-3
+    assert torch.equal(a[big], b[big])
+    assert (a - b).abs().max() <= 4 * 2.0 ** -24
 
 
 def _ref_ext():

@@ -1,6 +1,7 @@
 #!/bin/bash
 # Runs on the GPU box (via gpurun): parity tests in isolated processes (a trapping kernel poisons its CUDA context),
-# smoke, bench, and an ncu launch list.  Everything is logged under gpurun_out/.
+# smoke, bench, and optional ncu captures.  Everything is logged under gpurun_out/.
+#   tools/gpu_suite.sh [tests] [bench] [launches] [ncufull] [multi]
 set +e
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -10,21 +11,28 @@ run() { # name, timeout, command...
   local name=$1; local to=$2; shift 2
   echo "=== $name" | tee -a $OUT/summary.txt
   timeout $to "$@" > $OUT/$name.log 2>&1
-  echo "exit $? : $(tail -n 1 $OUT/$name.log)" | tee -a $OUT/summary.txt
+  echo "exit $? : $(tail -n 1 $OUT/$name.log | cut -c1-600)" | tee -a $OUT/summary.txt
 }
 : > $OUT/summary.txt
 PT="python -m pytest -q --tb=short -p no:cacheprovider"
-run t_corr_simt 600 $PT tests/test_corr_gpu.py -k "not tensor_cores and not full_size"
-run t_geom 600 $PT tests/test_geom_gpu.py
-run t_update_fp32 600 $PT tests/test_update_gpu.py -k "fp32 or gru"
-run t_step_fp32 900 $PT tests/test_step_gpu.py -k "golden or medium or bookkeeping"
-run t_conv_tc 300 $PT tests/test_update_gpu.py -k "tensor_core"
-run t_vol_tc 300 $PT tests/test_corr_gpu.py -k "tensor_cores or full_size"
-run t_half 300 $PT tests/test_update_gpu.py tests/test_step_gpu.py -k "half"
-run smoke 300 python __graft_entry__.py smoke
-run bench_fp32 600 python bench.py --steps 3 --warmup 3 --precision fp32
-run bench_fp16 600 python bench.py --steps 30 --warmup 5
-if [ "$1" == "ncu" ]; then
-  run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3
-fi
+for what in "$@"; do
+case $what in
+tests)
+  run t_corr 600 $PT tests/test_corr_gpu.py
+  run t_geom 600 $PT tests/test_geom_gpu.py
+  run t_update 600 $PT tests/test_update_gpu.py
+  run t_step 900 $PT tests/test_step_gpu.py
+  run smoke 300 python __graft_entry__.py smoke ;;
+bench)
+  run bench_fp16 900 python bench.py --steps 50 --warmup 5
+  run bench_fp16_nograph 900 python bench.py --steps 20 --warmup 5 --no-graph --profile-only
+  run bench_ref 900 python bench.py --impl reference --steps 3 --warmup 1 ;;
+launches)
+  run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 300 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-graph --profile-only ;;
+ncufull)
+  run ncu_full 1500 ncu --set full --clock-control none --import-source on -k regex:"corr_lookup_fused|conv_tc_kernel|conv3x3_small|ba_pass|ba_solve|corr_volume_tc" -s 40 -c 24 -o $OUT/prof_r01 -f python bench.py --steps 2 --warmup 3 --no-graph --profile-only ;;
+multi)
+  run bench_2gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 ;;
+esac
+done
 cat $OUT/summary.txt
