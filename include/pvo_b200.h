@@ -124,6 +124,9 @@ int pvo_colmean(const void* in, float* out, float* scratch /* E*32*C floats */, 
 /* flow-encoder input for the tensor-core path: (M,8) half motion features -> (M,64) with channel dxi*8+c = feature c
  *   of the pixel dxi-3 columns away, so the 7x7 conv (droid_net.py:179) runs as a 7x1 conv over 64 channels */
 int pvo_expand_x7(const void* motn, void* out, int nimg, int H, int Wd, void* stream);
+/* tensor-core path: finish the spatial mean from the gate conv's per-tile sums (epilogue 2 of pvo_conv2d_tc) + mat-vecs */
+int pvo_glo_reduce_matvec(const float* partial, int parts_per_img, int HW, const float* W, const float* b, float* out, int E,
+                          void* stream);
 int pvo_glo_matvec(const float* glo, const float* W, const float* b, float* out, int E, void* stream); /* gru.py:28-30 */
 /* torch_scatter.scatter_mean over edges sharing ii (droid_net.py:83-88); ptr/idx/meta from pvo_group_edges */
 int pvo_segment_mean(const void* in, int istride, int ioff, void* out, const int* ptr, const int* idx, const int* meta,

@@ -26,6 +26,7 @@ namespace {
 
 constexpr float kMinDepth = 0.25f;
 constexpr int kPix = 256;       // pixels (= threads) per block
+constexpr int kParts = 16;      // replicas of the reduced system (see Bufs::sys)
 
 struct Plan {          // lives in the integer part of the workspace
   int* frame2k;        // [nframes] frame index -> row in kx, or -1
@@ -40,9 +41,10 @@ struct Bufs {
   float* Ei;           // [K][6][HW]
   float* Q;            // [K][HW]
   float* w;            // [K][HW]
-  double* H;           // [n][n]  reduced camera system, n = 6P
-  double* b;           // [n]
-  double* dA;          // [n]     diagonal of the pose block alone (Python-BA damping, chol.py:55-57)
+  double* sys;         // [kParts][n*n + 2n]: per part {H [n][n] reduced camera system | b [n] | dA [n]}, n = 6P.
+                       // Blocks accumulate into part (blockIdx.x % kParts): same-address fp64 atomics serialise in L2 at
+                       // a few hundred cycles each, and with one copy the 19 pixel-slices of a frame all hit the same
+                       // 1764 addresses (measured: 53 us for the Schur pass).  The solve sums the parts in fixed order.
   float* dx;           // [P][6]
 };
 
@@ -50,7 +52,7 @@ struct Bufs {
 // plan: kx = unique(arange(t0,t1) U ii), edges grouped by source frame.  One block.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) ba_plan_kernel(const long* __restrict__ ii, int E, int nframes, int t0, int t1,
-                                                       int Kcap, Plan pl, double* H, double* b, double* dA, int n) {
+                                                       int Kcap, Plan pl, double* sys, int n) {
   __shared__ int s_warp[32];
   __shared__ int s_total;
   const int tid = threadIdx.x;
@@ -124,8 +126,8 @@ __global__ void __launch_bounds__(1024) ba_plan_kernel(const long* __restrict__ 
     for (int e = 0; e < E; e++)
       if (ii[e] == f) pl.src_idx[o++] = e;
   }
-  for (long i = tid; i < (long)n * n; i += blockDim.x) H[i] = 0.0;
-  for (int i = tid; i < n; i += blockDim.x) { b[i] = 0.0; dA[i] = 0.0; }
+  if (sys)
+    for (long i = tid; i < (long)kParts * ((long)n * n + 2 * n); i += blockDim.x) sys[i] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -188,6 +190,9 @@ __global__ void __launch_bounds__(kPix) ba_pass1_kernel(
   float C = 0.f, wacc = 0.f;
   __shared__ float red[kPix / 32][90];
   const int n = 6 * P;
+  double* Hp = bf.sys + (long)(blockIdx.x % kParts) * ((long)n * n + 2 * n);
+  double* bp = Hp + (long)n * n;
+  double* dAp = bp + n;
   for (int it = pl.src_ptr[k]; it < pl.src_ptr[k + 1]; it++) {
     const int e = pl.src_idx[it];
     const int jx = (int)jj[e];
@@ -247,14 +252,14 @@ __global__ void __launch_bounds__(kPix) ba_pass1_kernel(
         const int pa = a < 6 ? pi : pj, pb = bcol < 6 ? pi : pj;
         if (pa >= 0 && pa < P && pb >= 0 && pb < P) {
           const int row = 6 * pa + (a % 6), col = 6 * pb + (bcol % 6);
-          atomicAdd(&bf.H[(long)row * n + col], s);
-          if (row != col) atomicAdd(&bf.H[(long)col * n + row], s);
-          else if (sem) atomicAdd(&bf.dA[row], s);
+          atomicAdd(&Hp[(long)row * n + col], s);
+          if (row != col) atomicAdd(&Hp[(long)col * n + row], s);
+          else if (sem) atomicAdd(&dAp[row], s);
         }
       } else {
         const int a = tid - 78;
         const int pa = a < 6 ? pi : pj;
-        if (pa >= 0 && pa < P) atomicAdd(&bf.b[6 * pa + (a % 6)], s);
+        if (pa >= 0 && pa < P) atomicAdd(&bp[6 * pa + (a % 6)], s);
       }
     }
     __syncthreads();
@@ -297,6 +302,8 @@ __global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__
     rowpose[r] = (pose >= 0 && pose < P) ? pose : -1;
   }
   const int n = 6 * P;
+  double* Hp = bf.sys + (long)(blockIdx.x % kParts) * ((long)n * n + 2 * n);
+  double* bp = Hp + (long)n * n;
   const int pix0 = blockIdx.x * kPix;
   for (int c0 = 0; c0 < kPix; c0 += PC) {
     __syncthreads();
@@ -333,12 +340,12 @@ __global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__
       for (int p = 0; p < np; p++) s += tile[p * R6 + a] * Qs[p] * tile[p * R6 + b];
       const long i = 6 * pa + a % 6, j = 6 * pb + b % 6;
       if (a == b) {
-        atomicAdd(&bf.H[i * n + j], -(double)s);
+        atomicAdd(&Hp[i * n + j], -(double)s);
       } else if (i == j) {                                               // two rows of the same pose (duplicate edges)
-        atomicAdd(&bf.H[i * n + j], -2.0 * (double)s);
+        atomicAdd(&Hp[i * n + j], -2.0 * (double)s);
       } else {
-        atomicAdd(&bf.H[i * n + j], -(double)s);
-        atomicAdd(&bf.H[j * n + i], -(double)s);
+        atomicAdd(&Hp[i * n + j], -(double)s);
+        atomicAdd(&Hp[j * n + i], -(double)s);
       }
     }
     for (int a = tid; a < R6; a += kPix) {
@@ -346,125 +353,171 @@ __global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__
       if (pa < 0) continue;
       float s = 0.f;
       for (int p = 0; p < np; p++) s += QWs[p] * tile[p * R6 + a];
-      atomicAdd(&bf.b[6 * pa + a % 6], -(double)s);
+      atomicAdd(&bp[6 * pa + a % 6], -(double)s);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// solve: LM damping on the diagonal, dense Cholesky + two triangular solves in float64, one block.
+// solve: sum the kParts replicas, LM damping, blocked (6x6 = one pose) right-looking Cholesky + two blocked
+// triangular solves in float64.  One block; 7P block-level barriers (49 at P = 7) instead of ~7n.
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void damp(double* A, int ld, const double* dA, int P, float lm, float ep, int sem, int moba, int tid, int T) {
+  const int n = 6 * P;
+  if (moba) {
+    // geom/chol.py:32-44 block_solve: `H + (ep + lm*H) * eye(6)` broadcasts over the (N,N,6,6) block tensor, i.e. the
+    // diagonal of EVERY 6x6 block -- off-diagonal pose blocks included -- is damped.  Kept as the reference does it.
+    for (int idx = tid; idx < P * P * 6; idx += T) {
+      const int pq = idx / 6, a = idx - 6 * pq;
+      const long off = (long)(6 * (pq / P) + a) * ld + 6 * (pq % P) + a;
+      A[off] += (double)ep + (double)lm * A[off];
+    }
+  } else {
+    // sem 0: damp the Schur complement (droid_kernels.cu:1175-1176); sem 1: damp H before subtracting E Q E^T (chol.py:55-62)
+    for (int i = tid; i < n; i += T) A[(long)i * ld + i] += (double)ep + (double)lm * (sem ? dA[i] : A[(long)i * ld + i]);
+  }
+}
+
+// sums parts 1.. into part 0 and clears them (multi-GPU: part 0 is what gets all-reduced; large n: global-memory solve)
+__global__ void __launch_bounds__(256) ba_combine_kernel(Bufs bf, int P) {
+  const long psz = 36L * P * P + 12L * P;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < psz; i += (long)gridDim.x * blockDim.x) {
+    double s = bf.sys[i];
+    for (int g = 1; g < kParts; g++) { s += bf.sys[g * psz + i]; bf.sys[g * psz + i] = 0.0; }
+    bf.sys[i] = s;
+  }
+}
+
 template <bool IN_SMEM>
-__global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem) {
+__global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem, int moba) {
   extern __shared__ double smd[];
   __shared__ int s_fail;
   const int n = 6 * P;
   const int tid = threadIdx.x, T = blockDim.x;
-  double* A = IN_SMEM ? smd : bf.H;
-  double* y = IN_SMEM ? smd + (long)n * n : nullptr;
+  const long psz = (long)n * n + 2 * n;
+  const int ld = IN_SMEM ? n + 1 : n;
+  double* A = IN_SMEM ? smd : bf.sys;                      // !IN_SMEM: parts were combined into part 0 beforehand
+  double* y = IN_SMEM ? smd + (long)n * ld : bf.sys + (long)n * n;
+  double* dA = IN_SMEM ? y + n : bf.sys + (long)n * n + n;
   if (IN_SMEM) {
-    for (long i = tid; i < (long)n * n; i += T) A[i] = bf.H[i];
-    for (int i = tid; i < n; i += T) y[i] = bf.b[i];
-  } else {
-    y = bf.b;
+    for (long i = tid; i < (long)n * n + 2 * n; i += T) {
+      double v = 0.0;
+#pragma unroll 4
+      for (int g = 0; g < kParts; g++) v += bf.sys[g * psz + i];
+      if (i < (long)n * n) A[(i / n) * ld + (i % n)] = v; else y[i - (long)n * n] = v;      // y | dA are contiguous
+    }
   }
   if (tid == 0) s_fail = 0;
   __syncthreads();
-  // sem 0: damp the Schur complement (droid_kernels.cu:1175-1176); sem 1: damp H before subtracting E Q E^T (chol.py:55-62)
-  for (int i = tid; i < n; i += T) A[(long)i * n + i] += (double)ep + (double)lm * (sem ? bf.dA[i] : A[(long)i * n + i]);
+  damp(A, ld, dA, P, lm, ep, sem, moba, tid, T);
   __syncthreads();
-  for (int j = 0; j < n; j++) {
-    if (tid == 0) {
-      const double d = A[(long)j * n + j];
-      if (!(d > 0.0)) s_fail = 1;
-      A[(long)j * n + j] = sqrt(d > 0.0 ? d : 1.0);
+  for (int kb = 0; kb < P; kb++) {
+    const int c0 = 6 * kb;
+    if (tid == 0) {                                        // 6x6 diagonal block, serial in registers
+      double D[6][6];
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) D[i][j] = (j <= i) ? A[(long)(c0 + i) * ld + c0 + j] : 0.0;
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        double d = D[j][j];
+#pragma unroll
+        for (int t = 0; t < 6; t++) if (t < j) d -= D[j][t] * D[j][t];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        d = sqrt(d);
+        D[j][j] = d;
+        const double inv = 1.0 / d;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          if (i > j) {
+            double v = D[i][j];
+#pragma unroll
+            for (int t = 0; t < 6; t++) if (t < j) v -= D[i][t] * D[j][t];
+            D[i][j] = v * inv;
+          }
+        }
+      }
+      if (bad) s_fail = 1;
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) if (j <= i) A[(long)(c0 + i) * ld + c0 + j] = D[i][j];
     }
     __syncthreads();
     if (s_fail) break;
-    const double inv = 1.0 / A[(long)j * n + j];
-    for (int i = j + 1 + tid; i < n; i += T) A[(long)i * n + j] *= inv;
+    for (int r = c0 + 6 + tid; r < n; r += T) {            // panel: X Lkk^T = A[r][c0..c0+5]
+      double x[6];
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        double v = A[(long)r * ld + c0 + j];
+#pragma unroll
+        for (int t = 0; t < 6; t++) if (t < j) v -= x[t] * A[(long)(c0 + j) * ld + c0 + t];
+        x[j] = v / A[(long)(c0 + j) * ld + c0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 6; j++) A[(long)r * ld + c0 + j] = x[j];
+    }
     __syncthreads();
-    const int m = n - j - 1;
+    const int m = n - c0 - 6;                              // trailing update (lower triangle)
     for (int idx = tid; idx < m * m; idx += T) {
-      const int i = j + 1 + idx / m, c = j + 1 + idx % m;
-      if (c <= i) A[(long)i * n + c] -= A[(long)i * n + j] * A[(long)c * n + j];
+      const int i = c0 + 6 + idx / m, c = c0 + 6 + idx % m;
+      if (c > i) continue;
+      double v = A[(long)i * ld + c];
+#pragma unroll
+      for (int t = 0; t < 6; t++) v -= A[(long)i * ld + c0 + t] * A[(long)c * ld + c0 + t];
+      A[(long)i * ld + c] = v;
     }
     __syncthreads();
   }
   const bool fail = s_fail != 0;
   if (!fail) {
-    // L z = b
-    for (int j = 0; j < n; j++) {
-      if (tid == 0) y[j] /= A[(long)j * n + j];
+    for (int kb = 0; kb < P; kb++) {                       // L z = b
+      const int c0 = 6 * kb;
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          double v = y[c0 + j];
+#pragma unroll
+          for (int t = 0; t < 6; t++) if (t < j) v -= A[(long)(c0 + j) * ld + c0 + t] * y[c0 + t];
+          y[c0 + j] = v / A[(long)(c0 + j) * ld + c0 + j];
+        }
+      }
       __syncthreads();
-      const double yj = y[j];
-      for (int i = j + 1 + tid; i < n; i += T) y[i] -= A[(long)i * n + j] * yj;
+      for (int r = c0 + 6 + tid; r < n; r += T) {
+        double v = y[r];
+#pragma unroll
+        for (int t = 0; t < 6; t++) v -= A[(long)r * ld + c0 + t] * y[c0 + t];
+        y[r] = v;
+      }
       __syncthreads();
     }
-    // L^T x = z
-    for (int j = n - 1; j >= 0; j--) {
-      if (tid == 0) y[j] /= A[(long)j * n + j];
+    for (int kb = P - 1; kb >= 0; kb--) {                  // L^T x = z
+      const int c0 = 6 * kb;
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 5; j >= 0; j--) {
+          double v = y[c0 + j];
+#pragma unroll
+          for (int t = 0; t < 6; t++) if (t > j) v -= A[(long)(c0 + t) * ld + c0 + j] * y[c0 + t];
+          y[c0 + j] = v / A[(long)(c0 + j) * ld + c0 + j];
+        }
+      }
       __syncthreads();
-      const double yj = y[j];
-      for (int i = tid; i < j; i += T) y[i] -= A[(long)j * n + i] * yj;
+      for (int r = tid; r < c0; r += T) {
+        double v = y[r];
+#pragma unroll
+        for (int t = 0; t < 6; t++) v -= A[(long)(c0 + t) * ld + r] * y[c0 + t];
+        y[r] = v;
+      }
       __syncthreads();
     }
   }
   for (int i = tid; i < n; i += T) bf.dx[i] = fail ? 0.0f : (float)y[i];
   __syncthreads();
-  // leave the system zeroed for the next iteration / next call
-  for (long i = tid; i < (long)n * n; i += T) bf.H[i] = 0.0;
-  for (int i = tid; i < n; i += T) { bf.b[i] = 0.0; bf.dA[i] = 0.0; }
-}
-
-// n <= 64: one warp, left-looking Cholesky in shared memory with __syncwarp only (the block version above spends its
-// time in ~7n __syncthreads).  Same damping / failure semantics.
-__global__ void __launch_bounds__(32) ba_solve_warp_kernel(Bufs bf, int P, float lm, float ep, int sem) {
-  extern __shared__ double smw[];
-  const int n = 6 * P, ld = n + 1;
-  const int lane = threadIdx.x;
-  double* A = smw;
-  double* y = smw + (long)n * ld;
-  for (int i = lane; i < n * n; i += 32) A[(i / n) * ld + (i % n)] = bf.H[i];
-  for (int i = lane; i < n; i += 32) y[i] = bf.b[i];
-  __syncwarp();
-  for (int i = lane; i < n; i += 32) A[i * ld + i] += (double)ep + (double)lm * (sem ? bf.dA[i] : A[i * ld + i]);
-  __syncwarp();
-  bool fail = false;
-  for (int j = 0; j < n; j++) {
-    double s = 0.0;
-    for (int k = lane; k < j; k += 32) s += A[j * ld + k] * A[j * ld + k];
-    s = warp_sum_d(s);
-    const double djj = A[j * ld + j] - s;
-    if (!(djj > 0.0)) { fail = true; break; }
-    const double d = sqrt(djj), inv = 1.0 / d;
-    for (int i = j + 1 + lane; i < n; i += 32) {
-      double t = A[i * ld + j];
-      for (int k = 0; k < j; k++) t -= A[i * ld + k] * A[j * ld + k];
-      A[i * ld + j] = t * inv;
-    }
-    if (lane == 0) A[j * ld + j] = d;
-    __syncwarp();
-  }
-  if (!fail) {
-    for (int j = 0; j < n; j++) {                      // L z = b
-      if (lane == 0) y[j] /= A[j * ld + j];
-      __syncwarp();
-      const double yj = y[j];
-      for (int i = j + 1 + lane; i < n; i += 32) y[i] -= A[i * ld + j] * yj;
-      __syncwarp();
-    }
-    for (int j = n - 1; j >= 0; j--) {                 // L^T x = z
-      if (lane == 0) y[j] /= A[j * ld + j];
-      __syncwarp();
-      const double yj = y[j];
-      for (int i = lane; i < j; i += 32) y[i] -= A[j * ld + i] * yj;
-      __syncwarp();
-    }
-  }
-  for (int i = lane; i < n; i += 32) bf.dx[i] = fail ? 0.0f : (float)y[i];
-  for (int i = lane; i < n * n; i += 32) bf.H[i] = 0.0;
-  for (int i = lane; i < n; i += 32) { bf.b[i] = 0.0; bf.dA[i] = 0.0; }
+  // leave every replica zeroed for the next iteration / next call
+  for (long i = tid; i < (long)kParts * psz; i += T) bf.sys[i] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -528,7 +581,7 @@ __global__ void clamp_min_kernel(float* x, long n, float lo) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
-  size_t off_frame2k, off_kx, off_ptr, off_idx, off_meta, off_Eij, off_Ei, off_Q, off_w, off_H, off_b, off_dA, off_dx, total;
+  size_t off_frame2k, off_kx, off_ptr, off_idx, off_meta, off_Eij, off_Ei, off_Q, off_w, off_sys, off_dx, total;
 };
 
 Layout make_layout(int E, int nframes, int P, int K, int HW) {
@@ -544,9 +597,7 @@ Layout make_layout(int E, int nframes, int P, int K, int HW) {
   L.off_Ei = take(sizeof(float) * 6 * (size_t)K * HW);
   L.off_Q = take(sizeof(float) * (size_t)K * HW);
   L.off_w = take(sizeof(float) * (size_t)K * HW);
-  L.off_H = take(sizeof(double) * 36 * (size_t)P * P);
-  L.off_b = take(sizeof(double) * 6 * (size_t)P);
-  L.off_dA = take(sizeof(double) * 6 * (size_t)P);
+  L.off_sys = take(sizeof(double) * kParts * (36 * (size_t)P * P + 12 * (size_t)P));
   L.off_dx = take(sizeof(float) * 6 * (size_t)P);
   L.total = o;
   return L;
@@ -576,10 +627,10 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
   Plan pl{(int*)(ws + L.off_frame2k), (int*)(ws + L.off_kx), (int*)(ws + L.off_ptr), (int*)(ws + L.off_idx),
           (int*)(ws + L.off_meta)};
   Bufs bf{(float*)(ws + L.off_Eij), (float*)(ws + L.off_Ei), (float*)(ws + L.off_Q), (float*)(ws + L.off_w),
-          (double*)(ws + L.off_H), (double*)(ws + L.off_b), (double*)(ws + L.off_dA), (float*)(ws + L.off_dx)};
+          (double*)(ws + L.off_sys), (float*)(ws + L.off_dx)};
   cudaStream_t s = (cudaStream_t)stream;
   const int n = 6 * P;
-  if (!(flags & 1)) ba_plan_kernel<<<1, 1024, 0, s>>>(ii, E, nframes, t0, t1, K, pl, bf.H, bf.b, bf.dA, n);
+  if (!(flags & 1)) ba_plan_kernel<<<1, 1024, 0, s>>>(ii, E, nframes, t0, t1, K, pl, bf.sys, n);
   const dim3 grid(ceil_div(HW, kPix), K);
   static bool attr_set = false;
   const int deg_hint = (flags >> 8) & 0xFFF;
@@ -588,17 +639,15 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
     const long need = 4L * (256L * (6 * (deg_hint + 1) + 2) + ((deg_hint + 1 + 3) & ~3)) + 64;
     if (need < pass2_smem) pass2_smem = (int)need;
   }
-  const size_t solve_smem = sizeof(double) * ((size_t)n * n + n);
+  const size_t solve_smem = sizeof(double) * ((size_t)n * (n + 1) + 2 * n);
   const bool solve_in_smem = solve_smem <= 200 * 1024;
-  const size_t warp_smem = sizeof(double) * ((size_t)n * (n + 1) + n);
   if (!attr_set) {
     cudaFuncSetAttribute(ba_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(ba_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   // flags bits 1-2 select a phase for the multi-GPU path (pvo_b200/dist.py): 0 = whole iteration(s),
-  // 1 = assemble only (pass 1 + Schur: the reduced camera system is left in the workspace for an all-reduce),
+  // 1 = assemble only (pass 1 + Schur, replicas folded into part 0 which is then all-reduced),
   // 2 = solve + back-substitution + retraction only.
   const int phase = (flags >> 1) & 3;
   const int sem = (flags >> 3) & 1;      // 0: droid_backends.ba semantics, 1: geom/ba.py BA()/MoBA() semantics
@@ -609,13 +658,13 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
       if (!motion_only)
         ba_pass2_kernel<<<grid, kPix, pass2_smem, s>>>(jj, pl, bf, HW, t0, P, pass2_smem / 4);
     }
-    if (phase == 1) break;
-    if (n <= 64)
-      ba_solve_warp_kernel<<<1, 32, warp_smem, s>>>(bf, P, lm, ep, sem);
-    else if (solve_in_smem)
-      ba_solve_kernel<true><<<1, 512, solve_smem, s>>>(bf, P, lm, ep, sem);
-    else
-      ba_solve_kernel<false><<<1, 512, 0, s>>>(bf, P, lm, ep, sem);
+    if (phase == 1) { ba_combine_kernel<<<8, 256, 0, s>>>(bf, P); break; }
+    if (solve_in_smem) {
+      ba_solve_kernel<true><<<1, 128, solve_smem, s>>>(bf, P, lm, ep, sem, sem && motion_only);
+    } else {
+      ba_combine_kernel<<<8, 256, 0, s>>>(bf, P);
+      ba_solve_kernel<false><<<1, 128, 0, s>>>(bf, P, lm, ep, sem, sem && motion_only);
+    }
     const bool last = it == iterations - 1;
     if (last && dx_out)
       cudaMemcpyAsync(dx_out, bf.dx, sizeof(float) * n, cudaMemcpyDeviceToDevice, s);
@@ -630,7 +679,7 @@ extern "C" int pvo_group_edges(const long* ii, int E, int nframes, int t0, int t
                                int* ptr, int* idx, int* meta, void* stream) {
   if (E < 0 || nframes <= 0 || Kcap <= 0) return PVO_ERR_INVALID;
   Plan pl{frame2k, kx, ptr, idx, meta};
-  ba_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ii, E, nframes, t0, t1, Kcap, pl, nullptr, nullptr, nullptr, 0);
+  ba_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ii, E, nframes, t0, t1, Kcap, pl, nullptr, 0);
   return pvo_check_launch();
 }
 
@@ -646,8 +695,8 @@ extern "C" int pvo_clamp_min(float* x, long n, float lo, void* stream) {
 extern "C" int pvo_ba_system_range(int E, int nframes, int P, int K, int HW, long* offset, long* bytes) {
   if (E < 0 || nframes <= 0 || P <= 0 || K <= 0 || HW <= 0) return PVO_ERR_INVALID;
   const Layout L = make_layout(E > 0 ? E : 1, nframes, P, K, HW);
-  *offset = (long)L.off_H;
-  *bytes = (long)(L.off_dA + sizeof(double) * 6 * (size_t)P - L.off_H);
+  *offset = (long)L.off_sys;                                  // part 0 (ba_combine_kernel folds the other parts into it)
+  *bytes = (long)(sizeof(double) * (36 * (size_t)P * P + 12 * (size_t)P));
   return PVO_OK;
 }
 

@@ -266,8 +266,9 @@ __global__ void __launch_bounds__(128) conv3x3_small_kernel(const TI* __restrict
                                                             float* __restrict__ out, int ostride, int G, int H, int Wd,
                                                             int tiles_x, int tiles_y, int post) {
   constexpr int TH = 8, TW = 16, PH = TH + 2, PW = TW + 2;
+  constexpr int CH = 64;                                        // channels staged per pass (keeps 6 blocks / SM resident)
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  const int pstride = cin_g + 16 / (int)sizeof(TI);            // elements per patch pixel (+16 B pad)
+  constexpr int pstride = CH + 16 / (int)sizeof(TI);            // elements per patch pixel (+16 B pad: conflict-free LDS.128)
   TI* patch = reinterpret_cast<TI*>(sm_raw);
   float* wsm = reinterpret_cast<float*>(sm_raw + (((size_t)PH * PW * pstride * sizeof(TI) + 15) & ~size_t(15)));
   const int g = blockIdx.y;
@@ -277,55 +278,60 @@ __global__ void __launch_bounds__(128) conv3x3_small_kernel(const TI* __restrict
   const int y0 = (r / tiles_x) * TH, x0 = (r % tiles_x) * TW;
   const int tid = threadIdx.x;
   for (int i = tid; i < 9 * cin_g * CG; i += 128) wsm[i] = W[(long)g * 9 * cin_g * CG + i];
-  // stage the halo patch: 16-byte chunks, consecutive threads -> consecutive chunks of one pixel
-  const int cpp = cin_g * (int)sizeof(TI) / 16;                 // chunks per pixel
-  for (int i = tid; i < PH * PW * cpp; i += 128) {
-    const int pp = i / cpp, ch = i - pp * cpp;
-    const int py = y0 - 1 + pp / PW, px = x0 - 1 + pp % PW;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (py >= 0 && py < H && px >= 0 && px < Wd)
-      v = __ldg(reinterpret_cast<const uint4*>(in + ((long)(img * H + py) * Wd + px) * istride + g * cin_g) + ch);
-    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(patch + (long)pp * pstride) + 16 * ch) = v;
-  }
-  __syncthreads();
   const int ty = tid / TW, tx = tid % TW;
-  const int y = y0 + ty, x = x0 + tx;
-  float acc[CG];
+  float acc[CG][4];                                             // 4 independent chains per output (ILP)
 #pragma unroll
-  for (int o = 0; o < CG; o++) acc[o] = 0.0f;
+  for (int o = 0; o < CG; o++)
 #pragma unroll
-  for (int tap = 0; tap < 9; tap++) {
-    const TI* src = patch + (long)((ty + tap / 3) * PW + tx + tap % 3) * pstride;
-    const float* w = wsm + tap * cin_g * CG;
-    for (int c = 0; c < cin_g; c += 8) {
-      float v[8];
-      if (sizeof(TI) == 4) {
-        const float4 v0 = *reinterpret_cast<const float4*>(src + c);
-        const float4 v1 = *reinterpret_cast<const float4*>(src + c + 4);
-        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-      } else {
-        const uint4 u = *reinterpret_cast<const uint4*>(src + c);
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
+    for (int k = 0; k < 4; k++) acc[o][k] = 0.0f;
+  constexpr int cpp = CH * (int)sizeof(TI) / 16;                // 16-byte chunks per patch pixel
+  for (int cb = 0; cb < cin_g; cb += CH) {
+    __syncthreads();
+    for (int i = tid; i < PH * PW * cpp; i += 128) {
+      const int pp = i / cpp, ch = i - pp * cpp;
+      const int py = y0 - 1 + pp / PW, px = x0 - 1 + pp % PW;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (py >= 0 && py < H && px >= 0 && px < Wd && cb + ch * (16 / (int)sizeof(TI)) < cin_g)
+        v = __ldg(reinterpret_cast<const uint4*>(in + ((long)(img * H + py) * Wd + px) * istride + g * cin_g + cb) + ch);
+      *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(patch + (long)pp * pstride) + 16 * ch) = v;
+    }
+    __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 4; q++) { const float2 f = __half22float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
-      }
+    for (int tap = 0; tap < 9; tap++) {
+      const TI* src = patch + (long)((ty + tap / 3) * PW + tx + tap % 3) * pstride;
+      const float* w = wsm + (tap * cin_g + cb) * CG;
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
-        if (CG == 2) {
-          const float2 ww = *reinterpret_cast<const float2*>(w + (c + q) * 2);
-          acc[0] = fmaf(v[q], ww.x, acc[0]);
-          acc[CG - 1] = fmaf(v[q], ww.y, acc[CG - 1]);
+      for (int c = 0; c < CH; c += 8) {
+        float v[8];
+        if (sizeof(TI) == 4) {
+          const float4 v0 = *reinterpret_cast<const float4*>(src + c);
+          const float4 v1 = *reinterpret_cast<const float4*>(src + c + 4);
+          v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
         } else {
-          acc[0] = fmaf(v[q], w[c + q], acc[0]);
+          const uint4 u = *reinterpret_cast<const uint4*>(src + c);
+          const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; q++) { const float2 f = __half22float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          if (CG == 2) {
+            const float2 ww = *reinterpret_cast<const float2*>(w + (c + q) * 2);
+            acc[0][q & 3] = fmaf(v[q], ww.x, acc[0][q & 3]);
+            acc[CG - 1][q & 3] = fmaf(v[q], ww.y, acc[CG - 1][q & 3]);
+          } else {
+            acc[0][q & 3] = fmaf(v[q], w[c + q], acc[0][q & 3]);
+          }
         }
       }
     }
   }
+  const int y = y0 + ty, x = x0 + tx;
   if (y < H && x < Wd) {
     const long m = (long)(img * H + y) * Wd + x;
 #pragma unroll
     for (int o = 0; o < CG; o++) {
-      float v = acc[o] + bias[g * CG + o];
+      float v = ((acc[o][0] + acc[o][1]) + (acc[o][2] + acc[o][3])) + bias[g * CG + o];
       if (post == 1) v = 0.01f * ((v > 20.0f) ? v : log1pf(expf(v)));
       out[m * ostride + g * CG + o] = v;
     }
@@ -385,6 +391,27 @@ __global__ void __launch_bounds__(384) glo_matvec_kernel(const float* __restrict
   if (threadIdx.x < 128) g[threadIdx.x] = glo[(long)e * 128 + threadIdx.x];
   __syncthreads();
   const int row = threadIdx.x;                          // 0..383
+  const float* w = W + (long)row * 128;
+  float s = b[row];
+  for (int c = 0; c < 128; c++) s = fmaf(w[c], g[c], s);
+  out[(long)e * 384 + row] = s;
+}
+
+// tensor-core path: the gate conv's epilogue leaves per-tile sums in partial[e][tiles][4][128]; finish the spatial
+// mean (fixed order => deterministic) and apply the three glo mat-vecs in one launch.
+__global__ void __launch_bounds__(384) glo_reduce_matvec_kernel(const float* __restrict__ partial, int parts_per_img, float inv_hw,
+                                                                const float* __restrict__ W, const float* __restrict__ b,
+                                                                float* __restrict__ out) {
+  const int e = blockIdx.x;
+  __shared__ float g[128];
+  if (threadIdx.x < 128) {
+    float s = 0.0f;
+    const float* p = partial + (long)e * parts_per_img * 128 + threadIdx.x;
+    for (int k = 0; k < parts_per_img; k++) s += p[(long)k * 128];
+    g[threadIdx.x] = s * inv_hw;
+  }
+  __syncthreads();
+  const int row = threadIdx.x;
   const float* w = W + (long)row * 128;
   float s = b[row];
   for (int c = 0; c < 128; c++) s = fmaf(w[c], g[c], s);
@@ -518,9 +545,9 @@ extern "C" int pvo_conv3x3_small(const void* in, int istride, int cin_g, const f
   if (cin_g % 8 || (CG != 1 && CG != 2) || G < 1) return PVO_ERR_INVALID;
   if (nimg == 0) return PVO_OK;
   const size_t esz = dtype == PVO_DTYPE_F32 ? 4 : 2;
-  if ((istride * esz) % 16 || (cin_g * esz) % 16 || ((uintptr_t)in) % 16) return PVO_ERR_INVALID;
+  if ((istride * esz) % 16 || cin_g % 64 || ((uintptr_t)in) % 16) return PVO_ERR_INVALID;
   const int tiles_x = (Wd + 15) / 16, tiles_y = (H + 7) / 8;
-  const size_t patch = ((size_t)10 * 18 * (cin_g * esz + 16) + 15) & ~size_t(15);
+  const size_t patch = ((size_t)10 * 18 * (64 * esz + 16) + 15) & ~size_t(15);      // 64 channels staged per pass
   const size_t smem = patch + sizeof(float) * 9 * cin_g * CG;
   dim3 grid(nimg * tiles_x * tiles_y, G);
   cudaStream_t s = (cudaStream_t)stream;
@@ -559,6 +586,13 @@ extern "C" int pvo_expand_x7(const void* motn, void* out, int nimg, int H, int W
 extern "C" int pvo_glo_matvec(const float* glo, const float* W, const float* b, float* out, int E, void* stream) {
   if (E == 0) return PVO_OK;
   glo_matvec_kernel<<<E, 384, 0, (cudaStream_t)stream>>>(glo, W, b, out);
+  return pvo_check_launch();
+}
+
+extern "C" int pvo_glo_reduce_matvec(const float* partial, int parts_per_img, int HW, const float* W, const float* b, float* out,
+                                     int E, void* stream) {
+  if (E == 0) return PVO_OK;
+  glo_reduce_matvec_kernel<<<E, 384, 0, (cudaStream_t)stream>>>(partial, parts_per_img, 1.0f / (float)HW, W, b, out);
   return pvo_check_launch();
 }
 

@@ -11,8 +11,8 @@
 //             zero-filled by TMA, which is the convolution's zero padding)
 //   N tile  = BN output channels (64 / 128 / 256), K block = 64 channels of one tap (128-byte swizzled rows)
 //   UMMA 128 x BN x 16, fp16 operands, fp32 accumulators in TMEM, double-buffered (2 x BN columns)
-// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2-5 = epilogue (one TMEM lane quarter each).  smem ring of kStages {A 16 KB, B BN*128 B} stages.
+// Warp roles (320 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2-9 = epilogue (two per TMEM lane quarter, each draining half of the accumulator columns).  smem ring of kStages {A 16 KB, B BN*128 B} stages.
 // Roofline: tensor pipe; with single-CTA tiles the operand stream (48 KB per 512 MMA cycles at BN=256) makes L2 the
 // practical bound -- see DESIGN.md for the measured fraction and the 2-CTA / halo-reuse follow-ups.
 #include "tc_common.cuh"
@@ -22,7 +22,7 @@ namespace {
 using namespace tc;
 
 constexpr int kBM = 128, kBK = 64, kTileW = 16, kTileH = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kMaxSeg = 4;
 
 struct TcParams {
@@ -42,8 +42,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 // ---- epilogues: store16(m, e, n, v): 16 consecutive output channels n.. of pixel m (image/edge e) -------------
 struct EpBias {          // out = act(acc + bias)
   const float* bias; __half* out; int ostride; int ooff; int Cout; int relu;
-  __device__ __forceinline__ void store16(long m, long, int n, const float* v) const {
-    if (n >= Cout) return;
+  __device__ __forceinline__ void store16(long m, long, int n, const float* v, bool ok, int, int) const {
+    if (n >= Cout || !ok) return;
     __align__(16) __half h[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) {
@@ -61,26 +61,29 @@ struct EpBias {          // out = act(acc + bias)
   }
 };
 
-struct EpGlo {           // gru.py:25: sigmoid(w(net)) * net  (spatial mean taken by colmean)
-  const float* bias; const __half* net; int nstride; __half* out; int Cout;
-  __device__ __forceinline__ void store16(long m, long, int n, const float* v) const {
-    if (n >= Cout) return;
+struct EpGloSum {        // gru.py:25-26: sum over the tile's pixels of sigmoid(w(net)) * net -> partial[tile][quarter][128]
+  const float* bias; const __half* net; int nstride; float* partial; int Cout;
+  __device__ __forceinline__ void store16(long m, long, int n, const float* v, bool ok, int tile, int q) const {
+    if (n >= Cout) return;                       // warp-uniform
     __align__(16) __half hn[16];
-    __align__(16) __half h[16];
-    *reinterpret_cast<uint4*>(&hn[0]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + n));
-    *reinterpret_cast<uint4*>(&hn[8]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + n + 8));
+    if (ok) {
+      *reinterpret_cast<uint4*>(&hn[0]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + n));
+      *reinterpret_cast<uint4*>(&hn[8]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + n + 8));
+    }
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < 16; j++) h[j] = __float2half_rn(sigmoidf_(v[j] + __ldg(bias + n + j)) * __half2float(hn[j]));
-    __half* o = out + m * Cout + n;
-    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&h[0]);
-    *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+    for (int j = 0; j < 16; j++) {
+      float x = ok ? sigmoidf_(v[j] + __ldg(bias + n + j)) * __half2float(hn[j]) : 0.0f;
+      x = warp_sum(x);
+      if (lane == 0) partial[((long)tile * 4 + q) * Cout + n + j] = x;
+    }
   }
 };
 
 struct EpZR {            // gru.py:28-29 (see conv_simt.cu EpiZR)
   const float* bias; const float* glo; const __half* net; int nstride; __half* z; __half* rnet;
-  __device__ __forceinline__ void store16(long m, long e, int n, const float* v) const {
-    if (n >= 256) return;
+  __device__ __forceinline__ void store16(long m, long e, int n, const float* v, bool ok, int, int) const {
+    if (n >= 256 || !ok) return;
     __align__(16) __half h[16];
     __align__(16) __half hn[16];
     const bool isr = n >= 128;
@@ -103,8 +106,8 @@ struct EpZR {            // gru.py:28-29 (see conv_simt.cu EpiZR)
 
 struct EpQ {             // gru.py:30-32, state update in place
   const float* bias; const float* glo; const __half* z; __half* net; int nstride;
-  __device__ __forceinline__ void store16(long m, long e, int n, const float* v) const {
-    if (n >= 128) return;
+  __device__ __forceinline__ void store16(long m, long e, int n, const float* v, bool ok, int, int) const {
+    if (n >= 128 || !ok) return;
     __align__(16) __half hz[16];
     __align__(16) __half hn[16];
     __align__(16) __half h[16];
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int s = 0; s < p.nseg; s++) prefetch_tmap(&p.tmA[s]);
     prefetch_tmap(&p.tmB);
     for (int s = 0; s < C::kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -218,8 +221,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..9)
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                // which half of the accumulator columns this warp drains
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -233,13 +237,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const long m = ((long)img * p.H + y) * p.W + x;
       mbar_wait(&tfull[as], aphase);
       fence_after_sync();
-      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c, v);
+      for (int c = 0; c < BN / 2; c += 32) {         // two 16-column loads in flight per wait
+        uint32_t v0[16], v1[16];
+        tmem_ld16(taddr + c, v0);
+        tmem_ld16(taddr + c + 16, v1);
         tmem_ld_wait();
-        if (ok) epi.store16(m, img, nt * BN + c, reinterpret_cast<const float*>(v));
+        const int n = nt * BN + half * (BN / 2) + c;
+        epi.store16(m, img, n, reinterpret_cast<const float*>(v0), ok, mt, q);
+        epi.store16(m, img, n + 16, reinterpret_cast<const float*>(v1), ok, mt, q);
       }
       fence_before_sync();
       __syncwarp();
@@ -281,7 +288,7 @@ int dispatch_bn(const TcParams& p0, const Epi& epi, int bn, cudaStream_t s) {
 // Segments: pixel-major fp16 tensors (nimg*H*W, stride) whose channel slices are concatenated into the conv input;
 // seg_channels[s] need not be a multiple of 64 (the tail is zero-filled by TMA; the packed weights carry zeros there).
 // Wh: fp16 [Cout][taps * sum_s ceil64(seg_channels[s])], K ordered (tap, segment, channel) -- pack_conv_weight_tc.
-// epilogue: 0 bias, 1 bias+ReLU, 2 sigmoid(.)*net, 3 GRU z|r, 4 GRU q + state update (same meaning and aux pointers as pvo_conv2d).
+// epilogue: 0 bias, 1 bias+ReLU, 2 per-tile sums of sigmoid(.)*net, 3 GRU z|r, 4 GRU q + state update (same meaning and aux pointers as pvo_conv2d).
 extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels, const int* seg_stride, int nseg,
                              const void* Wh, const float* bias, int Cout, int KH, int KW, int nimg, int H, int Wd,
                              int epilogue, void* out, int ostride, int ooff, void* out2, const void* aux0, int aux_stride,
@@ -327,9 +334,9 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
     case 0: case 1:
       if ((ostride * 2) % 16 || (ooff * 2) % 16) return PVO_ERR_INVALID;
       return dispatch_bn(p, EpBias{bias, (__half*)out, ostride, ooff, Cout, epilogue}, bn, s);
-    case 2:
-      if (Cout % 16) return PVO_ERR_INVALID;
-      return dispatch_bn(p, EpGlo{bias, (const __half*)aux0, aux_stride, (__half*)out, Cout}, bn, s);
+    case 2:      // out = float partial sums [nimg * tiles][4][Cout] (reduced by pvo_glo_reduce_matvec)
+      if (Cout % 32) return PVO_ERR_INVALID;
+      return dispatch_bn(p, EpGloSum{bias, (const __half*)aux0, aux_stride, (float*)out, Cout}, bn, s);
     case 3:
       if (Cout != 256) return PVO_ERR_INVALID;
       return dispatch_bn(p, EpZR{bias, aux1, (const __half*)aux0, aux_stride, (__half*)out, (__half*)out2}, bn, s);

@@ -139,6 +139,7 @@ class UpdateEngine:
         self.motn = z(M, 8)
         self.motx = z(M, 64) if self.use_tc else None      # x-expanded motion features (tensor-core flow encoder)
         self.col_scratch = z(E * 32 * 128, dtype=torch.float32)
+        self.glo_part = z(E * ((H + 7) // 8) * ((W + 15) // 16) * 4 * 128, dtype=torch.float32) if self.use_tc else None
         self.c1 = z(M, 128)
         self.f1 = z(M, 128)
         self.glo_tmp = z(M, 128)
@@ -207,13 +208,21 @@ class UpdateEngine:
         with T('conv_flow2'):
             conv2d(self.c_flow2, [(self.f1, 128, 128)], E, H, W, dc, X, 448, 384, 1, use_tc=tc)
         # global context: mean_HW(sigmoid(w(net)) * net) -> three 128x128 mat-vecs
-        with T('conv_glo'):
-            conv2d(self.c_w, [(X, 128, 448)], E, H, W, dc, self.glo_tmp, 128, 0, 2, aux0=X, aux_stride=448, use_tc=tc)
-        with T('colmean'):
-            check(L.pvo_colmean(ptr(self.glo_tmp), ptr(self.glo), ptr(self.col_scratch), E, HW, 128, dc, stream()), 'colmean',
-                  launches=2)
-        with T('glo_matvec'):
-            check(L.pvo_glo_matvec(ptr(self.glo), ptr(self.glo_W), ptr(self.glo_b), ptr(self.glo3), E, stream()), 'glo_matvec')
+        if tc:       # gate conv on tensor cores; its epilogue reduces over each 8x16 tile, the tail finishes mean + mat-vecs
+            tiles = ((H + 7) // 8) * ((W + 15) // 16)
+            with T('conv_glo'):
+                conv2d(self.c_w, [(X, 128, 448)], E, H, W, dc, self.glo_part, 128, 0, 2, aux0=X, aux_stride=448, use_tc=True)
+            with T('glo_matvec'):
+                check(L.pvo_glo_reduce_matvec(ptr(self.glo_part), tiles * 4, HW, ptr(self.glo_W), ptr(self.glo_b), ptr(self.glo3),
+                                              E, stream()), 'glo_reduce_matvec')
+        else:
+            with T('conv_glo'):
+                conv2d(self.c_w, [(X, 128, 448)], E, H, W, dc, self.glo_tmp, 128, 0, 2, aux0=X, aux_stride=448)
+            with T('colmean'):
+                check(L.pvo_colmean(ptr(self.glo_tmp), ptr(self.glo), ptr(self.col_scratch), E, HW, 128, dc, stream()), 'colmean',
+                      launches=2)
+            with T('glo_matvec'):
+                check(L.pvo_glo_matvec(ptr(self.glo), ptr(self.glo_W), ptr(self.glo_b), ptr(self.glo3), E, stream()), 'glo_matvec')
         # z|r in one 448->256 conv; epilogue emits z and r*net
         with T('conv_zr'):
             conv2d(self.c_zr, [(X, 448, 448)], E, H, W, dc, self.z, 128, 0, 3, out2=self.rnet, aux0=X, aux_stride=448,

@@ -115,9 +115,9 @@ def test_ba_matches_oracle(cfg, motion_only):
     dx, dz = droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), tgt.cuda(), wgt.cuda(), eta.cuda(),
                                ii.cuda(), jj.cuda(), t0, t1, 2, 1e-4, 0.1, motion_only)
     F_ = cfg['F']
-    # the contract is on poses / depth (1e-4 relative).  dx itself is compared at 1e-4 for the full BA; the
-    # motion-only system has no depth variables and is far worse conditioned (gauge directions held only by ep=0.1),
-    # so float32 reduction-order noise in H shows up at ~1e-3 relative in dx while the poses still agree to 1e-6.
+    # the contract is on poses / depth (1e-4 relative).  dx (the LAST iteration's step) is compared at 1e-4 for the
+    # full BA.  Motion-only Gauss-Newton converges almost completely in its first step, so the second step is ~100x
+    # smaller than the first and a 1e-5 relative difference after step one becomes ~1e-3 relative to that tiny dx.
     assert _rel(dx.cpu(), dx_ref) < (2e-2 if motion_only else 1e-4)
     assert _rel(v.poses[:F_].cpu(), p_ref) < 1e-4
     assert torch.equal(v.poses[:t0].cpu(), c['poses'][:t0])            # frames before t0 are fixed
