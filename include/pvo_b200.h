@@ -110,7 +110,11 @@ int pvo_clamp_min(float* x, long n, float lo, void* stream);
 int pvo_conv2d(const void* const* seg_ptr, const int* seg_channels, const int* seg_stride, int nseg, const float* W,
                int wstride, const float* bias, int Cout, int KH, int KW, int pad, int nimg, int H, int Wd, int dtype,
                int epilogue, void* out, int ostride, int ooff, void* out2, const void* aux0, int aux_stride,
-               const float* aux1, void* stream);
+               const float* aux1, int stride, void* stream);
+/* nn.InstanceNorm2d (affine=False) + ReLU [+ residual add + ReLU] of BasicEncoder's fnet
+ *   (droid_slam/modules/extractor.py:28-32,47-55,129-130) on pixel-major (N,HW,C) data.  scratch: N*C*66 floats. */
+int pvo_instance_norm(const void* in, void* out, const void* res, float* scratch, int N, int HW, int C, int relu, int dtype,
+                      void* stream);
 /* the same contraction on tcgen05 tensor cores (float16 operands via TMA, fp32 accumulate in TMEM), 3x3 / 1x1 /
  *   7x1 kernels with Cin % 16 == 0 and Cout % 64 == 0.  See pvo_b200/csrc/conv_tc.cu. */
 int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels, const int* seg_stride, int nseg, const void* Wh,

@@ -30,7 +30,8 @@ _SIGS = {
     'pvo_ba_read_meta': (c_int, [c_void_p] + [c_int] * 5 + [c_void_p]),
     'pvo_clamp_min': (c_int, [c_void_p, c_long, c_float, c_void_p]),
     'pvo_conv2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 9 +
-                   [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+                   [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    'pvo_instance_norm': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'pvo_conv2d_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 7 +
                       [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'pvo_conv3x3_small': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),

@@ -278,8 +278,9 @@ __global__ void __launch_bounds__(kPix) ba_pass1_kernel(
 // every out-edge (Eij), restricted to poses inside [t0,t1).  S += sum_pix Erow_a Q Erow_b^T for ALL row pairs
 // (exactly the pair enumeration of schur_block :1236-1251), b -= sum_pix Q w Erow.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__ jj, Plan pl, Bufs bf, int HW, int t0,
-                                                        int P, int smem_floats) {
+constexpr int kPix2 = 128;      // pixels per block in the Schur pass (more, smaller blocks: 2+ resident per SM)
+__global__ void __launch_bounds__(256) ba_pass2_kernel(const long* __restrict__ jj, Plan pl, Bufs bf, int HW, int t0,
+                                                       int P, int smem_floats) {
   extern __shared__ float sm[];
   const int K = pl.meta[0];
   const int k = blockIdx.y;
@@ -292,25 +293,25 @@ __global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__
   int* rowpose = reinterpret_cast<int*>(sm);
   const int hdr = (R + 3) & ~3;
   int PC = (smem_floats - hdr) / (R6 + 2);
-  PC = min(kPix, PC & ~31);
+  PC = min(kPix2, PC & ~31);
   if (PC <= 0) { if (tid == 0) pl.meta[1] = 2; return; }
   float* Qs = sm + hdr;
   float* QWs = Qs + PC;
   float* tile = QWs + PC;
-  for (int r = tid; r < R; r += kPix) {
+  for (int r = tid; r < R; r += 256) {
     const int pose = (r == 0) ? f - t0 : (int)jj[pl.src_idx[pl.src_ptr[k] + r - 1]] - t0;
     rowpose[r] = (pose >= 0 && pose < P) ? pose : -1;
   }
   const int n = 6 * P;
   double* Hp = bf.sys + (long)(blockIdx.x % kParts) * ((long)n * n + 2 * n);
   double* bp = Hp + (long)n * n;
-  const int pix0 = blockIdx.x * kPix;
-  for (int c0 = 0; c0 < kPix; c0 += PC) {
+  const int pix0 = blockIdx.x * kPix2;
+  for (int c0 = 0; c0 < kPix2; c0 += PC) {
     __syncthreads();
     const int np = min(PC, HW - pix0 - c0);
     if (np <= 0) break;
     // load tile (coalesced along pixels), rows outside the window are zero
-    for (int idx = tid; idx < R6 * PC; idx += kPix) {
+    for (int idx = tid; idx < R6 * PC; idx += 256) {
       const int row = idx / PC, p = idx - row * PC;
       const int r = row / 6, m = row - 6 * r;
       float v = 0.f;
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__
       }
       tile[p * R6 + row] = v;
     }
-    for (int p = tid; p < PC; p += kPix) {
+    for (int p = tid; p < PC; p += 256) {
       const bool ok = p < np;
       const float q = ok ? bf.Q[(long)k * HW + pix0 + c0 + p] : 0.f;
       Qs[p] = q;
@@ -329,15 +330,21 @@ __global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__
     }
     __syncthreads();
     // S is symmetric: enumerate a <= b only (903 of 1764 entries at config 2) and mirror
-    for (int idx = tid; idx < R6 * (R6 + 1) / 2; idx += kPix) {
+    for (int idx = tid; idx < R6 * (R6 + 1) / 2; idx += 256) {
       int a = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);          // idx = a(a+1)/2 + b, b <= a  (then swap roles)
       while (a * (a + 1) / 2 > idx) a--;
       while ((a + 1) * (a + 2) / 2 <= idx) a++;
       const int b = idx - a * (a + 1) / 2;                               // b <= a
       const int pa = rowpose[a / 6], pb = rowpose[b / 6];
       if (pa < 0 || pb < 0) continue;
-      float s = 0.f;
-      for (int p = 0; p < np; p++) s += tile[p * R6 + a] * Qs[p] * tile[p * R6 + b];
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // 4 independent chains (tile rows past np are zero)
+      for (int p = 0; p < PC; p += 4) {
+        s0 = fmaf(tile[p * R6 + a] * Qs[p], tile[p * R6 + b], s0);
+        s1 = fmaf(tile[(p + 1) * R6 + a] * Qs[p + 1], tile[(p + 1) * R6 + b], s1);
+        s2 = fmaf(tile[(p + 2) * R6 + a] * Qs[p + 2], tile[(p + 2) * R6 + b], s2);
+        s3 = fmaf(tile[(p + 3) * R6 + a] * Qs[p + 3], tile[(p + 3) * R6 + b], s3);
+      }
+      const float s = (s0 + s1) + (s2 + s3);
       const long i = 6 * pa + a % 6, j = 6 * pb + b % 6;
       if (a == b) {
         atomicAdd(&Hp[i * n + j], -(double)s);
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__
         atomicAdd(&Hp[j * n + i], -(double)s);
       }
     }
-    for (int a = tid; a < R6; a += kPix) {
+    for (int a = tid; a < R6; a += 256) {
       const int pa = rowpose[a / 6];
       if (pa < 0) continue;
       float s = 0.f;
@@ -359,8 +366,8 @@ __global__ void __launch_bounds__(kPix) ba_pass2_kernel(const long* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------
-// solve: sum the kParts replicas, LM damping, blocked (6x6 = one pose) right-looking Cholesky + two blocked
-// triangular solves in float64.  One block; 7P block-level barriers (49 at P = 7) instead of ~7n.
+// solve: sum the kParts replicas, LM damping, blocked (6x6 = one pose) right-looking LDL^T + blocked triangular
+// solves in float64 (SPD test: every pivot d_j > 0, same acceptance as the reference's LLT).  One block; 7P block-level barriers (49 at P = 7) instead of ~7n.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void damp(double* A, int ld, const double* dA, int P, float lm, float ep, int sem, int moba, int tid, int T) {
   const int n = 6 * P;
@@ -411,10 +418,13 @@ __global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm,
   __syncthreads();
   damp(A, ld, dA, P, lm, ep, sem, moba, tid, T);
   __syncthreads();
+  // A = L D L^T (unit lower L, D > 0): one reciprocal per column and no square roots -- float64 div / sqrt are
+  // ~100-cycle software sequences and sit on the serial critical path of the factorisation.
+  double* dinv = dA;                                       // dA is dead after damp(): reuse it for 1/d_j
   for (int kb = 0; kb < P; kb++) {
     const int c0 = 6 * kb;
     if (tid == 0) {                                        // 6x6 diagonal block, serial in registers
-      double D[6][6];
+      double D[6][6], iv[6];
 #pragma unroll
       for (int i = 0; i < 6; i++)
 #pragma unroll
@@ -424,64 +434,65 @@ __global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm,
       for (int j = 0; j < 6; j++) {
         double d = D[j][j];
 #pragma unroll
-        for (int t = 0; t < 6; t++) if (t < j) d -= D[j][t] * D[j][t];
+        for (int t = 0; t < 6; t++) if (t < j) d -= D[j][t] * D[j][t] * D[t][t];
         if (!(d > 0.0)) { bad = true; d = 1.0; }
-        d = sqrt(d);
         D[j][j] = d;
-        const double inv = 1.0 / d;
+        iv[j] = 1.0 / d;
 #pragma unroll
         for (int i = 0; i < 6; i++) {
           if (i > j) {
             double v = D[i][j];
 #pragma unroll
-            for (int t = 0; t < 6; t++) if (t < j) v -= D[i][t] * D[j][t];
-            D[i][j] = v * inv;
+            for (int t = 0; t < 6; t++) if (t < j) v -= D[i][t] * D[j][t] * D[t][t];
+            D[i][j] = v * iv[j];
           }
         }
       }
       if (bad) s_fail = 1;
 #pragma unroll
-      for (int i = 0; i < 6; i++)
+      for (int i = 0; i < 6; i++) {
+        dinv[c0 + i] = iv[i];
 #pragma unroll
         for (int j = 0; j < 6; j++) if (j <= i) A[(long)(c0 + i) * ld + c0 + j] = D[i][j];
+      }
     }
     __syncthreads();
     if (s_fail) break;
-    for (int r = c0 + 6 + tid; r < n; r += T) {            // panel: X Lkk^T = A[r][c0..c0+5]
+    for (int r = c0 + 6 + tid; r < n; r += T) {            // panel: L_rk = A_rk L_kk^-T D_k^-1
       double x[6];
 #pragma unroll
       for (int j = 0; j < 6; j++) {
         double v = A[(long)r * ld + c0 + j];
 #pragma unroll
-        for (int t = 0; t < 6; t++) if (t < j) v -= x[t] * A[(long)(c0 + j) * ld + c0 + t];
-        x[j] = v / A[(long)(c0 + j) * ld + c0 + j];
+        for (int t = 0; t < 6; t++) if (t < j) v -= x[t] * A[(long)(c0 + t) * ld + c0 + t] * A[(long)(c0 + j) * ld + c0 + t];
+        x[j] = v * dinv[c0 + j];
       }
 #pragma unroll
       for (int j = 0; j < 6; j++) A[(long)r * ld + c0 + j] = x[j];
     }
     __syncthreads();
-    const int m = n - c0 - 6;                              // trailing update (lower triangle)
+    const int m = n - c0 - 6;                              // trailing update (lower triangle): A_ic -= sum_t L_it d_t L_ct
     for (int idx = tid; idx < m * m; idx += T) {
       const int i = c0 + 6 + idx / m, c = c0 + 6 + idx % m;
       if (c > i) continue;
       double v = A[(long)i * ld + c];
 #pragma unroll
-      for (int t = 0; t < 6; t++) v -= A[(long)i * ld + c0 + t] * A[(long)c * ld + c0 + t];
+      for (int t = 0; t < 6; t++) v -= A[(long)i * ld + c0 + t] * A[(long)(c0 + t) * ld + c0 + t] * A[(long)c * ld + c0 + t];
       A[(long)i * ld + c] = v;
     }
     __syncthreads();
   }
   const bool fail = s_fail != 0;
   if (!fail) {
-    for (int kb = 0; kb < P; kb++) {                       // L z = b
+    for (int kb = 0; kb < P; kb++) {                       // L z = b   (unit diagonal)
       const int c0 = 6 * kb;
       if (tid == 0) {
 #pragma unroll
-        for (int j = 0; j < 6; j++) {
+        for (int j = 1; j < 6; j++) {
           double v = y[c0 + j];
 #pragma unroll
           for (int t = 0; t < 6; t++) if (t < j) v -= A[(long)(c0 + j) * ld + c0 + t] * y[c0 + t];
-          y[c0 + j] = v / A[(long)(c0 + j) * ld + c0 + j];
+          y[c0 + j] = v;
         }
       }
       __syncthreads();
@@ -493,15 +504,17 @@ __global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm,
       }
       __syncthreads();
     }
-    for (int kb = P - 1; kb >= 0; kb--) {                  // L^T x = z
+    for (int i = tid; i < n; i += T) y[i] *= dinv[i];      // D w = z
+    __syncthreads();
+    for (int kb = P - 1; kb >= 0; kb--) {                  // L^T x = w
       const int c0 = 6 * kb;
       if (tid == 0) {
 #pragma unroll
-        for (int j = 5; j >= 0; j--) {
+        for (int j = 4; j >= 0; j--) {
           double v = y[c0 + j];
 #pragma unroll
           for (int t = 0; t < 6; t++) if (t > j) v -= A[(long)(c0 + t) * ld + c0 + j] * y[c0 + t];
-          y[c0 + j] = v / A[(long)(c0 + j) * ld + c0 + j];
+          y[c0 + j] = v;
         }
       }
       __syncthreads();
@@ -636,7 +649,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
   const int deg_hint = (flags >> 8) & 0xFFF;
   int pass2_smem = 160 * 1024;
   if (deg_hint > 0) {        // tile [256][6(deg+1)] + Q + QW + row table; smaller request => several blocks per SM, one wave
-    const long need = 4L * (256L * (6 * (deg_hint + 1) + 2) + ((deg_hint + 1 + 3) & ~3)) + 64;
+    const long need = 4L * (128L * (6 * (deg_hint + 1) + 2) + ((deg_hint + 1 + 3) & ~3)) + 64;
     if (need < pass2_smem) pass2_smem = (int)need;
   }
   const size_t solve_smem = sizeof(double) * ((size_t)n * (n + 1) + 2 * n);
@@ -656,7 +669,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
       ba_pass1_kernel<<<grid, kPix, 0, s>>>(poses, disps, intrinsics, targets, weights, eta, ii, jj, pl, bf, E, HW, wd,
                                             t0, P, interleaved, motion_only, sem);
       if (!motion_only)
-        ba_pass2_kernel<<<grid, kPix, pass2_smem, s>>>(jj, pl, bf, HW, t0, P, pass2_smem / 4);
+        ba_pass2_kernel<<<dim3(ceil_div(HW, kPix2), K), 256, pass2_smem, s>>>(jj, pl, bf, HW, t0, P, pass2_smem / 4);
     }
     if (phase == 1) { ba_combine_kernel<<<8, 256, 0, s>>>(bf, P); break; }
     if (solve_in_smem) {

@@ -27,7 +27,9 @@ struct ConvP {
   int Wstride;
   int Cout;
   int KH, KW, padH, padW;
-  int H, Wd;         // spatial size; M = nimg * H * Wd
+  int H, Wd;         // INPUT spatial size
+  int Ho, Wo;        // OUTPUT spatial size; M = nimg * Ho * Wo
+  int stride;
   long M;
 };
 
@@ -43,14 +45,15 @@ template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p
 // ------------------------------------------------------------------------------------------------ epilogues
 // store<V>(m, n, acc): V consecutive output channels n..n+V-1 of pixel m.
 template <typename TO>
-struct EpiBias {      // out = act(acc + bias)
-  const float* bias; TO* out; int ostride; int ooff; int Cout; int relu;
+struct EpiBias {      // out = act(acc + bias); with a residual: relu(res + act(acc + bias))  (extractor.py:47-55)
+  const float* bias; TO* out; int ostride; int ooff; int Cout; int relu; const TO* res; int rstride;
   template <int V> __device__ __forceinline__ void store(long m, int n, const float* a) const {
 #pragma unroll
     for (int j = 0; j < V; j++) {
       if (n + j < Cout) {
         float v = a[j] + bias[n + j];
         if (relu) v = fmaxf(v, 0.0f);
+        if (res) v = fmaxf(v + ldf(res + m * rstride + n + j), 0.0f);
         stf(out + m * ostride + ooff + n + j, v);
       }
     }
@@ -110,14 +113,14 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ 
   const long m0 = (long)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int Ktot = p.KH * p.KW * p.Cin;
-  const int HW = p.H * p.Wd;
-  // A-tile ownership: pixel row am, 8 consecutive k starting at ak
+  const int HW = p.H * p.Wd, HWo = p.Ho * p.Wo;
+  // A-tile ownership: output pixel row am, 8 consecutive k starting at ak
   const int am = tid >> 1, ak = (tid & 1) * 8;
   const long m = m0 + am;
   const bool mvalid = m < p.M;
-  const long img = mvalid ? m / HW : 0;
-  const int rem = mvalid ? (int)(m - img * HW) : 0;
-  const int py = rem / p.Wd, px = rem - py * p.Wd;
+  const long img = mvalid ? m / HWo : 0;
+  const int rem = mvalid ? (int)(m - img * HWo) : 0;
+  const int py = (rem / p.Wo) * p.stride, px = (rem - (rem / p.Wo) * p.Wo) * p.stride;
 
   float ra[8];
   float4 rb[(BK * BN / 4 + 255) / 256];
@@ -368,6 +371,52 @@ __global__ void __launch_bounds__(128) colsum_final_kernel(const float* __restri
   }
 }
 
+// nn.InstanceNorm2d (affine=False, eps=1e-5, biased variance; extractor.py:28-32,129-130) on pixel-major data, fused
+// with the ReLU that always follows it and, for the last norm of a residual block, the skip addition + ReLU.
+// stats: per (image, channel) sum / sum of squares in two deterministic stages (reuses the colsum layout).
+template <typename TI>
+__global__ void __launch_bounds__(64) in_stats_partial_kernel(const TI* __restrict__ in, float* __restrict__ part, int HW, int C) {
+  const int e = blockIdx.x, ch = blockIdx.y;
+  const int per = (HW + kColChunks - 1) / kColChunks;
+  const int p0 = ch * per, p1 = min(HW, p0 + per);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.0f, q = 0.0f;
+    for (int p = p0; p < p1; p++) {
+      const float v = ldf(in + ((long)e * HW + p) * C + c);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    part[(((long)e * kColChunks + ch) * C + c) * 2] = s;
+    part[(((long)e * kColChunks + ch) * C + c) * 2 + 1] = q;
+  }
+}
+__global__ void __launch_bounds__(128) in_stats_final_kernel(const float* __restrict__ part, float* __restrict__ stats, int HW, int C) {
+  const int e = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < kColChunks; k++) {
+      s += part[(((long)e * kColChunks + k) * C + c) * 2];
+      q += part[(((long)e * kColChunks + k) * C + c) * 2 + 1];
+    }
+    const double mean = s / HW;
+    const double var = fmax(q / HW - mean * mean, 0.0);
+    stats[((long)e * C + c) * 2] = (float)mean;
+    stats[((long)e * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+}
+template <typename TI>
+__global__ void __launch_bounds__(256) in_apply_kernel(const TI* __restrict__ in, const float* __restrict__ stats, const TI* __restrict__ res,
+                                                       TI* __restrict__ out, int HW, int C, long total, int relu) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long e = i / ((long)HW * C);
+  float v = (ldf(in + i) - stats[(e * C + c) * 2]) * stats[(e * C + c) * 2 + 1];
+  if (relu) v = fmaxf(v, 0.0f);
+  if (res) v = fmaxf(v + ldf(res + i), 0.0f);
+  stf(out + i, v);
+}
+
 // flow-encoder input for the tensor-core path: the 7x7 conv over 8 motion channels (droid_net.py:179) is run as a
 // 7x1 conv over 64 channels, where channel (dxi*8 + c) of pixel (y,x) holds motion channel c of pixel (y, x+dxi-3)
 // (zero outside the image) and channels 56..63 are zero.
@@ -404,12 +453,20 @@ __global__ void __launch_bounds__(384) glo_reduce_matvec_kernel(const float* __r
                                                                 float* __restrict__ out) {
   const int e = blockIdx.x;
   __shared__ float g[128];
-  if (threadIdx.x < 128) {
-    float s = 0.0f;
-    const float* p = partial + (long)e * parts_per_img * 128 + threadIdx.x;
-    for (int k = 0; k < parts_per_img; k++) s += p[(long)k * 128];
-    g[threadIdx.x] = s * inv_hw;
+  __shared__ float part3[3][128];
+  {
+    const int c = threadIdx.x & 127, grp = threadIdx.x >> 7;          // 3 groups of 128 threads split the partials
+    const float* p = partial + (long)e * parts_per_img * 128 + c;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int k = grp;
+    for (; k + 9 < parts_per_img; k += 12) {
+      s0 += p[(long)k * 128]; s1 += p[(long)(k + 3) * 128]; s2 += p[(long)(k + 6) * 128]; s3 += p[(long)(k + 9) * 128];
+    }
+    for (; k < parts_per_img; k += 3) s0 += p[(long)k * 128];
+    part3[grp][c] = (s0 + s1) + (s2 + s3);
   }
+  __syncthreads();
+  if (threadIdx.x < 128) g[threadIdx.x] = ((part3[0][threadIdx.x] + part3[1][threadIdx.x]) + part3[2][threadIdx.x]) * inv_hw;
   __syncthreads();
   const int row = threadIdx.x;
   const float* w = W + (long)row * 128;
@@ -424,17 +481,34 @@ __global__ void __launch_bounds__(256) segment_mean_kernel(const T* __restrict__
                                                            T* __restrict__ out, const int* __restrict__ ptr,
                                                            const int* __restrict__ idx, const int* __restrict__ meta,
                                                            int HW, int C) {
+  constexpr int V = 16 / (int)sizeof(T);                     // channels per 16-byte access
   const int k = blockIdx.y;
   if (k >= meta[0]) return;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)HW * C) return;
-  const long pix = i / C;
-  const int c = (int)(i - pix * C);
-  float s = 0.0f;
+  const int cv = C / V;
+  if (i >= (long)HW * cv) return;
+  const long pix = i / cv;
+  const int c = (int)(i - pix * cv) * V;
+  float s[V];
+#pragma unroll
+  for (int q = 0; q < V; q++) s[q] = 0.0f;
   const int b = ptr[k], e_ = ptr[k + 1];
-  for (int it = b; it < e_; it++) s += ldf(in + ((long)idx[it] * HW + pix) * istride + ioff + c);
-  const int cnt = e_ - b;
-  stf(out + ((long)k * HW + pix) * C + c, s / (float)(cnt > 0 ? cnt : 1));
+  for (int it = b; it < e_; it++) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((long)idx[it] * HW + pix) * istride + ioff + c));
+    if (sizeof(T) == 2) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const float2 f = __half22float2(h[q]); s[2 * q] += f.x; s[(2 * q + 1) % V] += f.y; }
+    } else {
+      const float* f = reinterpret_cast<const float*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; q++) s[q % V] += f[q];
+    }
+  }
+  const float inv = 1.0f / (float)((e_ - b) > 0 ? (e_ - b) : 1);
+  T* o = out + ((long)k * HW + pix) * C + c;
+#pragma unroll
+  for (int q = 0; q < V; q++) stf(o + q, s[q] * inv);
 }
 
 // layout / dtype conversion between the reference's planar (N,C,H,W) tensors and pixel-major (N,HW,Cs) buffers
@@ -502,13 +576,15 @@ int launch_conv(const ConvP& p, const Epi& epi, bool vec, cudaStream_t s) {
 // seg_ptr[s][m*seg_stride[s] + c]; the concatenation of the segments is the conv input (replaces torch.cat,
 // gru.py:20-21,30).  Weights are pre-packed [KH*KW*Cin][wstride] float32 (pack_conv_weight in pvo_b200/nn.py).
 // epilogue: 0 bias, 1 bias+ReLU, 2 sigmoid(.)*net ("glo" gate), 3 GRU z|r, 4 GRU q + state update.
+// stride: 1 or 2 (extractor.py's downsampling convs); output size = (H + 2*(K/2) - K)/stride + 1.
+// epilogues 0/1: aux0 (optional) = residual tensor (stride aux_stride): out = relu(residual + act(conv)).
 // aux pointers by epilogue:  2: aux0 = net (stride aux_stride)        3: aux0 = net, aux1 = glo[E][384], out = z, out2 = r*net
 //                            4: aux0 = z, aux1 = glo[E][384], out = net (in place, stride ostride)
 extern "C" int pvo_conv2d(const void* const* seg_ptr, const int* seg_channels, const int* seg_stride, int nseg,
                           const float* W, int wstride, const float* bias, int Cout, int KH, int KW, int pad, int nimg,
                           int H, int Wd, int dtype, int epilogue, void* out, int ostride, int ooff, void* out2,
-                          const void* aux0, int aux_stride, const float* aux1, void* stream) {
-  if (nseg < 1 || nseg > 4 || Cout < 1 || wstride % 4 || nimg < 0) return PVO_ERR_INVALID;
+                          const void* aux0, int aux_stride, const float* aux1, int stride, void* stream) {
+  if (nseg < 1 || nseg > 4 || Cout < 1 || wstride % 4 || nimg < 0 || stride < 1) return PVO_ERR_INVALID;
   if (nimg == 0) return PVO_OK;
   ConvP p;
   p.nseg = nseg;
@@ -523,12 +599,15 @@ extern "C" int pvo_conv2d(const void* const* seg_ptr, const int* seg_channels, c
   }
   for (int s = nseg; s < 4; s++) p.seg[s] = Seg{nullptr, 0, 0};
   p.W = W; p.Wstride = wstride; p.Cout = Cout; p.KH = KH; p.KW = KW; p.padH = KH / 2; p.padW = KW / 2; (void)pad;   /* 'same' padding is the only mode the path uses */ p.H = H; p.Wd = Wd;
-  p.M = (long)nimg * H * Wd;
+  p.stride = stride;
+  p.Ho = (H + 2 * (KH / 2) - KH) / stride + 1;
+  p.Wo = (Wd + 2 * (KW / 2) - KW) / stride + 1;
+  p.M = (long)nimg * p.Ho * p.Wo;
   cudaStream_t s = (cudaStream_t)stream;
-  const int HW = H * Wd;
+  const int HW = p.Ho * p.Wo;
 #define DISPATCH(TI)                                                                                               \
   switch (epilogue) {                                                                                              \
-    case 0: case 1: return launch_conv<TI>(p, EpiBias<TI>{bias, (TI*)out, ostride, ooff, Cout, epilogue}, vec, s); \
+    case 0: case 1: return launch_conv<TI>(p, EpiBias<TI>{bias, (TI*)out, ostride, ooff, Cout, epilogue, (const TI*)aux0, aux_stride}, vec, s); \
     case 2: return launch_conv<TI>(p, EpiGlo<TI>{bias, (const TI*)aux0, aux_stride, (TI*)out, Cout}, vec, s);      \
     case 3: return launch_conv<TI>(p, EpiZR<TI>{bias, aux1, (const TI*)aux0, aux_stride, (TI*)out, (TI*)out2, HW}, vec, s); \
     case 4: return launch_conv<TI>(p, EpiQ<TI>{bias, aux1, (const TI*)aux0, (TI*)out, ostride, HW}, vec, s);       \
@@ -576,6 +655,29 @@ extern "C" int pvo_colmean(const void* in, float* out, float* scratch, int E, in
   return pvo_check_launch();
 }
 
+// in, out, res: (N, HW, C) pixel-major (contiguous); scratch: N*32*C*2 + N*C*2 floats.  out = [relu](IN(in)); with res:
+// out = relu(res + [relu](IN(in))).  in == out is allowed.
+extern "C" int pvo_instance_norm(const void* in, void* out, const void* res, float* scratch, int N, int HW, int C, int relu,
+                                 int dtype, void* stream) {
+  if (N == 0) return PVO_OK;
+  if (!scratch) return PVO_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* part = scratch;
+  float* stats = scratch + (size_t)N * kColChunks * C * 2;
+  dim3 grid(N, kColChunks);
+  const long total = (long)N * HW * C;
+  if (dtype == PVO_DTYPE_F32) {
+    in_stats_partial_kernel<float><<<grid, 64, 0, s>>>((const float*)in, part, HW, C);
+    in_stats_final_kernel<<<N, 128, 0, s>>>(part, stats, HW, C);
+    in_apply_kernel<float><<<ceil_div(total, 256), 256, 0, s>>>((const float*)in, stats, (const float*)res, (float*)out, HW, C, total, relu);
+  } else {
+    in_stats_partial_kernel<__half><<<grid, 64, 0, s>>>((const __half*)in, part, HW, C);
+    in_stats_final_kernel<<<N, 128, 0, s>>>(part, stats, HW, C);
+    in_apply_kernel<__half><<<ceil_div(total, 256), 256, 0, s>>>((const __half*)in, stats, (const __half*)res, (__half*)out, HW, C, total, relu);
+  }
+  return pvo_check_launch();
+}
+
 extern "C" int pvo_expand_x7(const void* motn, void* out, int nimg, int H, int Wd, void* stream) {
   if (nimg == 0) return PVO_OK;
   const long M = (long)nimg * H * Wd;
@@ -599,7 +701,9 @@ extern "C" int pvo_glo_reduce_matvec(const float* partial, int parts_per_img, in
 extern "C" int pvo_segment_mean(const void* in, int istride, int ioff, void* out, const int* ptr, const int* idx,
                                 const int* meta, int Kmax, int HW, int C, int dtype, void* stream) {
   if (Kmax == 0) return PVO_OK;
-  dim3 grid(ceil_div((long)HW * C, 256), Kmax);
+  const size_t esz = dtype == PVO_DTYPE_F32 ? 4 : 2;
+  if ((C * esz) % 16 || (istride * esz) % 16 || (ioff * esz) % 16) return PVO_ERR_INVALID;
+  dim3 grid(ceil_div((long)HW * C * esz / 16, 256), Kmax);
   if (dtype == PVO_DTYPE_F32)
     segment_mean_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, istride, ioff, (float*)out, ptr, idx, meta, HW, C);
   else

@@ -37,26 +37,78 @@ struct TcParams {
   int Cout;
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// ---- epilogue helpers.  The epilogue warps are on the critical path of every short-K layer (measured: 19 instructions
+// per output element made the 1x1 gate conv 10x slower than its operand stream), so everything here is vectorised:
+// 16-byte bias / state loads, packed half conversions, MUFU tanh for the gates.
+__device__ __forceinline__ float fast_tanh(float x) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x)); return t; }
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(fast_tanh(0.5f * x), 0.5f, 0.5f); }   // = 1/(1+e^-x)
 
-// ---- epilogues: store16(m, e, n, v): 16 consecutive output channels n.. of pixel m (image/edge e) -------------
+__device__ __forceinline__ void ld16f(const float* p, float* o) {          // 16 consecutive floats, 16-byte aligned
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+    o[4 * q] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
+  }
+}
+template <bool LDG>
+__device__ __forceinline__ void ld16h(const __half* p, float* o) {         // 16 consecutive halves -> floats
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const uint4 t = LDG ? __ldg(reinterpret_cast<const uint4*>(p) + q) : *(reinterpret_cast<const uint4*>(p) + q);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      o[8 * q + 2 * k] = f.x; o[8 * q + 2 * k + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void st16h(__half* p, const float* x) {         // 16 floats -> 16 halves, two 16-byte stores
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const __half2 h = __floats2half2_rn(x[8 * q + 2 * k], x[8 * q + 2 * k + 1]);
+      w[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *(reinterpret_cast<uint4*>(p) + q) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// one step of the cross-lane transpose-reduce: lanes with `BIT` set keep columns [W, 2W), the others [0, W)
+template <int W, int BIT>
+__device__ __forceinline__ void xr_step(float* x, int lane) {
+  const bool up = lane & BIT;
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    const float send = up ? x[j] : x[j + W];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, BIT);
+    x[j] = (up ? x[j + W] : x[j]) + recv;
+  }
+}
+
+// ---- epilogues: store16(m, e, n, v, ok, tile, q): 16 consecutive output channels n.. of pixel m (image/edge e) ------
 struct EpBias {          // out = act(acc + bias)
   const float* bias; __half* out; int ostride; int ooff; int Cout; int relu;
   __device__ __forceinline__ void store16(long m, long, int n, const float* v, bool ok, int, int) const {
     if (n >= Cout || !ok) return;
-    __align__(16) __half h[16];
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-      float x = v[j] + ((n + j < Cout) ? __ldg(bias + n + j) : 0.0f);
-      if (relu) x = fmaxf(x, 0.0f);
-      h[j] = __float2half_rn(x);
-    }
     __half* o = out + m * ostride + ooff + n;
     if (n + 16 <= Cout) {
-      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&h[0]);
-      *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+      float b[16], x[16];
+      ld16f(bias + n, b);
+#pragma unroll
+      for (int j = 0; j < 16; j++) { x[j] = v[j] + b[j]; if (relu) x[j] = fmaxf(x[j], 0.0f); }
+      st16h(o, x);
     } else {
-      for (int j = 0; n + j < Cout; j++) o[j] = h[j];
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        if (n + j < Cout) {
+          float x = v[j] + __ldg(bias + n + j);
+          if (relu) x = fmaxf(x, 0.0f);
+          o[j] = __float2half_rn(x);
+        }
+      }
     }
   }
 };
@@ -65,18 +117,21 @@ struct EpGloSum {        // gru.py:25-26: sum over the tile's pixels of sigmoid(
   const float* bias; const __half* net; int nstride; float* partial; int Cout;
   __device__ __forceinline__ void store16(long m, long, int n, const float* v, bool ok, int tile, int q) const {
     if (n >= Cout) return;                       // warp-uniform
-    __align__(16) __half hn[16];
-    if (ok) {
-      *reinterpret_cast<uint4*>(&hn[0]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + n));
-      *reinterpret_cast<uint4*>(&hn[8]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + n + 8));
-    }
-    const int lane = threadIdx.x & 31;
+    float b[16], h[16], x[16];
+    ld16f(bias + n, b);
+    if (ok) ld16h<true>(net + m * nstride + n, h);
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      float x = ok ? sigmoidf_(v[j] + __ldg(bias + n + j)) * __half2float(hn[j]) : 0.0f;
-      x = warp_sum(x);
-      if (lane == 0) partial[((long)tile * 4 + q) * Cout + n + j] = x;
-    }
+    for (int j = 0; j < 16; j++) x[j] = ok ? fast_sigmoid(v[j] + b[j]) * h[j] : 0.0f;
+    // transpose-reduce over the 32 lanes: 8+4+2+1 exchanges halve the values held per lane, then one more step
+    const int lane = threadIdx.x & 31;
+    xr_step<8, 16>(x, lane);
+    xr_step<4, 8>(x, lane);
+    xr_step<2, 4>(x, lane);
+    xr_step<1, 2>(x, lane);
+    x[0] += __shfl_xor_sync(0xffffffffu, x[0], 1);            // lanes 2k, 2k+1 hold the same column
+    // column held by this lane pair: bit4 -> +8, bit3 -> +4, bit2 -> +2, bit1 -> +1
+    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    if (!(lane & 1)) partial[((long)tile * 4 + q) * Cout + n + col] = x[0];
   }
 };
 
@@ -84,23 +139,20 @@ struct EpZR {            // gru.py:28-29 (see conv_simt.cu EpiZR)
   const float* bias; const float* glo; const __half* net; int nstride; __half* z; __half* rnet;
   __device__ __forceinline__ void store16(long m, long e, int n, const float* v, bool ok, int, int) const {
     if (n >= 256 || !ok) return;
-    __align__(16) __half h[16];
-    __align__(16) __half hn[16];
     const bool isr = n >= 128;
     const int c0 = isr ? n - 128 : n;
-    if (isr) {
-      *reinterpret_cast<uint4*>(&hn[0]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + c0));
-      *reinterpret_cast<uint4*>(&hn[8]) = __ldg(reinterpret_cast<const uint4*>(net + m * nstride + c0 + 8));
-    }
+    float b[16], g[16], x[16];
+    ld16f(bias + n, b);
+    ld16f(glo + e * 384 + n, g);
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      float s = sigmoidf_(v[j] + __ldg(bias + n + j) + __ldg(glo + e * 384 + n + j));
-      if (isr) s *= __half2float(hn[j]);
-      h[j] = __float2half_rn(s);
+    for (int j = 0; j < 16; j++) x[j] = fast_sigmoid(v[j] + b[j] + g[j]);
+    if (isr) {
+      float h[16];
+      ld16h<true>(net + m * nstride + c0, h);
+#pragma unroll
+      for (int j = 0; j < 16; j++) x[j] *= h[j];
     }
-    __half* o = (isr ? rnet : z) + m * 128 + c0;
-    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&h[0]);
-    *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+    st16h((isr ? rnet : z) + m * 128 + c0, x);
   }
 };
 
@@ -108,22 +160,17 @@ struct EpQ {             // gru.py:30-32, state update in place
   const float* bias; const float* glo; const __half* z; __half* net; int nstride;
   __device__ __forceinline__ void store16(long m, long e, int n, const float* v, bool ok, int, int) const {
     if (n >= 128 || !ok) return;
-    __align__(16) __half hz[16];
-    __align__(16) __half hn[16];
-    __align__(16) __half h[16];
-    *reinterpret_cast<uint4*>(&hz[0]) = __ldg(reinterpret_cast<const uint4*>(z + m * 128 + n));
-    *reinterpret_cast<uint4*>(&hz[8]) = __ldg(reinterpret_cast<const uint4*>(z + m * 128 + n + 8));
-    *reinterpret_cast<uint4*>(&hn[0]) = *reinterpret_cast<const uint4*>(net + m * nstride + n);
-    *reinterpret_cast<uint4*>(&hn[8]) = *reinterpret_cast<const uint4*>(net + m * nstride + n + 8);
+    float b[16], g[16], zz[16], h[16], x[16];
+    ld16f(bias + n, b);
+    ld16f(glo + e * 384 + 256 + n, g);
+    ld16h<true>(z + m * 128 + n, zz);
+    ld16h<false>(net + m * nstride + n, h);
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-      const float q = tanhf(v[j] + __ldg(bias + n + j) + __ldg(glo + e * 384 + 256 + n + j));
-      const float zz = __half2float(hz[j]);
-      h[j] = __float2half_rn((1.0f - zz) * __half2float(hn[j]) + zz * q);
+      const float q = fast_tanh(v[j] + b[j] + g[j]);
+      x[j] = fmaf(zz[j], q - h[j], h[j]);                   // (1-z) h + z q
     }
-    __half* o = net + m * nstride + n;
-    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&h[0]);
-    *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+    st16h(net + m * nstride + n, x);
   }
 };
 

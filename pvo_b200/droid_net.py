@@ -132,3 +132,101 @@ class DynamicUpdateModule(nn.Module):
 
 
 UpdateModule = DynamicUpdateModule     # the stale reference class (droid_net.py:98-164) is never instantiated by PVO
+
+
+# ------------------------------------------------------------------------------------------------------
+# DroidNet: encoders + update operator + (Python-semantics) BA, pairwise / training-style entry point
+# ------------------------------------------------------------------------------------------------------
+def cvx_upsample(data, mask):
+    """convex 8x upsampling with a softmax-9 mask (droid_net.py:23-37)"""
+    batch, ht, wd, dim = data.shape
+    data = data.permute(0, 3, 1, 2)
+    mask = torch.softmax(mask.view(batch, 1, 9, 8, 8, ht, wd), dim=2)
+    up = torch.nn.functional.unfold(data, [3, 3], padding=1).view(batch, dim, 9, 1, 1, ht, wd)
+    up = torch.sum(mask * up, dim=2).permute(0, 4, 2, 5, 3, 1)
+    return up.reshape(batch, 8 * ht, 8 * wd, dim)
+
+
+def upsample_dim_1(disp, mask):
+    batch, num, ht, wd = disp.shape
+    return cvx_upsample(disp.reshape(batch * num, ht, wd, 1), mask.reshape(batch * num, -1, ht, wd)).view(batch, num, 8 * ht, 8 * wd)
+
+
+def upsample_inter(mask):
+    """bilinear x8, align_corners=True (droid_net.py:54-61)"""
+    batch, num, ht, wd, dim = mask.shape
+    m = mask.permute(0, 1, 4, 2, 3).reshape(batch * num, dim, ht, wd)
+    m = torch.nn.functional.interpolate(m, scale_factor=8, mode='bilinear', align_corners=True, recompute_scale_factor=True)
+    return m.permute(0, 2, 3, 1).reshape(batch, num, 8 * ht, 8 * wd, dim)
+
+
+class DroidNet(nn.Module):
+    """droid_net.py:317-440.  Checkpoint keys fnet.*, cnet.*, update.* as the reference.  forward() is the reference's
+    pairwise inference loop (evaluation_scripts/test_vo2.py:110-113): per step one correlation lookup, one update
+    operator call and two Gauss-Newton steps of geom.ba.BA -- all on the CUDA kernels; inference only."""
+
+    def __init__(self, use_aff_bri=False):
+        super().__init__()
+        from .modules.extractor import BasicEncoder
+        self.fnet = BasicEncoder(output_dim=128, norm_fn='instance')
+        self.cnet = BasicEncoder(output_dim=256, norm_fn='none')
+        self.update = DynamicUpdateModule(use_aff_bri)
+        self.use_aff_bri = use_aff_bri
+
+    def extract_features(self, images):
+        """droid_net.py:325-340"""
+        images = images[:, :, [2, 1, 0]] / 255.0
+        mean = torch.as_tensor([0.485, 0.456, 0.406], device=images.device)
+        std = torch.as_tensor([0.229, 0.224, 0.225], device=images.device)
+        images = images.sub_(mean[:, None, None]).div_(std[:, None, None])
+        fmaps = self.fnet(images)
+        net = self.cnet(images)
+        net, inp = net.split([128, 128], dim=2)
+        return fmaps, torch.tanh(net), torch.relu(inp)
+
+    @torch.no_grad()
+    def forward(self, Gs, images, disps, intrinsics, graph=None, num_steps=12, fixedp=2, ret_flow=False, downsample=False,
+                segments=None):
+        from .geom import projective_ops as pops
+        from .geom.ba import BA
+        from .modules.corr import CorrBlock
+        dev = images.device
+        ii = torch.as_tensor([u for u in graph for _ in graph[u]], dtype=torch.long, device=dev)      # graph_to_edge_list
+        jj = torch.as_tensor([v for u in graph for v in graph[u]], dtype=torch.long, device=dev)
+        fmaps, net, inp = self.extract_features(images)
+        net, inp = net[:, ii].contiguous(), inp[:, ii].contiguous()
+        corr_fn = CorrBlock(fmaps[:, ii].contiguous(), fmaps[:, jj].contiguous(), num_levels=4, radius=3)
+        ht, wd = images.shape[-2:]
+        coords0 = pops.coords_grid(ht // 8, wd // 8, device=dev)
+        coords1, _ = pops.projective_transform(Gs, disps, intrinsics, ii, jj)
+        target_cam = coords1.clone()
+        delta_dy = torch.zeros_like(coords1)
+        raw_mask = torch.zeros_like(coords1)
+        Gs_list, disp_list, residual_list, full_flow_list, mask_list = [], [], [], [], []
+        for step in range(num_steps):
+            corr = corr_fn(coords1)
+            resd = target_cam - coords1
+            cam_flow = coords1 - coords0
+            motion = torch.cat([cam_flow, cam_flow + delta_dy, resd, raw_mask], dim=-1)
+            motion = motion.permute(0, 1, 4, 2, 3).clamp(-64.0, 64.0).contiguous()
+            net, delta, weight, eta, upmask, delta_m = self.update(net, inp, corr, motion, ii, jj)
+            raw_mask = raw_mask + delta_m
+            mask = torch.sigmoid(raw_mask)
+            bin_mask = (mask >= 0.5).float()
+            target_cam = coords1 + delta[..., 0:2]
+            weight = torch.sigmoid(weight + (1 - bin_mask) * 10)
+            for _ in range(2):
+                Gs, disps = BA(target_cam, weight, eta, Gs, disps, intrinsics, ii, jj, fixedp=fixedp)
+            coords1, valid_mask = pops.projective_transform(Gs, disps, intrinsics, ii, jj)
+            residual = (target_cam - coords1) * valid_mask
+            delta_dy = delta[..., 2:4] * (1 - bin_mask)
+            target_all = coords1 + delta_dy
+            Gs_list.append(Gs)
+            disp_list.append(upsample_dim_1(disps, upmask['disp'].float()))
+            residual_list.append(residual)
+            mask_list.append(upsample_inter(mask))
+            if ret_flow:
+                full_flow_list.append(target_all - coords0 if downsample else upsample_inter((target_all - coords0) * 8))
+        if ret_flow:
+            return Gs_list, disp_list, residual_list, full_flow_list, mask_list
+        return Gs_list, disp_list, residual_list, mask_list

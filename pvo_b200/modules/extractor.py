@@ -1,0 +1,126 @@
+"""BasicEncoder (feature / context networks) with the reference's parameters
+(VO_Module/droid_slam/modules/extractor.py:6-55,118-198) on the pvo_b200 convolution kernels.
+
+Runs once per incoming frame (not per update iteration): 7x7/s2 stem, three residual stages (32, 64/s2, 128/s2), 1x1
+head.  Every conv is one launch of the implicit-GEMM kernel with bias / ReLU / residual-add fused; fnet's
+nn.InstanceNorm2d (+ReLU, + the block's skip addition) is a fused 3-launch deterministic reduction.  State-dict keys
+match the reference (conv1, layer{1,2,3}.{0,1}.conv{1,2}, layer{2,3}.0.downsample.0, conv2).
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .. import nn as pnn
+from .._lib import check, ptr, stream
+
+DIM = 32
+
+
+class ResidualBlock(nn.Module):
+    """extractor.py:6-55 (norm layers of the 'instance' / 'none' variants carry no parameters)."""
+
+    def __init__(self, in_planes, planes, norm_fn='none', stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_planes, planes, kernel_size=3, padding=1, stride=stride)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, padding=1)
+        self.stride = stride
+        self.downsample = None if stride == 1 else nn.Sequential(nn.Conv2d(in_planes, planes, kernel_size=1, stride=stride))
+
+
+class BasicEncoder(nn.Module):
+    def __init__(self, output_dim=128, norm_fn='batch', dropout=0.0, multidim=False):
+        super().__init__()
+        if norm_fn not in ('instance', 'none'):
+            raise NotImplementedError("BasicEncoder: PVO instantiates norm_fn='instance' (fnet) and 'none' (cnet) only "
+                                      '(droid_net.py:319-320)')
+        if multidim or dropout > 0:
+            raise NotImplementedError('BasicEncoder: multidim / dropout are unused by PVO')
+        self.norm_fn = norm_fn
+        self.conv1 = nn.Conv2d(3, DIM, kernel_size=7, stride=2, padding=3)
+        self.in_planes = DIM
+        self.layer1 = self._make_layer(DIM, stride=1)
+        self.layer2 = self._make_layer(2 * DIM, stride=2)
+        self.layer3 = self._make_layer(4 * DIM, stride=2)
+        self.conv2 = nn.Conv2d(4 * DIM, output_dim, kernel_size=1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+        self._packed = None
+        self.register_load_state_dict_post_hook(lambda m, k: setattr(m, '_packed', None))
+
+    def _make_layer(self, dim, stride=1):
+        layers = (ResidualBlock(self.in_planes, dim, self.norm_fn, stride=stride), ResidualBlock(dim, dim, self.norm_fn, stride=1))
+        self.in_planes = dim
+        return nn.Sequential(*layers)
+
+    # ------------------------------------------------------------------------------------------
+    def _pack(self, device):
+        if self._packed is None or self._packed['device'] != str(device):
+            sd = {k: v.detach().to(device) for k, v in self.state_dict().items()}
+            pk = {'device': str(device)}
+            for name in sorted(set(k.rsplit('.', 1)[0] for k in sd)):
+                pk[name] = pnn._Conv(sd[name + '.weight'], sd[name + '.bias'])
+            self._packed = pk
+        return self._packed
+
+    def forward(self, x):
+        """x (b,n,3,H,W) float -> (b,n,output_dim,H/8,W/8).  Inference only."""
+        if x.requires_grad:
+            raise NotImplementedError('BasicEncoder: inference only')
+        b, n, c1, h1, w1 = x.shape
+        N = b * n
+        half = x.dtype == torch.float16 or torch.is_autocast_enabled()
+        dt = torch.float16 if half else torch.float32
+        dc = _lib.F16 if half else _lib.F32
+        dev = x.device
+        pk = self._pack(dev)
+        L = _lib.lib()
+        inorm = self.norm_fn == 'instance'
+        x = x.reshape(N, c1, h1, w1).contiguous()
+        xin = torch.empty(N * h1 * w1, c1, dtype=dt, device=dev)
+        check(L.pvo_nchw_to_nhwc(ptr(x), _lib.dtype_code(x), ptr(xin), dc, N, c1, h1 * w1, c1, 0, stream()), 'nchw_to_nhwc')
+        scratch = torch.empty(N * 128 * 66 + 16, dtype=torch.float32, device=dev)
+
+        def osz(s, k, stride):
+            return (s + 2 * (k // 2) - k) // stride + 1
+
+        def conv(name, src, cin, H, W, stride, relu, res=None):
+            cv = pk[name]
+            Ho, Wo = osz(H, cv.kh, stride), osz(W, cv.kw, stride)
+            out = torch.empty(N * Ho * Wo, cv.cout, dtype=dt, device=dev)
+            pnn.conv2d(cv, [(src, cin, cin)], N, H, W, dc, out, cv.cout, 0, 1 if relu else 0, aux0=res,
+                       aux_stride=cv.cout if res is not None else 0, stride=stride)
+            return out, Ho, Wo
+
+        def inst_norm(t, HW, C, relu, res=None):
+            check(L.pvo_instance_norm(ptr(t), ptr(t), ptr(res), ptr(scratch), N, HW, C, 1 if relu else 0, dc, stream()),
+                  'instance_norm', launches=3)
+            return t
+
+        y, H, W = conv('conv1', xin, c1, h1, w1, 2, relu=not inorm)
+        if inorm:
+            inst_norm(y, H * W, DIM, True)
+        cin = DIM
+        for li, (dim, stride) in enumerate(((DIM, 1), (2 * DIM, 2), (4 * DIM, 2)), start=1):
+            for bi in (0, 1):
+                pre = 'layer%d.%d' % (li, bi)
+                s_ = stride if bi == 0 else 1
+                t1, Ho, Wo = conv(pre + '.conv1', y, cin, H, W, s_, relu=not inorm)
+                if inorm:
+                    inst_norm(t1, Ho * Wo, dim, True)
+                skip = y
+                if s_ != 1:
+                    skip, _, _ = conv(pre + '.downsample.0', y, cin, H, W, s_, relu=False)
+                    if inorm:
+                        inst_norm(skip, Ho * Wo, dim, False)
+                if inorm:
+                    t2, _, _ = conv(pre + '.conv2', t1, dim, Ho, Wo, 1, relu=False)
+                    y = inst_norm(t2, Ho * Wo, dim, True, res=skip)
+                else:
+                    y, _, _ = conv(pre + '.conv2', t1, dim, Ho, Wo, 1, relu=True, res=skip)
+                H, W, cin = Ho, Wo, dim
+        out, H, W = conv('conv2', y, cin, H, W, 1, relu=False)
+        cout = pk['conv2'].cout
+        res = torch.empty(N, cout, H, W, dtype=dt, device=dev)
+        check(L.pvo_nhwc_to_nchw(ptr(out), dc, cout, 0, ptr(res), dc, N, cout, H * W, stream()), 'nhwc_to_nchw')
+        return res.view(b, n, cout, H, W)

@@ -67,7 +67,7 @@ class _Conv:
 
 
 def conv2d(cv, segs, nimg, H, W, dtype, out, ostride, ooff=0, epilogue=0, out2=None, aux0=None, aux_stride=0,
-           aux1=None, use_tc=False):
+           aux1=None, use_tc=False, stride=1):
     """segs: list of (tensor_or_ptr, channels, stride).  All pointers are device pointers."""
     L = _lib.lib()
     n = len(segs)
@@ -80,7 +80,7 @@ def conv2d(cv, segs, nimg, H, W, dtype, out, ostride, ooff=0, epilogue=0, out2=N
               'conv2d_tc')
     else:
         check(L.pvo_conv2d(sp, sc, ss, n, ptr(cv.W), cv.wstride, ptr(cv.bias), cv.cout, cv.kh, cv.kw, cv.pad, nimg, H,
-                           W, dtype, epilogue, ptr(out), ostride, ooff, ptr(out2), ptr(aux0), aux_stride, ptr(aux1),
+                           W, dtype, epilogue, ptr(out), ostride, ooff, ptr(out2), ptr(aux0), aux_stride, ptr(aux1), stride,
                            stream()), 'conv2d')
 
 

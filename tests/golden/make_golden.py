@@ -92,6 +92,42 @@ def main():
                     'full_flow%d' % it: fg.full_flow.clone(), 'net%d' % it: fg.net.float()[:, :, ::8].clone(),
                     'damping%d' % it: fg.damping[:F_].clone()})
     save('graph_step.npz', **out)
+    make_droid_net(ref)
+
+
+def droid_net_state():
+    """seeded DroidNet state dict (fnet.*, cnet.*, update.*) shared by the golden generator and the GPU test"""
+    from oracle import encoder as oenc
+    sd = {}
+    sd.update({'fnet.' + k: v for k, v in oenc.init_params(128, seed=11).items()})
+    sd.update({'cnet.' + k: v for k, v in oenc.init_params(256, seed=12).items()})
+    sd.update({'update.' + k: v for k, v in oupd.init_params(0).items()})
+    return sd
+
+
+def droid_net_inputs():
+    from collections import OrderedDict
+    g = torch.Generator().manual_seed(21)
+    F_, H, W = 3, 128, 192
+    images = torch.randint(0, 256, (1, F_, 3, H, W), generator=g).float()
+    images = torch.nn.functional.avg_pool2d(images.view(F_, 3, H, W), 5, stride=1, padding=2).view(1, F_, 3, H, W)   # some structure
+    poses = cases.trajectory(F_, g)[None]
+    disps = cases.smooth_disps(F_, H // 8, W // 8, g)[None]
+    intr = cases.intrinsics_for(H // 8, W // 8).repeat(1, F_, 1)
+    graph = OrderedDict([(0, [1, 2]), (1, [0, 2]), (2, [0, 1])])
+    return images, poses, disps, intr, graph
+
+
+def make_droid_net(ref):
+    m = ref.droid_net.DroidNet()
+    m.load_state_dict(droid_net_state(), strict=True)
+    m.eval()
+    images, poses, disps, intr, graph = droid_net_inputs()
+    fm, net, inp = m.extract_features(images.clone())
+    Gs_list, disp_list, res_list, flow_list, mask_list = m(se3.SE3(poses), images.clone(), disps, intr, graph, num_steps=2,
+                                                           fixedp=2, ret_flow=True, downsample=True)
+    save('droid_net.npz', fmaps=fm[:, :, ::8], net=net[:, :, ::8], inp=inp[:, :, ::8], poses=Gs_list[-1].data,
+         disps_up=disp_list[-1][:, :, ::4, ::4], residual=res_list[-1], flow=flow_list[-1], mask=mask_list[-1][:, :, ::4, ::4])
 
 
 if __name__ == '__main__':

@@ -1,0 +1,50 @@
+"""GPU parity of the per-frame encoders and the pairwise DroidNet.forward entry point against golden vectors produced
+by the reference's own DroidNet run on CPU (tests/golden/droid_net.npz) and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder as oenc
+from tests.golden.make_golden import droid_net_inputs, droid_net_state
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+@pytest.mark.parametrize('norm,od', [('instance', 128), ('none', 256)])
+def test_basic_encoder_matches_oracle(norm, od):
+    from pvo_b200.modules.extractor import BasicEncoder
+    sd = oenc.init_params(od, seed=od)
+    m = BasicEncoder(od, norm).cuda()
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 2, 3, 72, 104, generator=g)            # odd sizes after /2: 36x52 -> 18x26 -> 9x13
+    with torch.no_grad():
+        ref = oenc.basic_encoder(sd, x, norm)
+        out = m(x.cuda())
+    assert out.shape == ref.shape
+    assert (out.cpu() - ref).abs().max() < 2e-4
+
+
+def test_droid_net_forward_matches_reference_golden():
+    from pvo_b200.droid_net import DroidNet
+    from pvo_b200.lietorch import SE3
+    gold = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, 'droid_net.npz')).items()}
+    m = DroidNet().cuda()
+    m.load_state_dict(droid_net_state())
+    m.update.precision = 'fp32'
+    images, poses, disps, intr, graph = droid_net_inputs()
+    with torch.no_grad():
+        fm, net, inp = m.extract_features(images.clone().cuda())
+    assert (fm.cpu()[:, :, ::8] - gold['fmaps']).abs().max() < 5e-4
+    assert (net.cpu()[:, :, ::8] - gold['net']).abs().max() < 5e-4
+    assert (inp.cpu()[:, :, ::8] - gold['inp']).abs().max() < 5e-4
+    Gs_list, disp_list, res_list, flow_list, mask_list = m(SE3(poses.cuda()), images.clone().cuda(), disps.cuda(), intr.cuda(), graph,
+                                                           num_steps=2, fixedp=2, ret_flow=True, downsample=True)
+    rel = lambda a, b: (a - b).abs().max().item() / max(b.abs().max().item(), 1e-9)
+    assert rel(Gs_list[-1].data.cpu(), gold['poses']) < 1e-4
+    assert rel(disp_list[-1].cpu()[:, :, ::4, ::4], gold['disps_up']) < 1e-3
+    assert (flow_list[-1].cpu() - gold['flow']).norm(dim=-1).mean().item() < 1e-3
+    assert (mask_list[-1].cpu()[:, :, ::4, ::4] - gold['mask']).abs().max() < 1e-3

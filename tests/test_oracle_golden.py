@@ -66,3 +66,19 @@ def test_graph_step_matches_reference_factor_graph():
             assert torch.allclose(st['damping'][:F_], gold['damping' + tag], atol=1e-7), it
     # the segment filter must actually have fired on this case, otherwise the test pins nothing
     assert (st['delta_dy'] != 0).any() and (st['weight'] > 0.999).any()
+
+
+def test_encoder_oracle_matches_reference_droidnet_features():
+    """oracle.encoder vs the reference DroidNet.extract_features (fnet instance-norm, cnet no-norm), droid_net.npz."""
+    from oracle import encoder as oenc
+    from tests.golden.make_golden import droid_net_inputs, droid_net_state
+    gold = _load('droid_net.npz')
+    sd = droid_net_state()
+    images, *_ = droid_net_inputs()
+    sf = {k[5:]: v for k, v in sd.items() if k.startswith('fnet.')}
+    sc = {k[5:]: v for k, v in sd.items() if k.startswith('cnet.')}
+    with torch.no_grad():
+        fm, net, inp = oenc.extract_features(sf, sc, images)
+    assert torch.allclose(fm[:, :, ::8], gold['fmaps'], atol=1e-5)
+    assert torch.allclose(net[:, :, ::8], gold['net'], atol=1e-5)
+    assert torch.allclose(inp[:, :, ::8], gold['inp'], atol=1e-5)

@@ -22,6 +22,7 @@ tests)
   run t_geom 600 $PT tests/test_geom_gpu.py
   run t_update 600 $PT tests/test_update_gpu.py
   run t_step 900 $PT tests/test_step_gpu.py
+  run t_net 600 $PT tests/test_net_gpu.py
   run smoke 300 python __graft_entry__.py smoke ;;
 bench)
   run bench_fp16 900 python bench.py --steps 50 --warmup 5
