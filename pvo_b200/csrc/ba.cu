@@ -26,7 +26,7 @@ namespace {
 
 constexpr float kMinDepth = 0.25f;
 constexpr int kPix = 256;       // pixels (= threads) per block
-constexpr int kParts = 16;      // replicas of the reduced system (see Bufs::sys)
+constexpr int kParts = 2;       // replicas of the reduced system (see Bufs::sys)
 
 struct Plan {          // lives in the integer part of the workspace
   int* frame2k;        // [nframes] frame index -> row in kx, or -1
@@ -42,9 +42,9 @@ struct Bufs {
   float* Q;            // [K][HW]
   float* w;            // [K][HW]
   double* sys;         // [kParts][n*n + 2n]: per part {H [n][n] reduced camera system | b [n] | dA [n]}, n = 6P.
-                       // Blocks accumulate into part (blockIdx.x % kParts): same-address fp64 atomics serialise in L2 at
-                       // a few hundred cycles each, and with one copy the 19 pixel-slices of a frame all hit the same
-                       // 1764 addresses (measured: 53 us for the Schur pass).  The solve sums the parts in fixed order.
+                       // Blocks accumulate into part (blockIdx.x % kParts) to spread same-address fp64 atomics; measured on
+                       // B200 the L2 absorbs them (1 vs 16 replicas: no change in the Schur pass) while every extra
+                       // replica costs the single-block solve a latency-bound read, so 2 are kept.
   float* dx;           // [P][6]
 };
 
@@ -133,6 +133,19 @@ __global__ void __launch_bounds__(1024) ba_plan_kernel(const long* __restrict__ 
 // ---------------------------------------------------------------------------------------------------
 // pass 1: residuals, Jacobians, per-edge Hessian blocks, per-frame C / w / Ei, per-edge Eij
 // ---------------------------------------------------------------------------------------------------
+// one step of a cross-lane transpose-reduce: lanes with BIT set keep values [W, 2W), the others [0, W); after the
+// steps (48,16) (24,8) (12,4) (6,2) (3,1) every lane holds 3 fully reduced values of a 96-vector
+template <int W, int BIT>
+__device__ __forceinline__ void xr_step(float* x, int lane) {
+  const bool up = lane & BIT;
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    const float send = up ? x[j] : x[j + W];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, BIT);
+    x[j] = (up ? x[j + W] : x[j]) + recv;
+  }
+}
+
 struct EdgeJac {
   float Ju[12], Jv[12];     // [Ji | Jj] for the x and y residual rows
   float Jzu, Jzv, wu, wv, ru, rv;
@@ -221,23 +234,29 @@ __global__ void __launch_bounds__(kPix) ba_pass1_kernel(
       C += au * J.Jzu + av * J.Jzv;
       wacc += au * J.ru + av * J.rv;
     }
-    // 12x12 lower triangle (78) + vi, vj (12): warp-shuffle reduce, then 8 warps through smem
+    // 12x12 lower triangle (78) + vi, vj (12) = 90 per-pixel values (padded to 96): cross-lane transpose-reduce
+    // (48+24+12+6+3 = 93 shuffles instead of 90 x 5), then the 8 warps combine through shared memory
     {
+      float h[96];
       int l = 0;
 #pragma unroll
       for (int a = 0; a < 12; a++) {
 #pragma unroll
-        for (int b = 0; b <= a; b++) {
-          const float v = warp_sum(J.wu * J.Ju[a] * J.Ju[b] + J.wv * J.Jv[a] * J.Jv[b]);
-          if (lane == 0) red[warp][l] = v;
-          l++;
-        }
+        for (int b = 0; b <= a; b++) h[l++] = J.wu * J.Ju[a] * J.Ju[b] + J.wv * J.Jv[a] * J.Jv[b];
       }
 #pragma unroll
-      for (int a = 0; a < 12; a++) {
-        const float v = warp_sum(J.wu * J.ru * J.Ju[a] + J.wv * J.rv * J.Jv[a]);
-        if (lane == 0) red[warp][78 + a] = v;
-      }
+      for (int a = 0; a < 12; a++) h[78 + a] = J.wu * J.ru * J.Ju[a] + J.wv * J.rv * J.Jv[a];
+#pragma unroll
+      for (int a = 90; a < 96; a++) h[a] = 0.0f;
+      xr_step<48, 16>(h, lane);
+      xr_step<24, 8>(h, lane);
+      xr_step<12, 4>(h, lane);
+      xr_step<6, 2>(h, lane);
+      xr_step<3, 1>(h, lane);
+      const int col = ((lane >> 4) & 1) * 48 + ((lane >> 3) & 1) * 24 + ((lane >> 2) & 1) * 12 + ((lane >> 1) & 1) * 6 + (lane & 1) * 3;
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+        if (col + q < 90) red[warp][col + q] = h[q];
     }
     __syncthreads();
     if (tid < 90) {
@@ -409,7 +428,7 @@ __global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm,
   if (IN_SMEM) {
     for (long i = tid; i < (long)n * n + 2 * n; i += T) {
       double v = 0.0;
-#pragma unroll 4
+#pragma unroll
       for (int g = 0; g < kParts; g++) v += bf.sys[g * psz + i];
       if (i < (long)n * n) A[(i / n) * ld + (i % n)] = v; else y[i - (long)n * n] = v;      // y | dA are contiguous
     }

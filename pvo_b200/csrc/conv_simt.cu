@@ -341,6 +341,101 @@ __global__ void __launch_bounds__(128) conv3x3_small_kernel(const TI* __restrict
   }
 }
 
+// Half-precision variant of the grouped head convolution on the legacy tensor-core path (mma.sync m16n8k16, fp32
+// accumulate): M = 16 consecutive pixels of a tile row, K = 16 channels of one tap, N = 8 (the group's 2 outputs + 6
+// zero columns).  Tiny N makes tcgen05 pointless here (its smallest N is 16 and the operand stream would dominate);
+// the CUDA-core version above is FMA/LDS bound at ~4x the time of this one.  A comes from the same staged halo patch
+// via ldmatrix, B fragments are pre-arranged in shared memory.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void hmma16816(float c[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) conv3x3_heads_mma_kernel(const __half* __restrict__ in, int istride, int cin_g,
+                                                                const float* __restrict__ W, const float* __restrict__ bias,
+                                                                float* __restrict__ out, int ostride, int H, int Wd,
+                                                                int tiles_x, int tiles_y) {
+  constexpr int TH = 8, TW = 16, PH = TH + 2, PW = TW + 2, CH = 64, CG = 2;
+  constexpr int pstride = CH + 8;                               // halves per patch pixel (144 B: ldmatrix conflict-free)
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  __half* patch = reinterpret_cast<__half*>(sm_raw);
+  uint2* wfrag = reinterpret_cast<uint2*>(sm_raw + (((size_t)PH * PW * pstride * 2 + 15) & ~size_t(15)));   // [9][cin_g/16][32]
+  const int g = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int img = tile / (tiles_x * tiles_y);
+  const int r = tile - img * (tiles_x * tiles_y);
+  const int y0 = (r / tiles_x) * TH, x0 = (r % tiles_x) * TW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nchunk = cin_g / 16;
+  // B fragments: lane holds B[k = (lane%4)*2 + {0,1}][n = lane/4] and the same for k+8; only n < 2 is non-zero
+  for (int i = tid; i < 9 * nchunk * 32; i += 128) {
+    const int l = i & 31, tc = i >> 5;                          // tc = tap * nchunk + chunk
+    const int tap = tc / nchunk, chunk = tc - tap * nchunk;
+    const int n = l >> 2, k0 = (l & 3) * 2;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < CG) {
+      const float* wp = W + (((long)g * 9 + tap) * cin_g + chunk * 16) * CG + n;
+      w[0] = wp[(k0) * CG]; w[1] = wp[(k0 + 1) * CG]; w[2] = wp[(k0 + 8) * CG]; w[3] = wp[(k0 + 9) * CG];
+    }
+    const __half2 lo = __floats2half2_rn(w[0], w[1]), hi = __floats2half2_rn(w[2], w[3]);
+    wfrag[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+  }
+  float acc[2][4];                                               // two 16-pixel rows per warp (tile rows 2*warp, 2*warp+1)
+#pragma unroll
+  for (int t = 0; t < 2; t++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) acc[t][q] = 0.0f;
+  constexpr int cpp = CH * 2 / 16;
+  for (int cb = 0; cb < cin_g; cb += CH) {
+    __syncthreads();
+    for (int i = tid; i < PH * PW * cpp; i += 128) {
+      const int pp = i / cpp, ch = i - pp * cpp;
+      const int py = y0 - 1 + pp / PW, px = x0 - 1 + pp % PW;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (py >= 0 && py < H && px >= 0 && px < Wd)
+        v = __ldg(reinterpret_cast<const uint4*>(in + ((long)(img * H + py) * Wd + px) * istride + g * cin_g + cb) + ch);
+      *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(patch + (long)pp * pstride) + 16 * ch) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tap = 0; tap < 9; tap++) {
+#pragma unroll
+      for (int c = 0; c < CH; c += 16) {
+        const uint2 b = wfrag[(tap * nchunk + (cb + c) / 16) * 32 + lane];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const int ty = 2 * warp + t;
+          // ldmatrix x4: lanes 0-15 address pixel rows 0..15 at channel c, lanes 16-31 the same rows at channel c+8
+          const __half* ap = patch + (long)((ty + tap / 3) * PW + (lane & 15) + tap % 3) * pstride + c + ((lane >> 4) << 3);
+          uint32_t a0, a1, a2, a3;
+          ldmatrix_x4(a0, a1, a2, a3, ap);
+          hmma16816(acc[t], a0, a1, a2, a3, b.x, b.y);
+        }
+      }
+    }
+  }
+  // C fragment: c0,c1 = (row lane/4, cols (lane%4)*2, +1), c2,c3 = row + 8: the two real outputs sit in lanes with lane%4 == 0
+  if ((lane & 3) == 0) {
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const int y = y0 + 2 * warp + t;
+#pragma unroll
+      for (int hrow = 0; hrow < 2; hrow++) {
+        const int x = x0 + (lane >> 2) + 8 * hrow;
+        if (y < H && x < Wd) {
+          float* o = out + ((long)(img * H + y) * Wd + x) * ostride + g * CG;
+          o[0] = acc[t][2 * hrow] + bias[g * CG];
+          o[1] = acc[t][2 * hrow + 1] + bias[g * CG + 1];
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ small helpers
 // mean over the HW pixels of each image: in [E][HW][C] -> out [E][C]   (gru.py:26).  Two deterministic stages:
 // kColChunks partial sums per image (coalesced rows, 2 channels per thread), then a fixed-order final sum.
@@ -636,7 +731,12 @@ extern "C" int pvo_conv3x3_small(const void* in, int istride, int cin_g, const f
     conv3x3_small_kernel<TI, CGV><<<grid, 128, smem, s>>>((const TI*)in, istride, cin_g, W, bias, out, ostride, G, H, Wd, \
                                                           tiles_x, tiles_y, post);                                  \
   }
-  if (dtype == PVO_DTYPE_F32) { if (CG == 1) L(float, 1) else L(float, 2) }
+  if (dtype == PVO_DTYPE_F16 && CG == 2 && post == 0) {
+    const size_t sm2 = (((size_t)10 * 18 * (64 + 8) * 2 + 15) & ~size_t(15)) + sizeof(uint2) * 9 * (cin_g / 16) * 32;
+    cudaFuncSetAttribute(conv3x3_heads_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    conv3x3_heads_mma_kernel<<<grid, 128, sm2, s>>>((const __half*)in, istride, cin_g, W, bias, out, ostride, H, Wd, tiles_x, tiles_y);
+  }
+  else if (dtype == PVO_DTYPE_F32) { if (CG == 1) L(float, 1) else L(float, 2) }
   else if (dtype == PVO_DTYPE_F16) { if (CG == 1) L(__half, 1) else L(__half, 2) }
   else return PVO_ERR_UNSUPPORTED;
 #undef L
