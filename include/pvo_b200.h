@@ -122,7 +122,8 @@ int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels, const int
                   int ostride, int ooff, void* out2, const void* aux0, int aux_stride, const float* aux1, void* stream);
 /* grouped 3x3 convolution with <= 2 outputs per group: the four 128->2 heads and GraphAgg's eta head */
 int pvo_conv3x3_small(const void* in, int istride, int cin_g, const float* W, const float* bias, float* out,
-                      int ostride, int G, int CG, int nimg, int H, int Wd, int dtype, int post, void* stream);
+                      int ostride, int G, int CG, int nimg, int H, int Wd, int dtype, int post, const void* Wfrag,
+                      void* stream);
 int pvo_colmean(const void* in, float* out, float* scratch /* E*32*C floats */, int E, int HW, int C, int dtype,
                 void* stream);                                                                    /* gru.py:26 */
 /* flow-encoder input for the tensor-core path: (M,8) half motion features -> (M,64) with channel dxi*8+c = feature c

@@ -34,7 +34,7 @@ _SIGS = {
     'pvo_instance_norm': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'pvo_conv2d_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 7 +
                       [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
-    'pvo_conv3x3_small': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    'pvo_conv3x3_small': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p, c_void_p]),
     'pvo_colmean': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     'pvo_expand_x7': (c_int, [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
     'pvo_glo_reduce_matvec': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

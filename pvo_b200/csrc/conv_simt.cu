@@ -356,7 +356,7 @@ __device__ __forceinline__ void hmma16816(float c[4], uint32_t a0, uint32_t a1, 
 }
 
 __global__ void __launch_bounds__(128) conv3x3_heads_mma_kernel(const __half* __restrict__ in, int istride, int cin_g,
-                                                                const float* __restrict__ W, const float* __restrict__ bias,
+                                                                const uint2* __restrict__ Wfrag, const float* __restrict__ bias,
                                                                 float* __restrict__ out, int ostride, int H, int Wd,
                                                                 int tiles_x, int tiles_y) {
   constexpr int TH = 8, TW = 16, PH = TH + 2, PW = TW + 2, CH = 64, CG = 2;
@@ -371,19 +371,9 @@ __global__ void __launch_bounds__(128) conv3x3_heads_mma_kernel(const __half* __
   const int y0 = (r / tiles_x) * TH, x0 = (r % tiles_x) * TW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunk = cin_g / 16;
-  // B fragments: lane holds B[k = (lane%4)*2 + {0,1}][n = lane/4] and the same for k+8; only n < 2 is non-zero
-  for (int i = tid; i < 9 * nchunk * 32; i += 128) {
-    const int l = i & 31, tc = i >> 5;                          // tc = tap * nchunk + chunk
-    const int tap = tc / nchunk, chunk = tc - tap * nchunk;
-    const int n = l >> 2, k0 = (l & 3) * 2;
-    float w[4] = {0.f, 0.f, 0.f, 0.f};
-    if (n < CG) {
-      const float* wp = W + (((long)g * 9 + tap) * cin_g + chunk * 16) * CG + n;
-      w[0] = wp[(k0) * CG]; w[1] = wp[(k0 + 1) * CG]; w[2] = wp[(k0 + 8) * CG]; w[3] = wp[(k0 + 9) * CG];
-    }
-    const __half2 lo = __floats2half2_rn(w[0], w[1]), hi = __floats2half2_rn(w[2], w[3]);
-    wfrag[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-  }
+  // B fragments (packed once on the host, nn.pack_heads_mma): lane holds B[k = (lane%4)*2 + {0,1}][n = lane/4] and the
+  // same for k+8 as two half2; only n < 2 is non-zero
+  for (int i = tid; i < 9 * nchunk * 32; i += 128) wfrag[i] = __ldg(Wfrag + (long)g * 9 * nchunk * 32 + i);
   float acc[2][4];                                               // two 16-pixel rows per warp (tile rows 2*warp, 2*warp+1)
 #pragma unroll
   for (int t = 0; t < 2; t++)
@@ -547,7 +537,7 @@ __global__ void __launch_bounds__(384) glo_reduce_matvec_kernel(const float* __r
                                                                 const float* __restrict__ W, const float* __restrict__ b,
                                                                 float* __restrict__ out) {
   const int e = blockIdx.x;
-  __shared__ float g[128];
+  __shared__ __align__(16) float g[128];
   __shared__ float part3[3][128];
   {
     const int c = threadIdx.x & 127, grp = threadIdx.x >> 7;          // 3 groups of 128 threads split the partials
@@ -563,11 +553,17 @@ __global__ void __launch_bounds__(384) glo_reduce_matvec_kernel(const float* __r
   __syncthreads();
   if (threadIdx.x < 128) g[threadIdx.x] = ((part3[0][threadIdx.x] + part3[1][threadIdx.x]) + part3[2][threadIdx.x]) * inv_hw;
   __syncthreads();
-  const int row = threadIdx.x;
-  const float* w = W + (long)row * 128;
-  float s = b[row];
-  for (int c = 0; c < 128; c++) s = fmaf(w[c], g[c], s);
-  out[(long)e * 384 + row] = s;
+  // 384 x 128 mat-vec: warp w owns rows [32w, 32w+32); a row is one coalesced 512-byte read (float4 per lane)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4 gv = *reinterpret_cast<const float4*>(&g[4 * lane]);
+#pragma unroll 4
+  for (int r = 0; r < 32; r++) {
+    const int row = warp * 32 + r;
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (long)row * 128) + lane);
+    float s = wv.x * gv.x + wv.y * gv.y + wv.z * gv.z + wv.w * gv.w;
+    s = warp_sum(s);
+    if (lane == 0) out[(long)e * 384 + row] = s + b[row];
+  }
 }
 
 // scatter_mean over edges sharing a source frame (droid_net.py:83-88): out[k][pix][c] = mean_{e in row k} in[e][pix][c]
@@ -714,8 +710,10 @@ extern "C" int pvo_conv2d(const void* const* seg_ptr, const int* seg_channels, c
   return PVO_ERR_UNSUPPORTED;
 }
 
+// Wfrag (optional, half mode, CG == 2): the weights pre-arranged as mma.sync B fragments [G][9][cin_g/16][32] x {half2,half2}
 extern "C" int pvo_conv3x3_small(const void* in, int istride, int cin_g, const float* W, const float* bias, float* out,
-                                 int ostride, int G, int CG, int nimg, int H, int Wd, int dtype, int post, void* stream) {
+                                 int ostride, int G, int CG, int nimg, int H, int Wd, int dtype, int post, const void* Wfrag,
+                                 void* stream) {
   if (cin_g % 8 || (CG != 1 && CG != 2) || G < 1) return PVO_ERR_INVALID;
   if (nimg == 0) return PVO_OK;
   const size_t esz = dtype == PVO_DTYPE_F32 ? 4 : 2;
@@ -731,10 +729,10 @@ extern "C" int pvo_conv3x3_small(const void* in, int istride, int cin_g, const f
     conv3x3_small_kernel<TI, CGV><<<grid, 128, smem, s>>>((const TI*)in, istride, cin_g, W, bias, out, ostride, G, H, Wd, \
                                                           tiles_x, tiles_y, post);                                  \
   }
-  if (dtype == PVO_DTYPE_F16 && CG == 2 && post == 0) {
+  if (dtype == PVO_DTYPE_F16 && CG == 2 && post == 0 && Wfrag) {
     const size_t sm2 = (((size_t)10 * 18 * (64 + 8) * 2 + 15) & ~size_t(15)) + sizeof(uint2) * 9 * (cin_g / 16) * 32;
     cudaFuncSetAttribute(conv3x3_heads_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-    conv3x3_heads_mma_kernel<<<grid, 128, sm2, s>>>((const __half*)in, istride, cin_g, W, bias, out, ostride, H, Wd, tiles_x, tiles_y);
+    conv3x3_heads_mma_kernel<<<grid, 128, sm2, s>>>((const __half*)in, istride, cin_g, (const uint2*)Wfrag, bias, out, ostride, H, Wd, tiles_x, tiles_y);
   }
   else if (dtype == PVO_DTYPE_F32) { if (CG == 1) L(float, 1) else L(float, 2) }
   else if (dtype == PVO_DTYPE_F16) { if (CG == 1) L(__half, 1) else L(__half, 2) }

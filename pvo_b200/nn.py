@@ -53,6 +53,22 @@ def pack_small_weight(ws):
     return torch.stack([w.float().permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]) for w in ws]).contiguous()
 
 
+def pack_heads_mma(ws):
+    """list of G tensors (2,Cg,3,3) -> mma.sync m16n8k16 B fragments [G][9][Cg/16][32 lanes][4 halves]:
+    lane l holds B[k][n] for n = l//4 and k = (l%4)*2 + {0, 1, 8, 9}; only the group's 2 real outputs (n < 2) are non-zero."""
+    G = len(ws)
+    cg = ws[0].shape[1]
+    w = torch.stack([x.float().permute(2, 3, 1, 0).reshape(9, cg, 2) for x in ws])           # [G][9][Cg][2]
+    wp = torch.zeros(G, 9, cg // 16, 16, 8, device=w.device)
+    wp[..., :2] = w.reshape(G, 9, cg // 16, 16, 2)
+    lanes = torch.arange(32, device=w.device)
+    n = lanes // 4
+    k0 = (lanes % 4) * 2
+    kidx = torch.stack([k0, k0 + 1, k0 + 8, k0 + 9], dim=1)                                    # [32][4]
+    frag = wp[:, :, :, kidx, n[:, None].expand(32, 4)]                                         # [G][9][Cg/16][32][4]
+    return frag.half().contiguous()
+
+
 class _Conv:
     """One packed convolution (weights for both arithmetic paths)."""
 
@@ -119,6 +135,7 @@ class UpdateEngine:
                               torch.cat([g(h + '.0.bias') for h in HEAD_NAMES] + [g('agg.conv1.bias')], 0), tc=tc)
         self.heads2_W = pack_small_weight([g(h + '.2.weight') for h in HEAD_NAMES])
         self.heads2_b = torch.cat([g(h + '.2.bias') for h in HEAD_NAMES], 0).float().contiguous()
+        self.heads2_frag = pack_heads_mma([g(h + '.2.weight') for h in HEAD_NAMES]) if mode == 'fp16' else None
         self.c_agg2 = _Conv(g('agg.conv2.weight'), g('agg.conv2.bias'), tc=tc)
         self.eta_W = pack_small_weight([g('agg.eta.0.weight')])
         self.eta_b = g('agg.eta.0.bias').float().contiguous()
@@ -236,7 +253,7 @@ class UpdateEngine:
             conv2d(self.c_heads1, [(X, 128, 448)], E, H, W, dc, self.Hb, 640, 0, 1, use_tc=tc)
         with T('heads2'):
             check(L.pvo_conv3x3_small(ptr(self.Hb), 640, 128, ptr(self.heads2_W), ptr(self.heads2_b), ptr(self.head_out), 8,
-                                      4, 2, E, H, W, dc, 0, stream()), 'heads2')
+                                      4, 2, E, H, W, dc, 0, ptr(self.heads2_frag), stream()), 'heads2')
         if with_agg:
             with T('segment_mean'):
                 check(L.pvo_segment_mean(ptr(self.Hb), 640, 512, ptr(self.A), ptr(self.g_ptr), ptr(self.g_idx),
@@ -245,7 +262,7 @@ class UpdateEngine:
                 conv2d(self.c_agg2, [(self.A, 128, 128)], K, H, W, dc, self.a2, 128, 0, 1, use_tc=tc)
             with T('eta'):
                 check(L.pvo_conv3x3_small(ptr(self.a2), 128, 128, ptr(self.eta_W), ptr(self.eta_b), ptr(self.eta), 1, 1, 1,
-                                          K, H, W, dc, 1, stream()), 'eta')
+                                          K, H, W, dc, 1, None, stream()), 'eta')
 
     def run_upmask(self):
         """GraphAgg.upmask_disp (droid_net.py:76-77,93): only DroidNet.forward consumes it; FactorGraph.update
