@@ -144,6 +144,19 @@ int pvo_nchw_to_nhwc(const void* src, int sdtype, void* dst, int ddtype, int N, 
 int pvo_nhwc_to_nchw(const void* src, int sdtype, int sstride, int soff, void* dst, int ddtype, int N, int C, int HW,
                      void* stream);
 
+/* ---- Panoptic-FPN forward helpers (VPS_Module/detectron2/modeling/...), pixel-major activations ---------------- */
+int pvo_maxpool3s2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream);     /* resnet.py:356-359 */
+int pvo_subsample2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream);     /* strided 1x1 convs */
+int pvo_upsample_add(void* lat, const void* top, int N, int H, int W, int C, int Ht, int Wt, int dtype, void* stream);  /* fpn.py:139-147 */
+int pvo_upsample_bilinear(const void* in, void* out, int N, int H, int W, int C, int scale, int accumulate, int dtype,
+                          void* stream);                                                                 /* semantic_seg.py:199-201,239-241 */
+int pvo_group_norm(const void* in, void* out, const float* gamma, const float* beta, float* scratch, int N, int HW, int C,
+                   int group_size, float eps, int relu, int dtype, void* stream);                        /* semantic_seg.py:186-196 */
+/* combine_semantic_and_instance_outputs (panoptic_fpn.py:497-588) for a batch, one block per image, no host sync */
+int pvo_panoptic_combine(const void* masks, const float* scores, const long* classes, const long* order, const int* inst_off,
+                         const long* sem, int* pan, int* info_out, int* counts_out, int N, int HW, int num_sem, float overlap_thr,
+                         int stuff_area_thr, float score_thr, int thing_cat0, int max_info, void* stream);
+
 /* FactorGraph.update post-processing (factor_graph.py:250-283): target_cam, raw_mask, bin_mask, panoptic segment
  *   filter (:256-276, integer counting on the device instead of numpy on the host), delta_dy, sigmoid weights. */
 long pvo_update_post_workspace_ints(int E);

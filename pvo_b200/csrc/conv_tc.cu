@@ -89,8 +89,8 @@ __device__ __forceinline__ void xr_step(float* x, int lane) {
 }
 
 // ---- epilogues: store16(m, e, n, v, ok, tile, q): 16 consecutive output channels n.. of pixel m (image/edge e) ------
-struct EpBias {          // out = act(acc + bias)
-  const float* bias; __half* out; int ostride; int ooff; int Cout; int relu;
+struct EpBias {          // out = act(acc + bias); with a residual: relu(res + act(acc + bias))  (ResNet bottleneck tail)
+  const float* bias; __half* out; int ostride; int ooff; int Cout; int relu; const __half* res; int rstride;
   __device__ __forceinline__ void store16(long m, long, int n, const float* v, bool ok, int, int) const {
     if (n >= Cout || !ok) return;
     __half* o = out + m * ostride + ooff + n;
@@ -99,6 +99,12 @@ struct EpBias {          // out = act(acc + bias)
       ld16f(bias + n, b);
 #pragma unroll
       for (int j = 0; j < 16; j++) { x[j] = v[j] + b[j]; if (relu) x[j] = fmaxf(x[j], 0.0f); }
+      if (res) {
+        float r[16];
+        ld16h<true>(res + m * rstride + n, r);
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] = fmaxf(x[j] + r[j], 0.0f);
+      }
       st16h(o, x);
     } else {
 #pragma unroll
@@ -106,6 +112,7 @@ struct EpBias {          // out = act(acc + bias)
         if (n + j < Cout) {
           float x = v[j] + __ldg(bias + n + j);
           if (relu) x = fmaxf(x, 0.0f);
+          if (res) x = fmaxf(x + __half2float(res[m * rstride + n + j]), 0.0f);
           o[j] = __float2half_rn(x);
         }
       }
@@ -335,6 +342,7 @@ int dispatch_bn(const TcParams& p0, const Epi& epi, int bn, cudaStream_t s) {
 // Segments: pixel-major fp16 tensors (nimg*H*W, stride) whose channel slices are concatenated into the conv input;
 // seg_channels[s] need not be a multiple of 64 (the tail is zero-filled by TMA; the packed weights carry zeros there).
 // Wh: fp16 [Cout][taps * sum_s ceil64(seg_channels[s])], K ordered (tap, segment, channel) -- pack_conv_weight_tc.
+// epilogues 0/1 accept an optional residual in aux0 (row stride aux_stride): out = relu(residual + act(conv)).
 // epilogue: 0 bias, 1 bias+ReLU, 2 per-tile sums of sigmoid(.)*net, 3 GRU z|r, 4 GRU q + state update (same meaning and aux pointers as pvo_conv2d).
 extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels, const int* seg_stride, int nseg,
                              const void* Wh, const float* bias, int Cout, int KH, int KW, int nimg, int H, int Wd,
@@ -380,7 +388,7 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
   switch (epilogue) {
     case 0: case 1:
       if ((ostride * 2) % 16 || (ooff * 2) % 16) return PVO_ERR_INVALID;
-      return dispatch_bn(p, EpBias{bias, (__half*)out, ostride, ooff, Cout, epilogue}, bn, s);
+      return dispatch_bn(p, EpBias{bias, (__half*)out, ostride, ooff, Cout, epilogue, (const __half*)aux0, aux_stride}, bn, s);
     case 2:      // out = float partial sums [nimg * tiles][4][Cout] (reduced by pvo_glo_reduce_matvec)
       if (Cout % 32) return PVO_ERR_INVALID;
       return dispatch_bn(p, EpGloSum{bias, (const __half*)aux0, aux_stride, (float*)out, Cout}, bn, s);

@@ -47,7 +47,7 @@ def system_view(ws, E, nframes, P, K, HW):
 
 
 def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only,
-               interleaved=False, group=None, workspace=None):
+               interleaved=False, group=None, workspace=None, max_degree=0):
     """droid_backends.ba for a rank's shard of the edges: assemble -> all-reduce -> solve + update, per iteration.
     poses must be identical on all ranks on entry and are identical on exit."""
     E = ii.shape[0]
@@ -60,7 +60,7 @@ def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, 
     L = _lib.lib()
 
     def call(phase, reuse):
-        flags = (1 if reuse else 0) | (phase << 1)
+        flags = (1 if reuse else 0) | (phase << 1) | ((int(max_degree) & 0xFFF) << 8)
         check(L.pvo_ba(ptr(poses), ptr(disps), ptr(intrinsics), ptr(targets), ptr(weights), ptr(eta), ptr(ii), ptr(jj), E,
                        nframes, ht, wd, int(t0), int(t1), K, 1, float(lm), float(ep), 1 if motion_only else 0,
                        1 if interleaved else 0, ptr(dx), ptr(dz), ptr(ws), ws.numel(), flags, stream()), 'ba',
@@ -77,9 +77,9 @@ def attach(fg, rank, world, frames_per_rank, group=None):
     video = fg.video
 
     def ba(target, weight, eta, ii, jj, t0=1, t1=None, itrs=2, lm=1e-4, ep=0.1, motion_only=False, interleaved=False,
-           reuse_plan=False):
+           reuse_plan=False, max_degree=0):
         out = ba_sharded(video.poses, video.disps, video.intrinsics[0].contiguous(), target, weight, eta, ii, jj, t0, t1,
-                         itrs, lm, ep, motion_only, interleaved=interleaved, group=group)
+                         itrs, lm, ep, motion_only, interleaved=interleaved, group=group, max_degree=max_degree)
         check(_lib.lib().pvo_clamp_min(ptr(video.disps), video.disps.numel(), 0.001, stream()), 'clamp_min')
         return out
     video.ba = ba

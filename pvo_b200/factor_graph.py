@@ -233,7 +233,10 @@ class FactorGraph:
         if entry == 'warm':
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # with a sharded graph the NCCL all-reduce of the BA system is captured too; thread_local keeps the
+            # process group's watchdog thread from tripping the capture
+            mode = 'thread_local' if getattr(self, 'world', 1) > 1 else 'global'
+            with torch.cuda.graph(g, capture_error_mode=mode):
                 self._update(t0, t1, itrs, use_inactive, EP, motion_only)
             c['graphs'][key] = g
             entry = g

@@ -1,0 +1,83 @@
+"""Known-answer tests lifted from Detectron2's own suite (the literal expectations, VPS_Module/tests/...) that pin the
+pieces of the Panoptic-FPN oracle that CAN be pinned without importing detectron2, plus a
+smoke run of the whole restated inference path."""
+import numpy as np
+import torch
+import torchvision
+
+from oracle import panoptic_fpn as ofpn
+
+
+def test_roi_align_known_answer():
+    """tests/layers/test_roi_align.py:14-45: 5x5 ramp, box [1,1,3,3], 4x4 output, aligned vs legacy."""
+    x = torch.arange(25, dtype=torch.float32).reshape(1, 1, 5, 5)
+    rois = torch.tensor([[0, 1, 1, 3, 3]], dtype=torch.float32)
+    old = torchvision.ops.roi_align(x, rois, (4, 4), 1.0, 0, aligned=False)
+    new = torchvision.ops.roi_align(x, rois, (4, 4), 1.0, 0, aligned=True)
+    old_results = [[7.5, 8, 8.5, 9], [10, 10.5, 11, 11.5], [12.5, 13, 13.5, 14], [15, 15.5, 16, 16.5]]
+    correct_results = [[4.5, 5.0, 5.5, 6.0], [7.0, 7.5, 8.0, 8.5], [9.5, 10.0, 10.5, 11.0], [12.0, 12.5, 13.0, 13.5]]
+    assert np.allclose(old.flatten().numpy(), np.asarray(old_results).flatten())
+    assert np.allclose(new.flatten().numpy(), np.asarray(correct_results).flatten())
+
+
+def test_anchor_grid_known_answer():
+    """tests/modeling/test_anchor_generator.py:14-42 (sizes [32,64], ratios [.25,1,4], stride 4, 1x2 feature map),
+    restated with the oracle's cell_anchors / grid construction."""
+    import math
+    cell = []
+    for size in (32, 64):
+        for ratio in (0.25, 1.0, 4.0):
+            w = math.sqrt(size * size / ratio)
+            h = ratio * w
+            cell.append([-w / 2, -h / 2, w / 2, h / 2])
+    cell = torch.tensor(cell)
+    shifts = torch.tensor([[0., 0., 0., 0.], [4., 0., 4., 0.]])
+    anchors = (shifts.view(-1, 1, 4) + cell.view(1, -1, 4)).reshape(-1, 4)
+    expected = torch.tensor([[-32.0, -8.0, 32.0, 8.0], [-16.0, -16.0, 16.0, 16.0], [-8.0, -32.0, 8.0, 32.0],
+                             [-64.0, -16.0, 64.0, 16.0], [-32.0, -32.0, 32.0, 32.0], [-16.0, -64.0, 16.0, 64.0],
+                             [-28.0, -8.0, 36.0, 8.0], [-12.0, -16.0, 20.0, 16.0], [-4.0, -32.0, 12.0, 32.0],
+                             [-60.0, -16.0, 68.0, 16.0], [-28.0, -32.0, 36.0, 32.0], [-12.0, -64.0, 20.0, 64.0]])
+    assert torch.allclose(anchors, expected)
+    # the oracle's own generator, one size per level, same construction
+    a = ofpn.grid_anchors(1, 2, 4, 32)
+    assert a.shape == (6, 4) and torch.allclose(a[0], torch.tensor([-32 / math.sqrt(2), -8 * math.sqrt(2), 32 / math.sqrt(2), 8 * math.sqrt(2)]), atol=1e-4)
+    assert torch.allclose(a[3] - a[0], torch.tensor([4., 0., 4., 0.]))
+
+
+def test_box2box_round_trip():
+    """tests/modeling/test_box2box_transform.py:17-31: apply_deltas(get_deltas(src, dst), src) == dst."""
+    g = torch.Generator().manual_seed(0)
+    weights = (5.0, 5.0, 10.0, 10.0)
+
+    def random_boxes(n):
+        b = torch.rand(n, 4, generator=g) * 100
+        b[:, 2:] += b[:, :2] + 1
+        return b
+    src, dst = random_boxes(10), random_boxes(10)
+    sw, sh = src[:, 2] - src[:, 0], src[:, 3] - src[:, 1]
+    scx, scy = src[:, 0] + 0.5 * sw, src[:, 1] + 0.5 * sh
+    dw, dh = dst[:, 2] - dst[:, 0], dst[:, 3] - dst[:, 1]
+    dcx, dcy = dst[:, 0] + 0.5 * dw, dst[:, 1] + 0.5 * dh
+    deltas = torch.stack([weights[0] * (dcx - scx) / sw, weights[1] * (dcy - scy) / sh,
+                          weights[2] * torch.log(dw / sw), weights[3] * torch.log(dh / sh)], dim=1)
+    assert torch.allclose(ofpn.apply_deltas(deltas, src, weights), dst, atol=1e-4)
+
+
+def test_restated_inference_runs_and_is_consistent():
+    sd = ofpn.init_params(0)
+    g = torch.Generator().manual_seed(2)
+    images = [torch.randint(0, 256, (3, 96, 160), generator=g).float(), torch.randint(0, 256, (3, 80, 128), generator=g).float()]
+    dbg = {}
+    with torch.no_grad():
+        res = ofpn.inference(sd, images, debug=dbg)
+    assert dbg['feats']['p2'].shape == (2, 256, 24, 40) and dbg['feats']['p6'].shape == (2, 256, 2, 3)
+    assert dbg['sem'].shape == (2, 12, 96, 160)
+    for r, im in zip(res, images):
+        h, w = im.shape[-2:]
+        pan, segs = r['panoptic_seg']
+        assert pan.shape == (h, w) and pan.dtype == torch.int32
+        ids = set(torch.unique(pan).tolist()) - {0}
+        assert ids == set(s['id'] for s in segs)
+        for s in segs:
+            assert s['category_id'] == s['id'] // 10000
+        assert r['instances']['pred_masks'].shape[1:] == (h, w)
