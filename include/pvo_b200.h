@@ -157,6 +157,16 @@ int pvo_panoptic_combine(const void* masks, const float* scores, const long* cla
                          const long* sem, int* pan, int* info_out, int* counts_out, int N, int HW, int num_sem, float overlap_thr,
                          int stuff_area_thr, float score_thr, int thing_cat0, int max_info, void* stream);
 
+/* ROIPooler (modeling/poolers.py:189-235: level by box size, canonical 224 @ level 4) + ROIAlignV2
+ * (layers/roi_align.py:49-58 -> torchvision roi_align aligned=True, sampling_ratio=0) over the 4 pixel-major pyramid
+ * levels p2..p5 (strides 4..32).  rois (R,5) = {image index, x0, y0, x1, y1} float32; out (R, S, S, C) pixel-major. */
+int pvo_roi_align_fpn(const void* const* feats, const int* Hs, const int* Ws, int C, const float* rois, int R, int S, void* out,
+                      int dtype, void* stream);
+/* Greedy NMS for G independent groups of n <= 1024 boxes sorted by descending score (layers/nms.py:9-22 batched_nms ->
+ * torchvision nms per category): keep[g][i] = 1 iff box i is valid and no kept earlier box overlaps it with IoU > thr. */
+int pvo_nms_groups(const float* boxes /*(G,n,4)*/, const unsigned char* valid /*(G,n)*/, int G, int n, float thr,
+                   unsigned char* keep /*(G,n)*/, void* stream);
+
 /* FactorGraph.update post-processing (factor_graph.py:250-283): target_cam, raw_mask, bin_mask, panoptic segment
  *   filter (:256-276, integer counting on the device instead of numpy on the host), delta_dy, sigmoid weights. */
 long pvo_update_post_workspace_ints(int E);

@@ -90,8 +90,11 @@ def param_shapes():
 
 
 def init_params(seed=0):
-    """Seeded c2_msra-style weights; FrozenBN stats (mean 0, var 1, gamma 1, beta 0) perturbed by N(0, 0.1)
-    (SURVEY.md section 8(d) config 4).  Head outputs are scaled so that proposals / detections are non-degenerate."""
+    """Seeded random weights with per-layer gains chosen so that activations stay O(1) through all ~55 layers (raw pixel
+    input has std ~60: the stem is scaled down by 64; bottleneck tails and un-rectified convs use smaller gains so the
+    residual stream does not grow) -- the fp16 path must not overflow where a trained checkpoint would not -- and so that
+    the RPN / box / mask heads give non-degenerate proposals, detections and masks.  FrozenBN statistics: mean 0, var 1,
+    gamma 1, beta 0, each perturbed by N(0, 0.1)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for name, shape in param_shapes().items():
@@ -103,11 +106,22 @@ def init_params(seed=0):
             sd[name] = 0.1 * torch.randn(shape, generator=g)
         elif name.endswith('.weight'):
             fan = shape[1] * (shape[2] * shape[3] if len(shape) == 4 else 1)
-            sd[name] = torch.randn(shape, generator=g) * (2.0 / fan) ** 0.5 * (0.7 if 'res' in name and 'conv3' in name else 1.0)
+            gain = 2.0 ** 0.5
+            if 'stem' in name:
+                gain = 2.0 ** 0.5 / 64.0
+            elif 'bottom_up' in name and 'conv3' in name:
+                gain = 0.5
+            elif 'shortcut' in name or 'fpn_' in name:
+                gain = 1.0
+            elif 'objectness' in name or 'predictor.weight' in name:
+                gain = 2.0
+            elif 'cls_score' in name:
+                gain = 0.4
+            elif 'anchor_deltas' in name or 'bbox_pred' in name:
+                gain = 0.3
+            sd[name] = torch.randn(shape, generator=g) * gain / fan ** 0.5
         else:
             sd[name] = 0.05 * torch.randn(shape, generator=g)
-    sd['roi_heads.box_predictor.bbox_pred.weight'] *= 0.2
-    sd['proposal_generator.rpn_head.anchor_deltas.weight'] *= 0.2
     return sd
 
 

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(1024) panoptic_combine_kernel(const unsigned c
     area = block_sum_int(area, sh);
     inter = block_sum_int(inter, sh);
     if (area == 0) continue;
-    if ((float)inter * 1.0f / (float)area > overlap_thr) continue;
+    if ((double)inter / (double)area > (double)overlap_thr) continue;       // the reference divides Python numbers (doubles)
     cur++;
     const int cat = thing_cat0 + (int)classes[r];
     const int id = cat * 10000 + cur;

@@ -72,12 +72,12 @@ def pack_heads_mma(ws):
 class _Conv:
     """One packed convolution (weights for both arithmetic paths)."""
 
-    def __init__(self, w, b, cin_pad=None, tc=False, segs=None):
+    def __init__(self, w, b, cin_pad=None, tc=False, segs=None, simt=True):
         self.cout, self.cin = w.shape[0], cin_pad or w.shape[1]
         self.kh, self.kw = w.shape[2], w.shape[3]
         self.pad = self.kh // 2
-        self.W = pack_conv_weight(w, cin_pad)
-        self.wstride = self.W.shape[1]
+        self.W = pack_conv_weight(w, cin_pad) if simt else None
+        self.wstride = self.W.shape[1] if simt else 0
         self.bias = b.float().contiguous()
         self.Wh = pack_conv_weight_tc(w, segs) if tc else None
 

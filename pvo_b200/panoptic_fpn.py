@@ -12,15 +12,15 @@ Where the time goes and what runs where:
     accumulate, bias / ReLU / bottleneck residual fused in the epilogue.  FC layers view the (R, C) matrix as a 16-wide
     image so the same kernel serves them.  The 7x7/3-channel stem runs on the CUDA-core conv.
   * max-pool, strided sampling, top-down nearest+add, GroupNorm+ReLU, bilinear upsampling -> csrc/fpn_ops.cu.
-  * ROIAlign, NMS, top-k: torchvision / torch, exactly the external ops the reference calls
-    (layers/roi_align.py:3,49-58, layers/nms.py:4,9-22).
+  * ROIAlign over the pyramid and the per-level / per-class NMS -> csrc/roi_ops.cu (pixel-major features, fp32 box
+    arithmetic; the reference calls torchvision's NCHW ops, layers/roi_align.py:49-58, layers/nms.py:9-22); top-k, sort
+    and the box decode stay torch tensor ops, batched over images.
   * panoptic merge: one CUDA block per image (csrc/fpn_ops.cu), no per-instance host syncs.
 """
 import math
 
 import torch
 import torch.nn.functional as F
-import torchvision
 
 from . import _lib
 from . import nn as pnn
@@ -59,12 +59,41 @@ def clip_boxes(b, size):
     return b
 
 
+def grid_anchors(h, w, stride, size, device):
+    """anchor_generator.py DefaultAnchorGenerator: 3 aspect ratios per cell, area size^2, anchor index fastest"""
+    cell = []
+    for ratio in (0.5, 1.0, 2.0):
+        aw = math.sqrt(size * size / ratio)
+        ah = ratio * aw
+        cell.append([-aw / 2.0, -ah / 2.0, aw / 2.0, ah / 2.0])
+    cell = torch.tensor(cell, device=device)
+    sx = torch.arange(0, w * stride, stride, dtype=torch.float32, device=device)
+    sy = torch.arange(0, h * stride, stride, dtype=torch.float32, device=device)
+    yy, xx = torch.meshgrid(sy, sx, indexing='ij')
+    shifts = torch.stack([xx.reshape(-1), yy.reshape(-1), xx.reshape(-1), yy.reshape(-1)], dim=1)
+    return (shifts.view(-1, 1, 4) + cell.view(1, -1, 4)).reshape(-1, 4)
+
+
+def paste_masks(masks, boxes, img_h, img_w, threshold=0.5):
+    """layers/mask_ops.py:17-152: bilinear resample of the 28x28 probabilities into the box, thresholded -> (R,H,W) bool"""
+    R = masks.shape[0]
+    if R == 0:
+        return torch.zeros(0, img_h, img_w, dtype=torch.bool, device=masks.device)
+    x0, y0, x1, y1 = torch.split(boxes, 1, dim=1)
+    img_y = (torch.arange(0, img_h, dtype=torch.float32, device=masks.device) + 0.5 - y0) / (y1 - y0) * 2 - 1
+    img_x = (torch.arange(0, img_w, dtype=torch.float32, device=masks.device) + 0.5 - x0) / (x1 - x0) * 2 - 1
+    grid = torch.stack([img_x[:, None, :].expand(R, img_h, img_w), img_y[:, :, None].expand(R, img_h, img_w)], dim=3)
+    return F.grid_sample(masks.float(), grid, align_corners=False)[:, 0] >= threshold
+
+
 class PanopticFPN:
-    def __init__(self, state_dict, device='cuda'):
+    def __init__(self, state_dict, device='cuda', use_cuda_graph=True):
         self.device = torch.device(device)
+        self.use_cuda_graph = use_cuda_graph     # replay the fixed-shape part (backbone, FPN, sem-seg and RPN heads) as one graph
+        self._graphs = {}
         sd = {k: v.detach().to(self.device).float() for k, v in state_dict.items()}
         self.cv = {}
-        tc = lambda w, b: pnn._Conv(w, b, tc=True)
+        tc = lambda w, b: pnn._Conv(w, b, tc=True, simt=False)
         w, b = _fold(sd, 'backbone.bottom_up.stem.conv1')
         self.cv['stem'] = pnn._Conv(w, b)                                        # 7x7, 3 channels: CUDA-core path
         for si, (nb, mid, cout) in enumerate(RES_STAGES):
@@ -87,7 +116,9 @@ class PanopticFPN:
                                            sd['proposal_generator.rpn_head.anchor_deltas.weight']], 0),
                                 torch.cat([sd['proposal_generator.rpn_head.objectness_logits.bias'],
                                            sd['proposal_generator.rpn_head.anchor_deltas.bias']], 0))
-        self.cv['fc1'] = tc(sd['roi_heads.box_head.fc1.weight'][:, :, None, None], sd['roi_heads.box_head.fc1.bias'])
+        fc1 = sd['roi_heads.box_head.fc1.weight']                                # columns (c, y, x) -> (y, x, c): pixel-major ROIAlign output
+        fc1 = fc1.view(fc1.shape[0], 256, 7, 7).permute(0, 2, 3, 1).reshape(fc1.shape[0], -1)
+        self.cv['fc1'] = tc(fc1[:, :, None, None].contiguous(), sd['roi_heads.box_head.fc1.bias'])
         self.cv['fc2'] = tc(sd['roi_heads.box_head.fc2.weight'][:, :, None, None], sd['roi_heads.box_head.fc2.bias'])
         self.cv['box_out'] = tc(torch.cat([sd['roi_heads.box_predictor.cls_score.weight'], sd['roi_heads.box_predictor.bbox_pred.weight']], 0)[:, :, None, None],
                                 torch.cat([sd['roi_heads.box_predictor.cls_score.bias'], sd['roi_heads.box_predictor.bbox_pred.bias']], 0))
@@ -180,6 +211,34 @@ class PanopticFPN:
         self.N = N
         return out
 
+    def dense(self, x):
+        """backbone + FPN + sem-seg head + RPN head: ~75 launches whose shapes depend only on the batch shape, so the
+        second call with a given shape captures them into a CUDA graph and later calls replay it (the per-launch host cost,
+        tensor-map encoding included, would otherwise exceed the GPU time).  Outputs live in the graph's buffers until the
+        next call with the same shape."""
+        def run(inp):
+            feats = self.backbone(inp)
+            return feats, self.sem_seg(feats), self.rpn_head(feats)
+        if not self.use_cuda_graph:
+            return run(x)
+        key = tuple(x.shape)
+        e = self._graphs.get(key)
+        if e is None:
+            self._graphs[key] = 'warm'
+            return run(x)
+        if e == 'warm':
+            xs = x.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = run(xs)
+            e = self._graphs[key] = (g, xs, out)
+        g, xs, out = e
+        xs.copy_(x)
+        g.replay()
+        self.N = x.shape[0]
+        return out
+
     def sem_seg(self, feats):
         """-> logits (N, H, W, 16) half at input resolution (channels 12..15 are padding)"""
         L = _lib.lib()
@@ -219,46 +278,183 @@ class PanopticFPN:
             res.append((o[..., :3], o[..., 3:15].reshape(N, h, w, 3, 4)))
         return res
 
+    def nms_groups(self, boxes, valid, thresh):
+        """boxes (G,n,4) float32, each group sorted by descending score; valid (G,n) bool -> keep (G,n) bool"""
+        G, n = valid.shape
+        boxes = boxes.float().contiguous()
+        v = valid.to(torch.uint8).contiguous()
+        keep = torch.empty(G, n, dtype=torch.uint8, device=self.device)
+        check(_lib.lib().pvo_nms_groups(ptr(boxes), ptr(v), G, n, float(thresh), ptr(keep), stream()), 'nms_groups')
+        return keep.bool()
+
+    def _limits(self, image_sizes):
+        hw = torch.tensor(image_sizes, dtype=torch.float32, device=self.device)
+        return hw[:, [1, 0, 1, 0]]                                     # per image clip limits for (x0, y0, x1, y1)
+
     def proposals(self, rpn_out, image_sizes, pre_nms_topk=1000, post_nms_topk=1000, nms_thresh=0.7):
-        """proposal_utils.py:22-126"""
-        from oracle_free_anchors import grid_anchors        # placeholder, replaced below
-        raise NotImplementedError
+        """find_top_rpn_proposals (proposal_utils.py:22-126): per-level top-k, decode, clip, drop empty, per-level NMS,
+        best post_nms_topk per image -- batched over images and levels, one device->host read (the counts)."""
+        N, P = self.N, pre_nms_topk
+        lim = self._limits(image_sizes)[:, None, :]
+        zero = torch.zeros((), device=self.device)
+        B, S, V = [], [], []
+        for (lg, dl), stride, size in zip(rpn_out, (4, 8, 16, 32, 64), (32, 64, 128, 256, 512)):
+            h, w = lg.shape[1:3]
+            anchors = grid_anchors(h, w, stride, size, self.device)
+            lg, dl = lg.reshape(N, -1), dl.reshape(N, -1, 4)
+            k = min(P, lg.shape[1])
+            top, idx = lg.topk(k, dim=1)                               # descending
+            d = torch.gather(dl, 1, idx[..., None].expand(-1, -1, 4))
+            boxes = apply_deltas(d.reshape(-1, 4), anchors[idx].reshape(-1, 4), (1.0, 1.0, 1.0, 1.0)).view(N, k, 4)
+            valid = torch.isfinite(boxes).all(dim=-1) & torch.isfinite(top)
+            boxes = torch.minimum(torch.maximum(boxes, zero), lim)
+            valid &= ((boxes[..., 2] - boxes[..., 0]) > 0) & ((boxes[..., 3] - boxes[..., 1]) > 0)   # min_box_size = 0
+            B.append(F.pad(boxes, (0, 0, 0, P - k)))
+            S.append(F.pad(top, (0, P - k), value=float('-inf')))
+            V.append(F.pad(valid, (0, P - k)))
+        boxes, scores, valid = torch.stack(B, 1), torch.stack(S, 1), torch.stack(V, 1)            # (N, 5, P, ...)
+        G = len(B)
+        keep = self.nms_groups(boxes.view(N * G, P, 4), valid.view(N * G, P), nms_thresh).view(N, G * P)
+        sc = torch.where(keep, scores.view(N, G * P), torch.full_like(scores.view(N, G * P), float('-inf')))
+        top, idx = sc.topk(min(post_nms_topk, G * P), dim=1)
+        bx = torch.gather(boxes.view(N, G * P, 4), 1, idx[..., None].expand(-1, -1, 4))
+        counts = keep.sum(dim=1).clamp(max=post_nms_topk).tolist()
+        return [(bx[n, :c], top[n, :c]) for n, c in enumerate(counts)]
+
+    def detections(self, cls, reg, props, image_sizes, score_thresh=0.05, nms_thresh=0.5, topk=100):
+        """FastRCNNOutputLayers.inference (fast_rcnn.py:117-170): softmax, per-class decode + clip, score threshold,
+        per-class NMS, best `topk` per image -> per image (boxes, scores, classes)"""
+        N, K = len(props), NUM_THING
+        counts = [p[0].shape[0] for p in props]
+        P = max(max(counts), 1)
+        cnt = torch.tensor(counts, device=self.device)
+        img = torch.repeat_interleave(torch.arange(N, device=self.device), cnt)
+        rank = torch.arange(sum(counts), device=self.device) - (torch.cumsum(cnt, 0) - cnt)[img]
+        pb = torch.cat([p[0] for p in props])
+        boxes = apply_deltas(reg, pb, (10.0, 10.0, 5.0, 5.0))
+        scores = F.softmax(cls, dim=-1)
+        ok = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
+        lim = self._limits(image_sizes)[img][:, None, :]
+        boxes = torch.minimum(torch.maximum(boxes.view(-1, K, 4), torch.zeros((), device=self.device)), lim)
+        sp = torch.zeros(N, P, K, device=self.device)
+        bp = torch.zeros(N, P, K, 4, device=self.device)
+        sp[img, rank] = torch.where(ok[:, None], scores[:, :K], torch.zeros_like(scores[:, :K]))
+        bp[img, rank] = boxes
+        ss, order = sp.permute(0, 2, 1).sort(dim=2, descending=True)                          # (N, K, P)
+        bs = torch.gather(bp.permute(0, 2, 1, 3), 2, order[..., None].expand(-1, -1, -1, 4))
+        keep = self.nms_groups(bs.reshape(N * K, P, 4), (ss > score_thresh).reshape(N * K, P), nms_thresh).view(N, K * P)
+        sc = torch.where(keep, ss.reshape(N, K * P), torch.full_like(ss.reshape(N, K * P), -1.0))
+        top, idx = sc.topk(min(topk, K * P), dim=1)
+        bx = torch.gather(bs.reshape(N, K * P, 4), 1, idx[..., None].expand(-1, -1, 4))
+        cl = torch.div(idx, P, rounding_mode='floor')
+        kept = keep.sum(dim=1).clamp(max=topk).tolist()
+        return [(bx[n, :c], top[n, :c], cl[n, :c]) for n, c in enumerate(kept)]
 
     # ------------------------------------------------------------------------------------------ ROI heads
-    def _nchw(self, feats, name):
-        x, h, w = feats[name]
-        return x.view(self.N, h, w, 256).permute(0, 3, 1, 2)
-
     def roi_pool(self, feats, boxes_per_image, out_size):
-        """poolers.py ROIPooler (ROIAlignV2 over p2..p5, canonical 224 @ level 4) -> (R, 256, S, S) half"""
+        """ROIPooler (poolers.py:189-235): ROIAlignV2 over p2..p5, level by box size -> (R, S, S, 256) half, pixel-major"""
         rois = torch.cat([torch.cat([torch.full((b.shape[0], 1), float(i), device=self.device), b.float()], dim=1)
-                          for i, b in enumerate(boxes_per_image)])
-        sizes = torch.sqrt(((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2])).clamp(min=0))
-        lv = torch.floor(4 + torch.log2(sizes / 224 + 1e-8)).clamp(min=2, max=5).to(torch.int64) - 2
-        out = torch.zeros(rois.shape[0], 256, out_size, out_size, dtype=torch.float16, device=self.device)
-        for l, (name, scale) in enumerate(zip(('p2', 'p3', 'p4', 'p5'), (1 / 4, 1 / 8, 1 / 16, 1 / 32))):
-            idx = (lv == l).nonzero().reshape(-1)
-            if idx.numel():
-                out[idx] = torchvision.ops.roi_align(self._nchw(feats, name), rois[idx].half(), (out_size, out_size),
-                                                     spatial_scale=scale, sampling_ratio=0, aligned=True)
+                          for i, b in enumerate(boxes_per_image)]).contiguous()
+        R = rois.shape[0]
+        out = self._buf(R, out_size, out_size, 256)
+        lv = [feats['p%d' % l] for l in (2, 3, 4, 5)]
+        fp = (_lib.c_void_p * 4)(*[t[0].data_ptr() for t in lv])
+        check(_lib.lib().pvo_roi_align_fpn(fp, _lib.int_array([t[1] for t in lv]), _lib.int_array([t[2] for t in lv]), 256, ptr(rois), R,
+                                           out_size, ptr(out), _lib.F16, stream()), 'roi_align_fpn')
         return out
 
     def box_head(self, pooled):
-        """(R,256,7,7) -> class logits (R,4), box deltas (R,12) float32"""
-        x = self._matmul('fc1', pooled.reshape(pooled.shape[0], -1), relu=True)
+        """(R,7,7,256) -> class logits (R,4), box deltas (R,12) float32"""
+        if pooled.shape[0] == 0:
+            return torch.zeros(0, NUM_THING + 1, device=self.device), torch.zeros(0, 4 * NUM_THING, device=self.device)
+        x = self._matmul('fc1', pooled.view(pooled.shape[0], -1), relu=True)
         x = self._matmul('fc2', x, relu=True)
         o = self._matmul('box_out', x, cpad=16).float()
         return o[:, :NUM_THING + 1], o[:, NUM_THING + 1:NUM_THING + 1 + 4 * NUM_THING]
 
     def mask_head(self, pooled):
-        """(R,256,14,14) -> mask logits (R, 3, 28, 28) float32"""
+        """(R,14,14,256) -> mask logits (R, 3, 28, 28) float32"""
         R = pooled.shape[0]
         if R == 0:
             return torch.zeros(0, NUM_THING, 28, 28, device=self.device)
-        x = pooled.permute(0, 2, 3, 1).reshape(R * 196, 256).contiguous()
+        x = pooled.view(R * 196, 256)
         for j in range(1, 5):
             x = self._conv('mask_fcn%d' % j, x, R, 14, 14, relu=True)
         x = self._matmul('deconv', x, relu=True)                                   # (R*196, 4*256): sub-positions (dy,dx)
         x = self._matmul('mask_pred', x.reshape(R * 196 * 4, 256), cpad=16).float()[:, :NUM_THING]
-        x = x.view(R, 14, 14, 2, 2, NUM_THING).permute(0, 5, 1, 3, 2, 4).reshape(R, NUM_THING, 28, 28)
-        return x
+        return x.view(R, 14, 14, 2, 2, NUM_THING).permute(0, 5, 1, 3, 2, 4).reshape(R, NUM_THING, 28, 28)
+
+    # ------------------------------------------------------------------------------------------ panoptic merge
+    def combine(self, dets_masks, sem_labels, overlap_threshold=0.5, stuff_area_thresh=4096, instances_score_thresh=0.5):
+        """combine_semantic_and_instance_outputs (panoptic_fpn.py:497-588) for images of one size, one launch.
+        dets_masks: per image (scores (R,), classes (R,), masks (R,H,W) bool); sem_labels (N,H,W) int64.
+        -> pan (N,H,W) int32, per-image segments_info lists."""
+        N, H, W = sem_labels.shape
+        scores = torch.cat([d[0] for d in dets_masks]).float().contiguous()
+        classes = torch.cat([d[1] for d in dets_masks]).long().contiguous()
+        masks = torch.cat([d[2].reshape(-1, H * W) for d in dets_masks]).contiguous()
+        order = torch.cat([torch.argsort(-d[0].float()) for d in dets_masks]).long().contiguous()
+        off = [0]
+        for d in dets_masks:
+            off.append(off[-1] + d[0].shape[0])
+        inst_off = torch.tensor(off, dtype=torch.int32, device=self.device)
+        max_info = 128
+        pan = torch.empty(N, H, W, dtype=torch.int32, device=self.device)
+        info = torch.zeros(N, max_info, 5, dtype=torch.int32, device=self.device)
+        counts = torch.zeros(N, dtype=torch.int32, device=self.device)
+        sem_labels = sem_labels.contiguous()
+        check(_lib.lib().pvo_panoptic_combine(ptr(masks), ptr(scores), ptr(classes), ptr(order), ptr(inst_off), ptr(sem_labels), ptr(pan),
+                                              ptr(info), ptr(counts), N, H * W, NUM_SEM, float(overlap_threshold), int(stuff_area_thresh),
+                                              float(instances_score_thresh), THING_CAT0, max_info, stream()), 'panoptic_combine')
+        info_h, counts_h, scores_h = info.cpu(), counts.cpu(), scores.cpu()                # the only device->host read
+        segs = []
+        for n in range(N):
+            lst = []
+            for k in range(min(int(counts_h[n]), max_info)):
+                sid, cat, thing, area, inst = info_h[n, k].tolist()
+                if thing:
+                    lst.append({'id': sid, 'isthing': True, 'score': float(scores_h[off[n] + inst]), 'category_id': cat, 'instance_id': inst})
+                else:
+                    lst.append({'id': sid, 'isthing': False, 'category_id': cat, 'area': area})
+            segs.append(lst)
+        return pan, segs
+
+    # ------------------------------------------------------------------------------------------ whole model
+    @torch.no_grad()
+    def inference(self, images, debug=None):
+        """PanopticFPN.inference (panoptic_fpn.py:453-494): list of (3,H,W) BGR images (or dicts with 'image') ->
+        per image {'sem_seg', 'instances', 'panoptic_seg': (ids (H,W) int32, segments_info)}"""
+        images = [im['image'] if isinstance(im, dict) else im for im in images]
+        x, sizes = self.preprocess(images)
+        feats, sem, rpn = self.dense(x)
+        props = self.proposals(rpn, sizes)
+        cls, reg = self.box_head(self.roi_pool(feats, [p[0] for p in props], 7))
+        dets = self.detections(cls, reg, props, sizes)
+        ml = self.mask_head(self.roi_pool(feats, [d[0] for d in dets], 14))
+        results, o, per_image = [], 0, []
+        for n, (b, s, c) in enumerate(dets):
+            R = b.shape[0]
+            prob = ml[o:o + R][torch.arange(R, device=self.device), c][:, None].sigmoid()
+            o += R
+            h, w = sizes[n]
+            per_image.append((s, c, paste_masks(prob, b, h, w)))
+        same = all(sz == sizes[0] for sz in sizes)
+        if same:
+            h, w = sizes[0]
+            pans, segs = self.combine(per_image, sem[:, :h, :w, :NUM_SEM].argmax(dim=-1))
+        else:
+            pans, segs = [], []
+            for n, (h, w) in enumerate(sizes):
+                p_, s_ = self.combine(per_image[n:n + 1], sem[n:n + 1, :h, :w, :NUM_SEM].argmax(dim=-1))
+                pans.append(p_[0])
+                segs.append(s_[0])
+        for n, (b, s, c) in enumerate(dets):
+            h, w = sizes[n]
+            results.append({'sem_seg': sem[n, :h, :w, :NUM_SEM].permute(2, 0, 1),
+                            'instances': {'pred_boxes': b, 'scores': s, 'pred_classes': c, 'pred_masks': per_image[n][2]},
+                            'panoptic_seg': (pans[n], segs[n])})
+        if debug is not None:
+            debug.update(feats=feats, sem=sem, rpn=rpn, proposals=props, box_cls=cls, box_reg=reg, detections=dets, mask_logits=ml)
+        return results
+
+    __call__ = inference

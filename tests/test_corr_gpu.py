@@ -160,9 +160,12 @@ def test_lookup_full_size_properties():
     blk2.corr_pyramid = [p * 2 for p in blk.corr_pyramid]
     c = grid + 0.37
     a, b = blk2(c).float(), blk(c).float() * 2
-    # (a subnormal PRODUCT inside an otherwise normal sum can still move the result by one ulp)
-    assert ((a - b).abs() <= 4e-3 * b.abs() + 1e-6).all()          # <= a few half ulps
-    assert (a == b).float().mean() > 0.99
+    # (a subnormal PRODUCT can round onto an exact tie of the running sum and flip ONE intermediate rounding, so the
+    #  bound is one half-ulp step of the largest intermediate, not of the -- possibly cancelled -- result; measured on
+    #  B200: 7 of 33.9M elements differ by more than a result-ulp, 1370 differ at all)
+    top = 2 * max(p.abs().max().item() for p in blk.corr_pyramid)
+    assert (a - b).abs().max().item() <= top * 2.0 ** -10
+    assert (a == b).float().mean() > 0.9999
 
 
 def _ref_ext():

@@ -32,6 +32,10 @@ launches)
   run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 300 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-graph --profile-only ;;
 ncufull)
   run ncu_full 1500 ncu --set full --clock-control none --import-source on -k regex:"corr_lookup_fused|conv_tc_kernel|conv3x3_small|ba_pass|ba_solve|corr_volume_tc" -s 40 -c 24 -o $OUT/prof_r01 -f python bench.py --steps 2 --warmup 3 --no-graph --profile-only ;;
+fpn)
+  run t_fpn 900 $PT tests/test_fpn_gpu.py ;;
+dist)
+  run t_dist 600 $PT tests/test_dist_gpu.py ;;
 multi)
   run bench_2gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 ;;
 esac
