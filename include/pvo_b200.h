@@ -146,16 +146,23 @@ int pvo_nhwc_to_nchw(const void* src, int sdtype, int sstride, int soff, void* d
 
 /* ---- Panoptic-FPN forward helpers (VPS_Module/detectron2/modeling/...), pixel-major activations ---------------- */
 int pvo_maxpool3s2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream);     /* resnet.py:356-359 */
+/* 7x7/s2 stem as a 5x1 tensor-core conv: x (N,H,W,3) half -> 2x2 space-to-depth, x-expanded (N,H/2,W/2,64) half (resnet.py:340-354) */
+int pvo_stem_expand(const void* x, void* E, int N, int H, int W, void* stream);
 int pvo_subsample2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream);     /* strided 1x1 convs */
 int pvo_upsample_add(void* lat, const void* top, int N, int H, int W, int C, int Ht, int Wt, int dtype, void* stream);  /* fpn.py:139-147 */
 int pvo_upsample_bilinear(const void* in, void* out, int N, int H, int W, int C, int scale, int accumulate, int dtype,
                           void* stream);                                                                 /* semantic_seg.py:199-201,239-241 */
 int pvo_group_norm(const void* in, void* out, const float* gamma, const float* beta, float* scratch, int N, int HW, int C,
                    int group_size, float eps, int relu, int dtype, void* stream);                        /* semantic_seg.py:186-196 */
-/* combine_semantic_and_instance_outputs (panoptic_fpn.py:497-588) for a batch, one block per image, no host sync */
-int pvo_panoptic_combine(const void* masks, const float* scores, const long* classes, const long* order, const int* inst_off,
-                         const long* sem, int* pan, int* info_out, int* counts_out, int N, int HW, int num_sem, float overlap_thr,
-                         int stuff_area_thr, float score_thr, int thing_cat0, int max_info, void* stream);
+/* paste_masks_in_image (layers/mask_ops.py:17-152, threshold 0.5): prob (R,S,S) float32 -> out (R,H,W) uint8 0/1; W % 4 == 0 */
+int pvo_paste_masks(const float* prob, const float* boxes /*(R,4)*/, int R, int S, int H, int W, float thr, void* out, void* stream);
+/* combine_semantic_and_instance_outputs (modeling/meta_arch/panoptic_fpn.py:497-588) for a batch of equal-size images,
+ * one 8-CTA cluster per image, no host sync.  masks (R,H*W) uint8; boxes (R,4) or NULL (limits each scan to the box);
+ * order: per-image ranks by descending score; sem (N,H*W) int64 labels -> pan (N,H*W) int32, info (N,max_info,5), counts (N) */
+int pvo_panoptic_combine(const void* masks, const float* boxes, const float* scores, const long* classes, const long* order,
+                         const int* inst_off, const long* sem, int* pan, int* info_out, int* counts_out, int N, int H, int W,
+                         int num_sem, float overlap_thr, int stuff_area_thr, float score_thr, int thing_cat0, int max_info,
+                         void* stream);
 
 /* ROIPooler (modeling/poolers.py:189-235: level by box size, canonical 224 @ level 4) + ROIAlignV2
  * (layers/roi_align.py:49-58 -> torchvision roi_align aligned=True, sampling_ratio=0) over the 4 pixel-major pyramid
@@ -165,7 +172,7 @@ int pvo_roi_align_fpn(const void* const* feats, const int* Hs, const int* Ws, in
 /* Greedy NMS for G independent groups of n <= 1024 boxes sorted by descending score (layers/nms.py:9-22 batched_nms ->
  * torchvision nms per category): keep[g][i] = 1 iff box i is valid and no kept earlier box overlaps it with IoU > thr. */
 int pvo_nms_groups(const float* boxes /*(G,n,4)*/, const unsigned char* valid /*(G,n)*/, int G, int n, float thr,
-                   unsigned char* keep /*(G,n)*/, void* stream);
+                   unsigned char* keep /*(G,n)*/, unsigned int* scratch /* G*n*32 words */, void* stream);
 
 /* FactorGraph.update post-processing (factor_graph.py:250-283): target_cam, raw_mask, bin_mask, panoptic segment
  *   filter (:256-276, integer counting on the device instead of numpy on the host), delta_dy, sigmoid weights. */

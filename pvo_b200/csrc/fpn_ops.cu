@@ -4,8 +4,6 @@
 //   stride-2 sampling for the strided 1x1s    modeling/backbone/resnet.py:152-160 (STRIDE_IN_1X1, defaults.py:489)
 //   top-down nearest x2 + lateral sum         modeling/backbone/fpn.py:139-147
 //   GroupNorm(32) + ReLU, bilinear x2         modeling/meta_arch/semantic_seg.py:186-207
-//   panoptic merge                            modeling/meta_arch/panoptic_fpn.py:497-588 (a Python loop with .item() syncs
-//                                             per instance / per label in the reference; one block per image here)
 #include "common.cuh"
 
 namespace {
@@ -17,24 +15,59 @@ template <typename T> __device__ __forceinline__ void stv(T* p, float v);
 template <> __device__ __forceinline__ void stv<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void stv<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
+// 16-byte channel vectors: 8 halves or 4 floats per thread (C % VE == 0 on every call site; pointers 16-B aligned)
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int VE = 4;
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec<__half> {
+  static constexpr int VE = 8;
+  static __device__ __forceinline__ void ld(const __half* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const float2 f = __half22float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void st(__half* p, const float (&v)[8]) {
+    uint4 t;
+    __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; j++) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
 // out[n][yo][xo][c] = max over the 3x3 window (stride 2, pad 1) of in
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C) {
-  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  constexpr int VE = Vec<T>::VE;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, CV = C / VE;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)N * Ho * Wo * C) return;
-  const int c = (int)(i % C);
-  long p = i / C;
+  if (i >= (long)N * Ho * Wo * CV) return;
+  const int c = (int)(i % CV) * VE;
+  long p = i / CV;
   const int xo = (int)(p % Wo); p /= Wo;
   const int yo = (int)(p % Ho);
   const long n = p / Ho;
-  float m = -INFINITY;
+  float m[VE];
+#pragma unroll
+  for (int j = 0; j < VE; j++) m[j] = -INFINITY;
   for (int dy = 0; dy < 3; dy++)
     for (int dx = 0; dx < 3; dx++) {
       const int y = 2 * yo - 1 + dy, x = 2 * xo - 1 + dx;
-      if (y >= 0 && y < H && x >= 0 && x < W) m = fmaxf(m, ldv(in + ((n * H + y) * W + x) * C + c));
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        float v[VE];
+        Vec<T>::ld(in + ((n * H + y) * W + x) * C + c, v);
+#pragma unroll
+        for (int j = 0; j < VE; j++) m[j] = fmaxf(m[j], v[j]);
+      }
     }
-  stv(out + i, m);
+  Vec<T>::st(out + ((n * Ho + yo) * Wo + xo) * C + c, m);
 }
 
 // out[n][yo][xo][:] = in[n][2yo][2xo][:]   (16-byte vectors)
@@ -54,26 +87,35 @@ __global__ void __launch_bounds__(256) subsample2_kernel(const uint4* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_add_kernel(T* __restrict__ lat, const T* __restrict__ top, int N, int H, int W, int C,
                                                            int Ht, int Wt) {
+  constexpr int VE = Vec<T>::VE;
+  const int CV = C / VE;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)N * H * W * C) return;
-  const int c = (int)(i % C);
-  long p = i / C;
+  if (i >= (long)N * H * W * CV) return;
+  const int c = (int)(i % CV) * VE;
+  long p = i / CV;
   const int x = (int)(p % W); p /= W;
   const int y = (int)(p % H);
   const long n = p / H;
   const int yt = min(y >> 1, Ht - 1), xt = min(x >> 1, Wt - 1);
-  stv(lat + i, ldv(lat + i) + ldv(top + ((n * Ht + yt) * Wt + xt) * C + c));
+  float a[VE], b[VE];
+  T* o = lat + ((n * H + y) * W + x) * C + c;
+  Vec<T>::ld(o, a);
+  Vec<T>::ld(top + ((n * Ht + yt) * Wt + xt) * C + c, b);
+#pragma unroll
+  for (int j = 0; j < VE; j++) a[j] += b[j];
+  Vec<T>::st(o, a);
 }
 
 // F.interpolate(scale_factor=S, mode='bilinear', align_corners=False); optional accumulate into out
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W,
                                                                 int C, int S, int accumulate) {
-  const int Ho = H * S, Wo = W * S;
+  constexpr int VE = Vec<T>::VE;
+  const int Ho = H * S, Wo = W * S, CV = C / VE;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)N * Ho * Wo * C) return;
-  const int c = (int)(i % C);
-  long p = i / C;
+  if (i >= (long)N * Ho * Wo * CV) return;
+  const int c = (int)(i % CV) * VE;
+  long p = i / CV;
   const int xo = (int)(p % Wo); p /= Wo;
   const int yo = (int)(p % Ho);
   const long n = p / Ho;
@@ -82,13 +124,58 @@ __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const T* __restr
   const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
   const float ly = sy - y0, lx = sx - x0;
   const T* b = in + n * (long)H * W * C + c;
-  float v = (1.f - ly) * ((1.f - lx) * ldv(b + ((long)y0 * W + x0) * C) + lx * ldv(b + ((long)y0 * W + x1) * C)) +
-            ly * ((1.f - lx) * ldv(b + ((long)y1 * W + x0) * C) + lx * ldv(b + ((long)y1 * W + x1) * C));
-  if (accumulate) v += ldv(out + i);
-  stv(out + i, v);
+  float v00[VE], v01[VE], v10[VE], v11[VE], r[VE];
+  Vec<T>::ld(b + ((long)y0 * W + x0) * C, v00);
+  Vec<T>::ld(b + ((long)y0 * W + x1) * C, v01);
+  Vec<T>::ld(b + ((long)y1 * W + x0) * C, v10);
+  Vec<T>::ld(b + ((long)y1 * W + x1) * C, v11);
+  T* o = out + ((n * Ho + yo) * Wo + xo) * C + c;
+  if (accumulate) Vec<T>::ld(o, r);
+#pragma unroll
+  for (int j = 0; j < VE; j++) {
+    const float v = (1.f - ly) * ((1.f - lx) * v00[j] + lx * v01[j]) + ly * ((1.f - lx) * v10[j] + lx * v11[j]);
+    r[j] = accumulate ? r[j] + v : v;
+  }
+  Vec<T>::st(o, r);
 }
 
-// GroupNorm statistics from per-(image, channel) partial sums produced by the instance-norm partial kernel layout:
+// GroupNorm statistics: part[n][chunk][c][2] = {sum, sum of squares} over the chunk's pixels; 256 threads = (C/VE) channel
+// vectors x row lanes, reduced through shared memory
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_partial_kernel(const T* __restrict__ in, float* __restrict__ part, int HW, int C, int chunks) {
+  constexpr int VE = Vec<T>::VE;
+  extern __shared__ float red[];                 // [rows][C][2]
+  const int e = blockIdx.x, ch = blockIdx.y, CV = C / VE;
+  const int rows = blockDim.x / CV;              // row lanes (host guarantees CV <= 256)
+  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+  const int per = (HW + chunks - 1) / chunks;
+  const int p0 = ch * per, p1 = min(HW, p0 + per);
+  float s[VE], q[VE];
+#pragma unroll
+  for (int j = 0; j < VE; j++) { s[j] = 0.0f; q[j] = 0.0f; }
+  if (rl < rows)
+    for (int p = p0 + rl; p < p1; p += rows) {
+      float v[VE];
+      Vec<T>::ld(in + ((long)e * HW + p) * C + cv * VE, v);
+#pragma unroll
+      for (int j = 0; j < VE; j++) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    }
+  if (rl < rows) {
+#pragma unroll
+    for (int j = 0; j < VE; j++) {
+      red[((long)rl * C + cv * VE + j) * 2] = s[j];
+      red[((long)rl * C + cv * VE + j) * 2 + 1] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float ts = 0.0f, tq = 0.0f;
+    for (int r = 0; r < rows; r++) { ts += red[((long)r * C + c) * 2]; tq += red[((long)r * C + c) * 2 + 1]; }
+    part[(((long)e * chunks + ch) * C + c) * 2] = ts;
+    part[(((long)e * chunks + ch) * C + c) * 2 + 1] = tq;
+  }
+}
+
 // part[n][chunk][c][2] -> stats[n][c][2] = {group mean, group rstd}
 __global__ void __launch_bounds__(128) gn_stats_final_kernel(const float* __restrict__ part, float* __restrict__ stats, int HW, int C,
                                                              int gs, int chunks, float eps) {
@@ -109,108 +196,52 @@ __global__ void __launch_bounds__(128) gn_stats_final_kernel(const float* __rest
     }
   }
 }
-template <typename T>
-__global__ void __launch_bounds__(64) gn_stats_partial_kernel(const T* __restrict__ in, float* __restrict__ part, int HW, int C, int chunks) {
-  const int e = blockIdx.x, ch = blockIdx.y;
-  const int per = (HW + chunks - 1) / chunks;
-  const int p0 = ch * per, p1 = min(HW, p0 + per);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.0f, q = 0.0f;
-    for (int p = p0; p < p1; p++) {
-      const float v = ldv(in + ((long)e * HW + p) * C + c);
-      s += v;
-      q = fmaf(v, v, q);
-    }
-    part[(((long)e * chunks + ch) * C + c) * 2] = s;
-    part[(((long)e * chunks + ch) * C + c) * 2 + 1] = q;
-  }
-}
+
 template <typename T>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ in, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, T* __restrict__ out, int HW, int C, long total, int relu) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int VE = Vec<T>::VE;
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * VE;
   if (i >= total) return;
   const int c = (int)(i % C);
   const long n = i / ((long)HW * C);
-  float v = (ldv(in + i) - stats[(n * C + c) * 2]) * stats[(n * C + c) * 2 + 1] * gamma[c] + beta[c];
-  if (relu) v = fmaxf(v, 0.0f);
-  stv(out + i, v);
+  float v[VE];
+  Vec<T>::ld(in + i, v);
+#pragma unroll
+  for (int j = 0; j < VE; j++) {
+    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + n * C + c + j);
+    v[j] = (v[j] - st.x) * st.y * __ldg(gamma + c + j) + __ldg(beta + c + j);
+    if (relu) v[j] = fmaxf(v[j], 0.0f);
+  }
+  Vec<T>::st(out + i, v);
 }
 
-// ---- panoptic merge: one block per image.  Instances are visited in descending score order (order[] prepared by the
-// caller); every decision is block-uniform, so the sequential dependency of the reference loop is kept exactly.
-// info_out[n][k] = {segment id, category, isthing, area, instance index}; counts_out[n] = number of segments.
-__device__ __forceinline__ int block_sum_int(int v, int* sh) {
-  v = __reduce_add_sync(0xffffffffu, v);
-  const int w = threadIdx.x >> 5;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sh[w] = v;
-  __syncthreads();
-  int t = 0;
-  for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[k];
-  return t;
-}
-
-__global__ void __launch_bounds__(1024) panoptic_combine_kernel(const unsigned char* __restrict__ masks /*[R][HW] bool*/, const float* __restrict__ scores,
-                                                                const long* __restrict__ classes, const long* __restrict__ order,
-                                                                const int* __restrict__ inst_off /*[N+1]*/, const long* __restrict__ sem /*[N][HW] argmax*/,
-                                                                int* __restrict__ pan /*[N][HW]*/, int* __restrict__ info_out, int* __restrict__ counts_out,
-                                                                int HW, int num_sem, float overlap_thr, int stuff_area_thr, float score_thr,
-                                                                int thing_cat0, int max_info) {
-  __shared__ int sh[32];
-  const int n = blockIdx.x;
-  int* P = pan + (long)n * HW;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) P[i] = 0;
-  __syncthreads();
-  int cur = 0;
-  const int r0 = inst_off[n], r1 = inst_off[n + 1];
-  for (int k = r0; k < r1; k++) {
-    const int r = r0 + (int)order[k];                       // order[] holds per-image ranks sorted by descending score
-    if (scores[r] < score_thr) break;
-    const unsigned char* M = masks + (long)r * HW;
-    int area = 0, inter = 0;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      const int m = M[i] != 0;
-      area += m;
-      inter += m && (P[i] > 0);
+// Stem input for the tensor-core path.  The 7x7 / stride-2 / 3-channel stem (resnet.py:340-354) is rewritten as a 5x1 stride-1
+// convolution over a 2x2 space-to-depth, x-expanded copy of the image:
+//   E[n][Yb][X][tx*12 + dy*6 + dx*3 + c] = x[n][2*Yb + dy][2*(X - 2 + tx) + dx][c]   (tx < 4; channels 48..63 zero)
+// so that out[Y][X] = sum_{ty, j} W2[ty][j] * E[Y + ty - 2][X][j] with W2[ty][(tx,dy,dx,c)] = w[ky = 2ty + dy - 1][kx = 2tx + dx - 1][c].
+__global__ void __launch_bounds__(256) stem_expand_kernel(const __half* __restrict__ x, __half* __restrict__ E, int N, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * Ho * Wo * 8) return;
+  const int q = (int)(i & 7);
+  long p = i >> 3;
+  const int X = (int)(p % Wo); p /= Wo;
+  const int Yb = (int)(p % Ho);
+  const long n = p / Ho;
+  __align__(16) __half v[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const int j = q * 8 + e;
+    __half val = __float2half_rn(0.0f);
+    if (j < 48) {
+      const int tx = j / 12, r = j % 12, dy = r / 6, dx = (r % 6) / 3, c = r % 3;
+      const int yy = 2 * Yb + dy, xx = 2 * (X - 2 + tx) + dx;
+      if (xx >= 0 && xx < W) val = __ldg(x + ((n * H + yy) * W + xx) * 3 + c);
     }
-    area = block_sum_int(area, sh);
-    inter = block_sum_int(inter, sh);
-    if (area == 0) continue;
-    if ((double)inter / (double)area > (double)overlap_thr) continue;       // the reference divides Python numbers (doubles)
-    cur++;
-    const int cat = thing_cat0 + (int)classes[r];
-    const int id = cat * 10000 + cur;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x)
-      if (M[i] && P[i] == 0) P[i] = id;
-    if (threadIdx.x == 0 && cur <= max_info) {
-      int* o = info_out + ((long)n * max_info + cur - 1) * 5;
-      o[0] = id; o[1] = cat; o[2] = 1; o[3] = area - inter; o[4] = r - r0;
-    }
-    __syncthreads();
+    v[e] = val;
   }
-  const long* S = sem + (long)n * HW;
-  for (int lab = 1; lab < num_sem; lab++) {                 // label 0 is the "thing" placeholder class (:560-561)
-    int area = 0, present = 0;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      const int is = S[i] == lab;
-      present |= is;
-      area += is && (P[i] == 0);
-    }
-    area = block_sum_int(area, sh);
-    present = block_sum_int(present, sh);
-    if (!present || area < stuff_area_thr) continue;
-    cur++;
-    const int id = lab * 10000;                             // stuff_id2cat is the identity on VKITTI trainIds 1..11
-    for (int i = threadIdx.x; i < HW; i += blockDim.x)
-      if (S[i] == lab && P[i] == 0) P[i] = id;
-    if (threadIdx.x == 0 && cur <= max_info) {
-      int* o = info_out + ((long)n * max_info + cur - 1) * 5;
-      o[0] = id; o[1] = lab; o[2] = 0; o[3] = area; o[4] = -1;
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) counts_out[n] = cur;
+  *reinterpret_cast<uint4*>(E + i * 8) = *reinterpret_cast<const uint4*>(v);
 }
 
 }  // namespace
@@ -218,8 +249,11 @@ __global__ void __launch_bounds__(1024) panoptic_combine_kernel(const unsigned c
 #define DISPATCH_T(dtype, CALL_F32, CALL_F16) \
   if ((dtype) == PVO_DTYPE_F32) { CALL_F32; } else if ((dtype) == PVO_DTYPE_F16) { CALL_F16; } else return PVO_ERR_UNSUPPORTED;
 
+#define VE_OF(dtype) ((dtype) == PVO_DTYPE_F32 ? 4 : 8)
+
 extern "C" int pvo_maxpool3s2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream) {
-  const long total = (long)N * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * C;
+  if (C % VE_OF(dtype)) return PVO_ERR_INVALID;
+  const long total = (long)N * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / VE_OF(dtype));
   if (total <= 0) return PVO_OK;
   cudaStream_t s = (cudaStream_t)stream;
   DISPATCH_T(dtype, (maxpool3s2_kernel<float><<<ceil_div(total, 256), 256, 0, s>>>((const float*)in, (float*)out, N, H, W, C)),
@@ -238,7 +272,8 @@ extern "C" int pvo_subsample2(const void* in, void* out, int N, int H, int W, in
 }
 
 extern "C" int pvo_upsample_add(void* lat, const void* top, int N, int H, int W, int C, int Ht, int Wt, int dtype, void* stream) {
-  const long total = (long)N * H * W * C;
+  if (C % VE_OF(dtype)) return PVO_ERR_INVALID;
+  const long total = (long)N * H * W * (C / VE_OF(dtype));
   if (total <= 0) return PVO_OK;
   cudaStream_t s = (cudaStream_t)stream;
   DISPATCH_T(dtype, (upsample_add_kernel<float><<<ceil_div(total, 256), 256, 0, s>>>((float*)lat, (const float*)top, N, H, W, C, Ht, Wt)),
@@ -248,7 +283,8 @@ extern "C" int pvo_upsample_add(void* lat, const void* top, int N, int H, int W,
 
 extern "C" int pvo_upsample_bilinear(const void* in, void* out, int N, int H, int W, int C, int scale, int accumulate, int dtype,
                                      void* stream) {
-  const long total = (long)N * H * scale * W * scale * C;
+  if (C % VE_OF(dtype)) return PVO_ERR_INVALID;
+  const long total = (long)N * H * scale * W * scale * (C / VE_OF(dtype));
   if (total <= 0) return PVO_OK;
   cudaStream_t s = (cudaStream_t)stream;
   DISPATCH_T(dtype, (upsample_bilinear_kernel<float><<<ceil_div(total, 256), 256, 0, s>>>((const float*)in, (float*)out, N, H, W, C, scale, accumulate)),
@@ -256,34 +292,33 @@ extern "C" int pvo_upsample_bilinear(const void* in, void* out, int N, int H, in
   return pvo_check_launch();
 }
 
-// GroupNorm(num_groups = C / group_size, eps) with affine, fused ReLU; in == out allowed.  scratch: N*32*C*2 + N*C*2 floats
+// GroupNorm(num_groups = C / group_size, eps) with affine, fused ReLU; in == out allowed.  scratch: N*64*C*2 + N*C*2 floats
 extern "C" int pvo_group_norm(const void* in, void* out, const float* gamma, const float* beta, float* scratch, int N, int HW, int C,
                               int group_size, float eps, int relu, int dtype, void* stream) {
   if (N == 0) return PVO_OK;
-  if (!scratch || C % group_size) return PVO_ERR_INVALID;
-  constexpr int chunks = 32;
+  const int ve = VE_OF(dtype);
+  if (!scratch || C % group_size || C % ve || C / ve > 256) return PVO_ERR_INVALID;
+  constexpr int chunks = 64;
   cudaStream_t s = (cudaStream_t)stream;
   float* part = scratch;
   float* stats = scratch + (size_t)N * chunks * C * 2;
   dim3 grid(N, chunks);
   const long total = (long)N * HW * C;
-  if (dtype == PVO_DTYPE_F32) gn_stats_partial_kernel<float><<<grid, 64, 0, s>>>((const float*)in, part, HW, C, chunks);
-  else gn_stats_partial_kernel<__half><<<grid, 64, 0, s>>>((const __half*)in, part, HW, C, chunks);
+  const size_t smem = (size_t)(256 / (C / ve)) * C * 2 * sizeof(float);
+  if (smem > 48 * 1024) return PVO_ERR_UNSUPPORTED;
+  if (dtype == PVO_DTYPE_F32) gn_stats_partial_kernel<float><<<grid, 256, smem, s>>>((const float*)in, part, HW, C, chunks);
+  else gn_stats_partial_kernel<__half><<<grid, 256, smem, s>>>((const __half*)in, part, HW, C, chunks);
   gn_stats_final_kernel<<<N, 128, 0, s>>>(part, stats, HW, C, group_size, chunks, eps);
-  DISPATCH_T(dtype, (gn_apply_kernel<float><<<ceil_div(total, 256), 256, 0, s>>>((const float*)in, stats, gamma, beta, (float*)out, HW, C, total, relu)),
-             (gn_apply_kernel<__half><<<ceil_div(total, 256), 256, 0, s>>>((const __half*)in, stats, gamma, beta, (__half*)out, HW, C, total, relu)))
+  DISPATCH_T(dtype, (gn_apply_kernel<float><<<ceil_div(total / ve, 256), 256, 0, s>>>((const float*)in, stats, gamma, beta, (float*)out, HW, C, total, relu)),
+             (gn_apply_kernel<__half><<<ceil_div(total / ve, 256), 256, 0, s>>>((const __half*)in, stats, gamma, beta, (__half*)out, HW, C, total, relu)))
   return pvo_check_launch();
 }
 
-// combine_semantic_and_instance_outputs for a batch: masks (R,HW) uint8 (all images, image n owns rows inst_off[n]..inst_off[n+1]),
-// order = per-image rank lists (descending score) concatenated, sem (N,HW) int64 argmax labels.  Outputs: pan (N,HW) int32,
-// info (N,max_info,5) int32, counts (N) int32.
-extern "C" int pvo_panoptic_combine(const void* masks, const float* scores, const long* classes, const long* order, const int* inst_off,
-                                    const long* sem, int* pan, int* info_out, int* counts_out, int N, int HW, int num_sem,
-                                    float overlap_thr, int stuff_area_thr, float score_thr, int thing_cat0, int max_info, void* stream) {
-  if (N == 0) return PVO_OK;
-  panoptic_combine_kernel<<<N, 1024, 0, (cudaStream_t)stream>>>((const unsigned char*)masks, scores, classes, order, inst_off, sem, pan,
-                                                                 info_out, counts_out, HW, num_sem, overlap_thr, stuff_area_thr, score_thr,
-                                                                 thing_cat0, max_info);
+/* x (N,H,W,3) half, H and W even -> E (N,H/2,W/2,64) half (see stem_expand_kernel) */
+extern "C" int pvo_stem_expand(const void* x, void* E, int N, int H, int W, void* stream) {
+  if ((H | W) & 1) return PVO_ERR_INVALID;
+  const long total = (long)N * (H / 2) * (W / 2) * 8;
+  if (total <= 0) return PVO_OK;
+  stem_expand_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)E, N, H, W);
   return pvo_check_launch();
 }

@@ -1,0 +1,200 @@
+// Mask pasting and the panoptic merge of the Panoptic-FPN post-processing.  References under VPS_Module/detectron2/:
+//   paste_masks_in_image / _do_paste_mask      layers/mask_ops.py:17-152 (F.grid_sample of every 28x28 mask over the image)
+//   combine_semantic_and_instance_outputs      modeling/meta_arch/panoptic_fpn.py:497-588 (a Python loop with .item()
+//                                              syncs per instance and per label)
+// Here: one kernel pastes all masks (only pixels inside a detection's box are sampled, the rest are written as zeros),
+// and one thread-block CLUSTER per image (8 CTAs, each owning a strip of rows) runs the sequential merge on chip: per
+// instance one pass over the box region for {area, overlap}, one cluster barrier + distributed-shared-memory exchange
+// for the accept decision, one pass to paint.  No host synchronisation.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kCluster = 8;
+constexpr int kMaxSem = 64;
+
+// ---- paste: out[r][y][x] = bilinear(prob[r], grid(y, x)) >= thr, the arithmetic of mask_ops.py:46-71 + at::grid_sampler_2d
+// (bilinear, zeros padding, align_corners=False), operation for operation in fp32.
+__device__ __forceinline__ float unnormalize(float c, int size) { return fmaf(__fadd_rn(c, 1.0f), (float)size, -1.0f) / 2.0f; }
+
+__device__ __forceinline__ bool paste_px(const float* __restrict__ P, int S, float gx, float gy, float thr) {
+  const float ix = unnormalize(gx, S), iy = unnormalize(gy, S);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const float nw = (fx + 1.0f - ix) * (fy + 1.0f - iy), ne = (ix - fx) * (fy + 1.0f - iy);
+  const float sw = (fx + 1.0f - ix) * (iy - fy), se = (ix - fx) * (iy - fy);
+  float acc = 0.0f;
+  const bool xin0 = x0 >= 0 && x0 < S, xin1 = x1 >= 0 && x1 < S, yin0 = y0 >= 0 && y0 < S, yin1 = y1 >= 0 && y1 < S;
+  if (yin0 && xin0) acc = fmaf(P[y0 * S + x0], nw, acc);
+  if (yin0 && xin1) acc = fmaf(P[y0 * S + x1], ne, acc);
+  if (yin1 && xin0) acc = fmaf(P[y1 * S + x0], sw, acc);
+  if (yin1 && xin1) acc = fmaf(P[y1 * S + x1], se, acc);
+  return acc >= thr;
+}
+
+// grid (ceil(H*W/4 / 256), R); thread <-> 4 consecutive pixels of a row (W % 4 == 0), one 32-bit store
+__global__ void __launch_bounds__(256) paste_masks_kernel(const float* __restrict__ prob /*[R][S][S]*/, const float* __restrict__ boxes /*[R][4]*/,
+                                                          int S, int H, int W, float thr, unsigned char* __restrict__ out /*[R][H][W]*/) {
+  extern __shared__ float P[];
+  const int r = blockIdx.y;
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) P[i] = prob[(long)r * S * S + i];
+  __syncthreads();
+  const float bx0 = boxes[r * 4 + 0], by0 = boxes[r * 4 + 1], bx1 = boxes[r * 4 + 2], by1 = boxes[r * 4 + 3];
+  const float bw = __fsub_rn(bx1, bx0), bh = __fsub_rn(by1, by0);
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= H * W / 4) return;
+  const int y = (q * 4) / W, x = (q * 4) % W;
+  unsigned int bits = 0;
+  // a pixel centre outside the box samples beyond the border texels' half-cell: the interpolated value is < 0.5 * max
+  const float cy = (float)y + 0.5f;
+  if (cy >= by0 - 1.0f && cy <= by1 + 1.0f && (float)x + 4.5f >= bx0 - 1.0f && (float)x + 0.5f <= bx1 + 1.0f) {
+    const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(cy, by0), bh), 2.0f), 1.0f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float cx = (float)(x + k) + 0.5f;
+      const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(cx, bx0), bw), 2.0f), 1.0f);
+      if (paste_px(P, S, gx, gy, thr)) bits |= 1u << (8 * k);
+    }
+  }
+  reinterpret_cast<unsigned int*>(out + (long)r * H * W)[q] = bits;
+}
+
+// ---- merge
+__device__ __forceinline__ int block_sum_int(int v, int* sh) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[w] = v;
+  __syncthreads();
+  int t = 0;
+  for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[k];
+  return t;
+}
+
+// info_out[n][k] = {segment id, category, isthing, area, instance index}; counts_out[n] = number of segments.
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(1024)
+    panoptic_combine_kernel(const unsigned char* __restrict__ masks /*[R][H*W] bool*/, const float* __restrict__ boxes /*[R][4] or null*/,
+                            const float* __restrict__ scores, const long* __restrict__ classes, const long* __restrict__ order,
+                            const int* __restrict__ inst_off /*[N+1]*/, const long* __restrict__ sem /*[N][H*W] argmax*/,
+                            int* __restrict__ pan /*[N][H*W]*/, int* __restrict__ info_out, int* __restrict__ counts_out, int H, int W,
+                            int num_sem, float overlap_thr, int stuff_area_thr, float score_thr, int thing_cat0, int max_info) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ int sh[32];
+  __shared__ int slot[2][2];                     // {area, overlap} of this CTA's strip, double buffered by instance parity
+  __shared__ int hist[kMaxSem], hist_all[kMaxSem];
+  const int rank = (int)cluster.block_rank();
+  const int n = blockIdx.x / kCluster;
+  const int rows = (H + kCluster - 1) / kCluster;
+  const int ys = min(rank * rows, H), ye = min(ys + rows, H);            // this CTA's strip of rows
+  const long HW = (long)H * W;
+  int* P = pan + n * HW;
+  for (long i = (long)ys * W + threadIdx.x; i < (long)ye * W; i += blockDim.x) P[i] = 0;
+  __syncthreads();
+  int cur = 0, step = 0;
+  const int r0 = inst_off[n], r1 = inst_off[n + 1];
+  for (int k = r0; k < r1; k++) {
+    const int r = r0 + (int)order[k];                       // order[] holds per-image ranks sorted by descending score
+    if (scores[r] < score_thr) break;
+    const unsigned char* M = masks + (long)r * HW;
+    int y0 = ys, y1 = ye, x0 = 0, x1 = W;                   // region that can hold mask pixels (pixel centres within the box)
+    if (boxes) {
+      x0 = max(0, (int)floorf(boxes[r * 4 + 0] - 1.5f)); y0 = max(ys, (int)floorf(boxes[r * 4 + 1] - 1.5f));
+      x1 = min(W, (int)ceilf(boxes[r * 4 + 2] + 1.5f)); y1 = min(ye, (int)ceilf(boxes[r * 4 + 3] + 1.5f));
+    }
+    const int rw = max(x1 - x0, 0), cnt = rw * max(y1 - y0, 0);
+    int area = 0, inter = 0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const long px = (long)(y0 + i / rw) * W + x0 + i % rw;
+      const int m = M[px] != 0;
+      area += m;
+      inter += m && (P[px] > 0);
+    }
+    area = block_sum_int(area, sh);
+    inter = block_sum_int(inter, sh);
+    if (threadIdx.x == 0) { slot[step & 1][0] = area; slot[step & 1][1] = inter; }
+    cluster.sync();
+    area = 0; inter = 0;
+    for (int c = 0; c < kCluster; c++) {
+      const int* rs = cluster.map_shared_rank(&slot[step & 1][0], c);
+      area += rs[0]; inter += rs[1];
+    }
+    step++;
+    if (area == 0) continue;
+    if ((double)inter / (double)area > (double)overlap_thr) continue;       // the reference divides Python numbers (doubles)
+    cur++;
+    const int cat = thing_cat0 + (int)classes[r];
+    const int id = cat * 10000 + cur;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const long px = (long)(y0 + i / rw) * W + x0 + i % rw;
+      if (M[px] && P[px] == 0) P[px] = id;
+    }
+    if (rank == 0 && threadIdx.x == 0 && cur <= max_info) {
+      int* o = info_out + ((long)n * max_info + cur - 1) * 5;
+      o[0] = id; o[1] = cat; o[2] = 1; o[3] = area - inter; o[4] = r - r0;
+    }
+    __syncthreads();
+  }
+  // stuff: per label the area not taken by things (label 0 is the "thing" placeholder class, :560-561)
+  const long* S = sem + n * HW;
+  for (int i = threadIdx.x; i < kMaxSem; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (long i = (long)ys * W + threadIdx.x; i < (long)ye * W; i += blockDim.x) {
+    const int lab = (int)S[i];
+    if (lab > 0 && lab < num_sem && P[i] == 0) atomicAdd(&hist[lab], 1);
+  }
+  cluster.sync();
+  for (int lab = threadIdx.x; lab < num_sem; lab += blockDim.x) {
+    int t = 0;
+    for (int c = 0; c < kCluster; c++) t += cluster.map_shared_rank(&hist[0], c)[lab];
+    hist_all[lab] = t;
+  }
+  __syncthreads();
+  for (long i = (long)ys * W + threadIdx.x; i < (long)ye * W; i += blockDim.x) {
+    const int lab = (int)S[i];
+    if (lab > 0 && lab < num_sem && P[i] == 0 && hist_all[lab] >= stuff_area_thr) P[i] = lab * 10000;   // stuff_id2cat: identity on trainIds
+  }
+  if (rank == 0 && threadIdx.x == 0) {
+    for (int lab = 1; lab < num_sem; lab++) {
+      if (hist_all[lab] < stuff_area_thr || hist_all[lab] == 0) continue;
+      cur++;
+      if (cur <= max_info) {
+        int* o = info_out + ((long)n * max_info + cur - 1) * 5;
+        o[0] = lab * 10000; o[1] = lab; o[2] = 0; o[3] = hist_all[lab]; o[4] = -1;
+      }
+    }
+    counts_out[n] = cur;
+  }
+  cluster.sync();                                // keep every CTA's shared memory alive until all remote reads are done
+}
+
+}  // namespace
+
+// paste_masks_in_image for R detections of images of one size: prob (R,S,S) float32 probabilities of the predicted class,
+// boxes (R,4) float32, out (R,H,W) uint8 (0/1).  W % 4 == 0.
+extern "C" int pvo_paste_masks(const float* prob, const float* boxes, int R, int S, int H, int W, float thr, void* out, void* stream) {
+  if (R == 0) return PVO_OK;
+  if (W % 4 || S < 1 || S > 64) return PVO_ERR_INVALID;
+  dim3 grid(ceil_div((long)H * W / 4, 256), R);
+  paste_masks_kernel<<<grid, 256, S * S * sizeof(float), (cudaStream_t)stream>>>(prob, boxes, S, H, W, thr, (unsigned char*)out);
+  return pvo_check_launch();
+}
+
+// combine_semantic_and_instance_outputs for a batch: masks (R,H*W) uint8 (all images; image n owns rows inst_off[n]..inst_off[n+1]),
+// boxes (R,4) or NULL (restricts each instance's scan to its box; masks pasted by pvo_paste_masks are zero outside it),
+// order = per-image rank lists (descending score) concatenated, sem (N,H*W) int64 argmax labels.
+// Outputs: pan (N,H*W) int32, info (N,max_info,5) int32, counts (N) int32.
+extern "C" int pvo_panoptic_combine(const void* masks, const float* boxes, const float* scores, const long* classes, const long* order,
+                                    const int* inst_off, const long* sem, int* pan, int* info_out, int* counts_out, int N, int H, int W,
+                                    int num_sem, float overlap_thr, int stuff_area_thr, float score_thr, int thing_cat0, int max_info,
+                                    void* stream) {
+  if (N == 0) return PVO_OK;
+  if (num_sem > kMaxSem) return PVO_ERR_UNSUPPORTED;
+  panoptic_combine_kernel<<<N * kCluster, 1024, 0, (cudaStream_t)stream>>>((const unsigned char*)masks, boxes, scores, classes, order, inst_off,
+                                                                            sem, pan, info_out, counts_out, H, W, num_sem, overlap_thr,
+                                                                            stuff_area_thr, score_thr, thing_cat0, max_info);
+  return pvo_check_launch();
+}

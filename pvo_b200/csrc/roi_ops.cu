@@ -14,23 +14,40 @@ struct Pyr {
   int H[4], W[4];
 };
 
-template <typename T> struct V2;
-template <> struct V2<__half> {
-  static __device__ __forceinline__ float2 ld(const __half* p) { return __half22float2(__ldg(reinterpret_cast<const __half2*>(p))); }
-  static __device__ __forceinline__ void st(__half* p, float2 v) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y); }
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int VE = 4;
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 };
-template <> struct V2<float> {
-  static __device__ __forceinline__ float2 ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-  static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+template <> struct Vec<__half> {
+  static constexpr int VE = 8;
+  static __device__ __forceinline__ void ld(const __half* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const float2 f = __half22float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void st(__half* p, const float (&v)[8]) {
+    uint4 t;
+    __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; j++) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
 };
 
-// one block per (roi, output bin); thread t owns channels 2t, 2t+1
+// one block per (roi, output row ph); warp w computes the bins pw = w, w + 4, ...; lane l owns channels [VE*l, VE*l + VE)
+// of every 32*VE-channel slab, so each bilinear tap is one 512-byte coalesced read and neighbouring bins hit in L1.
 template <typename T>
 __global__ void __launch_bounds__(128) roi_align_fpn_kernel(const __grid_constant__ Pyr pyr, int C, const float* __restrict__ rois, int S,
                                                             T* __restrict__ out) {
-  const int r = blockIdx.x / (S * S);
-  const int bin = blockIdx.x % (S * S);
-  const int ph = bin / S, pw = bin % S;
+  constexpr int VE = Vec<T>::VE;
+  const int r = blockIdx.x / S, ph = blockIdx.x % S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* roi = rois + (long)r * 5;
   const int n = (int)roi[0];
   const float x0 = roi[1], y0 = roi[2], x1 = roi[3], y1 = roi[4];
@@ -46,29 +63,37 @@ __global__ void __launch_bounds__(128) roi_align_fpn_kernel(const __grid_constan
   const float bw = rw / (float)S, bh = rh / (float)S;
   const int gh = (int)ceilf(rh / (float)S), gw = (int)ceilf(rw / (float)S);
   const float count = fmaxf((float)(gh * gw), 1.0f);
-  for (int c = 2 * threadIdx.x; c < C; c += 2 * blockDim.x) {
-    float2 acc = make_float2(0.0f, 0.0f);
-    for (int iy = 0; iy < gh; iy++) {
-      float y = sh + ph * bh + (iy + 0.5f) * bh / (float)gh;
-      for (int ix = 0; ix < gw; ix++) {
-        float x = sw + pw * bw + (ix + 0.5f) * bw / (float)gw;
-        float yy = y;
-        if (yy < -1.0f || yy > (float)H || x < -1.0f || x > (float)W) continue;
-        if (yy <= 0.0f) yy = 0.0f;
-        if (x <= 0.0f) x = 0.0f;
-        int yl = (int)yy, xl = (int)x, yh, xh;
-        if (yl >= H - 1) { yh = yl = H - 1; yy = (float)yl; } else yh = yl + 1;
-        if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
-        const float ly = yy - yl, lx = x - xl, hy = 1.0f - ly, hx = 1.0f - lx;
-        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-        const float2 v1 = V2<T>::ld(F + ((long)yl * W + xl) * C + c), v2 = V2<T>::ld(F + ((long)yl * W + xh) * C + c);
-        const float2 v3 = V2<T>::ld(F + ((long)yh * W + xl) * C + c), v4 = V2<T>::ld(F + ((long)yh * W + xh) * C + c);
-        acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
-        acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+  for (int pw = warp; pw < S; pw += 4) {
+    for (int c = VE * lane; c < C; c += 32 * VE) {
+      float acc[VE];
+#pragma unroll
+      for (int j = 0; j < VE; j++) acc[j] = 0.0f;
+      for (int iy = 0; iy < gh; iy++) {
+        const float y = sh + ph * bh + (iy + 0.5f) * bh / (float)gh;
+        for (int ix = 0; ix < gw; ix++) {
+          float x = sw + pw * bw + (ix + 0.5f) * bw / (float)gw;
+          float yy = y;
+          if (yy < -1.0f || yy > (float)H || x < -1.0f || x > (float)W) continue;
+          if (yy <= 0.0f) yy = 0.0f;
+          if (x <= 0.0f) x = 0.0f;
+          int yl = (int)yy, xl = (int)x, yh, xh;
+          if (yl >= H - 1) { yh = yl = H - 1; yy = (float)yl; } else yh = yl + 1;
+          if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+          const float ly = yy - yl, lx = x - xl, hy = 1.0f - ly, hx = 1.0f - lx;
+          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+          float v1[VE], v2[VE], v3[VE], v4[VE];
+          Vec<T>::ld(F + ((long)yl * W + xl) * C + c, v1);
+          Vec<T>::ld(F + ((long)yl * W + xh) * C + c, v2);
+          Vec<T>::ld(F + ((long)yh * W + xl) * C + c, v3);
+          Vec<T>::ld(F + ((long)yh * W + xh) * C + c, v4);
+#pragma unroll
+          for (int j = 0; j < VE; j++) acc[j] += w1 * v1[j] + w2 * v2[j] + w3 * v3[j] + w4 * v4[j];
+        }
       }
+#pragma unroll
+      for (int j = 0; j < VE; j++) acc[j] /= count;
+      Vec<T>::st(out + (((long)r * S + ph) * S + pw) * C + c, acc);
     }
-    acc.x /= count; acc.y /= count;
-    V2<T>::st(out + ((long)r * S * S + bin) * C + c, acc);
   }
 }
 
@@ -82,48 +107,56 @@ __device__ __forceinline__ bool iou_over(const float4 a, const float4 b, float t
   return inter / (sa + sb - inter) > thr;
 }
 
-// One block per group; boxes of a group are sorted by descending score.  Phase 1: for every row i, the bitmask of
-// later boxes j > i it would suppress (n <= 1024 -> 32 words per row, in shared memory).  Phase 2: warp 0 sweeps the rows in
-// score order carrying the "removed" bitmask in registers (lane w owns word w) -- the sequential greedy NMS, on chip.
-__global__ void __launch_bounds__(1024) nms_groups_kernel(const float4* __restrict__ boxes, const unsigned char* __restrict__ valid, int n,
-                                                          float thr, unsigned char* __restrict__ keep) {
-  extern __shared__ unsigned int sm[];
-  float4* B = reinterpret_cast<float4*>(sm);                  // [n]
-  unsigned int* M = sm + 4 * n;                               // [n][32]
+// Greedy NMS in two launches.  (1) mask: for every row i the bitmask of later boxes j > i it would suppress, one warp per
+// (row, 32-box word), spread over the whole GPU.  (2) sweep: one block per group stages its n x 32-word mask in shared
+// memory and warp 0 walks the rows in score order carrying the "removed" set in registers (lane w owns word w).
+__global__ void __launch_bounds__(256) nms_mask_kernel(const float4* __restrict__ boxes, int n, float thr, unsigned int* __restrict__ mask) {
   const long g = blockIdx.x;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) B[i] = boxes[g * n + i];
-  __syncthreads();
+  const int i = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
   const int nw = (n + 31) >> 5;
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int t = warp; t < n * nw; t += nwarps) {             // one (row, word) per warp step: lane <-> candidate j
-      const int i = t / nw, w = t % nw, j0 = w << 5;
-      unsigned int bits = 0;
-      if (j0 + 31 > i) {                                      // warp-uniform
-        const int j = j0 + lane;
-        const bool sup = j > i && j < n && iou_over(B[i], B[min(j, n - 1)], thr);
-        bits = __ballot_sync(0xffffffffu, sup);
-      }
-      if (lane == 0) M[i * 32 + w] = bits;
+  const float4 a = __ldg(boxes + g * n + i);
+  unsigned int* row = mask + (g * n + i) * 32;
+  for (int w = 0; w < nw; w++) {
+    unsigned int bits = 0;
+    const int j = (w << 5) + lane;
+    if ((w << 5) + 31 > i) {                                  // warp-uniform
+      const bool sup = j > i && j < n && iou_over(a, __ldg(boxes + g * n + min(j, n - 1)), thr);
+      bits = __ballot_sync(0xffffffffu, sup);
     }
+    if (lane == 0) row[w] = bits;
   }
+}
+
+__global__ void __launch_bounds__(1024) nms_sweep_kernel(const unsigned int* __restrict__ mask, const unsigned char* __restrict__ valid, int n,
+                                                         unsigned char* __restrict__ keep) {
+  extern __shared__ unsigned int M[];                         // [n][32]
+  const long g = blockIdx.x;
+  const int nw = (n + 31) >> 5;
+  for (int t = threadIdx.x; t < n * 32; t += blockDim.x)
+    if ((t & 31) < nw) M[t] = mask[g * n * 32 + t];
   __syncthreads();
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     unsigned int removed = 0;                                 // word `lane` of the removed set
     for (int w = 0; w < nw; w++) {
       // invalid entries (empty boxes, padding, below the score threshold) start out removed
-      unsigned int inv = 0;
       const int j = (w << 5) + lane;
       const bool ok = j < n && valid[g * n + j];
-      inv = __ballot_sync(0xffffffffu, !ok);
+      const unsigned int inv = __ballot_sync(0xffffffffu, !ok);
       if (lane == w) removed |= inv;
     }
+    unsigned int mine = 0;                                    // keep bits of word `lane`
     for (int i = 0; i < n; i++) {
       const unsigned int word = __shfl_sync(0xffffffffu, removed, i >> 5);
       const bool alive = !((word >> (i & 31)) & 1u);
       if (alive && lane < nw) removed |= M[i * 32 + lane];
-      if (lane == 0) keep[g * n + i] = alive ? 1 : 0;
+      if (alive && lane == (i >> 5)) mine |= 1u << (i & 31);
+    }
+    for (int w = 0; w < nw; w++) {
+      const unsigned int bits = __shfl_sync(0xffffffffu, mine, w);
+      const int j = (w << 5) + lane;
+      if (j < n) keep[g * n + j] = (bits >> lane) & 1u;
     }
   }
 }
@@ -133,22 +166,26 @@ __global__ void __launch_bounds__(1024) nms_groups_kernel(const float4* __restri
 extern "C" int pvo_roi_align_fpn(const void* const* feats, const int* Hs, const int* Ws, int C, const float* rois, int R, int S, void* out,
                                  int dtype, void* stream) {
   if (R == 0) return PVO_OK;
-  if (C % 2 || S < 1) return PVO_ERR_INVALID;
+  if (C % (dtype == PVO_DTYPE_F32 ? 4 : 8) || S < 1) return PVO_ERR_INVALID;
   Pyr p;
   for (int l = 0; l < 4; l++) { p.f[l] = feats[l]; p.H[l] = Hs[l]; p.W[l] = Ws[l]; }
   cudaStream_t s = (cudaStream_t)stream;
-  const unsigned grid = (unsigned)((long)R * S * S);
+  const unsigned grid = (unsigned)((long)R * S);
   if (dtype == PVO_DTYPE_F16) roi_align_fpn_kernel<__half><<<grid, 128, 0, s>>>(p, C, rois, S, (__half*)out);
   else if (dtype == PVO_DTYPE_F32) roi_align_fpn_kernel<float><<<grid, 128, 0, s>>>(p, C, rois, S, (float*)out);
   else return PVO_ERR_UNSUPPORTED;
   return pvo_check_launch();
 }
 
-extern "C" int pvo_nms_groups(const float* boxes, const unsigned char* valid, int G, int n, float thr, unsigned char* keep, void* stream) {
+// scratch: G * n * 32 uint32 (the suppression bitmasks)
+extern "C" int pvo_nms_groups(const float* boxes, const unsigned char* valid, int G, int n, float thr, unsigned char* keep,
+                              unsigned int* scratch, void* stream) {
   if (G == 0 || n == 0) return PVO_OK;
-  if (n > 1024) return PVO_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)n * 16 + (size_t)n * 32 * 4;
-  cudaFuncSetAttribute(nms_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  nms_groups_kernel<<<G, 1024, smem, (cudaStream_t)stream>>>((const float4*)boxes, valid, n, thr, keep);
+  if (n > 1024 || !scratch) return PVO_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  nms_mask_kernel<<<dim3(G, (n + 7) / 8), 256, 0, s>>>((const float4*)boxes, n, thr, scratch);
+  const size_t smem = (size_t)n * 32 * 4;
+  cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  nms_sweep_kernel<<<G, 1024, smem, s>>>(scratch, valid, n, keep);
   return pvo_check_launch();
 }

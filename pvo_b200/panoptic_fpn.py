@@ -86,6 +86,21 @@ def paste_masks(masks, boxes, img_h, img_w, threshold=0.5):
     return F.grid_sample(masks.float(), grid, align_corners=False)[:, 0] >= threshold
 
 
+def _cat_rows(ts):
+    """torch.cat(ts) along dim 0, without the copy when the pieces are consecutive row blocks of one buffer"""
+    if len(ts) == 1:
+        return ts[0].contiguous()
+    t0 = ts[0]
+    off, ok = t0.storage_offset(), all(t.is_contiguous() for t in ts)
+    for t in ts:
+        ok = ok and t.untyped_storage().data_ptr() == t0.untyped_storage().data_ptr() and t.storage_offset() == off and t.shape[1:] == t0.shape[1:]
+        off += t.numel()
+    if ok:
+        rows = sum(t.shape[0] for t in ts)
+        return torch.as_strided(t0, (rows,) + tuple(t0.shape[1:]), t0.stride(), t0.storage_offset())
+    return torch.cat(ts).contiguous()
+
+
 class PanopticFPN:
     def __init__(self, state_dict, device='cuda', use_cuda_graph=True):
         self.device = torch.device(device)
@@ -95,7 +110,17 @@ class PanopticFPN:
         self.cv = {}
         tc = lambda w, b: pnn._Conv(w, b, tc=True, simt=False)
         w, b = _fold(sd, 'backbone.bottom_up.stem.conv1')
-        self.cv['stem'] = pnn._Conv(w, b)                                        # 7x7, 3 channels: CUDA-core path
+        # 7x7/s2 on 3 channels -> 5x1/s1 on the 48-channel space-to-depth, x-expanded image (csrc/fpn_ops.cu stem_expand)
+        w2 = torch.zeros(64, 48, 5, 1, device=self.device)
+        for ty in range(5):
+            for tx in range(4):
+                for dy in range(2):
+                    for dx in range(2):
+                        ky, kx = 2 * ty + dy - 1, 2 * tx + dx - 1
+                        if 0 <= ky < 7 and 0 <= kx < 7:
+                            j = tx * 12 + dy * 6 + dx * 3
+                            w2[:, j:j + 3, ty, 0] = w[:, :, ky, kx]
+        self.cv['stem'] = tc(w2, b)
         for si, (nb, mid, cout) in enumerate(RES_STAGES):
             for bi in range(nb):
                 pre = 'backbone.bottom_up.res%d.%d' % (si + 2, bi)
@@ -174,10 +199,10 @@ class PanopticFPN:
         """x (N,H,W,3) half -> {'p2'..'p6': ((N*h*w, 256) half, h, w)}"""
         L = _lib.lib()
         N, H, W, _ = x.shape
-        cv = self.cv['stem']
-        H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-        y = self._buf(N * H1 * W1, 64)
-        pnn.conv2d(cv, [(x.view(-1, 3), 3, 3)], N, H, W, _lib.F16, y, 64, 0, 1, stride=2)
+        H1, W1 = H // 2, W // 2
+        E = self._buf(N * H1 * W1, 64)
+        check(L.pvo_stem_expand(ptr(x), ptr(E), N, H, W, stream()), 'stem_expand')
+        y = self._conv('stem', E, N, H1, W1, relu=True)
         H2, W2 = (H1 - 1) // 2 + 1, (W1 - 1) // 2 + 1
         t = self._buf(N * H2 * W2, 64)
         check(L.pvo_maxpool3s2(ptr(y), ptr(t), N, H1, W1, 64, _lib.F16, stream()), 'maxpool3s2')
@@ -251,7 +276,7 @@ class PanopticFPN:
                 name = 'sem_seg_head.p%d.%d' % (lvl, 2 * j if stride != 4 else j)
                 x = self._conv(name, x, N, h, w)
                 g, b = self.gn[name]
-                check(L.pvo_group_norm(ptr(x), ptr(x), ptr(g), ptr(b), ptr(self._scr(N * 128 * 66 + 64)), N, h * w, 128, 4, 1e-5, 1,
+                check(L.pvo_group_norm(ptr(x), ptr(x), ptr(g), ptr(b), ptr(self._scr(N * 128 * 130 + 64)), N, h * w, 128, 4, 1e-5, 1,
                                        _lib.F16, stream()), 'group_norm', launches=3)
                 if stride != 4:
                     last = j == k - 1
@@ -284,7 +309,8 @@ class PanopticFPN:
         boxes = boxes.float().contiguous()
         v = valid.to(torch.uint8).contiguous()
         keep = torch.empty(G, n, dtype=torch.uint8, device=self.device)
-        check(_lib.lib().pvo_nms_groups(ptr(boxes), ptr(v), G, n, float(thresh), ptr(keep), stream()), 'nms_groups')
+        scratch = torch.empty(G * n * 32, dtype=torch.int32, device=self.device)
+        check(_lib.lib().pvo_nms_groups(ptr(boxes), ptr(v), G, n, float(thresh), ptr(keep), ptr(scratch), stream()), 'nms_groups', launches=2)
         return keep.bool()
 
     def _limits(self, image_sizes):
@@ -385,14 +411,25 @@ class PanopticFPN:
         return x.view(R, 14, 14, 2, 2, NUM_THING).permute(0, 5, 1, 3, 2, 4).reshape(R, NUM_THING, 28, 28)
 
     # ------------------------------------------------------------------------------------------ panoptic merge
-    def combine(self, dets_masks, sem_labels, overlap_threshold=0.5, stuff_area_thresh=4096, instances_score_thresh=0.5):
+    def paste(self, prob, boxes, H, W, threshold=0.5):
+        """paste_masks_in_image (mask_ops.py:74-152): prob (R,1,28,28) probabilities, boxes (R,4) -> (R,H,W) bool"""
+        R = prob.shape[0]
+        if W % 4:
+            return paste_masks(prob, boxes, H, W, threshold)
+        out = torch.empty(R, H, W, dtype=torch.uint8, device=self.device)
+        prob, boxes = prob.float().contiguous(), boxes.float().contiguous()
+        check(_lib.lib().pvo_paste_masks(ptr(prob), ptr(boxes), R, prob.shape[-1], H, W, float(threshold), ptr(out), stream()), 'paste_masks')
+        return out.view(torch.bool)
+
+    def combine(self, dets_masks, sem_labels, overlap_threshold=0.5, stuff_area_thresh=4096, instances_score_thresh=0.5, boxes=None):
         """combine_semantic_and_instance_outputs (panoptic_fpn.py:497-588) for images of one size, one launch.
-        dets_masks: per image (scores (R,), classes (R,), masks (R,H,W) bool); sem_labels (N,H,W) int64.
+        dets_masks: per image (scores (R,), classes (R,), masks (R,H,W) bool); sem_labels (N,H,W) int64; boxes: optional
+        per-image (R,4) detection boxes that bound the masks (limits each instance's scan to its box).
         -> pan (N,H,W) int32, per-image segments_info lists."""
         N, H, W = sem_labels.shape
         scores = torch.cat([d[0] for d in dets_masks]).float().contiguous()
         classes = torch.cat([d[1] for d in dets_masks]).long().contiguous()
-        masks = torch.cat([d[2].reshape(-1, H * W) for d in dets_masks]).contiguous()
+        masks = _cat_rows([d[2] for d in dets_masks])
         order = torch.cat([torch.argsort(-d[0].float()) for d in dets_masks]).long().contiguous()
         off = [0]
         for d in dets_masks:
@@ -403,8 +440,9 @@ class PanopticFPN:
         info = torch.zeros(N, max_info, 5, dtype=torch.int32, device=self.device)
         counts = torch.zeros(N, dtype=torch.int32, device=self.device)
         sem_labels = sem_labels.contiguous()
-        check(_lib.lib().pvo_panoptic_combine(ptr(masks), ptr(scores), ptr(classes), ptr(order), ptr(inst_off), ptr(sem_labels), ptr(pan),
-                                              ptr(info), ptr(counts), N, H * W, NUM_SEM, float(overlap_threshold), int(stuff_area_thresh),
+        bx = torch.cat(boxes).float().contiguous() if boxes is not None else None
+        check(_lib.lib().pvo_panoptic_combine(ptr(masks), ptr(bx), ptr(scores), ptr(classes), ptr(order), ptr(inst_off), ptr(sem_labels), ptr(pan),
+                                              ptr(info), ptr(counts), N, H, W, NUM_SEM, float(overlap_threshold), int(stuff_area_thresh),
                                               float(instances_score_thresh), THING_CAT0, max_info, stream()), 'panoptic_combine')
         info_h, counts_h, scores_h = info.cpu(), counts.cpu(), scores.cpu()                # the only device->host read
         segs = []
@@ -431,21 +469,25 @@ class PanopticFPN:
         cls, reg = self.box_head(self.roi_pool(feats, [p[0] for p in props], 7))
         dets = self.detections(cls, reg, props, sizes)
         ml = self.mask_head(self.roi_pool(feats, [d[0] for d in dets], 14))
-        results, o, per_image = [], 0, []
+        results, per_image = [], []
+        same = all(sz == sizes[0] for sz in sizes)
+        R_all = ml.shape[0]
+        cls_all = torch.cat([d[2] for d in dets]) if R_all else torch.zeros(0, dtype=torch.long, device=self.device)
+        prob_all = ml[torch.arange(R_all, device=self.device), cls_all][:, None].sigmoid()      # mask of the predicted class
+        if same:                                            # one paste launch for the batch; per-image views, no concatenation later
+            masks_all = self.paste(prob_all, torch.cat([d[0] for d in dets]), sizes[0][0], sizes[0][1])
+        o = 0
         for n, (b, s, c) in enumerate(dets):
             R = b.shape[0]
-            prob = ml[o:o + R][torch.arange(R, device=self.device), c][:, None].sigmoid()
+            per_image.append((s, c, masks_all[o:o + R] if same else self.paste(prob_all[o:o + R], b, sizes[n][0], sizes[n][1])))
             o += R
-            h, w = sizes[n]
-            per_image.append((s, c, paste_masks(prob, b, h, w)))
-        same = all(sz == sizes[0] for sz in sizes)
         if same:
             h, w = sizes[0]
-            pans, segs = self.combine(per_image, sem[:, :h, :w, :NUM_SEM].argmax(dim=-1))
+            pans, segs = self.combine(per_image, sem[:, :h, :w, :NUM_SEM].argmax(dim=-1), boxes=[d[0] for d in dets])
         else:
             pans, segs = [], []
             for n, (h, w) in enumerate(sizes):
-                p_, s_ = self.combine(per_image[n:n + 1], sem[n:n + 1, :h, :w, :NUM_SEM].argmax(dim=-1))
+                p_, s_ = self.combine(per_image[n:n + 1], sem[n:n + 1, :h, :w, :NUM_SEM].argmax(dim=-1), boxes=[dets[n][0]])
                 pans.append(p_[0])
                 segs.append(s_[0])
         for n, (b, s, c) in enumerate(dets):

@@ -131,6 +131,34 @@ def test_roi_align_fpn_matches_torchvision():
         assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max() < 1e-4 * ref.abs().max()
 
 
+def test_paste_masks_matches_grid_sample():
+    """the paste kernel restates mask_ops.py's grid construction + grid_sample operation for operation: same booleans"""
+    from pvo_b200.panoptic_fpn import PanopticFPN, paste_masks
+    m = PanopticFPN.__new__(PanopticFPN)
+    m.device = torch.device('cuda')
+    g = torch.Generator().manual_seed(11)
+    h, w, R = 120, 200, 64
+    c = torch.rand(R, 2, generator=g) * torch.tensor([w, h])
+    wh = torch.exp(torch.rand(R, 2, generator=g) * 4.5) + 2
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+    boxes[0] = torch.tensor([0., 0., float(w), float(h)])
+    boxes[1] = torch.tensor([-30.3, 10.2, 50.7, 300.0])
+    boxes[2] = torch.tensor([10., 20., 38., 48.])               # integer box: pixel centres exactly on cell borders
+    prob = torch.nn.functional.avg_pool2d(torch.rand(R, 1, 30, 30, generator=g), 3, 1).clamp(0, 1)
+    prob[3] = 1.0
+    ref = paste_masks(prob.cuda(), boxes.cuda(), h, w)
+    out = m.paste(prob.cuda(), boxes.cuda(), h, w)
+    bad = (ref != out).sum().item()
+    NOTES['paste_mismatch_px'] = [bad, ref.numel()]
+    assert bad == 0, bad
+    # masks never extend beyond the box (what lets the merge scan only the box region)
+    ys, xs = torch.arange(h, device='cuda') + 0.5, torch.arange(w, device='cuda') + 0.5
+    b = boxes.cuda()
+    inside = ((ys[None, :, None] >= b[:, 1, None, None] - 1) & (ys[None, :, None] <= b[:, 3, None, None] + 1) &
+              (xs[None, None, :] >= b[:, 0, None, None] - 1) & (xs[None, None, :] <= b[:, 2, None, None] + 1))
+    assert not (ref & ~inside).any()
+
+
 def test_panoptic_merge_bit_exact(setup):
     sd, images, ref, dbg, m = setup
     per_image, sems = [], []
@@ -138,11 +166,12 @@ def test_panoptic_merge_bit_exact(setup):
         inst = r['instances']
         per_image.append((inst['scores'].cuda(), inst['pred_classes'].cuda(), inst['pred_masks'].cuda()))
         sems.append(r['sem_seg'].argmax(0))
-    pan, segs = m.combine(per_image, torch.stack(sems).cuda())
-    for n, r in enumerate(ref):
-        assert torch.equal(pan[n].cpu(), r['panoptic_seg'][0])
-        assert [s['id'] for s in segs[n]] == [s['id'] for s in r['panoptic_seg'][1]]
-        assert [s.get('instance_id') for s in segs[n]] == [s.get('instance_id') for s in r['panoptic_seg'][1]]
+    for boxes in (None, [r['instances']['pred_boxes'].cuda() for r in ref]):     # full-image scan / box-limited scan
+        pan, segs = m.combine(per_image, torch.stack(sems).cuda(), boxes=boxes)
+        for n, r in enumerate(ref):
+            assert torch.equal(pan[n].cpu(), r['panoptic_seg'][0])
+            assert [s['id'] for s in segs[n]] == [s['id'] for s in r['panoptic_seg'][1]]
+            assert [s.get('instance_id') for s in segs[n]] == [s.get('instance_id') for s in r['panoptic_seg'][1]]
 
 
 def test_panoptic_merge_synthetic():

@@ -53,6 +53,8 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--cpu-sample', action='store_true')
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--profile-only', action='store_true', help='warm up, run --steps inferences, print nothing (for ncu)')
     args = ap.parse_args()
     import torch
     from oracle import panoptic_fpn as ofpn          # seeded weights only (and the optional CPU baseline leg)
@@ -62,7 +64,7 @@ def main():
     g = torch.Generator().manual_seed(0)
     host = [torch.nn.functional.avg_pool2d(torch.randint(0, 256, (1, 3, args.height, args.width), generator=g).float(), 5, 1, 2)[0].pin_memory()
             for _ in range(args.batch)]
-    m = PanopticFPN(sd, device='cuda')
+    m = PanopticFPN(sd, device='cuda', use_cuda_graph=not args.no_graph)
     dev_imgs = [h.cuda() for h in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 
@@ -82,14 +84,16 @@ def main():
         cls, reg = m.box_head(m.roi_pool(feats, [p[0] for p in props], 7)); mark('roi_align7_box_head')
         dets = m.detections(cls, reg, props, sizes); mark('detections_nms')
         ml = m.mask_head(m.roi_pool(feats, [d[0] for d in dets], 14)); mark('roi_align14_mask_head')
+        cls_all = torch.cat([d[2] for d in dets])
+        prob = ml[torch.arange(ml.shape[0], device='cuda'), cls_all][:, None].sigmoid()
+        masks = m.paste(prob, torch.cat([d[0] for d in dets]), sizes[0][0], sizes[0][1])
         per_image, o = [], 0
         for n, (b, s_, c) in enumerate(dets):
-            R = b.shape[0]
-            prob = ml[o:o + R][torch.arange(R, device='cuda'), c][:, None].sigmoid()
-            o += R
-            per_image.append((s_, c, paste_masks(prob, b, sizes[n][0], sizes[n][1])))
+            per_image.append((s_, c, masks[o:o + b.shape[0]]))
+            o += b.shape[0]
         mark('paste_masks')
-        m.combine(per_image, sem[:, :sizes[0][0], :sizes[0][1], :12].argmax(dim=-1)); mark('panoptic_merge')
+        labels = sem[:, :sizes[0][0], :sizes[0][1], :12].argmax(dim=-1); mark('sem_argmax')
+        m.combine(per_image, labels, boxes=[d[0] for d in dets]); mark('panoptic_merge')
         torch.cuda.synchronize()
         for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
             stages.setdefault(n1, []).append(e0.elapsed_time(e1))
@@ -98,6 +102,11 @@ def main():
     for _ in range(args.warmup):
         m.inference(dev_imgs)
     torch.cuda.synchronize()
+    if args.profile_only:
+        for _ in range(args.steps):
+            m.inference(dev_imgs)
+        torch.cuda.synchronize()
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms = []
     _lib.LAUNCHES[0] = 0
