@@ -169,6 +169,17 @@ int pvo_panoptic_combine(const void* masks, const float* boxes, const float* sco
  * levels p2..p5 (strides 4..32).  rois (R,5) = {image index, x0, y0, x1, y1} float32; out (R, S, S, C) pixel-major. */
 int pvo_roi_align_fpn(const void* const* feats, const int* Hs, const int* Ws, int C, const float* rois, int R, int S, void* out,
                       int dtype, void* stream);
+/* find_top_rpn_proposals' decode stage (proposal_generator/proposal_utils.py:59-100) for all images and the 5 levels in one
+ * launch: rpn_out[l] (N,h,w,16) half = objectness x3 | deltas 3x4, topk_idx[l] (N,ks[l]) indices into (h,w,3) ->
+ * boxes (N,5,P,4) decoded + clipped to limits (N,4), scores (N,5,P) (-inf padding), valid (N,5,P).  cell_anchors: HOST (5,3,4). */
+int pvo_rpn_decode(const void* const* rpn_out, const long* const* topk_idx, const int* hs, const int* ws, const int* ks, const int* strides,
+                   const float* cell_anchors, const float* limits, int N, int P, float* boxes, float* scores, unsigned char* valid,
+                   void* stream);
+/* FastRCNNOutputLayers.predict_probs / predict_boxes (roi_heads/fast_rcnn.py:400-440): softmax + per-class decode
+ * (weights 10,10,5,5) + clip; rois of image n are rows offsets[n]..offsets[n+1] -> class-major padded scores (N,K,P),
+ * boxes (N,K,P,4), both zero-initialised by the caller. */
+int pvo_det_decode(const float* cls /*(R,K+1)*/, const float* reg /*(R,4K)*/, const float* props /*(R,4)*/, const int* offsets,
+                   const float* limits /*(N,4)*/, int R, int N, int P, int K, float* scores, float* boxes, void* stream);
 /* Greedy NMS for G independent groups of n <= 1024 boxes sorted by descending score (layers/nms.py:9-22 batched_nms ->
  * torchvision nms per category): keep[g][i] = 1 iff box i is valid and no kept earlier box overlaps it with IoU > thr. */
 int pvo_nms_groups(const float* boxes /*(G,n,4)*/, const unsigned char* valid /*(G,n)*/, int G, int n, float thr,

@@ -94,7 +94,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(1024)
   int* P = pan + n * HW;
   for (long i = (long)ys * W + threadIdx.x; i < (long)ye * W; i += blockDim.x) P[i] = 0;
   __syncthreads();
-  int cur = 0, step = 0;
+  int cur = 0, it = 0;
   const int r0 = inst_off[n], r1 = inst_off[n + 1];
   for (int k = r0; k < r1; k++) {
     const int r = r0 + (int)order[k];                       // order[] holds per-image ranks sorted by descending score
@@ -105,32 +105,58 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(1024)
       x0 = max(0, (int)floorf(boxes[r * 4 + 0] - 1.5f)); y0 = max(ys, (int)floorf(boxes[r * 4 + 1] - 1.5f));
       x1 = min(W, (int)ceilf(boxes[r * 4 + 2] + 1.5f)); y1 = min(ye, (int)ceilf(boxes[r * 4 + 3] + 1.5f));
     }
-    const int rw = max(x1 - x0, 0), cnt = rw * max(y1 - y0, 0);
+    // 4 pixels per thread when rows are 4-aligned (W % 4 == 0): one 32-bit mask load, the pan ids only where it is set
+    const bool vec = (W & 3) == 0;
+    if (vec) { x0 &= ~3; x1 = min(W, (x1 + 3) & ~3); }
+    const int step = vec ? 4 : 1;
+    const int rw = max(x1 - x0, 0) / step, cnt = rw * max(y1 - y0, 0);
     int area = 0, inter = 0;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const long px = (long)(y0 + i / rw) * W + x0 + i % rw;
-      const int m = M[px] != 0;
-      area += m;
-      inter += m && (P[px] > 0);
+      const long px = (long)(y0 + i / rw) * W + x0 + (i % rw) * step;
+      if (vec) {
+        const unsigned int m4 = __ldg(reinterpret_cast<const unsigned int*>(M + px));
+        if (m4) {
+          const int4 p4 = *reinterpret_cast<const int4*>(P + px);
+          const int b0 = (m4 & 0xffu) != 0, b1 = (m4 & 0xff00u) != 0, b2 = (m4 & 0xff0000u) != 0, b3 = (m4 & 0xff000000u) != 0;
+          area += b0 + b1 + b2 + b3;
+          inter += (b0 && p4.x > 0) + (b1 && p4.y > 0) + (b2 && p4.z > 0) + (b3 && p4.w > 0);
+        }
+      } else {
+        const int m = M[px] != 0;
+        area += m;
+        inter += m && (P[px] > 0);
+      }
     }
     area = block_sum_int(area, sh);
     inter = block_sum_int(inter, sh);
-    if (threadIdx.x == 0) { slot[step & 1][0] = area; slot[step & 1][1] = inter; }
+    if (threadIdx.x == 0) { slot[it & 1][0] = area; slot[it & 1][1] = inter; }
     cluster.sync();
     area = 0; inter = 0;
     for (int c = 0; c < kCluster; c++) {
-      const int* rs = cluster.map_shared_rank(&slot[step & 1][0], c);
+      const int* rs = cluster.map_shared_rank(&slot[it & 1][0], c);
       area += rs[0]; inter += rs[1];
     }
-    step++;
+    it++;
     if (area == 0) continue;
     if ((double)inter / (double)area > (double)overlap_thr) continue;       // the reference divides Python numbers (doubles)
     cur++;
     const int cat = thing_cat0 + (int)classes[r];
     const int id = cat * 10000 + cur;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const long px = (long)(y0 + i / rw) * W + x0 + i % rw;
-      if (M[px] && P[px] == 0) P[px] = id;
+      const long px = (long)(y0 + i / rw) * W + x0 + (i % rw) * step;
+      if (vec) {
+        const unsigned int m4 = __ldg(reinterpret_cast<const unsigned int*>(M + px));
+        if (m4) {
+          int4 p4 = *reinterpret_cast<const int4*>(P + px);
+          if ((m4 & 0xffu) && p4.x == 0) p4.x = id;
+          if ((m4 & 0xff00u) && p4.y == 0) p4.y = id;
+          if ((m4 & 0xff0000u) && p4.z == 0) p4.z = id;
+          if ((m4 & 0xff000000u) && p4.w == 0) p4.w = id;
+          *reinterpret_cast<int4*>(P + px) = p4;
+        }
+      } else if (M[px] && P[px] == 0) {
+        P[px] = id;
+      }
     }
     if (rank == 0 && threadIdx.x == 0 && cur <= max_info) {
       int* o = info_out + ((long)n * max_info + cur - 1) * 5;

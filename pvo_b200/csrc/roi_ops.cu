@@ -161,7 +161,124 @@ __global__ void __launch_bounds__(1024) nms_sweep_kernel(const unsigned int* __r
   }
 }
 
+// ---- box decoding, fused.  Box2BoxTransform.apply_deltas (modeling/box_regression.py:76-116) evaluated with the same
+// individually rounded fp32 operations as the reference's tensor expressions (no FMA contraction), then Boxes.clip and the
+// non-empty test (structures/boxes.py:185-215).
+struct Box4 { float x0, y0, x1, y1; };
+__device__ __forceinline__ Box4 apply_deltas(const float4 b, float dx, float dy, float dw, float dh, float wx, float wy, float ww, float wh) {
+  const float kClamp = 4.135166556742356f;                    // log(1000 / 16)
+  const float widths = __fsub_rn(b.z, b.x), heights = __fsub_rn(b.w, b.y);
+  const float cx = __fadd_rn(b.x, __fmul_rn(0.5f, widths)), cy = __fadd_rn(b.y, __fmul_rn(0.5f, heights));
+  dx = __fdiv_rn(dx, wx); dy = __fdiv_rn(dy, wy);
+  dw = fminf(__fdiv_rn(dw, ww), kClamp); dh = fminf(__fdiv_rn(dh, wh), kClamp);
+  const float pcx = __fadd_rn(__fmul_rn(dx, widths), cx), pcy = __fadd_rn(__fmul_rn(dy, heights), cy);
+  const float pw = __fmul_rn(expf(dw), widths), ph = __fmul_rn(expf(dh), heights);
+  Box4 o;
+  o.x0 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)); o.y0 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+  o.x1 = __fadd_rn(pcx, __fmul_rn(0.5f, pw)); o.y1 = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+  return o;
+}
+__device__ __forceinline__ float clampf(float v, float hi) { return fminf(fmaxf(v, 0.0f), hi); }   // NaN -> 0..hi, flagged invalid before
+
+struct RpnLevels {
+  const __half* out[5];     // (N, h, w, 16): objectness x3 | deltas 3x4 | pad
+  const long* idx[5];       // (N, k) top-k indices into (h, w, 3)
+  int h[5], w[5], k[5], stride[5];
+  float cell[5][3][4];      // cell anchors (anchor_generator.py generate_cell_anchors)
+};
+
+// grid (ceil(P/128), 5, N): one thread per (image, level, rank) -> boxes (N,5,P,4), scores (N,5,P), valid (N,5,P)
+__global__ void __launch_bounds__(128) rpn_decode_kernel(const __grid_constant__ RpnLevels L, const float* __restrict__ limits /*(N,4)*/, int P,
+                                                         float4* __restrict__ boxes, float* __restrict__ scores, unsigned char* __restrict__ valid) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y, n = blockIdx.z;
+  if (r >= P) return;
+  const long o = ((long)n * 5 + l) * P + r;
+  if (r >= L.k[l]) {
+    boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    scores[o] = -INFINITY;
+    valid[o] = 0;
+    return;
+  }
+  const long id = L.idx[l][(long)n * L.k[l] + r];
+  const int a = (int)(id % 3);
+  const long cell = id / 3;
+  const int x = (int)(cell % L.w[l]), y = (int)(cell / L.w[l]);
+  const __half* q = L.out[l] + ((long)n * L.h[l] * L.w[l] + cell) * 16;
+  const float sx = (float)(x * L.stride[l]), sy = (float)(y * L.stride[l]);
+  const float4 anc = make_float4(__fadd_rn(sx, L.cell[l][a][0]), __fadd_rn(sy, L.cell[l][a][1]), __fadd_rn(sx, L.cell[l][a][2]),
+                                 __fadd_rn(sy, L.cell[l][a][3]));
+  const float score = __half2float(q[a]);
+  Box4 b = apply_deltas(anc, __half2float(q[3 + 4 * a]), __half2float(q[4 + 4 * a]), __half2float(q[5 + 4 * a]), __half2float(q[6 + 4 * a]),
+                        1.f, 1.f, 1.f, 1.f);
+  bool ok = isfinite(b.x0) && isfinite(b.y0) && isfinite(b.x1) && isfinite(b.y1) && isfinite(score);
+  const float4 lim = __ldg(reinterpret_cast<const float4*>(limits) + n);
+  b.x0 = clampf(b.x0, lim.x); b.y0 = clampf(b.y0, lim.y); b.x1 = clampf(b.x1, lim.z); b.y1 = clampf(b.y1, lim.w);
+  ok = ok && (b.x1 - b.x0) > 0.0f && (b.y1 - b.y0) > 0.0f;    // min_box_size = 0
+  boxes[o] = make_float4(b.x0, b.y0, b.x1, b.y1);
+  scores[o] = score;
+  valid[o] = ok ? 1 : 0;
+}
+
+// FastRCNNOutputLayers.predict_boxes / predict_probs (fast_rcnn.py:400-440): softmax over K+1 logits, per-class decode with
+// weights (10,10,5,5), clip.  One thread per (roi, class) -> class-major padded scores (N,K,P) / boxes (N,K,P,4) (zero-initialised).
+__global__ void __launch_bounds__(128) det_decode_kernel(const float* __restrict__ cls, const float* __restrict__ reg, const float4* __restrict__ props,
+                                                         const int* __restrict__ offs /*(N+1)*/, const float* __restrict__ limits, int R, int N,
+                                                         int P, int K, float* __restrict__ scores, float4* __restrict__ boxes) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= R * K) return;
+  const int r = t / K, k = t % K;
+  int n = 0;
+  while (n + 1 < N && r >= offs[n + 1]) n++;
+  const int rank = r - offs[n];
+  const float* c = cls + (long)r * (K + 1);
+  float mx = c[0];
+  for (int j = 1; j <= K; j++) mx = fmaxf(mx, c[j]);
+  float sum = 0.0f;
+  for (int j = 0; j <= K; j++) sum += expf(c[j] - mx);
+  const float score = expf(c[k] - mx) / sum;
+  bool ok = true;
+  for (int j = 0; j <= K; j++) ok = ok && isfinite(c[j]);
+  const float* d = reg + (long)r * 4 * K;
+  for (int j = 0; j < 4 * K; j++) ok = ok && isfinite(d[j]);                 // the reference drops the row if ANY of its boxes is non-finite
+  Box4 b = apply_deltas(__ldg(props + r), d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3], 10.f, 10.f, 5.f, 5.f);
+  if (ok) {                                                                  // ... which needs every class's decode
+    const float4 pb = __ldg(props + r);
+    for (int j = 0; j < K; j++) {
+      const Box4 bj = apply_deltas(pb, d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3], 10.f, 10.f, 5.f, 5.f);
+      ok = ok && isfinite(bj.x0) && isfinite(bj.y0) && isfinite(bj.x1) && isfinite(bj.y1);
+    }
+  }
+  const float4 lim = __ldg(reinterpret_cast<const float4*>(limits) + n);
+  const long o = ((long)n * K + k) * P + rank;
+  scores[o] = ok ? score : 0.0f;
+  boxes[o] = make_float4(clampf(b.x0, lim.x), clampf(b.y0, lim.y), clampf(b.x1, lim.z), clampf(b.y1, lim.w));
+}
+
 }  // namespace
+
+extern "C" int pvo_rpn_decode(const void* const* rpn_out, const long* const* topk_idx, const int* hs, const int* ws, const int* ks,
+                              const int* strides, const float* cell_anchors /*host (5,3,4)*/, const float* limits, int N, int P,
+                              float* boxes, float* scores, unsigned char* valid, void* stream) {
+  if (N == 0 || P == 0) return PVO_OK;
+  RpnLevels L;
+  for (int l = 0; l < 5; l++) {
+    L.out[l] = (const __half*)rpn_out[l]; L.idx[l] = topk_idx[l];
+    L.h[l] = hs[l]; L.w[l] = ws[l]; L.k[l] = ks[l]; L.stride[l] = strides[l];
+    for (int a = 0; a < 3; a++)
+      for (int c = 0; c < 4; c++) L.cell[l][a][c] = cell_anchors[(l * 3 + a) * 4 + c];
+  }
+  rpn_decode_kernel<<<dim3((P + 127) / 128, 5, N), 128, 0, (cudaStream_t)stream>>>(L, limits, P, (float4*)boxes, scores, valid);
+  return pvo_check_launch();
+}
+
+extern "C" int pvo_det_decode(const float* cls, const float* reg, const float* props, const int* offsets, const float* limits, int R, int N,
+                              int P, int K, float* scores, float* boxes, void* stream) {
+  if (R == 0) return PVO_OK;
+  if (K < 1 || K > 16) return PVO_ERR_INVALID;
+  det_decode_kernel<<<(R * K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cls, reg, (const float4*)props, offsets, limits, R, N, P, K, scores,
+                                                                            (float4*)boxes);
+  return pvo_check_launch();
+}
 
 extern "C" int pvo_roi_align_fpn(const void* const* feats, const int* Hs, const int* Ws, int C, const float* rois, int R, int S, void* out,
                                  int dtype, void* stream) {

@@ -59,14 +59,19 @@ def clip_boxes(b, size):
     return b
 
 
-def grid_anchors(h, w, stride, size, device):
-    """anchor_generator.py DefaultAnchorGenerator: 3 aspect ratios per cell, area size^2, anchor index fastest"""
+def cell_anchors(size):
+    """anchor_generator.py generate_cell_anchors: 3 aspect ratios, area size^2, centred on the cell origin"""
     cell = []
     for ratio in (0.5, 1.0, 2.0):
         aw = math.sqrt(size * size / ratio)
         ah = ratio * aw
         cell.append([-aw / 2.0, -ah / 2.0, aw / 2.0, ah / 2.0])
-    cell = torch.tensor(cell, device=device)
+    return cell
+
+
+def grid_anchors(h, w, stride, size, device):
+    """anchor_generator.py DefaultAnchorGenerator: anchor index fastest"""
+    cell = torch.tensor(cell_anchors(size), device=device)
     sx = torch.arange(0, w * stride, stride, dtype=torch.float32, device=device)
     sy = torch.arange(0, h * stride, stride, dtype=torch.float32, device=device)
     yy, xx = torch.meshgrid(sy, sx, indexing='ij')
@@ -293,14 +298,13 @@ class PanopticFPN:
         return out.view(N, 4 * h4, 4 * w4, 16)
 
     def rpn_head(self, feats):
-        """-> per level (objectness (N,h,w,3), deltas (N,h,w,3,4)) float32"""
+        """-> per level the fused head output (N,h,w,16) half: objectness (3 anchors) | anchor deltas (3x4) | pad"""
         N = self.N
         res = []
         for lvl in (2, 3, 4, 5, 6):
             x, h, w = feats['p%d' % lvl]
             t = self._conv('rpn_conv', x, N, h, w, relu=True)
-            o = self._conv('rpn_out', t, N, h, w, cpad=16).view(N, h, w, 16).float()
-            res.append((o[..., :3], o[..., 3:15].reshape(N, h, w, 3, 4)))
+            res.append(self._conv('rpn_out', t, N, h, w, cpad=16).view(N, h, w, 16))
         return res
 
     def nms_groups(self, boxes, valid, thresh):
@@ -319,31 +323,28 @@ class PanopticFPN:
 
     def proposals(self, rpn_out, image_sizes, pre_nms_topk=1000, post_nms_topk=1000, nms_thresh=0.7):
         """find_top_rpn_proposals (proposal_utils.py:22-126): per-level top-k, decode, clip, drop empty, per-level NMS,
-        best post_nms_topk per image -- batched over images and levels, one device->host read (the counts)."""
+        best post_nms_topk per image -- batched over images and levels, one device->host read (the counts).
+        rpn_out: per level the raw head output (N,h,w,16) half (objectness x3 | deltas 3x4 | pad)."""
         N, P = self.N, pre_nms_topk
-        lim = self._limits(image_sizes)[:, None, :]
-        zero = torch.zeros((), device=self.device)
-        B, S, V = [], [], []
-        for (lg, dl), stride, size in zip(rpn_out, (4, 8, 16, 32, 64), (32, 64, 128, 256, 512)):
-            h, w = lg.shape[1:3]
-            anchors = grid_anchors(h, w, stride, size, self.device)
-            lg, dl = lg.reshape(N, -1), dl.reshape(N, -1, 4)
+        L = _lib.lib()
+        idx, ks = [], []
+        for o in rpn_out:
+            lg = o[..., :3].reshape(N, -1).float()
             k = min(P, lg.shape[1])
-            top, idx = lg.topk(k, dim=1)                               # descending
-            d = torch.gather(dl, 1, idx[..., None].expand(-1, -1, 4))
-            boxes = apply_deltas(d.reshape(-1, 4), anchors[idx].reshape(-1, 4), (1.0, 1.0, 1.0, 1.0)).view(N, k, 4)
-            valid = torch.isfinite(boxes).all(dim=-1) & torch.isfinite(top)
-            boxes = torch.minimum(torch.maximum(boxes, zero), lim)
-            valid &= ((boxes[..., 2] - boxes[..., 0]) > 0) & ((boxes[..., 3] - boxes[..., 1]) > 0)   # min_box_size = 0
-            B.append(F.pad(boxes, (0, 0, 0, P - k)))
-            S.append(F.pad(top, (0, P - k), value=float('-inf')))
-            V.append(F.pad(valid, (0, P - k)))
-        boxes, scores, valid = torch.stack(B, 1), torch.stack(S, 1), torch.stack(V, 1)            # (N, 5, P, ...)
-        G = len(B)
+            idx.append(lg.topk(k, dim=1)[1].contiguous())             # descending
+            ks.append(k)
+        G = len(rpn_out)
+        boxes = torch.empty(N, G, P, 4, device=self.device)
+        scores = torch.empty(N, G, P, device=self.device)
+        valid = torch.empty(N, G, P, dtype=torch.uint8, device=self.device)
+        cells = (_lib.c_float * 60)(*[v for size in (32, 64, 128, 256, 512) for a in cell_anchors(size) for v in a])
+        check(L.pvo_rpn_decode(_lib.ptr_array(rpn_out), _lib.ptr_array(idx), _lib.int_array([o.shape[1] for o in rpn_out]),
+                               _lib.int_array([o.shape[2] for o in rpn_out]), _lib.int_array(ks), _lib.int_array([4, 8, 16, 32, 64]), cells,
+                               ptr(self._limits(image_sizes)), N, P, ptr(boxes), ptr(scores), ptr(valid), stream()), 'rpn_decode')
         keep = self.nms_groups(boxes.view(N * G, P, 4), valid.view(N * G, P), nms_thresh).view(N, G * P)
         sc = torch.where(keep, scores.view(N, G * P), torch.full_like(scores.view(N, G * P), float('-inf')))
-        top, idx = sc.topk(min(post_nms_topk, G * P), dim=1)
-        bx = torch.gather(boxes.view(N, G * P, 4), 1, idx[..., None].expand(-1, -1, 4))
+        top, ti = sc.topk(min(post_nms_topk, G * P), dim=1)
+        bx = torch.gather(boxes.view(N, G * P, 4), 1, ti[..., None].expand(-1, -1, 4))
         counts = keep.sum(dim=1).clamp(max=post_nms_topk).tolist()
         return [(bx[n, :c], top[n, :c]) for n, c in enumerate(counts)]
 
@@ -352,27 +353,24 @@ class PanopticFPN:
         per-class NMS, best `topk` per image -> per image (boxes, scores, classes)"""
         N, K = len(props), NUM_THING
         counts = [p[0].shape[0] for p in props]
-        P = max(max(counts), 1)
-        cnt = torch.tensor(counts, device=self.device)
-        img = torch.repeat_interleave(torch.arange(N, device=self.device), cnt)
-        rank = torch.arange(sum(counts), device=self.device) - (torch.cumsum(cnt, 0) - cnt)[img]
-        pb = torch.cat([p[0] for p in props])
-        boxes = apply_deltas(reg, pb, (10.0, 10.0, 5.0, 5.0))
-        scores = F.softmax(cls, dim=-1)
-        ok = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
-        lim = self._limits(image_sizes)[img][:, None, :]
-        boxes = torch.minimum(torch.maximum(boxes.view(-1, K, 4), torch.zeros((), device=self.device)), lim)
-        sp = torch.zeros(N, P, K, device=self.device)
-        bp = torch.zeros(N, P, K, 4, device=self.device)
-        sp[img, rank] = torch.where(ok[:, None], scores[:, :K], torch.zeros_like(scores[:, :K]))
-        bp[img, rank] = boxes
-        ss, order = sp.permute(0, 2, 1).sort(dim=2, descending=True)                          # (N, K, P)
-        bs = torch.gather(bp.permute(0, 2, 1, 3), 2, order[..., None].expand(-1, -1, -1, 4))
-        keep = self.nms_groups(bs.reshape(N * K, P, 4), (ss > score_thresh).reshape(N * K, P), nms_thresh).view(N, K * P)
-        sc = torch.where(keep, ss.reshape(N, K * P), torch.full_like(ss.reshape(N, K * P), -1.0))
-        top, idx = sc.topk(min(topk, K * P), dim=1)
-        bx = torch.gather(bs.reshape(N, K * P, 4), 1, idx[..., None].expand(-1, -1, 4))
-        cl = torch.div(idx, P, rounding_mode='floor')
+        R, P = sum(counts), max(max(counts), 1)
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        offsets = torch.tensor(offs, dtype=torch.int32, device=self.device)
+        pb = _cat_rows([p[0] for p in props]).float()
+        sp = torch.zeros(N, K, P, device=self.device)
+        bp = torch.zeros(N, K, P, 4, device=self.device)
+        cls, reg = cls.float().contiguous(), reg.float().contiguous()
+        check(_lib.lib().pvo_det_decode(ptr(cls), ptr(reg), ptr(pb), ptr(offsets), ptr(self._limits(image_sizes)), R, N, P, K, ptr(sp), ptr(bp),
+                                        stream()), 'det_decode')
+        ss, order = sp.sort(dim=2, descending=True)                                           # (N, K, P)
+        bs = torch.gather(bp, 2, order[..., None].expand(-1, -1, -1, 4))
+        keep = self.nms_groups(bs.view(N * K, P, 4), (ss > score_thresh).view(N * K, P), nms_thresh).view(N, K * P)
+        sc = torch.where(keep, ss.view(N, K * P), torch.full_like(ss.view(N, K * P), -1.0))
+        top, ti = sc.topk(min(topk, K * P), dim=1)
+        bx = torch.gather(bs.view(N, K * P, 4), 1, ti[..., None].expand(-1, -1, 4))
+        cl = torch.div(ti, P, rounding_mode='floor')
         kept = keep.sum(dim=1).clamp(max=topk).tolist()
         return [(bx[n, :c], top[n, :c], cl[n, :c]) for n, c in enumerate(kept)]
 

@@ -58,8 +58,9 @@ def test_backbone_and_heads(setup):
     assert e < 2e-2, e
     assert (sem[..., :12].argmax(-1).cpu() == dbg['sem'].argmax(1)).float().mean() > 0.97
     rpn = m.rpn_head(feats)
-    for i, ((lg, dl), rl, rd) in enumerate(zip(rpn, dbg['rpn_logits'], dbg['rpn_deltas'])):
+    for i, (o, rl, rd) in enumerate(zip(rpn, dbg['rpn_logits'], dbg['rpn_deltas'])):
         N, A, h, w = rl.shape
+        lg, dl = o[..., :3].float(), o[..., 3:15].reshape(N, h, w, 3, 4).float()
         assert rel(lg, rl.permute(0, 2, 3, 1), 'rpn_logits_p%d' % (i + 2)) < 3e-2
         assert rel(dl, rd.view(N, A, 4, h, w).permute(0, 3, 4, 1, 2), 'rpn_deltas_p%d' % (i + 2)) < 3e-2
 
@@ -80,6 +81,40 @@ def test_roi_heads_on_oracle_boxes(setup):
     ml = m.mask_head(m.roi_pool(feats, [d[0] for d in dets], 14))
     assert ml.shape == dbg['mask_logits'].shape
     assert rel(ml, dbg['mask_logits'], 'mask_logits') < 3e-2
+
+
+def test_proposals_and_detections_on_oracle_head_outputs(setup):
+    """the batched decode / clip / NMS / top-k stages reproduce the oracle's proposal and detection lists when both sides
+    start from the same (half-rounded) head outputs"""
+    sd, images, ref, dbg, m = setup
+    m.N = 2
+    sizes = [(H, W), (H, W)]
+    packed, lgs, dls = [], [], []
+    for rl, rd in zip(dbg['rpn_logits'], dbg['rpn_deltas']):
+        N, A, h, w = rl.shape
+        o = torch.cat([rl.permute(0, 2, 3, 1), rd.permute(0, 2, 3, 1), torch.zeros(N, h, w, 1)], -1).half()
+        packed.append(o.cuda().contiguous())
+        lgs.append(o[..., :3].float().permute(0, 3, 1, 2).contiguous())
+        dls.append(o[..., 3:15].float().permute(0, 3, 1, 2).contiguous())
+    want = ofpn.rpn_proposals(lgs, dls, sizes)
+    got = m.proposals(packed, sizes)
+    for (wb, ws), (gb, gs) in zip(want, got):
+        assert gb.shape == wb.shape
+        assert torch.equal(gs.cpu(), ws)                              # same survivors, same order
+        assert (gb.cpu() - wb).abs().max() < 1e-4                     # decode + clip (expf differs by an ulp between CPU and GPU)
+    props = [(b.cuda(), s_.cuda()) for b, s_ in dbg['proposals']]        # the rows box_cls / box_reg were computed for
+    cls, reg = dbg['box_cls'].cuda(), dbg['box_reg'].cuda()
+    dets = m.detections(cls, reg, props, sizes)
+    o = 0
+    for n, (pb, _) in enumerate(dbg['proposals']):
+        R = pb.shape[0]
+        boxes = ofpn.apply_deltas(dbg['box_reg'][o:o + R], pb, (10.0, 10.0, 5.0, 5.0))
+        scores = torch.softmax(dbg['box_cls'][o:o + R], dim=-1)
+        wb, ws, wc = ofpn.fast_rcnn_inference_single(boxes, scores, sizes[n])
+        o += R
+        gb, gs, gc = dets[n]
+        assert gb.shape == wb.shape and torch.equal(gc.cpu(), wc)
+        assert (gs.cpu() - ws).abs().max() < 1e-6 and (gb.cpu() - wb).abs().max() < 1e-4
 
 
 def test_nms_groups_match_torchvision():
