@@ -181,17 +181,28 @@ struct EpQ {             // gru.py:30-32, state update in place
   }
 };
 
+constexpr int kMaxKb = 512;   // k-blocks per tile the on-chip k-block table holds (taps x 64-channel blocks)
+
+// A pipeline stage carries kG consecutive k-blocks (each: A 128x64 + B BNx64 halves), so one barrier round trip
+// (producer wait / expect_tx, consumer wait / commit) is paid per kG k-blocks.  Measured (tools/diag_conv.py): with one
+// k-block per stage, short-K layers ran at ~0.5 us per k-block whether or not they loaded or multiplied anything --
+// the single-thread producer / issuer loops and their barrier operations were the bound, not bytes or FLOPs.
 template <int BN> struct Cfg {
   static constexpr int kStageA = kBM * kBK * 2;                 // 16 KB
   static constexpr int kStageB = BN * kBK * 2;
-  static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kKb = kStageA + kStageB;                 // one k-block of operands
+  static constexpr int kG = (BN == 64) ? 2 : 1;
+  static constexpr int kStage = kG * kKb;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 2);
+  // BN <= 128 tiles are bound by the per-k-block issue overhead of the single producer / issuer threads, not by the
+  // tensor pipe: two co-resident CTAs per SM (96 KB of stages and <= 256 TMEM columns each) double that throughput.
+  static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN; // 128 / 256 / 512: powers of two
-  static constexpr int kSmem = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmem = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/ + kMaxKb * 4 /*k-block table*/;
 };
 
 template <int BN, typename Epi>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p, const Epi epi) {
+__global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm) conv_tc_kernel(const __grid_constant__ TcParams p, const Epi epi) {
   using C = Cfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B)
@@ -202,10 +213,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   uint64_t* tfull = bars + 2 * C::kStages;     // [2]        MMA -> epilogue
   uint64_t* tempty = tfull + 2;                // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  int* kbt = reinterpret_cast<int*>(bars) + 64;    // [nkb] k-block table: cb | seg << 12 | (dy + 8) << 16 | (dx + 8) << 20
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.taps * p.blocks_per_tap;
 
+  for (int kb = threadIdx.x; kb < nkb; kb += blockDim.x) {      // (tap, segment, channel block) of every k-block, once per CTA
+    const int tap = kb / p.blocks_per_tap;
+    int rem = kb - tap * p.blocks_per_tap, seg = 0;
+    while (rem >= p.seg_blocks[seg]) { rem -= p.seg_blocks[seg]; seg++; }
+    kbt[kb] = rem | seg << 12 | (tap / p.KW - p.padH + 8) << 16 | (tap % p.KW - p.padW + 8) << 20;
+  }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; s++) prefetch_tmap(&p.tmA[s]);
     prefetch_tmap(&p.tmB);
@@ -220,30 +238,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int mt = tile / p.n_tiles;
-        const int img = mt / (p.tiles_x * p.tiles_y);
-        const int r = mt - img * (p.tiles_x * p.tiles_y);
-        const int y0 = (r / p.tiles_x) * kTileH, x0 = (r % p.tiles_x) * kTileW;
-        for (int tap = 0; tap < p.taps; tap++) {
-          const int dy = tap / p.KW - p.padH, dx = tap % p.KW - p.padW;
-          int kb = tap * p.blocks_per_tap;
-          for (int s = 0; s < p.nseg; s++) {
-            for (int cb = 0; cb < p.seg_blocks[s]; cb++, kb++) {
-              mbar_wait(&empty[stage], phase ^ 1);
-              unsigned char* sa = ring + stage * C::kStage;
-              mbar_arrive_expect_tx(&full[stage], C::kStage);
-              tma_load_4d(&p.tmA[s], &full[stage], sa, cb * kBK, x0 + dx, y0 + dy, img);
-              tma_load_2d(&p.tmB, &full[stage], sa + C::kStageA, kb * kBK, nt * BN);
-              if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+    // ===================================================================== TMA producer (warp-uniform; one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      const int img = mt / (p.tiles_x * p.tiles_y);
+      const int r = mt - img * (p.tiles_x * p.tiles_y);
+      const int y0 = (r / p.tiles_x) * kTileH, x0 = (r % p.tiles_x) * kTileW;
+      for (int kb0 = 0; kb0 < nkb; kb0 += C::kG) {
+        const int g = min(C::kG, nkb - kb0);
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          unsigned char* sa = ring + stage * C::kStage;
+          mbar_arrive_expect_tx(&full[stage], g * C::kKb);
+#pragma unroll
+          for (int j = 0; j < C::kG; j++) {
+            if (j < g) {
+              const int e = kbt[kb0 + j];
+              tma_load_4d(&p.tmA[(e >> 12) & 3], &full[stage], sa + j * C::kKb, (e & 0xfff) * kBK, x0 + ((e >> 20) & 15) - 8,
+                          y0 + ((e >> 16) & 15) - 8, img);
+              tma_load_2d(&p.tmB, &full[stage], sa + j * C::kKb + C::kStageA, (kb0 + j) * kBK, nt * BN);
             }
           }
         }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -257,17 +278,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_wait(&tempty[as], aphase ^ 1);
       fence_after_sync();
       const uint32_t tmem_d = tmem_base + as * BN;
-      for (int kb = 0; kb < nkb; kb++) {
+      for (int kb0 = 0; kb0 < nkb; kb0 += C::kG) {
+        const int g = min(C::kG, nkb - kb0);
         mbar_wait(&full[stage], phase);
         fence_after_sync();
         if (elect_one()) {
           const uint32_t sa = smem_u32(ring + stage * C::kStage);
-          const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + C::kStageA);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; k++)         // advance 32 B (= 16 halves) inside the swizzle atom: +2 in >>4 units
-            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int j = 0; j < C::kG; j++) {
+            if (j < g) {
+              const uint64_t da = smem_desc_sw128(sa + j * C::kKb), db = smem_desc_sw128(sa + j * C::kKb + C::kStageA);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; k++)     // advance 32 B (= 16 halves) inside the swizzle atom: +2 in >>4 units
+                umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb0 | j | k) != 0);
+            }
+          }
           umma_commit(&empty[stage]);                // frees the smem stage when these MMAs retire
-          if (kb == nkb - 1) umma_commit(&tfull[as]);
+          if (kb0 + C::kG >= nkb) umma_commit(&tfull[as]);
         }
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -322,7 +349,8 @@ int launch_tc(const TcParams& p, const Epi& epi, cudaStream_t s) {
       return PVO_ERR_CUDA;
     set = true;
   }
-  const int grid = p.total_tiles < PVO_SM_COUNT ? p.total_tiles : PVO_SM_COUNT;
+  const int slots = PVO_SM_COUNT * C::kCtasPerSm;
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
   conv_tc_kernel<BN, Epi><<<grid, kThreads, C::kSmem, s>>>(p, epi);
   return pvo_check_launch();
 }
@@ -348,7 +376,7 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
                              const void* Wh, const float* bias, int Cout, int KH, int KW, int nimg, int H, int Wd,
                              int epilogue, void* out, int ostride, int ooff, void* out2, const void* aux0, int aux_stride,
                              const float* aux1, void* stream) {
-  if (nseg < 1 || nseg > kMaxSeg || Cout < 1 || nimg < 0 || !(KH & 1) || !(KW & 1)) return PVO_ERR_INVALID;
+  if (nseg < 1 || nseg > kMaxSeg || Cout < 1 || nimg < 0 || !(KH & 1) || !(KW & 1) || KH > 15 || KW > 15) return PVO_ERR_INVALID;
   if (nimg == 0) return PVO_OK;
   TcParams p;
   p.nseg = nseg;
@@ -370,6 +398,7 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
   p.tiles_x = (Wd + kTileW - 1) / kTileW;
   p.tiles_y = (H + kTileH - 1) / kTileH;
   p.Cout = Cout;
+  if (p.taps * p.blocks_per_tap > kMaxKb) return PVO_ERR_UNSUPPORTED;
   const long Ktot = (long)p.taps * p.blocks_per_tap * kBK;
   int bn = Cout >= 256 ? 256 : (Cout >= 128 ? 128 : 64);
   // keep at least ~2 waves of tiles: prefer the narrower tile when the wide one leaves SMs idle

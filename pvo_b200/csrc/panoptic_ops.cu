@@ -83,7 +83,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(1024)
                             int* __restrict__ pan /*[N][H*W]*/, int* __restrict__ info_out, int* __restrict__ counts_out, int H, int W,
                             int num_sem, float overlap_thr, int stuff_area_thr, float score_thr, int thing_cat0, int max_info) {
   cg::cluster_group cluster = cg::this_cluster();
-  __shared__ int sh[32];
+  __shared__ int sh[64];
   __shared__ int slot[2][2];                     // {area, overlap} of this CTA's strip, double buffered by instance parity
   __shared__ int hist[kMaxSem], hist_all[kMaxSem];
   const int rank = (int)cluster.block_rank();
@@ -96,40 +96,85 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(1024)
   __syncthreads();
   int cur = 0, it = 0;
   const int r0 = inst_off[n], r1 = inst_off[n + 1];
-  for (int k = r0; k < r1; k++) {
-    const int r = r0 + (int)order[k];                       // order[] holds per-image ranks sorted by descending score
-    if (scores[r] < score_thr) break;
-    const unsigned char* M = masks + (long)r * HW;
+  const bool vec = (W & 3) == 0;                            // 4 pixels per "word" when rows are 4-aligned, else 1
+  const int step = vec ? 4 : 1;
+  // An instance's mask words for this strip live in registers: they are fetched while the PREVIOUS instance is being
+  // reduced / decided / painted (the fetch does not depend on any decision), and reused for the paint pass.
+  constexpr int kBuf = 10;
+  struct Region { const unsigned char* M; int r, x0, y0, rw, cnt; bool live; };
+  auto region = [&](int k) {
+    Region g;
+    g.live = k < r1;
+    g.r = g.live ? r0 + (int)order[k] : 0;                  // order[] holds per-image ranks sorted by descending score
+    g.live = g.live && !(scores[g.r] < score_thr);          // the reference loop breaks at the first score below the threshold
+    g.M = masks + (long)g.r * HW;
     int y0 = ys, y1 = ye, x0 = 0, x1 = W;                   // region that can hold mask pixels (pixel centres within the box)
-    if (boxes) {
-      x0 = max(0, (int)floorf(boxes[r * 4 + 0] - 1.5f)); y0 = max(ys, (int)floorf(boxes[r * 4 + 1] - 1.5f));
-      x1 = min(W, (int)ceilf(boxes[r * 4 + 2] + 1.5f)); y1 = min(ye, (int)ceilf(boxes[r * 4 + 3] + 1.5f));
+    if (boxes && g.live) {
+      x0 = max(0, (int)floorf(boxes[g.r * 4 + 0] - 1.5f)); y0 = max(ys, (int)floorf(boxes[g.r * 4 + 1] - 1.5f));
+      x1 = min(W, (int)ceilf(boxes[g.r * 4 + 2] + 1.5f)); y1 = min(ye, (int)ceilf(boxes[g.r * 4 + 3] + 1.5f));
     }
-    // 4 pixels per thread when rows are 4-aligned (W % 4 == 0): one 32-bit mask load, the pan ids only where it is set
-    const bool vec = (W & 3) == 0;
     if (vec) { x0 &= ~3; x1 = min(W, (x1 + 3) & ~3); }
-    const int step = vec ? 4 : 1;
-    const int rw = max(x1 - x0, 0) / step, cnt = rw * max(y1 - y0, 0);
-    int area = 0, inter = 0;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const long px = (long)(y0 + i / rw) * W + x0 + (i % rw) * step;
-      if (vec) {
-        const unsigned int m4 = __ldg(reinterpret_cast<const unsigned int*>(M + px));
-        if (m4) {
-          const int4 p4 = *reinterpret_cast<const int4*>(P + px);
-          const int b0 = (m4 & 0xffu) != 0, b1 = (m4 & 0xff00u) != 0, b2 = (m4 & 0xff0000u) != 0, b3 = (m4 & 0xff000000u) != 0;
-          area += b0 + b1 + b2 + b3;
-          inter += (b0 && p4.x > 0) + (b1 && p4.y > 0) + (b2 && p4.z > 0) + (b3 && p4.w > 0);
-        }
-      } else {
-        const int m = M[px] != 0;
-        area += m;
-        inter += m && (P[px] > 0);
-      }
+    g.x0 = x0; g.y0 = y0;
+    g.rw = max(x1 - x0, 0) / step;
+    g.cnt = g.live ? g.rw * max(y1 - y0, 0) : 0;
+    return g;
+  };
+  auto pixel = [&](const Region& g, int i) { return (long)(g.y0 + i / g.rw) * W + g.x0 + (i % g.rw) * step; };
+  auto word = [&](const Region& g, int i) -> unsigned int {
+    const long px = pixel(g, i);
+    return vec ? __ldg(reinterpret_cast<const unsigned int*>(g.M + px)) : (unsigned int)g.M[px];
+  };
+  auto count = [&](unsigned int m4, long px, int& area, int& inter) {
+    if (!m4) return;
+    if (vec) {
+      const int4 p4 = *reinterpret_cast<const int4*>(P + px);
+      const int b0 = (m4 & 0xffu) != 0, b1 = (m4 & 0xff00u) != 0, b2 = (m4 & 0xff0000u) != 0, b3 = (m4 & 0xff000000u) != 0;
+      area += b0 + b1 + b2 + b3;
+      inter += (b0 && p4.x > 0) + (b1 && p4.y > 0) + (b2 && p4.z > 0) + (b3 && p4.w > 0);
+    } else {
+      area += 1;
+      inter += P[px] > 0;
     }
-    area = block_sum_int(area, sh);
-    inter = block_sum_int(inter, sh);
-    if (threadIdx.x == 0) { slot[it & 1][0] = area; slot[it & 1][1] = inter; }
+  };
+  auto paint = [&](unsigned int m4, long px, int id) {
+    if (!m4) return;
+    if (vec) {
+      int4 p4 = *reinterpret_cast<const int4*>(P + px);
+      if ((m4 & 0xffu) && p4.x == 0) p4.x = id;
+      if ((m4 & 0xff00u) && p4.y == 0) p4.y = id;
+      if ((m4 & 0xff0000u) && p4.z == 0) p4.z = id;
+      if ((m4 & 0xff000000u) && p4.w == 0) p4.w = id;
+      *reinterpret_cast<int4*>(P + px) = p4;
+    } else if (P[px] == 0) {
+      P[px] = id;
+    }
+  };
+  int k = r0;
+  Region nx = region(k);
+  unsigned int nbuf[kBuf];
+#pragma unroll
+  for (int j = 0; j < kBuf; j++) { const int i = threadIdx.x + j * 1024; nbuf[j] = i < nx.cnt ? word(nx, i) : 0u; }
+  while (nx.live) {
+    const Region g = nx;
+    unsigned int buf[kBuf];
+#pragma unroll
+    for (int j = 0; j < kBuf; j++) buf[j] = nbuf[j];
+    nx = region(++k);
+#pragma unroll
+    for (int j = 0; j < kBuf; j++) { const int i = threadIdx.x + j * 1024; nbuf[j] = i < nx.cnt ? word(nx, i) : 0u; }
+    int area = 0, inter = 0;
+#pragma unroll
+    for (int j = 0; j < kBuf; j++) { const int i = threadIdx.x + j * 1024; if (i < g.cnt) count(buf[j], pixel(g, i), area, inter); }
+    for (int i = threadIdx.x + kBuf * 1024; i < g.cnt; i += 1024) count(word(g, i), pixel(g, i), area, inter);   // oversized regions
+    area = __reduce_add_sync(0xffffffffu, area);
+    inter = __reduce_add_sync(0xffffffffu, inter);
+    if ((threadIdx.x & 31) == 0) { sh[(threadIdx.x >> 5) * 2] = area; sh[(threadIdx.x >> 5) * 2 + 1] = inter; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int ta = 0, ti = 0;
+      for (int w = 0; w < 32; w++) { ta += sh[2 * w]; ti += sh[2 * w + 1]; }
+      slot[it & 1][0] = ta; slot[it & 1][1] = ti;
+    }
     cluster.sync();
     area = 0; inter = 0;
     for (int c = 0; c < kCluster; c++) {
@@ -140,27 +185,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(1024)
     if (area == 0) continue;
     if ((double)inter / (double)area > (double)overlap_thr) continue;       // the reference divides Python numbers (doubles)
     cur++;
-    const int cat = thing_cat0 + (int)classes[r];
+    const int cat = thing_cat0 + (int)classes[g.r];
     const int id = cat * 10000 + cur;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const long px = (long)(y0 + i / rw) * W + x0 + (i % rw) * step;
-      if (vec) {
-        const unsigned int m4 = __ldg(reinterpret_cast<const unsigned int*>(M + px));
-        if (m4) {
-          int4 p4 = *reinterpret_cast<const int4*>(P + px);
-          if ((m4 & 0xffu) && p4.x == 0) p4.x = id;
-          if ((m4 & 0xff00u) && p4.y == 0) p4.y = id;
-          if ((m4 & 0xff0000u) && p4.z == 0) p4.z = id;
-          if ((m4 & 0xff000000u) && p4.w == 0) p4.w = id;
-          *reinterpret_cast<int4*>(P + px) = p4;
-        }
-      } else if (M[px] && P[px] == 0) {
-        P[px] = id;
-      }
-    }
+#pragma unroll
+    for (int j = 0; j < kBuf; j++) { const int i = threadIdx.x + j * 1024; if (i < g.cnt) paint(buf[j], pixel(g, i), id); }
+    for (int i = threadIdx.x + kBuf * 1024; i < g.cnt; i += 1024) paint(word(g, i), pixel(g, i), id);
     if (rank == 0 && threadIdx.x == 0 && cur <= max_info) {
       int* o = info_out + ((long)n * max_info + cur - 1) * 5;
-      o[0] = id; o[1] = cat; o[2] = 1; o[3] = area - inter; o[4] = r - r0;
+      o[0] = id; o[1] = cat; o[2] = 1; o[3] = area - inter; o[4] = g.r - r0;
     }
     __syncthreads();
   }

@@ -442,14 +442,13 @@ class PanopticFPN:
         check(_lib.lib().pvo_panoptic_combine(ptr(masks), ptr(bx), ptr(scores), ptr(classes), ptr(order), ptr(inst_off), ptr(sem_labels), ptr(pan),
                                               ptr(info), ptr(counts), N, H, W, NUM_SEM, float(overlap_threshold), int(stuff_area_thresh),
                                               float(instances_score_thresh), THING_CAT0, max_info, stream()), 'panoptic_combine')
-        info_h, counts_h, scores_h = info.cpu(), counts.cpu(), scores.cpu()                # the only device->host read
+        info_l, counts_l, scores_l = info.tolist(), counts.tolist(), scores.tolist()       # the only device->host reads
         segs = []
         for n in range(N):
             lst = []
-            for k in range(min(int(counts_h[n]), max_info)):
-                sid, cat, thing, area, inst = info_h[n, k].tolist()
+            for sid, cat, thing, area, inst in info_l[n][:min(counts_l[n], max_info)]:
                 if thing:
-                    lst.append({'id': sid, 'isthing': True, 'score': float(scores_h[off[n] + inst]), 'category_id': cat, 'instance_id': inst})
+                    lst.append({'id': sid, 'isthing': True, 'score': scores_l[off[n] + inst], 'category_id': cat, 'instance_id': inst})
                 else:
                     lst.append({'id': sid, 'isthing': False, 'category_id': cat, 'area': area})
             segs.append(lst)

@@ -90,17 +90,29 @@ def test_proposals_and_detections_on_oracle_head_outputs(setup):
     m.N = 2
     sizes = [(H, W), (H, W)]
     packed, lgs, dls = [], [], []
+    # objectness goes through half: map the oracle's logits monotonically onto DISTINCT half values so that neither side
+    # has score ties (tie order is unspecified in top-k / sort / NMS on both sides)
+    halves = torch.arange(0x3000, 0x4800, dtype=torch.int32).to(torch.int16).view(torch.float16).float()     # 0.125 .. 8, all distinct
+    halves = torch.cat([-halves.flip(0), halves])
     for rl, rd in zip(dbg['rpn_logits'], dbg['rpn_deltas']):
         N, A, h, w = rl.shape
+        rank = rl.flatten().argsort().argsort()
+        rl = halves[(rank * (halves.numel() // rank.numel())).long()].view(rl.shape)
         o = torch.cat([rl.permute(0, 2, 3, 1), rd.permute(0, 2, 3, 1), torch.zeros(N, h, w, 1)], -1).half()
         packed.append(o.cuda().contiguous())
         lgs.append(o[..., :3].float().permute(0, 3, 1, 2).contiguous())
         dls.append(o[..., 3:15].float().permute(0, 3, 1, 2).contiguous())
     want = ofpn.rpn_proposals(lgs, dls, sizes)
     got = m.proposals(packed, sizes)
+    def canon(b, s_):                                                 # the same half value can occur on two levels: order ties by box
+        import numpy as np
+        b, s_ = b.cpu().numpy(), s_.cpu().numpy()
+        o = np.lexsort((np.round(b[:, 3], 2), np.round(b[:, 2], 2), np.round(b[:, 1], 2), np.round(b[:, 0], 2), -s_))
+        return torch.from_numpy(b[o]), torch.from_numpy(s_[o])
     for (wb, ws), (gb, gs) in zip(want, got):
         assert gb.shape == wb.shape
         assert torch.equal(gs.cpu(), ws)                              # same survivors, same order
+        (wb, ws), (gb, gs) = canon(wb, ws), canon(gb, gs)
         assert (gb.cpu() - wb).abs().max() < 1e-4                     # decode + clip (expf differs by an ulp between CPU and GPU)
     props = [(b.cuda(), s_.cuda()) for b, s_ in dbg['proposals']]        # the rows box_cls / box_reg were computed for
     cls, reg = dbg['box_cls'].cuda(), dbg['box_reg'].cuda()
