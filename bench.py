@@ -258,6 +258,7 @@ def run_ours(args, rank, world, local_rank):
     ba_ms = sum(v_ for k_, v_ in kernel_ms.items() if k_.startswith('ba'))
     upd_ms = sum(v_ for k_, v_ in kernel_ms.items() if k_.startswith('conv') or k_ in ('colmean', 'glo_matvec', 'heads2', 'segment_mean', 'eta'))
     cpu = cpu_baseline_sample()
+    gpu_ref = gpu_reference_sample(fg, c, dev) if world == 1 else None
     line = {
         'metric': METRIC, 'value': round(value, 3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -278,6 +279,7 @@ def run_ours(args, rank, world, local_rank):
                      'edge_add_ms': round(edge_add_ms, 3)},
         'update_op_tflops': round(update_flops(E, K, hw) / (upd_ms * 1e-3) / 1e12, 1) if upd_ms else None,
         'cpu_baseline': cpu,
+        'reference_gpu_path': gpu_ref,
     }
     print(json.dumps(line))
 
@@ -324,6 +326,67 @@ def cpu_baseline_sample():
                           '(fastest of a small sweep): %.2f s' % (nthr, t)}
     except Exception as ex:       # the baseline must never take the GPU number down with it
         return {'value': None, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
+
+
+def gpu_reference_sample(fg, c, dev):
+    """The reference's own GPU path for the stages that can be had on this box, timed on the same B200 next to ours
+    (SURVEY.md section 8(d) "reference timed beside it"):
+      * lookup: the reference's corr_index_forward kernel itself (correlation_kernels.cu compiled by oracle/build_ref.py
+        into oracle/_ref/, called the way CorrBlock.__call__ calls it: 4 launches + zero fills + cat), on OUR volume.
+      * update operator: the reference's module structure as plain torch convolutions (cuDNN) under half autocast --
+        what DynamicUpdateModule.forward executes -- through the restatement in oracle/update_op.py on CUDA tensors.
+      * BA: droid_kernels.cu cannot be built (vendored Eigen is incomplete) -> no number.
+    Baseline only: nothing here is on the product path."""
+    import torch
+    out = {'lookup_ms': None, 'update_operator_ms': None, 'ba_ms': None,
+           'note': 'reference BA (droid_kernels.cu) is unbuildable as shipped: vendored Eigen lacks Eigen/Core'}
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    try:
+        from oracle import build_ref
+        ref = build_ref.load()
+        E = c['E']
+        coords = (fg.coords0[None, None] + 0.37).repeat(1, E, 1, 1, 1)
+        if ref is not None:
+            pyr = fg.corr.corr_pyramid
+
+            def ref_lookup():                                  # modules/corr.py:40-50
+                cs = coords[0].permute(0, 3, 1, 2).contiguous()
+                outs = []
+                for i, vol in enumerate(pyr):
+                    o, = ref.corr_index_forward(vol, (cs / 2 ** i).contiguous(), 3)
+                    outs.append(o.view(1, E, -1, HT, WD))
+                return torch.cat(outs, dim=2).contiguous()
+            out['lookup_ms'] = round(timed(ref_lookup), 4)
+        else:
+            out['note'] += '; oracle/_ref/droid_corr_ref.so absent (built only where the reference tree is mounted)'
+    except Exception as ex:
+        out['note'] += '; reference lookup failed: %r' % (ex,)
+    try:
+        from oracle import update_op as oupd
+        sd = {k: v.to(dev).half() for k, v in oupd.init_params(0).items()}
+        E = c['E']
+        g = torch.Generator(device=dev).manual_seed(0)
+        net = torch.tanh(torch.randn(1, E, 128, HT, WD, device=dev, generator=g)).half()
+        inp = torch.relu(torch.randn(1, E, 128, HT, WD, device=dev, generator=g)).half()
+        corr = torch.randn(1, E, 196, HT, WD, device=dev, generator=g).half()
+        flow = torch.randn(1, E, 8, HT, WD, device=dev, generator=g).half()
+        ii = c['ii'].to(dev)
+        with torch.autocast('cuda', dtype=torch.float16):
+            out['update_operator_ms'] = round(timed(lambda: oupd.update_op(sd, net, inp, corr, flow, ii)), 4)
+    except Exception as ex:
+        out['note'] += '; cuDNN update operator failed: %r' % (ex,)
+    return out
 
 
 def run_reference(args, rank, world):

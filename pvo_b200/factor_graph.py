@@ -189,6 +189,21 @@ class FactorGraph:
         keep = ((ii - jj).abs() > 0) & ((ii - jj).abs() <= r)
         self.add_factors(ii[keep], jj[keep])
 
+    def add_proximity_factors(self, t0=0, t1=0, rad=2, nms=2, beta=0.25, thresh=16.0, remove=False):
+        """add edges based on frame distance (factor_graph.py:372-429): `frame_distance` on the device, one copy of the
+        distance matrix to the host, greedy selection + NMS there (graph_select.py)"""
+        from .graph_select import select_proximity_edges
+        t = self.video.counter.value
+        ii, jj = torch.meshgrid(torch.arange(t0, t), torch.arange(t1, t), indexing='ij')
+        d = self.video.distance(ii.reshape(-1), jj.reshape(-1), beta=beta).float().cpu().numpy()
+        existing = torch.stack([torch.cat([self.ii, self.ii_bad, self.ii_inac], 0),
+                                torch.cat([self.jj, self.jj_bad, self.jj_inac], 0)], 1).cpu().tolist()
+        es = select_proximity_edges(d, existing, t0, t1, t, rad=rad, nms=nms, thresh=thresh)
+        if not es:
+            return
+        e = torch.as_tensor(es, dtype=torch.long, device=self.device)
+        self.add_factors(e[:, 0], e[:, 1], remove)
+
     # ------------------------------------------------------------------ the hot loop body
     def _prepare(self):
         """Per-edge-set constants.  The only host synchronisation of the hot path, paid when edges change."""

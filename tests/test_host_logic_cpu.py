@@ -138,3 +138,20 @@ def test_oracle_lookup_half_matches_float_on_exact_inputs():
         cx, cy = int(coords[n, 0, y, x]), int(coords[n, 1, y, x])
         if 0 <= cx < 11 and 0 <= cy < 9:
             assert a[n, 3, 3, y, x] == vol[n, y, x, cy, cx]
+
+
+def test_proximity_edge_selection_matches_reference_golden():
+    """pvo_b200.graph_select vs the reference's FactorGraph.add_proximity_factors run on prescribed distances
+    (tests/golden/make_golden_proximity.py): identical edge lists, in order."""
+    import os
+    import numpy as np
+    from pvo_b200.graph_select import select_proximity_edges
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'proximity.npz'))
+    k = 0
+    while 'd%d' % k in z:
+        t, t0, t1, rad, nms, thresh, ne = z['cfg%d' % k]
+        es = select_proximity_edges(z['d%d' % k], z['ex%d' % k].tolist(), int(t0), int(t1), int(t), rad=int(rad), nms=int(nms),
+                                    thresh=float(thresh))
+        assert np.array_equal(np.asarray(es, dtype=np.int64).reshape(-1, 2), z['es%d' % k]), k
+        k += 1
+    assert k == 6

@@ -119,3 +119,25 @@ def test_edge_bookkeeping_round_trip():
     assert fg.ii_inac.shape[0] == int(mask.sum())
     fg.update(itrs=1)
     assert torch.isfinite(v.poses).all() and torch.isfinite(v.disps).all()
+
+
+def test_add_proximity_factors_selects_the_reference_edges():
+    """frame_distance on the device + the host selection == the reference's selection applied to the same distances
+    (the selection itself is pinned to the reference on CPU: tests/test_host_logic_cpu.py)"""
+    from pvo_b200.depth_video import DepthVideo
+    from pvo_b200.droid_net import DynamicUpdateModule
+    from pvo_b200.factor_graph import FactorGraph
+    from pvo_b200.graph_select import select_proximity_edges
+    c = cases.graph_case(F=9, radius=1, h=16, w=24, seed=8)
+    v, fg = build_graph(c, 'fp32')
+    t = v.counter.value
+    before = torch.stack([fg.ii, fg.jj], 1).cpu().tolist()
+    ii, jj = torch.meshgrid(torch.arange(0, t), torch.arange(0, t), indexing='ij')
+    d = v.distance(ii.reshape(-1), jj.reshape(-1), beta=0.25).cpu().numpy()
+    want = select_proximity_edges(d, before, 0, 0, t, rad=2, nms=2, thresh=1e3)
+    fg.add_proximity_factors(t0=0, t1=0, rad=2, nms=2, beta=0.25, thresh=1e3)
+    have = set(map(tuple, torch.stack([fg.ii, fg.jj], 1).cpu().tolist()))
+    assert have == set(map(tuple, before)) | set(want)
+    assert fg.corr.corr_pyramid[0].shape[0] == fg.ii.shape[0] == fg.net.shape[1]
+    fg.update(itrs=1)
+    assert torch.isfinite(v.poses).all()
