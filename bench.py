@@ -105,7 +105,16 @@ def run_ours(args, rank, world, local_rank):
         own = (ii // F_PER_GPU) == rank
         ii, jj = ii[own], jj[own]
     E = ii.shape[0]
-    v = DepthVideo(image_size=(8 * HT, 8 * WD), buffer=max(nf + 8, 16), device=dev, store_images=False)
+    segm_on = args.workload == 'vkitti'
+    v = DepthVideo(image_size=(8 * HT, 8 * WD), buffer=max(nf + 8, 16), device=dev, store_images=False, segm_filter=segm_on, thresh=0.8)
+    if segm_on:                                 # synthetic panoptic ids: 4 stuff bands + 8 rectangular things per frame
+        g = torch.Generator().manual_seed(5)
+        seg = (torch.arange(HT)[:, None] * 4 // HT + 1).repeat(1, WD)[None].repeat(nf, 1, 1) * 10000
+        for f in range(nf):
+            for k in range(8):
+                y, x = int(torch.randint(0, HT - 8, (1,), generator=g)), int(torch.randint(0, WD - 16, (1,), generator=g))
+                seg[f, y:y + 8, x:x + 16] = 120000 + k + 1
+        v.segms[:nf, 0] = seg.to(v.segms.dtype).to(dev)
     v.poses[:nf] = c['poses'].to(dev)
     v.disps[:nf] = c['disps'].to(dev)
     v.intrinsics[:] = c['intrinsics'][0].to(dev)
@@ -263,11 +272,11 @@ def run_ours(args, rank, world, local_rank):
         'metric': METRIC, 'value': round(value, 3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f16' if args.precision == 'fp16' else 'f32', 'data': 'synthetic (seeded random features / random-init weights)',
-        'config': {'workload': 'BASELINE configs[1]: %d-keyframe 480x640 factor graph per GPU, r=3 corr, %d edges/GPU, 2 BA iters per update; '
+        'config': {'workload': ('BASELINE configs[2] shape (VKITTI2 240x808, segment filter on): ' if args.workload == 'vkitti' else 'BASELINE configs[1]: ') + '%d-keyframe factor graph per GPU, r=3 corr, %d edges/GPU, 2 BA iters per update; '
                                'update-op iterations feed back state' % (F_PER_GPU, E),
                    'edges': E * world, 'keyframes': nf, 'grid': [HT, WD], 'precision': args.precision,
                    'l2': 'per-step working set (2.2 GB volume + 0.9 GB activations) >> 126 MB L2; 256 MB flush between timed steps',
-                   'parallelism': 'edges sharded by source keyframe, NCCL all-reduce of the reduced camera system' if world > 1 else 'single GPU'},
+                   'parallelism': ('edges sharded by source keyframe; reduced camera system all-reduced per BA iteration by ' + getattr(fg, 'allreduce_kind', 'ncclAllReduce')) if world > 1 else 'single GPU'},
         'e2e': {'value': round(e2e_value, 3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'what': 'mutable graph state (poses, disps, target, weight, masks, hidden state) H2D from pinned host memory, '
                         'FactorGraph.update, results (poses, disps, flow, hidden state) D2H, every step'},
@@ -429,7 +438,20 @@ def main():
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     ap.add_argument('--profile-only', action='store_true', help='skip the e2e and CPU legs (for ncu runs)')
-    args = ap.parse_args()
+    ap.add_argument('--workload', default='vo', choices=['vo', 'vkitti', 'fpn'],
+                    help='vo = BASELINE configs[1] (the contract line); vkitti = configs[2] shape: 240x808 frames (30x101 grid), 12 keyframes, '
+                         'radius 2, panoptic segment filter ON; fpn = configs[3] (delegates to tools/bench_fpn.py)')
+    args, rest = ap.parse_known_args()
+    if args.workload == 'fpn':
+        sys.argv = [os.path.join(ROOT, 'tools', 'bench_fpn.py'), '--steps', str(min(args.steps, 10)), '--warmup', str(args.warmup)] + rest
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import bench_fpn
+        bench_fpn.main()
+        return
+    if args.workload == 'vkitti':
+        global F_PER_GPU, RADIUS, HT, WD, METRIC
+        F_PER_GPU, RADIUS, HT, WD = 12, 2, 30, 101
+        METRIC = 'VO update-op iters/sec (240x808 VKITTI2 shape, 12 KF, radius 2, segment filter on)'
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

@@ -185,6 +185,13 @@ int pvo_det_decode(const float* cls /*(R,K+1)*/, const float* reg /*(R,4K)*/, co
 int pvo_nms_groups(const float* boxes /*(G,n,4)*/, const unsigned char* valid /*(G,n)*/, int G, int n, float thr,
                    unsigned char* keep /*(G,n)*/, unsigned int* scratch /* G*n*32 words */, void* stream);
 
+/* One-shot all-reduce (sum, fp64, in place) of the BA reduced camera system over NVLink peer memory: every rank pushes its
+ * partial into a staging slot in each peer's symmetric buffer, flags it, and sums what arrived locally (one launch, graph
+ * capturable).  stage_ptrs[i]: rank i's [2][world][n_max] doubles; flag_ptrs[i]: rank i's [world][256] ints (zeroed once);
+ * epochs: local [256] ints (zeroed once).  Replaces the ncclAllReduce of SURVEY.md section 8(e). */
+int pvo_allreduce_oneshot(double* data, void* const* stage_ptrs, void* const* flag_ptrs, int* epochs, int rank, int world, long n,
+                          long n_max, void* stream);
+
 /* FactorGraph.update post-processing (factor_graph.py:250-283): target_cam, raw_mask, bin_mask, panoptic segment
  *   filter (:256-276, integer counting on the device instead of numpy on the host), delta_dy, sigmoid weights. */
 long pvo_update_post_workspace_ints(int E);

@@ -89,7 +89,7 @@ def projective_transform(poses, depths, intrinsics, ii, jj, jacobian=False):
 
 def scatter_sum(src, index, dim_size):
     """torch_scatter.scatter_sum(src, index, dim=1, dim_size=...)."""
-    out = torch.zeros(src.shape[:1] + (dim_size,) + src.shape[2:], dtype=src.dtype)
+    out = torch.zeros(src.shape[:1] + (dim_size,) + src.shape[2:], dtype=src.dtype, device=src.device)
     if index.numel():
         out.index_add_(1, index, src)
     return out
@@ -100,7 +100,7 @@ def scatter_mean(src, index, dim_size=None):
     if dim_size is None:
         dim_size = int(index.max()) + 1
     s = scatter_sum(src, index, dim_size)
-    cnt = torch.zeros(dim_size, dtype=src.dtype).index_add_(0, index, torch.ones_like(index, dtype=src.dtype))
+    cnt = torch.zeros(dim_size, dtype=src.dtype, device=src.device).index_add_(0, index, torch.ones_like(index, dtype=src.dtype))
     cnt = cnt.clamp(min=1).reshape((1, dim_size) + (1,) * (src.dim() - 2))
     return s / cnt
 

@@ -39,6 +39,48 @@ def allreduce_system(buf, group=None):
     return buf
 
 
+class PeerAllReduce:
+    """One-shot sum of a small fp64 vector across the ranks of one NVLink domain, in one kernel launch
+    (csrc/allreduce_p2p.cu): every rank pushes its partial into a staging slot in each peer's memory and sums what
+    arrived in its own.  The staging buffers are a torch symmetric-memory allocation (CUDA IPC / fabric handles exchanged
+    by `rendezvous`); only raw peer pointers cross into the C ABI."""
+    N_MAX = 160_000          # doubles; the reduced camera system of up to P = 64 free poses (36 P^2 + 7 P)
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        stage_bytes = 2 * self.world * self.N_MAX * 8
+        self.buf = symm.empty(stage_bytes + self.world * 256 * 4, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.stage_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.flag_ptrs = (ctypes.c_void_p * self.world)(*[p + stage_bytes for p in ptrs])
+        self.epochs = torch.zeros(256, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                   # every rank's flags are zero before anyone pushes
+
+    def __call__(self, t):
+        assert t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= self.N_MAX
+        check(_lib.lib().pvo_allreduce_oneshot(ptr(t), self.stage_ptrs, self.flag_ptrs, ptr(self.epochs), self.rank, self.world,
+                                               t.numel(), self.N_MAX, stream()), 'allreduce_oneshot')
+        return t
+
+
+def make_reducer(device, group=None):
+    """PeerAllReduce when the ranks share an NVLink / P2P domain, else None (allreduce_system then uses NCCL in-stream)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1 and dist.get_backend(group) == 'nccl'):
+        return None
+    ok = torch.ones(1, device=device)
+    try:
+        red = PeerAllReduce(device, group)
+    except Exception as ex:                                   # no symmetric memory on this system: stay on NCCL, say so
+        red, ok = None, torch.zeros(1, device=device)
+        print('[pvo_b200.dist] peer-memory all-reduce unavailable (%r); using ncclAllReduce' % (ex,), flush=True)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)    # all ranks must take the same path
+    return red if ok.item() > 0 else None
+
+
 def system_view(ws, E, nframes, P, K, HW):
     """float64 view of the reduced camera system inside a BA workspace (torch.uint8 tensor)."""
     off, nb = ctypes.c_long(0), ctypes.c_long(0)
@@ -47,7 +89,7 @@ def system_view(ws, E, nframes, P, K, HW):
 
 
 def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only,
-               interleaved=False, group=None, workspace=None, max_degree=0):
+               interleaved=False, group=None, workspace=None, max_degree=0, reducer=None):
     """droid_backends.ba for a rank's shard of the edges: assemble -> all-reduce -> solve + update, per iteration.
     poses must be identical on all ranks on entry and are identical on exit."""
     E = ii.shape[0]
@@ -67,7 +109,10 @@ def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, 
               launches=(0 if reuse else 1) + 2)
     for it in range(int(iterations)):
         call(1, it > 0)
-        allreduce_system(sysbuf, group)
+        if reducer is not None:
+            reducer(sysbuf)
+        else:
+            allreduce_system(sysbuf, group)
         call(2, True)
     return [dx, dz]
 
@@ -75,11 +120,13 @@ def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, 
 def attach(fg, rank, world, frames_per_rank, group=None):
     """Make a FactorGraph's BA go through ba_sharded.  The caller adds only this rank's edges (shard_edges)."""
     video = fg.video
+    reducer = make_reducer(video.poses.device, group) if video.poses.is_cuda else None
+    fg.allreduce_kind = 'one-shot push over NVLink peer memory (own kernel)' if reducer is not None else 'ncclAllReduce'
 
     def ba(target, weight, eta, ii, jj, t0=1, t1=None, itrs=2, lm=1e-4, ep=0.1, motion_only=False, interleaved=False,
            reuse_plan=False, max_degree=0):
         out = ba_sharded(video.poses, video.disps, video.intrinsics[0].contiguous(), target, weight, eta, ii, jj, t0, t1,
-                         itrs, lm, ep, motion_only, interleaved=interleaved, group=group, max_degree=max_degree)
+                         itrs, lm, ep, motion_only, interleaved=interleaved, group=group, max_degree=max_degree, reducer=reducer)
         check(_lib.lib().pvo_clamp_min(ptr(video.disps), video.disps.numel(), 0.001, stream()), 'clamp_min')
         return out
     video.ba = ba
