@@ -414,6 +414,129 @@ __global__ void __launch_bounds__(256) ba_combine_kernel(Bufs bf, int P) {
   }
 }
 
+// Dense (row-major, leading dimension ld) or band-packed view of the symmetric system's lower triangle.  Band-packed:
+// row r keeps columns [6*(r/6) - band, r]: exactly the entries the band-limited factorisation touches.
+template <bool BAND> struct SysMat {
+  double* p; int ld; int band;
+  __device__ __forceinline__ double& operator()(int r, int c) const {
+    if (BAND) return p[(long)r * ld + c - max(0, 6 * (r / 6) - band)];
+    return p[(long)r * ld + c];
+  }
+};
+
+// A = L D L^T restricted to the block band, then L z = b, D w = z, L^T x = w in place in y.  dinv: scratch [n].
+template <class M>
+__device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, int tid, int T, int* s_fail) {
+  // A = L D L^T (unit lower L, D > 0): one reciprocal per column and no square roots -- float64 div / sqrt are
+  // ~100-cycle software sequences and sit on the serial critical path of the factorisation.
+  for (int kb = 0; kb < P; kb++) {
+    const int c0 = 6 * kb;
+    if (tid == 0) {                                        // 6x6 diagonal block, serial in registers
+      double D[6][6], iv[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) D[i][j] = (j <= i) ? A((c0 + i), c0 + j) : 0.0;
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        double d = D[j][j];
+#pragma unroll
+        for (int t = 0; t < 6; t++) if (t < j) d -= D[j][t] * D[j][t] * D[t][t];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        D[j][j] = d;
+        iv[j] = 1.0 / d;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          if (i > j) {
+            double v = D[i][j];
+#pragma unroll
+            for (int t = 0; t < 6; t++) if (t < j) v -= D[i][t] * D[j][t] * D[t][t];
+            D[i][j] = v * iv[j];
+          }
+        }
+      }
+      if (bad) *s_fail = 1;
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        dinv[c0 + i] = iv[i];
+#pragma unroll
+        for (int j = 0; j < 6; j++) if (j <= i) A((c0 + i), c0 + j) = D[i][j];
+      }
+    }
+    __syncthreads();
+    if (*s_fail) break;
+    const int rend = min(n, c0 + 6 + band);
+    for (int r = c0 + 6 + tid; r < rend; r += T) {         // panel: L_rk = A_rk L_kk^-T D_k^-1
+      double x[6];
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        double v = A(r, c0 + j);
+#pragma unroll
+        for (int t = 0; t < 6; t++) if (t < j) v -= x[t] * A((c0 + t), c0 + t) * A((c0 + j), c0 + t);
+        x[j] = v * dinv[c0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 6; j++) A(r, c0 + j) = x[j];
+    }
+    __syncthreads();
+    const int m = rend - c0 - 6;                           // trailing update (lower triangle): A_ic -= sum_t L_it d_t L_ct
+    for (int idx = tid; idx < m * m; idx += T) {
+      const int i = c0 + 6 + idx / m, c = c0 + 6 + idx % m;
+      if (c > i) continue;
+      double v = A(i, c);
+#pragma unroll
+      for (int t = 0; t < 6; t++) v -= A(i, c0 + t) * A((c0 + t), c0 + t) * A(c, c0 + t);
+      A(i, c) = v;
+    }
+    __syncthreads();
+  }
+  if (!*s_fail) {
+    for (int kb = 0; kb < P; kb++) {                       // L z = b   (unit diagonal)
+      const int c0 = 6 * kb;
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 1; j < 6; j++) {
+          double v = y[c0 + j];
+#pragma unroll
+          for (int t = 0; t < 6; t++) if (t < j) v -= A((c0 + j), c0 + t) * y[c0 + t];
+          y[c0 + j] = v;
+        }
+      }
+      __syncthreads();
+      for (int r = c0 + 6 + tid; r < min(n, c0 + 6 + band); r += T) {
+        double v = y[r];
+#pragma unroll
+        for (int t = 0; t < 6; t++) v -= A(r, c0 + t) * y[c0 + t];
+        y[r] = v;
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < n; i += T) y[i] *= dinv[i];      // D w = z
+    __syncthreads();
+    for (int kb = P - 1; kb >= 0; kb--) {                  // L^T x = w
+      const int c0 = 6 * kb;
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 4; j >= 0; j--) {
+          double v = y[c0 + j];
+#pragma unroll
+          for (int t = 0; t < 6; t++) if (t > j) v -= A((c0 + t), c0 + j) * y[c0 + t];
+          y[c0 + j] = v;
+        }
+      }
+      __syncthreads();
+      for (int r = max(0, c0 - band) + tid; r < c0; r += T) {
+        double v = y[r];
+#pragma unroll
+        for (int t = 0; t < 6; t++) v -= A((c0 + t), r) * y[c0 + t];
+        y[r] = v;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 template <bool IN_SMEM>
 __global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem, int moba) {
   extern __shared__ double smd[];
@@ -437,115 +560,42 @@ __global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm,
   __syncthreads();
   damp(A, ld, dA, P, lm, ep, sem, moba, tid, T);
   __syncthreads();
-  // A = L D L^T (unit lower L, D > 0): one reciprocal per column and no square roots -- float64 div / sqrt are
-  // ~100-cycle software sequences and sit on the serial critical path of the factorisation.
+  // Block bandwidth of the system: frame graphs connect |i - j| <= r, so the Schur complement couples poses at most 2r
+  // frames apart and the factorisation never fills outside that band.  Everything below works on rows c0+6 .. rend only:
+  // O(n b^2) instead of O(n^3) -- what keeps the redundant per-rank solve cheap when 8 GPUs share a 63-pose window.
+  __shared__ int s_bw;
+  if (tid == 0) s_bw = 0;
+  __syncthreads();
+  for (int b = tid; b < P * P; b += T) {
+    const int bi = b / P, bj = b % P;
+    if (bj >= bi || bi - bj <= s_bw) continue;
+    bool nz = false;
+    for (int e = 0; e < 36 && !nz; e++) nz = A[(long)(6 * bi + e / 6) * ld + 6 * bj + e % 6] != 0.0;
+    if (nz) atomicMax(&s_bw, bi - bj);
+  }
+  __syncthreads();
+  const int band = 6 * s_bw;
   double* dinv = dA;                                       // dA is dead after damp(): reuse it for 1/d_j
-  for (int kb = 0; kb < P; kb++) {
-    const int c0 = 6 * kb;
-    if (tid == 0) {                                        // 6x6 diagonal block, serial in registers
-      double D[6][6], iv[6];
-#pragma unroll
-      for (int i = 0; i < 6; i++)
-#pragma unroll
-        for (int j = 0; j < 6; j++) D[i][j] = (j <= i) ? A[(long)(c0 + i) * ld + c0 + j] : 0.0;
-      bool bad = false;
-#pragma unroll
-      for (int j = 0; j < 6; j++) {
-        double d = D[j][j];
-#pragma unroll
-        for (int t = 0; t < 6; t++) if (t < j) d -= D[j][t] * D[j][t] * D[t][t];
-        if (!(d > 0.0)) { bad = true; d = 1.0; }
-        D[j][j] = d;
-        iv[j] = 1.0 / d;
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-          if (i > j) {
-            double v = D[i][j];
-#pragma unroll
-            for (int t = 0; t < 6; t++) if (t < j) v -= D[i][t] * D[j][t] * D[t][t];
-            D[i][j] = v * iv[j];
-          }
-        }
-      }
-      if (bad) s_fail = 1;
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        dinv[c0 + i] = iv[i];
-#pragma unroll
-        for (int j = 0; j < 6; j++) if (j <= i) A[(long)(c0 + i) * ld + c0 + j] = D[i][j];
-      }
+  if (!IN_SMEM && sizeof(double) * ((size_t)n * (band + 6) + 2 * n) <= 200 * 1024) {
+    // too large for a dense copy, but the band fits: pack it into shared memory (8 GPUs x 8 keyframes: n = 378, band 36)
+    const int W = band + 6;
+    double* Ab = smd;
+    double* yb = smd + (long)n * W;
+    double* db = yb + n;
+    for (long i = tid; i < (long)n * W; i += T) {
+      const int r = (int)(i / W), c = (int)(i % W) + max(0, 6 * (r / 6) - band);
+      Ab[i] = c <= r ? A[(long)r * ld + c] : 0.0;
     }
+    for (int i = tid; i < n; i += T) yb[i] = y[i];
     __syncthreads();
-    if (s_fail) break;
-    for (int r = c0 + 6 + tid; r < n; r += T) {            // panel: L_rk = A_rk L_kk^-T D_k^-1
-      double x[6];
-#pragma unroll
-      for (int j = 0; j < 6; j++) {
-        double v = A[(long)r * ld + c0 + j];
-#pragma unroll
-        for (int t = 0; t < 6; t++) if (t < j) v -= x[t] * A[(long)(c0 + t) * ld + c0 + t] * A[(long)(c0 + j) * ld + c0 + t];
-        x[j] = v * dinv[c0 + j];
-      }
-#pragma unroll
-      for (int j = 0; j < 6; j++) A[(long)r * ld + c0 + j] = x[j];
-    }
+    ldl_solve(SysMat<true>{Ab, W, band}, yb, db, P, n, band, tid, T, &s_fail);
     __syncthreads();
-    const int m = n - c0 - 6;                              // trailing update (lower triangle): A_ic -= sum_t L_it d_t L_ct
-    for (int idx = tid; idx < m * m; idx += T) {
-      const int i = c0 + 6 + idx / m, c = c0 + 6 + idx % m;
-      if (c > i) continue;
-      double v = A[(long)i * ld + c];
-#pragma unroll
-      for (int t = 0; t < 6; t++) v -= A[(long)i * ld + c0 + t] * A[(long)(c0 + t) * ld + c0 + t] * A[(long)c * ld + c0 + t];
-      A[(long)i * ld + c] = v;
-    }
+    for (int i = tid; i < n; i += T) y[i] = yb[i];
     __syncthreads();
+  } else {
+    ldl_solve(SysMat<false>{A, ld, band}, y, dinv, P, n, band, tid, T, &s_fail);
   }
   const bool fail = s_fail != 0;
-  if (!fail) {
-    for (int kb = 0; kb < P; kb++) {                       // L z = b   (unit diagonal)
-      const int c0 = 6 * kb;
-      if (tid == 0) {
-#pragma unroll
-        for (int j = 1; j < 6; j++) {
-          double v = y[c0 + j];
-#pragma unroll
-          for (int t = 0; t < 6; t++) if (t < j) v -= A[(long)(c0 + j) * ld + c0 + t] * y[c0 + t];
-          y[c0 + j] = v;
-        }
-      }
-      __syncthreads();
-      for (int r = c0 + 6 + tid; r < n; r += T) {
-        double v = y[r];
-#pragma unroll
-        for (int t = 0; t < 6; t++) v -= A[(long)r * ld + c0 + t] * y[c0 + t];
-        y[r] = v;
-      }
-      __syncthreads();
-    }
-    for (int i = tid; i < n; i += T) y[i] *= dinv[i];      // D w = z
-    __syncthreads();
-    for (int kb = P - 1; kb >= 0; kb--) {                  // L^T x = w
-      const int c0 = 6 * kb;
-      if (tid == 0) {
-#pragma unroll
-        for (int j = 4; j >= 0; j--) {
-          double v = y[c0 + j];
-#pragma unroll
-          for (int t = 0; t < 6; t++) if (t > j) v -= A[(long)(c0 + t) * ld + c0 + j] * y[c0 + t];
-          y[c0 + j] = v;
-        }
-      }
-      __syncthreads();
-      for (int r = tid; r < c0; r += T) {
-        double v = y[r];
-#pragma unroll
-        for (int t = 0; t < 6; t++) v -= A[(long)(c0 + t) * ld + r] * y[c0 + t];
-        y[r] = v;
-      }
-      __syncthreads();
-    }
-  }
   for (int i = tid; i < n; i += T) bf.dx[i] = fail ? 0.0f : (float)y[i];
   __syncthreads();
   // leave every replica zeroed for the next iteration / next call
@@ -676,6 +726,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
   if (!attr_set) {
     cudaFuncSetAttribute(ba_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(ba_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   // flags bits 1-2 select a phase for the multi-GPU path (pvo_b200/dist.py): 0 = whole iteration(s),
@@ -695,7 +746,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
       ba_solve_kernel<true><<<1, 128, solve_smem, s>>>(bf, P, lm, ep, sem, sem && motion_only);
     } else {
       ba_combine_kernel<<<8, 256, 0, s>>>(bf, P);
-      ba_solve_kernel<false><<<1, 128, 0, s>>>(bf, P, lm, ep, sem, sem && motion_only);
+      ba_solve_kernel<false><<<1, 128, 200 * 1024, s>>>(bf, P, lm, ep, sem, sem && motion_only);   // band-packed copy in smem when it fits
     }
     const bool last = it == iterations - 1;
     if (last && dx_out)

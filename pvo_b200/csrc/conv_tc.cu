@@ -90,7 +90,26 @@ __device__ __forceinline__ void xr_step(float* x, int lane) {
 
 // ---- epilogues: store16(m, e, n, v, ok, tile, q): 16 consecutive output channels n.. of pixel m (image/edge e) ------
 struct EpBias {          // out = act(acc + bias); with a residual: relu(res + act(acc + bias))  (ResNet bottleneck tail)
+  static constexpr bool kStaged = true;   // BN = 256 tiles transpose the output through shared memory (see the epilogue loop)
   const float* bias; __half* out; int ostride; int ooff; int Cout; int relu; const __half* res; int rstride;
+  // 16 columns of one pixel -> 8 packed half2 words (bias, activation, residual applied); full 16-column chunks only
+  __device__ __forceinline__ void apply16(long m, int n, const float* v, bool ok, uint32_t* w) const {
+    float b[16], x[16];
+    ld16f(bias + n, b);
+#pragma unroll
+    for (int j = 0; j < 16; j++) { x[j] = v[j] + b[j]; if (relu) x[j] = fmaxf(x[j], 0.0f); }
+    if (res && ok) {
+      float r[16];
+      ld16h<true>(res + m * rstride + n, r);
+#pragma unroll
+      for (int j = 0; j < 16; j++) x[j] = fmaxf(x[j] + r[j], 0.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const __half2 h = __floats2half2_rn(x[2 * k], x[2 * k + 1]);
+      w[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
   __device__ __forceinline__ void store16(long m, long, int n, const float* v, bool ok, int, int) const {
     if (n >= Cout || !ok) return;
     __half* o = out + m * ostride + ooff + n;
@@ -120,7 +139,8 @@ struct EpBias {          // out = act(acc + bias); with a residual: relu(res + a
   }
 };
 
-struct EpGloSum {        // gru.py:25-26: sum over the tile's pixels of sigmoid(w(net)) * net -> partial[tile][quarter][128]
+struct EpGloSum {
+  static constexpr bool kStaged = false;        // gru.py:25-26: sum over the tile's pixels of sigmoid(w(net)) * net -> partial[tile][quarter][128]
   const float* bias; const __half* net; int nstride; float* partial; int Cout;
   __device__ __forceinline__ void store16(long m, long, int n, const float* v, bool ok, int tile, int q) const {
     if (n >= Cout) return;                       // warp-uniform
@@ -142,7 +162,8 @@ struct EpGloSum {        // gru.py:25-26: sum over the tile's pixels of sigmoid(
   }
 };
 
-struct EpZR {            // gru.py:28-29 (see conv_simt.cu EpiZR)
+struct EpZR {
+  static constexpr bool kStaged = false;            // gru.py:28-29 (see conv_simt.cu EpiZR)
   const float* bias; const float* glo; const __half* net; int nstride; __half* z; __half* rnet;
   __device__ __forceinline__ void store16(long m, long e, int n, const float* v, bool ok, int, int) const {
     if (n >= 256 || !ok) return;
@@ -163,7 +184,8 @@ struct EpZR {            // gru.py:28-29 (see conv_simt.cu EpiZR)
   }
 };
 
-struct EpQ {             // gru.py:30-32, state update in place
+struct EpQ {
+  static constexpr bool kStaged = false;             // gru.py:30-32, state update in place
   const float* bias; const float* glo; const __half* z; __half* net; int nstride;
   __device__ __forceinline__ void store16(long m, long e, int n, const float* v, bool ok, int, int) const {
     if (n >= 128 || !ok) return;
@@ -198,7 +220,8 @@ template <int BN> struct Cfg {
   // tensor pipe: two co-resident CTAs per SM (96 KB of stages and <= 256 TMEM columns each) double that throughput.
   static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN; // 128 / 256 / 512: powers of two
-  static constexpr int kSmem = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/ + kMaxKb * 4 /*k-block table*/;
+  static constexpr int kStaging = (BN == 256) ? 8 * 2048 : 0;   // 8 epilogue warps x (32 rows x 64 B): output transpose for coalesced stores
+  static constexpr int kSmem = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/ + kMaxKb * 4 /*k-block table*/ + kStaging;
 };
 
 template <int BN, typename Epi>
@@ -326,6 +349,35 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm) conv_tc_kernel(
         tmem_ld16(taddr + c + 16, v1);
         tmem_ld_wait();
         const int n = nt * BN + half * (BN / 2) + c;
+        if constexpr (Epi::kStaged && BN == 256) {
+          // Each thread owns one pixel (row), so a direct store touches 32 different rows per instruction (32 L1
+          // wavefronts).  Transpose 32 rows x 32 columns through shared memory instead: 4 lanes then write 64 contiguous
+          // bytes of one row, 8 rows per instruction.  Chunk position is XOR-swizzled by the row pair: conflict-free both ways.
+          if (n + 32 <= epi.Cout) {
+            unsigned char* stg = reinterpret_cast<unsigned char*>(kbt + kMaxKb) + (warp - 2) * 2048;
+            uint32_t w0[8], w1[8];
+            epi.apply16(m, n, reinterpret_cast<const float*>(v0), ok, w0);
+            epi.apply16(m, n + 16, reinterpret_cast<const float*>(v1), ok, w1);
+            const int sw = (lane >> 1) & 3;
+            uint4* rowp = reinterpret_cast<uint4*>(stg + lane * 64);
+            rowp[0 ^ sw] = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+            rowp[1 ^ sw] = make_uint4(w0[4], w0[5], w0[6], w0[7]);
+            rowp[2 ^ sw] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+            rowp[3 ^ sw] = make_uint4(w1[4], w1[5], w1[6], w1[7]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+              const int rr = it * 8 + (lane >> 2), ch = lane & 3;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+              const int pr = q * 32 + rr;
+              const int yy = (r / p.tiles_x) * kTileH + pr / kTileW, xx = (r % p.tiles_x) * kTileW + pr % kTileW;
+              if (yy < p.H && xx < p.W)
+                *reinterpret_cast<uint4*>(epi.out + (((long)img * p.H + yy) * p.W + xx) * epi.ostride + epi.ooff + n + ch * 8) = val;
+            }
+            __syncwarp();
+            continue;
+          }
+        }
         epi.store16(m, img, n, reinterpret_cast<const float*>(v0), ok, mt, q);
         epi.store16(m, img, n + 16, reinterpret_cast<const float*>(v1), ok, mt, q);
       }

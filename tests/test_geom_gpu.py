@@ -99,7 +99,9 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize('cfg', [dict(F=5, radius=2, h=16, w=24, t0=1), dict(F=8, radius=3, h=24, w=32, t0=1),
-                                 dict(F=7, radius=2, h=16, w=24, t0=3), dict(F=6, radius=5, h=12, w=16, t0=2)])
+                                 dict(F=7, radius=2, h=16, w=24, t0=3), dict(F=6, radius=5, h=12, w=16, t0=2),
+                                 dict(F=22, radius=2, h=8, w=12, t0=1),      # banded system (bandwidth 4 of 21 blocks): band-limited LDL^T
+                                 dict(F=34, radius=1, h=8, w=12, t0=2)])     # P = 32 > 26: the factorisation runs out of global memory
 @pytest.mark.parametrize('motion_only', [False, True])
 def test_ba_matches_oracle(cfg, motion_only):
     """droid_backends.ba: in-place poses/disps, returned dx/dz, 2 Gauss-Newton iterations.  Tolerance 1e-4 relative
