@@ -181,7 +181,10 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    units_per_step = (E * world) / 36.0 if world > 1 else 1.0       # 8-KF-graph equivalents processed per step
+    # work unit = one config-2 graph's worth of edges (36): the sharded graph has c['E'] edges in total (interior ranks own
+    # 48, the two end ranks 42), so the whole job processes c['E'] / 36 units per step
+    E_total = int(c['E']) if world > 1 else E
+    units_per_step = E_total / 36.0 if world > 1 else 1.0
     value = units_per_step * 1000.0 / ms_per_step
 
     # ---- instrumented pass: per-launch CUDA events on the launching stream
@@ -274,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
         'dtype': 'f16' if args.precision == 'fp16' else 'f32', 'data': 'synthetic (seeded random features / random-init weights)',
         'config': {'workload': ('BASELINE configs[2] shape (VKITTI2 240x808, segment filter on): ' if args.workload == 'vkitti' else 'BASELINE configs[1]: ') + '%d-keyframe factor graph per GPU, r=3 corr, %d edges/GPU, 2 BA iters per update; '
                                'update-op iterations feed back state' % (F_PER_GPU, E),
-                   'edges': E * world, 'keyframes': nf, 'grid': [HT, WD], 'precision': args.precision,
+                   'edges': E_total, 'edges_this_rank': E, 'keyframes': nf, 'grid': [HT, WD], 'precision': args.precision,
                    'l2': 'per-step working set (2.2 GB volume + 0.9 GB activations) >> 126 MB L2; 256 MB flush between timed steps',
                    'parallelism': ('edges sharded by source keyframe; reduced camera system all-reduced per BA iteration by ' + getattr(fg, 'allreduce_kind', 'ncclAllReduce')) if world > 1 else 'single GPU'},
         'e2e': {'value': round(e2e_value, 3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
