@@ -261,12 +261,20 @@ def run_ours(args, rank, world, local_rank):
                 'peak': pk['tf_burst'], 'unit': 'TFLOP/s', 'frac': round(ach / pk['tf_burst'], 4), 'traffic': None,
                 'peak_source': pk['src'] + ' (burst: kernel timed per launch)', 'ms_per_launch': round(zr_ms, 4),
                 'flops_per_launch': zr_flops}
+    try:                                        # DRAM traffic of the same kernels from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+    except Exception:
+        traffic = {}
+    if roof is not None and traffic:
+        roof['traffic'] = traffic.get('conv_tc_kernel<256,EpZR>')
+        roof['traffic_source'] = traffic.get('source')
     look_ms = kernel_ms.get('corr_lookup')
     secondary = {}
     if look_ms:
         lb = E * hw * (4 * 64 * 2 + 8 + 208 * 2)
         secondary['corr_lookup'] = {'bound': 'hbm', 'achieved': round(lb / (look_ms * 1e-3) / 1e9, 1), 'peak': pk['hbm'], 'unit': 'GB/s',
-                                    'frac': round(lb / (look_ms * 1e-3) / 1e9 / pk['hbm'], 4), 'bytes_per_launch': lb}
+                                    'frac': round(lb / (look_ms * 1e-3) / 1e9 / pk['hbm'], 4), 'bytes_per_launch': lb,
+                                    'traffic': traffic.get('corr_lookup_fused_kernel')}
     ba_ms = sum(v_ for k_, v_ in kernel_ms.items() if k_.startswith('ba'))
     upd_ms = sum(v_ for k_, v_ in kernel_ms.items() if k_.startswith('conv') or k_ in ('colmean', 'glo_matvec', 'heads2', 'segment_mean', 'eta'))
     cpu = cpu_baseline_sample()
