@@ -219,27 +219,51 @@ def run_ours(args, rank, world, local_rank):
     h2d = sum(t_.numel() * t_.element_size() for t_ in host.values())
     d2h = sum(t_.numel() * t_.element_size() for t_ in out_host.values())
 
-    def e2e_step():
-        v.poses[:nf].copy_(host['poses'], non_blocking=True)
-        v.disps[:nf].copy_(host['disps'], non_blocking=True)
-        fg.target_cam.copy_(host['target'], non_blocking=True)
-        fg.weight.copy_(host['weight'], non_blocking=True)
-        fg.raw_mask.copy_(host['raw_mask'], non_blocking=True)
-        fg.delta_dy.copy_(host['delta_dy'], non_blocking=True)
-        eng.X[:, :128].copy_(host['net'], non_blocking=True)
-        fg.update(t0=1, t1=nf, itrs=2)
-        out_host['poses'].copy_(v.poses[:nf], non_blocking=True)
-        out_host['disps'].copy_(v.disps[:nf], non_blocking=True)
-        out_host['full_flow'].copy_(fg.full_flow, non_blocking=True)
-        out_host['net'].copy_(eng.X[:, :128], non_blocking=True)
+    # Three streams: H2D of step k+1 and D2H of step k-1 overlap the compute of step k (each step's inputs come from the
+    # host, so consecutive steps are independent).  Host <-> device traffic goes through double-buffered device staging so
+    # a copy never touches the live graph state while a step is reading it.
+    live_in = {'poses': v.poses[:nf], 'disps': v.disps[:nf], 'target': fg.target_cam, 'weight': fg.weight, 'raw_mask': fg.raw_mask,
+               'delta_dy': fg.delta_dy, 'net': eng.X[:, :128]}
+    live_out = lambda: {'poses': v.poses[:nf], 'disps': v.disps[:nf], 'full_flow': fg.full_flow, 'net': eng.X[:, :128]}
+    stage_in = [{n: torch.empty_like(host[n], device=dev) for n in host} for _ in range(2)]
+    stage_out = [{n: torch.empty_like(out_host[n], device=dev) for n in out_host} for _ in range(2)]
+    s_in, s_out, cur = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
+    E_ = lambda: torch.cuda.Event()
+    in_ready, in_free, out_ready, out_free = [E_(), E_()], [E_(), E_()], [E_(), E_()], [E_(), E_()]
+    for b in range(2):
+        in_free[b].record(cur)
+        out_free[b].record(cur)
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_step(k):
+        b = k & 1
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(in_free[b])
+            for n in host:
+                stage_in[b][n].copy_(host[n], non_blocking=True)
+            in_ready[b].record(s_in)
+        cur.wait_event(in_ready[b])
+        for n, t_ in live_in.items():
+            t_.copy_(stage_in[b][n], non_blocking=True)
+        in_free[b].record(cur)
+        fg.update(t0=1, t1=nf, itrs=2)
+        cur.wait_event(out_free[b])
+        for n, t_ in live_out().items():
+            stage_out[b][n].copy_(t_, non_blocking=True)
+        out_ready[b].record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(out_ready[b])
+            for n in out_host:
+                out_host[n].copy_(stage_out[b][n], non_blocking=True)
+            out_free[b].record(s_out)
+
+    for k in range(4):
+        e2e_step(k)
     sync()
-    n_e2e = max(3, min(args.steps, 20))
+    n_e2e = max(4, min(args.steps, 20))
     ev0.record()
-    for _ in range(n_e2e):
-        e2e_step()
+    for k in range(n_e2e):
+        e2e_step(k)
+    cur.wait_stream(s_out)                      # the last results are on the host before the clock stops
     ev1.record()
     sync()
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -289,8 +313,9 @@ def run_ours(args, rank, world, local_rank):
                    'l2': 'per-step working set (2.2 GB volume + 0.9 GB activations) >> 126 MB L2; 256 MB flush between timed steps',
                    'parallelism': ('edges sharded by source keyframe; reduced camera system all-reduced per BA iteration by ' + getattr(fg, 'allreduce_kind', 'ncclAllReduce')) if world > 1 else 'single GPU'},
         'e2e': {'value': round(e2e_value, 3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'what': 'mutable graph state (poses, disps, target, weight, masks, hidden state) H2D from pinned host memory, '
-                        'FactorGraph.update, results (poses, disps, flow, hidden state) D2H, every step'},
+                'what': 'every step: mutable graph state (poses, disps, target, weight, masks, hidden state) H2D from pinned host memory, '
+                        'FactorGraph.update, results (poses, disps, flow, hidden state) D2H to pinned host memory; copies of '
+                        'neighbouring steps overlap the compute on separate streams (double-buffered staging)'},
         'gpu_launches': launches,
         'clocks': clocks.result(),
         'roofline': roof, 'roofline_other': secondary,

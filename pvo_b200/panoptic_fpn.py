@@ -91,6 +91,24 @@ def paste_masks(masks, boxes, img_h, img_w, threshold=0.5):
     return F.grid_sample(masks.float(), grid, align_corners=False)[:, 0] >= threshold
 
 
+def segments_for_vo(pan, size=None):
+    """In-process hand-off of a panoptic id map to VO_Module (replaces the PNG round trip panoptic_evaluation.py ->
+    split_init_segm.py -> evaluation_scripts/test_vo.py:44-50): nearest resize to the VO input size, then nearest 1/8
+    down-sampling -> (1, 1, h//8, w//8) int32, what `Droid.track(..., segments=)` / `DepthVideo.segms` take.
+    Faithful to the reference as written: its crop `segm[:h1-h1%8, :w1-w1%8]` slices the batch / channel dims of a 4-D
+    tensor (a no-op), so the second interpolate maps h1 -> h1//8 rows with scale h1/(h1//8) (= 8 when 8 | h1).
+    Nearest interpolation picks source index floor(dst * in/out): the whole chain is two strided gathers on the device."""
+    H, W = pan.shape[-2:]
+    h1, w1 = size if size is not None else (H, W)
+
+    def nearest(n_out, n_in, dev):          # at::upsample_nearest: min(floor(dst * (float)n_in / n_out), n_in - 1) in fp32
+        i = (torch.arange(n_out, device=dev, dtype=torch.float32) * (float(n_in) / float(n_out))).floor().long()
+        return i.clamp(max=n_in - 1)
+    ys = nearest(h1, H, pan.device)[nearest(h1 // 8, h1, pan.device)]
+    xs = nearest(w1, W, pan.device)[nearest(w1 // 8, w1, pan.device)]
+    return pan[..., ys[:, None], xs[None, :]].to(torch.int32)[None, None]
+
+
 def _cat_rows(ts):
     """torch.cat(ts) along dim 0, without the copy when the pieces are consecutive row blocks of one buffer"""
     if len(ts) == 1:

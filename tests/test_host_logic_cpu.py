@@ -155,3 +155,19 @@ def test_proximity_edge_selection_matches_reference_golden():
         assert np.array_equal(np.asarray(es, dtype=np.int64).reshape(-1, 2), z['es%d' % k]), k
         k += 1
     assert k == 6
+
+
+def test_segments_for_vo_matches_the_reference_resize_chain():
+    """pvo_b200.panoptic_fpn.segments_for_vo == evaluation_scripts/test_vo.py:44-50 (interpolate -> crop -> interpolate 1/8)"""
+    import torch.nn.functional as F
+    from pvo_b200.panoptic_fpn import segments_for_vo
+    g = torch.Generator().manual_seed(0)
+    for (H, W), size in (((375, 1242), (240, 808)), ((480, 640), None), ((376, 1241), (243, 811))):
+        pan = torch.randint(0, 150000, (H, W), generator=g, dtype=torch.int32)
+        h1, w1 = size if size is not None else (H, W)
+        segm = pan[None, None].float()
+        segm = F.interpolate(segm, size=(h1, w1))
+        segm = segm[:h1 - h1 % 8, :w1 - w1 % 8]                # as written in the reference: slices dims 0, 1 of a 4-D tensor (no-op)
+        want = F.interpolate(segm, scale_factor=1 / 8, recompute_scale_factor=True).int()
+        got = segments_for_vo(pan, size)
+        assert got.shape == want.shape and torch.equal(got, want), (H, W, size)
