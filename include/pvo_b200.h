@@ -192,6 +192,10 @@ int pvo_nms_groups(const float* boxes /*(G,n,4)*/, const unsigned char* valid /*
 int pvo_allreduce_oneshot(double* data, void* const* stage_ptrs, void* const* flag_ptrs, int* epochs, int rank, int world, long n,
                           long n_max, void* stream);
 
+/* heads' second convolution (droid_net.py:195-214), tensor-core form: T = block-diagonal 1x1 conv of the four heads' hidden
+ * layers onto (tap, output) pairs, [M][128] half from pvo_conv2d_tc; this kernel sums the 9 shifted taps + bias -> out[M][ostride] f32 */
+int pvo_heads_stencil(const void* T, const float* bias, float* out, int ostride, int nimg, int H, int W, void* stream);
+
 /* FactorGraph.update post-processing (factor_graph.py:250-283): target_cam, raw_mask, bin_mask, panoptic segment
  *   filter (:256-276, integer counting on the device instead of numpy on the host), delta_dy, sigmoid weights. */
 long pvo_update_post_workspace_ints(int E);

@@ -424,117 +424,122 @@ template <bool BAND> struct SysMat {
   }
 };
 
-// A = L D L^T restricted to the block band, then L z = b, D w = z, L^T x = w in place in y.  dinv: scratch [n].
+// 6x6 diagonal block at c0: A_kk = L D L^T in place (unit lower L below the diagonal, d on it), 1/d -> dinv, and the
+// block's share of the forward substitution (y_k <- L_kk^-1 y_k).  One thread: float64 div / sqrt are ~100-cycle software
+// sequences, so the factorisation keeps one reciprocal per column and no square roots.
 template <class M>
-__device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, int tid, int T, int* s_fail) {
-  // A = L D L^T (unit lower L, D > 0): one reciprocal per column and no square roots -- float64 div / sqrt are
-  // ~100-cycle software sequences and sit on the serial critical path of the factorisation.
-  for (int kb = 0; kb < P; kb++) {
-    const int c0 = 6 * kb;
-    if (tid == 0) {                                        // 6x6 diagonal block, serial in registers
-      double D[6][6], iv[6];
+__device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int c0, int* s_fail) {
+  double D[6][6], iv[6];
 #pragma unroll
-      for (int i = 0; i < 6; i++)
+  for (int i = 0; i < 6; i++)
 #pragma unroll
-        for (int j = 0; j < 6; j++) D[i][j] = (j <= i) ? A((c0 + i), c0 + j) : 0.0;
-      bool bad = false;
+    for (int j = 0; j < 6; j++) D[i][j] = (j <= i) ? A((c0 + i), c0 + j) : 0.0;
+  bool bad = false;
 #pragma unroll
-      for (int j = 0; j < 6; j++) {
-        double d = D[j][j];
+  for (int j = 0; j < 6; j++) {
+    double d = D[j][j];
 #pragma unroll
-        for (int t = 0; t < 6; t++) if (t < j) d -= D[j][t] * D[j][t] * D[t][t];
-        if (!(d > 0.0)) { bad = true; d = 1.0; }
-        D[j][j] = d;
-        iv[j] = 1.0 / d;
+    for (int t = 0; t < 6; t++) if (t < j) d -= D[j][t] * D[j][t] * D[t][t];
+    if (!(d > 0.0)) { bad = true; d = 1.0; }
+    D[j][j] = d;
+    iv[j] = 1.0 / d;
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
-          if (i > j) {
-            double v = D[i][j];
+    for (int i = 0; i < 6; i++) {
+      if (i > j) {
+        double v = D[i][j];
 #pragma unroll
-            for (int t = 0; t < 6; t++) if (t < j) v -= D[i][t] * D[j][t] * D[t][t];
-            D[i][j] = v * iv[j];
-          }
-        }
-      }
-      if (bad) *s_fail = 1;
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        dinv[c0 + i] = iv[i];
-#pragma unroll
-        for (int j = 0; j < 6; j++) if (j <= i) A((c0 + i), c0 + j) = D[i][j];
+        for (int t = 0; t < 6; t++) if (t < j) v -= D[i][t] * D[j][t] * D[t][t];
+        D[i][j] = v * iv[j];
       }
     }
-    __syncthreads();
-    if (*s_fail) break;
+  }
+  if (bad) *s_fail = 1;
+  double z[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    dinv[c0 + i] = iv[i];
+    double v = y[c0 + i];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      if (j <= i) A((c0 + i), c0 + j) = D[i][j];
+      if (j < i) v -= D[i][j] * z[j];
+    }
+    z[i] = v;
+    y[c0 + i] = v;
+  }
+}
+
+// A = L D L^T restricted to the block band, then L z = b, D w = z, L^T x = w in place in y.  dinv: scratch [n].
+// Schedule per 6-wide block column k (two block barriers instead of five, and the serial 6x6 step is off the critical
+// path): [panel: L_rk for the band rows + their forward-substitution update] | [trailing update by warps 1.. while warp 0
+// updates, factors and forward-solves the NEXT diagonal block].  The backward substitution runs in warp 0 alone with
+// warp-level reductions (no block barriers at all).
+template <class M>
+__device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, int tid, int T, int* s_fail) {
+  const int lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) ldl_diag_block(A, y, dinv, 0, s_fail);
+  __syncthreads();
+  for (int kb = 0; kb < P && !*s_fail; kb++) {
+    const int c0 = 6 * kb;
     const int rend = min(n, c0 + 6 + band);
-    for (int r = c0 + 6 + tid; r < rend; r += T) {         // panel: L_rk = A_rk L_kk^-T D_k^-1
+    for (int r = c0 + 6 + tid; r < rend; r += T) {         // panel: L_rk = A_rk L_kk^-T D_k^-1; y_r -= L_rk z_k
       double x[6];
+      double yr = y[r];
 #pragma unroll
       for (int j = 0; j < 6; j++) {
         double v = A(r, c0 + j);
 #pragma unroll
         for (int t = 0; t < 6; t++) if (t < j) v -= x[t] * A((c0 + t), c0 + t) * A((c0 + j), c0 + t);
         x[j] = v * dinv[c0 + j];
+        yr -= x[j] * y[c0 + j];
       }
 #pragma unroll
       for (int j = 0; j < 6; j++) A(r, c0 + j) = x[j];
+      y[r] = yr;
     }
     __syncthreads();
     const int m = rend - c0 - 6;                           // trailing update (lower triangle): A_ic -= sum_t L_it d_t L_ct
-    for (int idx = tid; idx < m * m; idx += T) {
-      const int i = c0 + 6 + idx / m, c = c0 + 6 + idx % m;
-      if (c > i) continue;
-      double v = A(i, c);
+    if (m > 0) {
+      if (warp == 0) {
+        // the next diagonal block first (21 entries), then its factorisation while the other warps do the rest
+        if (lane < 21) {
+          int bi = 0, bj = lane;
+          while (bj > bi) { bj -= bi + 1; bi++; }
+          const int i = c0 + 6 + bi, c = c0 + 6 + bj;
+          double v = A(i, c);
 #pragma unroll
-      for (int t = 0; t < 6; t++) v -= A(i, c0 + t) * A((c0 + t), c0 + t) * A(c, c0 + t);
-      A(i, c) = v;
+          for (int t = 0; t < 6; t++) v -= A(i, c0 + t) * A((c0 + t), c0 + t) * A(c, c0 + t);
+          A(i, c) = v;
+        }
+        __syncwarp();
+        if (lane == 0) ldl_diag_block(A, y, dinv, c0 + 6, s_fail);
+      } else {
+        for (int idx = tid - 32; idx < m * m; idx += T - 32) {
+          const int i = c0 + 6 + idx / m, c = c0 + 6 + idx % m;
+          if (c > i || i < c0 + 12) continue;              // rows of the next diagonal block belong to warp 0
+          double v = A(i, c);
+#pragma unroll
+          for (int t = 0; t < 6; t++) v -= A(i, c0 + t) * A((c0 + t), c0 + t) * A(c, c0 + t);
+          A(i, c) = v;
+        }
+      }
     }
     __syncthreads();
   }
-  if (!*s_fail) {
-    for (int kb = 0; kb < P; kb++) {                       // L z = b   (unit diagonal)
-      const int c0 = 6 * kb;
-      if (tid == 0) {
-#pragma unroll
-        for (int j = 1; j < 6; j++) {
-          double v = y[c0 + j];
-#pragma unroll
-          for (int t = 0; t < 6; t++) if (t < j) v -= A((c0 + j), c0 + t) * y[c0 + t];
-          y[c0 + j] = v;
-        }
-      }
-      __syncthreads();
-      for (int r = c0 + 6 + tid; r < min(n, c0 + 6 + band); r += T) {
-        double v = y[r];
-#pragma unroll
-        for (int t = 0; t < 6; t++) v -= A(r, c0 + t) * y[c0 + t];
-        y[r] = v;
-      }
-      __syncthreads();
-    }
-    for (int i = tid; i < n; i += T) y[i] *= dinv[i];      // D w = z
-    __syncthreads();
-    for (int kb = P - 1; kb >= 0; kb--) {                  // L^T x = w
-      const int c0 = 6 * kb;
-      if (tid == 0) {
-#pragma unroll
-        for (int j = 4; j >= 0; j--) {
-          double v = y[c0 + j];
-#pragma unroll
-          for (int t = 0; t < 6; t++) if (t > j) v -= A((c0 + t), c0 + j) * y[c0 + t];
-          y[c0 + j] = v;
-        }
-      }
-      __syncthreads();
-      for (int r = max(0, c0 - band) + tid; r < c0; r += T) {
-        double v = y[r];
-#pragma unroll
-        for (int t = 0; t < 6; t++) v -= A((c0 + t), r) * y[c0 + t];
-        y[r] = v;
-      }
-      __syncthreads();
+  if (*s_fail) return;
+  for (int i = tid; i < n; i += T) y[i] *= dinv[i];        // D w = z
+  __syncthreads();
+  if (warp == 0) {                                         // L^T x = w: row by row from the bottom, one warp, no block barriers
+    for (int row = n - 1; row >= 0; row--) {
+      const int rlast = min(n, 6 * (row / 6) + 6 + band);  // rows r > row with L(r, row) != 0 stay within the band
+      double acc = 0.0;
+      for (int r = row + 1 + lane; r < rlast; r += 32) acc += A(r, row) * y[r];
+      acc = warp_sum_d(acc);
+      if (lane == 0) y[row] -= acc;
+      __syncwarp();
     }
   }
+  __syncthreads();
 }
 
 template <bool IN_SMEM>

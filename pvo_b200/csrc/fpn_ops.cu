@@ -8,13 +8,6 @@
 
 namespace {
 
-template <typename T> __device__ __forceinline__ float ldv(const T* p);
-template <> __device__ __forceinline__ float ldv<float>(const float* p) { return __ldg(p); }
-template <> __device__ __forceinline__ float ldv<__half>(const __half* p) { return __half2float(__ldg(p)); }
-template <typename T> __device__ __forceinline__ void stv(T* p, float v);
-template <> __device__ __forceinline__ void stv<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void stv<__half>(__half* p, float v) { *p = __float2half_rn(v); }
-
 // 16-byte channel vectors: 8 halves or 4 floats per thread (C % VE == 0 on every call site; pointers 16-B aligned)
 template <typename T> struct Vec;
 template <> struct Vec<float> {

@@ -64,17 +64,6 @@ __global__ void __launch_bounds__(256) paste_masks_kernel(const float* __restric
 }
 
 // ---- merge
-__device__ __forceinline__ int block_sum_int(int v, int* sh) {
-  v = __reduce_add_sync(0xffffffffu, v);
-  const int w = threadIdx.x >> 5;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sh[w] = v;
-  __syncthreads();
-  int t = 0;
-  for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[k];
-  return t;
-}
-
 // info_out[n][k] = {segment id, category, isthing, area, instance index}; counts_out[n] = number of segments.
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(1024)
     panoptic_combine_kernel(const unsigned char* __restrict__ masks /*[R][H*W] bool*/, const float* __restrict__ boxes /*[R][4] or null*/,

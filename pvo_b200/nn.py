@@ -136,6 +136,15 @@ class UpdateEngine:
         self.heads2_W = pack_small_weight([g(h + '.2.weight') for h in HEAD_NAMES])
         self.heads2_b = torch.cat([g(h + '.2.bias') for h in HEAD_NAMES], 0).float().contiguous()
         self.heads2_frag = pack_heads_mma([g(h + '.2.weight') for h in HEAD_NAMES]) if mode == 'fp16' else None
+        self.c_heads2t = None
+        if mode == 'fp16' and tc:
+            # tensor-core form of the 3x3 128->2 head convs: block-diagonal 1x1 conv onto (tap, output) pairs + a 9-tap
+            # gather-sum (csrc/heads_stencil.cu).  Row g*32 + tap*2 + o, column g*128 + c  <-  w_g[o, c, tap]
+            wbd = torch.zeros(128, 512, 1, 1, device=self.device)
+            for gi, h in enumerate(HEAD_NAMES):
+                w2 = g(h + '.2.weight').float()                                 # (2, 128, 3, 3)
+                wbd[gi * 32:gi * 32 + 18, gi * 128:(gi + 1) * 128, 0, 0] = w2.permute(2, 3, 0, 1).reshape(18, 128)
+            self.c_heads2t = _Conv(wbd, torch.zeros(128, device=self.device), tc=True, simt=False, segs=[128, 128, 128, 128])
         self.c_agg2 = _Conv(g('agg.conv2.weight'), g('agg.conv2.bias'), tc=tc)
         self.eta_W = pack_small_weight([g('agg.eta.0.weight')])
         self.eta_b = g('agg.eta.0.bias').float().contiguous()
@@ -166,6 +175,7 @@ class UpdateEngine:
         self.rnet = z(M, 128)
         self.Hb = z(M, 640)            # relu(first conv) of the 4 heads | relu(agg.conv1)
         self.head_out = z(M, 8, dtype=torch.float32)       # [delta | delta_dy | weight | delta_mask]
+        self.T2 = z(M, 128) if self.c_heads2t is not None else None   # per-tap partial outputs of the heads' second conv
         self.A = z(K * HW, 128)
         self.a2 = z(K * HW, 128)
         self.eta = z(K, H, W, dtype=torch.float32)
@@ -252,8 +262,14 @@ class UpdateEngine:
         with T('conv_heads1'):
             conv2d(self.c_heads1, [(X, 128, 448)], E, H, W, dc, self.Hb, 640, 0, 1, use_tc=tc)
         with T('heads2'):
-            check(L.pvo_conv3x3_small(ptr(self.Hb), 640, 128, ptr(self.heads2_W), ptr(self.heads2_b), ptr(self.head_out), 8,
-                                      4, 2, E, H, W, dc, 0, ptr(self.heads2_frag), stream()), 'heads2')
+            if self.c_heads2t is not None:
+                hb = self.Hb.data_ptr()
+                conv2d(self.c_heads2t, [(hb + gi * 128 * esz, 128, 640) for gi in range(4)], E, H, W, dc, self.T2, 128, 0, 0,
+                       use_tc=True)
+                check(L.pvo_heads_stencil(ptr(self.T2), ptr(self.heads2_b), ptr(self.head_out), 8, E, H, W, stream()), 'heads_stencil')
+            else:
+                check(L.pvo_conv3x3_small(ptr(self.Hb), 640, 128, ptr(self.heads2_W), ptr(self.heads2_b), ptr(self.head_out), 8,
+                                          4, 2, E, H, W, dc, 0, ptr(self.heads2_frag), stream()), 'heads2')
         if with_agg:
             with T('segment_mean'):
                 check(L.pvo_segment_mean(ptr(self.Hb), 640, 512, ptr(self.A), ptr(self.g_ptr), ptr(self.g_idx),
