@@ -89,7 +89,9 @@ int pvo_frame_distance(const float* poses, const float* disps, const float* intr
  *   In place on poses (nframes,7) / disps (nframes,ht,wd).  intrinsics (4,).  targets/weights (E,2,ht,wd)
  *   [interleaved = 0, the reference layout] or (E,ht,wd,2) [interleaved = 1].  eta (K,ht,wd),
  *   K = |unique(arange(t0,t1) U ii)|.  dx_out (t1-t0,6) / dz_out (K,ht*wd) may be NULL.
- *   workspace >= pvo_ba_workspace_bytes(...).  flags bit0: reuse the edge plan already in the workspace. */
+ *   workspace >= pvo_ba_workspace_bytes(...).  flags bit0: reuse the edge plan already in the workspace;
+ *   bits 1-2: phase (multi-GPU, below); bit 3: geom/ba.py semantics; bits 8-19: max out-degree hint; bits 20-27: 1 + block
+ *   bandwidth of the pose system (<= 2 max|ii-jj| over the whole graph; 0 = unknown, the solver scans for it). */
 long pvo_ba_workspace_bytes(int E, int nframes, int P, int K, int HW);
 int pvo_ba(float* poses, float* disps, const float* intrinsics, const float* targets, const float* weights,
            const float* eta, const long* ii, const long* jj, int E, int nframes, int ht, int wd, int t0, int t1, int K,

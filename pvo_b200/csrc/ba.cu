@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(256) ba_pass2_kernel(const long* __restrict__ 
   const int f = pl.kx[k];
   const int tid = threadIdx.x;
   const int deg = pl.src_ptr[k + 1] - pl.src_ptr[k];
+  if (deg == 0) return;                              // no out-edges here (e.g. a frame another rank owns): E_k = 0, nothing to eliminate
   const int R = deg + 1, R6 = 6 * R;                 // row 0 = self, rows 1.. = out-edges (CSR order)
   // smem: rowpose[R] ints | Qs[PC] | QWs[PC] | tile[PC][R6]
   int* rowpose = reinterpret_cast<int*>(sm);
@@ -529,13 +530,30 @@ __device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, 
   if (*s_fail) return;
   for (int i = tid; i < n; i += T) y[i] *= dinv[i];        // D w = z
   __syncthreads();
-  if (warp == 0) {                                         // L^T x = w: row by row from the bottom, one warp, no block barriers
-    for (int row = n - 1; row >= 0; row--) {
-      const int rlast = min(n, 6 * (row / 6) + 6 + band);  // rows r > row with L(r, row) != 0 stay within the band
-      double acc = 0.0;
-      for (int r = row + 1 + lane; r < rlast; r += 32) acc += A(r, row) * y[r];
-      acc = warp_sum_d(acc);
-      if (lane == 0) y[row] -= acc;
+  if (warp == 0) {                                         // L^T x = w: block rows from the bottom, one warp, no block barriers
+    for (int kb = P - 1; kb >= 0; kb--) {
+      const int c0 = 6 * kb;
+      const int rlast = min(n, c0 + 6 + band);             // rows below this block with L(r, c0..c0+5) != 0 stay within the band
+      double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int r = c0 + 6 + lane; r < rlast; r += 32) {
+        const double yr = y[r];
+#pragma unroll
+        for (int j = 0; j < 6; j++) acc[j] += A(r, c0 + j) * yr;
+      }
+#pragma unroll
+      for (int j = 0; j < 6; j++) acc[j] = warp_sum_d(acc[j]);
+      if (lane == 0) {                                     // unit upper-triangular 6x6 (L_kk^T) by back substitution
+        double x[6];
+#pragma unroll
+        for (int j = 5; j >= 0; j--) {
+          double v = y[c0 + j] - acc[j];
+#pragma unroll
+          for (int t = 0; t < 6; t++) if (t > j) v -= A((c0 + t), c0 + j) * x[t];
+          x[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 6; j++) y[c0 + j] = x[j];
+      }
       __syncwarp();
     }
   }
@@ -543,7 +561,7 @@ __device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, 
 }
 
 template <bool IN_SMEM>
-__global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem, int moba) {
+__global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem, int moba, int bw_hint) {
   extern __shared__ double smd[];
   __shared__ int s_fail;
   const int n = 6 * P;
@@ -568,10 +586,11 @@ __global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm,
   // Block bandwidth of the system: frame graphs connect |i - j| <= r, so the Schur complement couples poses at most 2r
   // frames apart and the factorisation never fills outside that band.  Everything below works on rows c0+6 .. rend only:
   // O(n b^2) instead of O(n^3) -- what keeps the redundant per-rank solve cheap when 8 GPUs share a 63-pose window.
+  // bw_hint >= 0: the caller knows the graph (block bandwidth <= 2 max|ii - jj|, FactorGraph passes it); -1: scan the matrix.
   __shared__ int s_bw;
-  if (tid == 0) s_bw = 0;
+  if (tid == 0) s_bw = (bw_hint >= 0 && !moba) ? min(bw_hint, P - 1) : 0;
   __syncthreads();
-  for (int b = tid; b < P * P; b += T) {
+  for (int b = tid; b < ((bw_hint >= 0 && !moba) ? 0 : P * P); b += T) {
     const int bi = b / P, bj = b % P;
     if (bj >= bi || bi - bj <= s_bw) continue;
     bool nz = false;
@@ -603,8 +622,14 @@ __global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm,
   const bool fail = s_fail != 0;
   for (int i = tid; i < n; i += T) bf.dx[i] = fail ? 0.0f : (float)y[i];
   __syncthreads();
-  // leave every replica zeroed for the next iteration / next call
-  for (long i = tid; i < (long)kParts * psz; i += T) bf.sys[i] = 0.0;
+  // leave every replica zeroed for the next iteration / next call (large systems: ba_zero_kernel, many blocks)
+  if (IN_SMEM)
+    for (long i = tid; i < (long)kParts * psz; i += T) bf.sys[i] = 0.0;
+}
+
+__global__ void __launch_bounds__(256) ba_zero_kernel(Bufs bf, int P) {
+  const long tot = (long)kParts * (36L * P * P + 12L * P);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long)gridDim.x * blockDim.x) bf.sys[i] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -721,6 +746,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
   const dim3 grid(ceil_div(HW, kPix), K);
   static bool attr_set = false;
   const int deg_hint = (flags >> 8) & 0xFFF;
+  const int bw_hint = ((flags >> 20) & 0xFF) - 1;          // bits 20-27: 1 + block bandwidth of the pose system (0 = unknown: scan)
   int pass2_smem = 160 * 1024;
   if (deg_hint > 0) {        // tile [256][6(deg+1)] + Q + QW + row table; smaller request => several blocks per SM, one wave
     const long need = 4L * (128L * (6 * (deg_hint + 1) + 2) + ((deg_hint + 1 + 3) & ~3)) + 64;
@@ -746,12 +772,14 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
       if (!motion_only)
         ba_pass2_kernel<<<dim3(ceil_div(HW, kPix2), K), 256, pass2_smem, s>>>(jj, pl, bf, HW, t0, P, pass2_smem / 4);
     }
-    if (phase == 1) { ba_combine_kernel<<<8, 256, 0, s>>>(bf, P); break; }
+    const int comb_blocks = ceil_div(36L * P * P + 12L * P, 2048) < 148 ? (ceil_div(36L * P * P + 12L * P, 2048) < 8 ? 8 : ceil_div(36L * P * P + 12L * P, 2048)) : 148;
+    if (phase == 1) { ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P); break; }
     if (solve_in_smem) {
-      ba_solve_kernel<true><<<1, 128, solve_smem, s>>>(bf, P, lm, ep, sem, sem && motion_only);
+      ba_solve_kernel<true><<<1, 128, solve_smem, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint);
     } else {
-      ba_combine_kernel<<<8, 256, 0, s>>>(bf, P);
-      ba_solve_kernel<false><<<1, 128, 200 * 1024, s>>>(bf, P, lm, ep, sem, sem && motion_only);   // band-packed copy in smem when it fits
+      ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);
+      ba_solve_kernel<false><<<1, 128, 200 * 1024, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint);   // band-packed copy in smem when it fits
+      ba_zero_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);
     }
     const bool last = it == iterations - 1;
     if (last && dx_out)

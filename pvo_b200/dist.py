@@ -89,7 +89,7 @@ def system_view(ws, E, nframes, P, K, HW):
 
 
 def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only,
-               interleaved=False, group=None, workspace=None, max_degree=0, reducer=None):
+               interleaved=False, group=None, workspace=None, max_degree=0, reducer=None, max_span=None):
     """droid_backends.ba for a rank's shard of the edges: assemble -> all-reduce -> solve + update, per iteration.
     poses must be identical on all ranks on entry and are identical on exit."""
     E = ii.shape[0]
@@ -102,7 +102,7 @@ def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, 
     L = _lib.lib()
 
     def call(phase, reuse):
-        flags = (1 if reuse else 0) | (phase << 1) | ((int(max_degree) & 0xFFF) << 8)
+        flags = (1 if reuse else 0) | (phase << 1) | ((int(max_degree) & 0xFFF) << 8) | droid_backends.band_flag(max_span)
         check(L.pvo_ba(ptr(poses), ptr(disps), ptr(intrinsics), ptr(targets), ptr(weights), ptr(eta), ptr(ii), ptr(jj), E,
                        nframes, ht, wd, int(t0), int(t1), K, 1, float(lm), float(ep), 1 if motion_only else 0,
                        1 if interleaved else 0, ptr(dx), ptr(dz), ptr(ws), ws.numel(), flags, stream()), 'ba',
@@ -121,12 +121,21 @@ def attach(fg, rank, world, frames_per_rank, group=None):
     """Make a FactorGraph's BA go through ba_sharded.  The caller adds only this rank's edges (shard_edges)."""
     video = fg.video
     reducer = make_reducer(video.poses.device, group) if video.poses.is_cuda else None
+    span_cache = {}
     fg.allreduce_kind = 'one-shot push over NVLink peer memory (own kernel)' if reducer is not None else 'ncclAllReduce'
 
     def ba(target, weight, eta, ii, jj, t0=1, t1=None, itrs=2, lm=1e-4, ep=0.1, motion_only=False, interleaved=False,
-           reuse_plan=False, max_degree=0):
+           reuse_plan=False, max_degree=0, max_span=None):
+        if max_span is not None:                               # the bound must hold for the all-reduced system: max over ranks
+            if max_span not in span_cache:
+                t = torch.tensor([int(max_span)], device=video.poses.device)
+                if dist.is_initialized() and dist.get_world_size(group) > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+                span_cache[max_span] = int(t.item())
+            max_span = span_cache[max_span]
         out = ba_sharded(video.poses, video.disps, video.intrinsics[0].contiguous(), target, weight, eta, ii, jj, t0, t1,
-                         itrs, lm, ep, motion_only, interleaved=interleaved, group=group, max_degree=max_degree, reducer=reducer)
+                         itrs, lm, ep, motion_only, interleaved=interleaved, group=group, max_degree=max_degree, reducer=reducer,
+                         max_span=max_span)
         check(_lib.lib().pvo_clamp_min(ptr(video.disps), video.disps.numel(), 0.001, stream()), 'clamp_min')
         return out
     video.ba = ba

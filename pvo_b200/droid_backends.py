@@ -77,12 +77,19 @@ def ba_workspace(E, nframes, P, K, HW, device):
     return ws
 
 
+def band_flag(max_span):
+    """pvo_ba flags bits 20-27: 1 + block bandwidth of the reduced camera system (0 = unknown)"""
+    return 0 if max_span is None else ((min(2 * int(max_span), 254) + 1) << 20)
+
+
 def ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only,
-       interleaved=False, reuse_plan=False, workspace=None, max_degree=0):
+       interleaved=False, reuse_plan=False, workspace=None, max_degree=0, max_span=None):
     """src/droid_kernels.cu:1293-1410.  Mutates poses (buf,7) and disps (buf,ht,wd) in place; returns [dx, dz].
 
     targets / weights: (E,2,ht,wd) as the reference passes them (factor_graph.py:297-300), or (E,ht,wd,2) with
-    ``interleaved=True`` (saves the permute+contiguous copies).  eta: (K,ht,wd)."""
+    ``interleaved=True`` (saves the permute+contiguous copies).  eta: (K,ht,wd).
+    max_span: optional max |ii - jj| over the WHOLE graph (all shards): the pose system then has block bandwidth <= 2 max_span
+    and the solver skips its own sparsity scan."""
     require_cuda(poses, disps, intrinsics, targets, weights, eta, ii, jj)
     if ii.dtype != torch.long or jj.dtype != torch.long:
         raise RuntimeError('ba: ii/jj must be int64')
@@ -96,7 +103,7 @@ def ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iteratio
     check(_lib.lib().pvo_ba(ptr(poses), ptr(disps), ptr(intrinsics), ptr(targets), ptr(weights), ptr(eta), ptr(ii),
                             ptr(jj), E, nframes, ht, wd, int(t0), int(t1), K, int(iterations), float(lm), float(ep),
                             1 if motion_only else 0, 1 if interleaved else 0, ptr(dx), ptr(dz), ptr(ws), ws.numel(),
-                            (1 if reuse_plan else 0) | ((int(max_degree) & 0xFFF) << 8), stream()), 'ba',
+                            (1 if reuse_plan else 0) | ((int(max_degree) & 0xFFF) << 8) | band_flag(max_span), stream()), 'ba',
           launches=(0 if reuse_plan else 1) + int(iterations) * (3 if motion_only else 4))
     return [dx, dz]
 

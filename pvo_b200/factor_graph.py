@@ -222,7 +222,8 @@ class FactorGraph:
         c = dict(E=E, K=K, kx=kx, t0_default=max(1, int(self.ii.min().item()) + 1),
                  t1_default=int(max(self.ii.max().item(), self.jj.max().item())) + 1,
                  ba_key=None, ba_kx={}, graphs={},
-                 max_degree=int(torch.bincount(self.ii).max().item()))
+                 max_degree=int(torch.bincount(self.ii).max().item()),
+                 max_span=int((self.ii - self.jj).abs().max().item()))
         c['coords1'] = torch.empty(1, E, self.ht, self.wd, 2, device=self.device)
         c['seg_ws'] = torch.zeros(int(L.pvo_update_post_workspace_ints(E)), dtype=torch.int32, device=self.device)
         c['segm'] = self.segm[0, :, 0].contiguous() if self.segm is not None else None
@@ -313,7 +314,8 @@ class FactorGraph:
         # (5) dense bundle adjustment, in place on video.poses / video.disps
         with T('ba_total'):
             v.ba(target_cam[0], weight[0], damping, ii, jj, t0, t1, itrs=itrs, lm=1e-4, ep=0.1, motion_only=motion_only,
-                 interleaved=True, reuse_plan=reuse, max_degree=0 if use_inactive else c['max_degree'])
+                 interleaved=True, reuse_plan=reuse, max_degree=0 if use_inactive else c['max_degree'],
+                 max_span=None if use_inactive else c['max_span'])
         self.age += 1
         self.launch_count = _lib.LAUNCHES[0] - n0
 

@@ -101,6 +101,7 @@ def _rel(a, b):
 @pytest.mark.parametrize('cfg', [dict(F=5, radius=2, h=16, w=24, t0=1), dict(F=8, radius=3, h=24, w=32, t0=1),
                                  dict(F=7, radius=2, h=16, w=24, t0=3), dict(F=6, radius=5, h=12, w=16, t0=2),
                                  dict(F=22, radius=2, h=8, w=12, t0=1),      # banded system (bandwidth 4 of 21 blocks): band-limited LDL^T
+                                 dict(F=20, radius=3, h=8, w=12, t0=1),      # same, bandwidth found by the solver's own scan
                                  dict(F=34, radius=1, h=8, w=12, t0=2)])     # P = 32 > 26: the factorisation runs out of global memory
 @pytest.mark.parametrize('motion_only', [False, True])
 def test_ba_matches_oracle(cfg, motion_only):
@@ -114,8 +115,10 @@ def test_ba_matches_oracle(cfg, motion_only):
     p_ref, d_ref = c['poses'].clone(), c['disps'].clone()
     dx_ref, dz_ref = ba_cuda.ba(p_ref, d_ref, c['intrinsics'][0], tgt, wgt, eta, ii, jj, t0, t1, 2, 1e-4, 0.1, motion_only)
     v = _video(c, buffer=cfg['F'] + 5)
+    # large windows also exercise the caller-supplied bandwidth bound (what FactorGraph passes) instead of the sparsity scan
+    span = cfg['radius'] if cfg['F'] > 20 else None
     dx, dz = droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), tgt.cuda(), wgt.cuda(), eta.cuda(),
-                               ii.cuda(), jj.cuda(), t0, t1, 2, 1e-4, 0.1, motion_only)
+                               ii.cuda(), jj.cuda(), t0, t1, 2, 1e-4, 0.1, motion_only, max_span=span)
     F_ = cfg['F']
     # the contract is on poses / depth (1e-4 relative).  dx (the LAST iteration's step) is compared at 1e-4 for the
     # full BA.  Motion-only Gauss-Newton converges almost completely in its first step, so the second step is ~100x
