@@ -106,6 +106,41 @@ def graph_update(sd, st, t0=None, t1=None, itrs=2, EP=1e-7, motion_only=False,
     return st
 
 
+def graph_update_lowmem(sd, st, fmaps, inps, t, itrs=2, EP=1e-7, steps=2, chunk=8):
+    """FactorGraph.update_lowmem (factor_graph.py:309-360): the global-BA form of the update -- correlation features
+    computed on the fly from the feature pyramid (AltCorrBlock), the update operator run on chunks of edges grouped by
+    source frame (8 frames per chunk), ONE dense BA over the whole window [1, t) with lm=1e-5, ep=1e-2 per step.
+    Mutates ``st`` (same keys as graph_update; no correlation pyramid needed).  fmaps / inps: (buf,128,h,w)."""
+    ii, jj = st['ii'], st['jj']
+    ht, wd = st['disps'].shape[1:]
+    coords0 = geom.coords_grid(ht, wd)
+    for _ in range(steps):
+        coords1, _ = reproject(st['poses'], st['disps'], st['intrinsics'], ii, jj)
+        motn = torch.cat([st['target_cam'] - coords0, st['target_cam'] - coords0 + st['delta_dy'],
+                          st['target_cam'] - coords1, st['raw_mask']], dim=-1)
+        motn = motn.permute(0, 1, 4, 2, 3).clamp(-64.0, 64.0)
+        for i in range(0, int(jj.max()) + 1, chunk):
+            v = (ii >= i) & (ii < i + chunk)
+            if not bool(v.any()):
+                continue
+            iis, jjs = ii[v], jj[v]
+            corr1 = ocorr.alt_corr_lookup(fmaps[None, :t].float(), coords1[:, v], iis, jjs)
+            net, delta, weight, damping, _, delta_m = oupd.update_op(sd, st['net'][:, v].float(), inps[None, iis].float(), corr1,
+                                                                     motn[:, v], iis)
+            st['net'][:, v] = net.to(st['net'].dtype)
+            st['target_cam'][:, v] = coords1[:, v] + delta[..., 0:2]
+            st['damping'][torch.unique(iis)] = damping[0]
+            st['raw_mask'][:, v] = st['raw_mask'][:, v] + delta_m
+            bin_mask = (torch.sigmoid(st['raw_mask'][:, v]) >= DY_THRESH).float()
+            st['delta_dy'][:, v] = delta[..., 2:4] * (1 - bin_mask)
+            st['weight'][:, v] = torch.sigmoid(weight + (1 - bin_mask) * 10)
+        eta = st['damping'][torch.unique(ii)].contiguous() + EP
+        target = st['target_cam'].view(-1, ht, wd, 2).permute(0, 3, 1, 2).contiguous()
+        wgt = st['weight'].view(-1, ht, wd, 2).permute(0, 3, 1, 2).contiguous()
+        ba_cuda.depth_video_ba(st['poses'], st['disps'], st['intrinsics'][0], target, wgt, eta, ii, jj, 1, t, itrs, 1e-5, 1e-2, False)
+    return st
+
+
 def make_state(case, fdtype=None):
     """FactorGraph.__init__ + add_factors (factor_graph.py:12-58, 107-161) for a tests/golden/cases.py
     graph case: volume pyramid for every edge, net/inp gathered by ii, target = reprojection,

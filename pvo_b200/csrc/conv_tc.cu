@@ -12,9 +12,12 @@
 //   N tile  = BN output channels (64 / 128 / 256), K block = 64 channels of one tap (128-byte swizzled rows)
 //   UMMA 128 x BN x 16, fp16 operands, fp32 accumulators in TMEM, double-buffered (2 x BN columns)
 // Warp roles (320 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2-9 = epilogue (two per TMEM lane quarter, each draining half of the accumulator columns).  smem ring of kStages {A 16 KB, B BN*128 B} stages.
-// Roofline: tensor pipe; with single-CTA tiles the operand stream (48 KB per 512 MMA cycles at BN=256) makes L2 the
-// practical bound -- see DESIGN.md for the measured fraction and the 2-CTA / halo-reuse follow-ups.
+// warps 2-9 = epilogue (two per TMEM lane quarter, each draining half of the accumulator columns).  A pipeline stage holds
+// 1-2 k-blocks of {A 16 KB, B BN*128 B}; BN <= 128 runs two CTAs per SM.  BN = 256 bias tiles transpose their output
+// through shared memory so that stores are row-contiguous.
+// Roofline: tensor pipe.  Measured bounds, in the order they bite: per-k-block issue overhead on
+// short-K layers, the row rate of the 4-D A-operand TMA boxes (~0.35 us per k-block per SM, so only N = 256 tiles approach
+// the MMA peak), row-strided epilogue stores on 1x1 channel expansions.
 #include "tc_common.cuh"
 
 namespace {

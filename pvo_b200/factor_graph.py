@@ -319,6 +319,45 @@ class FactorGraph:
         self.age += 1
         self.launch_count = _lib.LAUNCHES[0] - n0
 
+    @torch.no_grad()
+    def update_lowmem(self, t0=None, t1=None, itrs=2, use_inactive=False, EP=1e-7, steps=8):
+        """run the update operator on the factor graph, reduced-memory form (factor_graph.py:309-360; the global-BA path of
+        droid_backend.py): no materialised volumes -- AltCorrBlock computes the correlation features of each chunk of
+        edges (grouped by source frame, 8 frames per chunk) on the fly -- and one dense BA over the whole window [1, t)
+        with lm=1e-5, ep=1e-2 per step.  Same state updates as the reference, chunk by chunk."""
+        v = self.video
+        t = v.counter.value
+        corr_op = AltCorrBlock(v.fmaps[None, :t])
+        ht, wd = self.ht, self.wd
+        for _ in range(steps):
+            coords1, _ = v.reproject(self.ii, self.jj)
+            motn = torch.cat([self.target_cam - self.coords0, self.target_cam - self.coords0 + self.delta_dy,
+                              self.target_cam - coords1, self.raw_mask * torch.ones_like(coords1)[..., 0:self.mask_num]], dim=-1)
+            motn = motn.permute(0, 1, 4, 2, 3).clamp(-64.0, 64.0)
+            net_all = self.net                              # reference-layout hidden state (pulled out of the engine)
+            s = 8
+            for i in range(0, int(self.jj.max()) + 1, s):
+                m = (self.ii >= i) & (self.ii < i + s)
+                if not bool(m.any()):
+                    continue
+                iis, jjs = self.ii[m], self.jj[m]
+                corr1 = corr_op(coords1[:, m], iis, jjs)
+                net, delta, weight, damping, _, delta_m = self.update_op(net_all[:, m], v.inps[None, iis], corr1, motn[:, m], iis, jjs)
+                net_all[:, m] = net.to(net_all.dtype)
+                self.target_cam[:, m] = coords1[:, m] + delta[..., 0:2].float()
+                self.damping[torch.unique(iis)] = damping[0].float()
+                self.raw_mask[:, m] = self.raw_mask[:, m] + delta_m.float()
+                bin_mask = (torch.sigmoid(self.raw_mask[:, m]) >= self.dy_thresh).float()
+                self.delta_dy[:, m] = delta[..., 2:4].float() * (1 - bin_mask)
+                self.weight[:, m] = torch.sigmoid(weight.float() + (1 - bin_mask) * 10)
+            self.net = net_all
+            damping = self.damping[torch.unique(self.ii)].contiguous() + EP
+            target_cam = self.target_cam.view(-1, ht, wd, 2).permute(0, 3, 1, 2).contiguous()
+            weight = self.weight.view(-1, ht, wd, 2).permute(0, 3, 1, 2).contiguous()
+            v.ba(target_cam, weight, damping, self.ii, self.jj, 1, t, itrs=itrs, lm=1e-5, ep=1e-2, motion_only=False)
+            if hasattr(v, 'dirty'):
+                v.dirty[:t] = True
+
     def _lookup_mixed(self, coords1, eng):
         """volume dtype != engine dtype (e.g. half volume feeding the float32 parity engine)"""
         E = coords1.shape[1]
