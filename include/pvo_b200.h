@@ -198,6 +198,10 @@ int pvo_allreduce_oneshot(double* data, void* const* stage_ptrs, void* const* fl
  * layers onto (tap, output) pairs, [M][128] half from pvo_conv2d_tc; this kernel sums the 9 shifted taps + bias -> out[M][ostride] f32 */
 int pvo_heads_stencil(const void* T, const float* bias, float* out, int ostride, int nimg, int H, int W, void* stream);
 
+/* Hardware probe (test infrastructure; no reference counterpart): one 128x64x64 tcgen05 MMA whose A descriptor starts row_off
+ * rows into a swizzled shared-memory patch with 8-row groups sbo_bytes apart -- tools/probe_umma.py reads off which addressings work. */
+int pvo_umma_probe(const void* G, const void* B, int rows_g, int row_off, int sbo_bytes, int base_offset, float* D, void* stream);
+
 /* FactorGraph.update post-processing (factor_graph.py:250-283): target_cam, raw_mask, bin_mask, panoptic segment
  *   filter (:256-276, integer counting on the device instead of numpy on the host), delta_dy, sigmoid weights. */
 long pvo_update_post_workspace_ints(int E);

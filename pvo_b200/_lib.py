@@ -57,6 +57,7 @@ _SIGS = {
     'pvo_nms_groups': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     'pvo_allreduce_oneshot': (c_int, [c_void_p] * 4 + [c_int, c_int, c_long, c_long, c_void_p]),
     'pvo_heads_stencil': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    'pvo_umma_probe': (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p, c_void_p]),
     'pvo_update_post_workspace_ints': (c_long, [c_int]),
     'pvo_update_post': (c_int, [c_void_p, c_void_p, c_void_p, c_double] + [c_void_p] * 6 + [c_long] + [c_int] * 3 + [c_void_p]),
 }

@@ -18,6 +18,8 @@
 // Roofline: tensor pipe.  Measured bounds, in the order they bite: per-k-block issue overhead on
 // short-K layers, the row rate of the 4-D A-operand TMA boxes (~0.35 us per k-block per SM, so only N = 256 tiles approach
 // the MMA peak), row-strided epilogue stores on 1x1 channel expansions.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -38,6 +40,7 @@ struct TcParams {
   int H, W, nimg;
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int Cout;
+  int halo;                  // 3x3 halo-reuse kernel: tiles are 16 rows x 8 pixels, tmA boxes are the haloed patches
 };
 
 // ---- epilogue helpers.  The epilogue warps are on the critical path of every short-K layer (measured: 19 instructions
@@ -410,11 +413,219 @@ int launch_tc(const TcParams& p, const Epi& epi, cudaStream_t s) {
   return pvo_check_launch();
 }
 
+// =====================================================================================================================
+// 3x3 convolutions with HALO REUSE.  The generic kernel above fetches one 8x16-pixel A box per (tap, channel block): nine TMA
+// boxes of 128 pixel rows for every 64 input channels.  Here the M tile is 16 rows x 8 pixels and ONE (16+2) x (8+2) haloed
+// patch per channel block (180 pixel rows, 23 KB) serves all nine taps: tap (dy, dx) is the same patch read through a UMMA
+// descriptor that starts (dy*10 + dx) rows in, with the 8-row groups (one tile row each) 10 rows = 1280 B apart.  That
+// addressing is legal because the 128-byte swizzle depends only on shared-memory address bits (tc_common.cuh, umma_probe.cu).
+// A-operand TMA rows per channel block: 180 instead of 1152; the weight tiles stream through their own ring, one tap each.
+constexpr int kHTW = 8, kHTH = 16, kPW = kHTW + 2, kPH = kHTH + 2;
+constexpr int kPatchBytes = kPW * kPH * 128;                    // 23040
+constexpr int kPatchSlot = 23 * 1024;                           // 1024-aligned slot
+
+template <int BN> struct HCfg {
+  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kAStages = 2;
+  static constexpr int kBStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kStaging = (BN == 256) ? 8 * 2048 : 0;
+  static constexpr int kRing = kAStages * kPatchSlot + kBStages * kStageB;
+  static constexpr int kSmem = kRing + 1024 /*align*/ + 256 /*barriers*/ + kMaxKb * 4 /*channel-block table*/ + kStaging;
+};
+
+template <int BN, typename Epi>
+__global__ void __launch_bounds__(kThreads, HCfg<BN>::kCtasPerSm) conv_tc_halo_kernel(const __grid_constant__ TcParams p, const Epi epi) {
+  using C = HCfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* ringA = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* ringB = ringA + C::kAStages * kPatchSlot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ringA + C::kRing);
+  uint64_t* afull = bars;                              // [kAStages]
+  uint64_t* aempty = afull + C::kAStages;              // [kAStages]
+  uint64_t* bfull = aempty + C::kAStages;              // [kBStages]
+  uint64_t* bempty = bfull + C::kBStages;              // [kBStages]
+  uint64_t* tfull = bempty + C::kBStages;              // [2]
+  uint64_t* tempty = tfull + 2;                        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  int* cbt = reinterpret_cast<int*>(bars) + 64;        // [blocks_per_tap] channel-block table: cb | seg << 12
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncb = p.blocks_per_tap;
+  for (int i = threadIdx.x; i < ncb; i += blockDim.x) {
+    int rem = i, seg = 0;
+    while (rem >= p.seg_blocks[seg]) { rem -= p.seg_blocks[seg]; seg++; }
+    cbt[i] = rem | seg << 12;
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; s++) prefetch_tmap(&p.tmA[s]);
+    prefetch_tmap(&p.tmB);
+    for (int s = 0; s < C::kAStages; s++) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < C::kBStages; s++) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      const int img = mt / (p.tiles_x * p.tiles_y);
+      const int r = mt - img * (p.tiles_x * p.tiles_y);
+      const int y0 = (r / p.tiles_x) * kHTH, x0 = (r % p.tiles_x) * kHTW;
+      for (int cbg = 0; cbg < ncb; cbg++) {
+        const int e = cbt[cbg];
+        mbar_wait(&aempty[sa], pa ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&afull[sa], kPatchBytes);
+          tma_load_4d(&p.tmA[(e >> 12) & 3], &afull[sa], ringA + sa * kPatchSlot, (e & 0xfff) * kBK, x0 - 1, y0 - 1, img);
+        }
+        __syncwarp();
+        if (++sa == C::kAStages) { sa = 0; pa ^= 1; }
+        for (int tap = 0; tap < 9; tap++) {
+          mbar_wait(&bempty[sb], pb ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bfull[sb], C::kStageB);
+            tma_load_2d(&p.tmB, &bfull[sb], ringB + sb * C::kStageB, (tap * ncb + cbg) * kBK, nt * BN);
+          }
+          __syncwarp();
+          if (++sb == C::kBStages) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = idesc_f16(kBM, BN);
+    int sa = 0, sb = 0, as = 0;
+    uint32_t pa = 0, pb = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      fence_after_sync();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int cbg = 0; cbg < ncb; cbg++) {
+        mbar_wait(&afull[sa], pa);
+        const uint32_t patch = smem_u32(ringA + sa * kPatchSlot);
+        for (int tap = 0; tap < 9; tap++) {
+          mbar_wait(&bfull[sb], pb);
+          fence_after_sync();
+          if (elect_one()) {
+            const uint64_t da = smem_desc_sw128_sbo(patch + ((tap / 3) * kPW + tap % 3) * 128, kPW * 128);
+            const uint64_t db = smem_desc_sw128(smem_u32(ringB + sb * C::kStageB));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; k++) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (cbg | tap | k) != 0);
+            umma_commit(&bempty[sb]);
+            if (tap == 8) {
+              umma_commit(&aempty[sa]);              // the patch is free once all nine taps' MMAs retire
+              if (cbg == ncb - 1) umma_commit(&tfull[as]);
+            }
+          }
+          __syncwarp();
+          if (++sb == C::kBStages) { sb = 0; pb ^= 1; }
+        }
+        if (++sa == C::kAStages) { sa = 0; pa ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..9), 16 x 8 pixel tile
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      const int img = mt / (p.tiles_x * p.tiles_y);
+      const int r = mt - img * (p.tiles_x * p.tiles_y);
+      const int row = q * 32 + lane;
+      const int y = (r / p.tiles_x) * kHTH + row / kHTW, x = (r % p.tiles_x) * kHTW + row % kHTW;
+      const bool ok = y < p.H && x < p.W;
+      const long m = ((long)img * p.H + y) * p.W + x;
+      if (lane == 0) mbar_wait(&tfull[as], aphase);
+      __syncwarp();
+      fence_after_sync();
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
+#pragma unroll 1
+      for (int c = 0; c < BN / 2; c += 32) {
+        uint32_t v0[16], v1[16];
+        tmem_ld16(taddr + c, v0);
+        tmem_ld16(taddr + c + 16, v1);
+        tmem_ld_wait();
+        const int n = nt * BN + half * (BN / 2) + c;
+        if constexpr (Epi::kStaged && BN == 256) {
+          if (n + 32 <= epi.Cout) {                   // transposed store through shared memory (see conv_tc_kernel)
+            unsigned char* stg = reinterpret_cast<unsigned char*>(cbt + kMaxKb) + (warp - 2) * 2048;
+            uint32_t w0[8], w1[8];
+            epi.apply16(m, n, reinterpret_cast<const float*>(v0), ok, w0);
+            epi.apply16(m, n + 16, reinterpret_cast<const float*>(v1), ok, w1);
+            const int sw = (lane >> 1) & 3;
+            uint4* rowp = reinterpret_cast<uint4*>(stg + lane * 64);
+            rowp[0 ^ sw] = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+            rowp[1 ^ sw] = make_uint4(w0[4], w0[5], w0[6], w0[7]);
+            rowp[2 ^ sw] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+            rowp[3 ^ sw] = make_uint4(w1[4], w1[5], w1[6], w1[7]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+              const int rr = it * 8 + (lane >> 2), ch = lane & 3;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+              const int pr = q * 32 + rr;
+              const int yy = (r / p.tiles_x) * kHTH + pr / kHTW, xx = (r % p.tiles_x) * kHTW + pr % kHTW;
+              if (yy < p.H && xx < p.W)
+                *reinterpret_cast<uint4*>(epi.out + (((long)img * p.H + yy) * p.W + xx) * epi.ostride + epi.ooff + n + ch * 8) = val;
+            }
+            __syncwarp();
+            continue;
+          }
+        }
+        epi.store16(m, img, n, reinterpret_cast<const float*>(v0), ok, mt, q);
+        epi.store16(m, img, n + 16, reinterpret_cast<const float*>(v1), ok, mt, q);
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+template <int BN, typename Epi>
+int launch_tc_halo(const TcParams& p, const Epi& epi, cudaStream_t s) {
+  using C = HCfg<BN>;
+  static bool set = false;
+  if (!set) {
+    if (cudaFuncSetAttribute(conv_tc_halo_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) != cudaSuccess)
+      return PVO_ERR_CUDA;
+    set = true;
+  }
+  const int slots = PVO_SM_COUNT * C::kCtasPerSm;
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  conv_tc_halo_kernel<BN, Epi><<<grid, kThreads, C::kSmem, s>>>(p, epi);
+  return pvo_check_launch();
+}
+
 template <typename Epi>
 int dispatch_bn(const TcParams& p0, const Epi& epi, int bn, cudaStream_t s) {
   TcParams p = p0;
   p.n_tiles = (p.Cout + bn - 1) / bn;
   p.total_tiles = p.nimg * p.tiles_x * p.tiles_y * p.n_tiles;
+  if (p.halo) {
+    if (bn == 256) return launch_tc_halo<256>(p, epi, s);
+    if (bn == 128) return launch_tc_halo<128>(p, epi, s);
+    return launch_tc_halo<64>(p, epi, s);
+  }
   if (bn == 256) return launch_tc<256>(p, epi, s);
   if (bn == 128) return launch_tc<128>(p, epi, s);
   return launch_tc<64>(p, epi, s);
@@ -434,6 +645,8 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
   if (nseg < 1 || nseg > kMaxSeg || Cout < 1 || nimg < 0 || !(KH & 1) || !(KW & 1) || KH > 15 || KW > 15) return PVO_ERR_INVALID;
   if (nimg == 0) return PVO_OK;
   TcParams p;
+  static const bool no_halo = getenv("PVO_TC_NO_HALO") != nullptr;     // A/B switch for measurements
+  p.halo = (KH == 3 && KW == 3 && !no_halo) ? 1 : 0;
   p.nseg = nseg;
   p.blocks_per_tap = 0;
   for (int s = 0; s < kMaxSeg; s++) p.seg_blocks[s] = 0;
@@ -443,15 +656,15 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
     p.blocks_per_tap += p.seg_blocks[s];
     const uint64_t dims[4] = {(uint64_t)seg_channels[s], (uint64_t)Wd, (uint64_t)H, (uint64_t)nimg};
     const uint64_t strides[3] = {(uint64_t)seg_stride[s] * 2, (uint64_t)seg_stride[s] * 2 * Wd, (uint64_t)seg_stride[s] * 2 * Wd * H};
-    const uint32_t box[4] = {kBK, kTileW, kTileH, 1};
+    const uint32_t box[4] = {kBK, (uint32_t)(p.halo ? kPW : kTileW), (uint32_t)(p.halo ? kPH : kTileH), 1};
     const int rc = make_tmap_f16(&p.tmA[s], seg_ptr[s], 4, dims, strides, box);
     if (rc != PVO_OK) return rc;
   }
   for (int s = nseg; s < kMaxSeg; s++) p.tmA[s] = p.tmA[0];
   p.taps = KH * KW; p.KW = KW; p.padH = KH / 2; p.padW = KW / 2;
   p.H = H; p.W = Wd; p.nimg = nimg;
-  p.tiles_x = (Wd + kTileW - 1) / kTileW;
-  p.tiles_y = (H + kTileH - 1) / kTileH;
+  p.tiles_x = p.halo ? (Wd + kHTW - 1) / kHTW : (Wd + kTileW - 1) / kTileW;
+  p.tiles_y = p.halo ? (H + kHTH - 1) / kHTH : (H + kTileH - 1) / kTileH;
   p.Cout = Cout;
   if (p.taps * p.blocks_per_tap > kMaxKb) return PVO_ERR_UNSUPPORTED;
   const long Ktot = (long)p.taps * p.blocks_per_tap * kBK;

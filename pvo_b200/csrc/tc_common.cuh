@@ -101,6 +101,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
   return d;
 }
+// Same, with the 8-row groups `sbo_bytes` apart and a start address that need not be 1024-byte aligned.  Probed on B200
+// (csrc/umma_probe.cu, tools/probe_umma.py): with base_offset = 0 the 128-byte swizzle is a pure function of the shared-memory
+// ADDRESS bits, so any 128-byte-aligned start and any 16-byte-multiple group stride read back exactly what TMA wrote.
+__device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // cute::UMMA::InstrDescriptor for kind::f16: D=F32 (bits 4-5 = 1), A=B=F16 (0), K-major both, N>>3 at 17, M>>4 at 24
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
