@@ -281,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
     roof = None
     if zr_ms:
         ach = zr_flops / (zr_ms * 1e-3) / 1e12
-        roof = {'bound': 'tensor', 'kernel': 'conv_tc_kernel<256,EpZR> (GRU z|r gates, 448->256 3x3)', 'achieved': round(ach, 1),
+        roof = {'bound': 'tensor', 'kernel': 'conv_tc_halo_kernel<256,EpZR> (GRU z|r gates, 448->256 3x3)', 'achieved': round(ach, 1),
                 'peak': pk['tf_burst'], 'unit': 'TFLOP/s', 'frac': round(ach / pk['tf_burst'], 4), 'traffic': None,
                 'peak_source': pk['src'] + ' (burst: kernel timed per launch)', 'ms_per_launch': round(zr_ms, 4),
                 'flops_per_launch': zr_flops}
@@ -290,7 +290,7 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         traffic = {}
     if roof is not None and traffic:
-        roof['traffic'] = traffic.get('conv_tc_kernel<256,EpZR>')
+        roof['traffic'] = traffic.get('conv_tc_halo_kernel<256,EpZR>')
         roof['traffic_source'] = traffic.get('source')
     look_ms = kernel_ms.get('corr_lookup')
     secondary = {}

@@ -33,7 +33,7 @@ bench)
 launches)
   run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 300 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-graph --profile-only ;;
 ncufull)
-  run ncu_full 1500 ncu --set full --clock-control none --import-source on -k regex:"corr_lookup_fused|conv_tc_kernel|conv3x3_heads_mma|ba_pass|ba_solve|corr_volume_tc" -s 40 -c 30 -o $OUT/prof_r01 -f python bench.py --steps 2 --warmup 3 --no-graph --profile-only ;;
+  run ncu_full 1500 ncu --set full --clock-control none --import-source on -k regex:"corr_lookup_fused|conv_tc|heads_stencil|ba_pass|ba_solve|corr_volume_tc" -s 40 -c 30 -o $OUT/prof_r01 -f python bench.py --steps 2 --warmup 3 --no-graph --profile-only ;;
 fpn)
   run t_fpn 900 $PT tests/test_fpn_gpu.py ;;
 dist)
