@@ -124,3 +124,20 @@ def test_gru_module_alone():
         ref = oupd.conv_gru(sd, net, torch.cat([a, b_, c], 1))
         out = m(net.cuda(), a.cuda(), b_.cuda(), c.cuda())
     assert (out.cpu() - ref).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize('sbo,row_off', [(1024, 0), (1024, 9), (2048, 3), (1280, 0), (1280, 11), (1280, 22), (1152, 5)])
+def test_umma_swizzle_is_a_function_of_the_address(sbo, row_off):
+    """The hardware fact the halo-reuse convolution rests on (csrc/umma_probe.cu): a SWIZZLE_128B K-major A operand whose
+    descriptor starts `row_off` 128-byte rows into a TMA-written patch, with 8-row groups `sbo` bytes apart and
+    base_offset = 0, multiplies exactly the rows it addresses -- the swizzle follows the shared-memory address bits."""
+    from pvo_b200 import _lib
+    from pvo_b200._lib import check, ptr, stream
+    g = torch.Generator(device='cuda').manual_seed(sbo + row_off)
+    G = torch.randn(512, 64, device='cuda', generator=g).half()
+    B = torch.randn(64, 64, device='cuda', generator=g).half()
+    D = torch.zeros(128, 64, device='cuda')
+    idx = torch.tensor([row_off + (i // 8) * (sbo // 128) + (i % 8) for i in range(128)], device='cuda')
+    check(_lib.lib().pvo_umma_probe(ptr(G), ptr(B), 512, row_off, sbo, 0, ptr(D), stream()), 'umma_probe')
+    want = G[idx].float() @ B.float().t()
+    assert (D - want).abs().max() < 1e-3 * want.abs().max()
