@@ -40,7 +40,7 @@ struct TcParams {
   int H, W, nimg;
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int Cout;
-  int halo;                  // 3x3 halo-reuse kernel: tiles are 16 rows x 8 pixels, tmA boxes are the haloed patches
+  int halo;                  // 3x3 halo-reuse kernel: 1 = 16 x 8 pixel tiles, 2 = two stacked (32 x 8); tmA boxes are the haloed patches
 };
 
 // ---- epilogue helpers.  The epilogue warps are on the critical path of every short-K layer (measured: 19 instructions
@@ -420,27 +420,32 @@ int launch_tc(const TcParams& p, const Epi& epi, cudaStream_t s) {
 // descriptor that starts (dy*10 + dx) rows in, with the 8-row groups (one tile row each) 10 rows = 1280 B apart.  That
 // addressing is legal because the 128-byte swizzle depends only on shared-memory address bits (tc_common.cuh, umma_probe.cu).
 // A-operand TMA rows per channel block: 180 instead of 1152; the weight tiles stream through their own ring, one tap each.
-constexpr int kHTW = 8, kHTH = 16, kPW = kHTW + 2, kPH = kHTH + 2;
-constexpr int kPatchBytes = kPW * kPH * 128;                    // 23040
-constexpr int kPatchSlot = 23 * 1024;                           // 1024-aligned slot
+// MT = 2 (N <= 128 layers): the CTA tile is TWO stacked M tiles (32 rows x 8 pixels, one 34 x 10 patch) that share every weight
+// tile -- two MMAs per k-step into two accumulators -- which halves the B-operand stream that bounds those layers after halo reuse.
+constexpr int kHTW = 8, kPW = kHTW + 2;
 
-template <int BN> struct HCfg {
+template <int BN, int MT> struct HCfg {
+  static constexpr int kTH = 16 * MT, kPH = kTH + 2;            // tile rows, haloed patch rows
+  static constexpr int kPatchBytes = kPW * kPH * 128;           // 23040 / 43520
+  static constexpr int kPatchSlot = (kPatchBytes + 1023) / 1024 * 1024;
   static constexpr int kStageB = BN * kBK * 2;
   static constexpr int kAStages = 2;
-  static constexpr int kBStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
-  static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kBStages = (BN == 256) ? 4 : (MT == 2 ? 4 : (BN == 128 ? 3 : 4));
+  static constexpr int kCtasPerSm = (BN == 256 || MT == 2) ? 1 : 2;
+  static constexpr int kAccCols = MT * BN;                      // TMEM columns of one accumulator buffer
+  static constexpr int kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;
   static constexpr int kStaging = (BN == 256) ? 8 * 2048 : 0;
   static constexpr int kRing = kAStages * kPatchSlot + kBStages * kStageB;
   static constexpr int kSmem = kRing + 1024 /*align*/ + 256 /*barriers*/ + kMaxKb * 4 /*channel-block table*/ + kStaging;
 };
 
-template <int BN, typename Epi>
-__global__ void __launch_bounds__(kThreads, HCfg<BN>::kCtasPerSm) conv_tc_halo_kernel(const __grid_constant__ TcParams p, const Epi epi) {
-  using C = HCfg<BN>;
+template <int BN, int MT, typename Epi>
+__global__ void __launch_bounds__(kThreads, HCfg<BN, MT>::kCtasPerSm) conv_tc_halo_kernel(const __grid_constant__ TcParams p, const Epi epi) {
+  using C = HCfg<BN, MT>;
+  static_assert(MT == 1 || BN <= 128, "two stacked M tiles need 2 x 2 x BN TMEM columns");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* ringA = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* ringB = ringA + C::kAStages * kPatchSlot;
+  unsigned char* ringB = ringA + C::kAStages * C::kPatchSlot;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ringA + C::kRing);
   uint64_t* afull = bars;                              // [kAStages]
   uint64_t* aempty = afull + C::kAStages;              // [kAStages]
@@ -481,13 +486,13 @@ __global__ void __launch_bounds__(kThreads, HCfg<BN>::kCtasPerSm) conv_tc_halo_k
       const int mt = tile / p.n_tiles;
       const int img = mt / (p.tiles_x * p.tiles_y);
       const int r = mt - img * (p.tiles_x * p.tiles_y);
-      const int y0 = (r / p.tiles_x) * kHTH, x0 = (r % p.tiles_x) * kHTW;
+      const int y0 = (r / p.tiles_x) * C::kTH, x0 = (r % p.tiles_x) * kHTW;
       for (int cbg = 0; cbg < ncb; cbg++) {
         const int e = cbt[cbg];
         mbar_wait(&aempty[sa], pa ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&afull[sa], kPatchBytes);
-          tma_load_4d(&p.tmA[(e >> 12) & 3], &afull[sa], ringA + sa * kPatchSlot, (e & 0xfff) * kBK, x0 - 1, y0 - 1, img);
+          mbar_arrive_expect_tx(&afull[sa], C::kPatchBytes);
+          tma_load_4d(&p.tmA[(e >> 12) & 3], &afull[sa], ringA + sa * C::kPatchSlot, (e & 0xfff) * kBK, x0 - 1, y0 - 1, img);
         }
         __syncwarp();
         if (++sa == C::kAStages) { sa = 0; pa ^= 1; }
@@ -510,10 +515,10 @@ __global__ void __launch_bounds__(kThreads, HCfg<BN>::kCtasPerSm) conv_tc_halo_k
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[as], aphase ^ 1);
       fence_after_sync();
-      const uint32_t tmem_d = tmem_base + as * BN;
+      const uint32_t tmem_d = tmem_base + as * C::kAccCols;
       for (int cbg = 0; cbg < ncb; cbg++) {
         mbar_wait(&afull[sa], pa);
-        const uint32_t patch = smem_u32(ringA + sa * kPatchSlot);
+        const uint32_t patch = smem_u32(ringA + sa * C::kPatchSlot);
         for (int tap = 0; tap < 9; tap++) {
           mbar_wait(&bfull[sb], pb);
           fence_after_sync();
@@ -521,7 +526,11 @@ __global__ void __launch_bounds__(kThreads, HCfg<BN>::kCtasPerSm) conv_tc_halo_k
             const uint64_t da = smem_desc_sw128_sbo(patch + ((tap / 3) * kPW + tap % 3) * 128, kPW * 128);
             const uint64_t db = smem_desc_sw128(smem_u32(ringB + sb * C::kStageB));
 #pragma unroll
-            for (int k = 0; k < kBK / 16; k++) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (cbg | tap | k) != 0);
+            for (int k = 0; k < kBK / 16; k++) {
+              umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (cbg | tap | k) != 0);
+              if (MT == 2)                            // lower 16 tile rows: same weights, patch rows 16 further down
+                umma_f16(tmem_d + BN, da + 2 * k + ((16 * kPW * 128) >> 4), db + 2 * k, idesc, (cbg | tap | k) != 0);
+            }
             umma_commit(&bempty[sb]);
             if (tap == 8) {
               umma_commit(&aempty[sa]);              // the patch is free once all nine taps' MMAs retire
@@ -536,9 +545,11 @@ __global__ void __launch_bounds__(kThreads, HCfg<BN>::kCtasPerSm) conv_tc_halo_k
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..9), 16 x 8 pixel tile
+    // ===================================================================== epilogue (warps 2..9)
+    // MT = 1: two warps per TMEM lane quarter split the BN columns; MT = 2: they split the two stacked M tiles instead.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    constexpr int kCols = (MT == 2) ? BN : BN / 2;   // columns this warp drains
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -547,20 +558,21 @@ __global__ void __launch_bounds__(kThreads, HCfg<BN>::kCtasPerSm) conv_tc_halo_k
       const int img = mt / (p.tiles_x * p.tiles_y);
       const int r = mt - img * (p.tiles_x * p.tiles_y);
       const int row = q * 32 + lane;
-      const int y = (r / p.tiles_x) * kHTH + row / kHTW, x = (r % p.tiles_x) * kHTW + row % kHTW;
+      const int ty0 = (r / p.tiles_x) * C::kTH + (MT == 2 ? half * 16 : 0), tx0 = (r % p.tiles_x) * kHTW;
+      const int y = ty0 + row / kHTW, x = tx0 + row % kHTW;
       const bool ok = y < p.H && x < p.W;
       const long m = ((long)img * p.H + y) * p.W + x;
       if (lane == 0) mbar_wait(&tfull[as], aphase);
       __syncwarp();
       fence_after_sync();
-      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
+      const uint32_t taddr = tmem_base + as * C::kAccCols + ((uint32_t)(q * 32) << 16) + (MT == 2 ? half * BN : half * (BN / 2));
 #pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 32) {
+      for (int c = 0; c < kCols; c += 32) {
         uint32_t v0[16], v1[16];
         tmem_ld16(taddr + c, v0);
         tmem_ld16(taddr + c + 16, v1);
         tmem_ld_wait();
-        const int n = nt * BN + half * (BN / 2) + c;
+        const int n = nt * BN + (MT == 2 ? 0 : half * (BN / 2)) + c;
         if constexpr (Epi::kStaged && BN == 256) {
           if (n + 32 <= epi.Cout) {                   // transposed store through shared memory (see conv_tc_kernel)
             unsigned char* stg = reinterpret_cast<unsigned char*>(cbt + kMaxKb) + (warp - 2) * 2048;
@@ -579,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, HCfg<BN>::kCtasPerSm) conv_tc_halo_k
               const int rr = it * 8 + (lane >> 2), ch = lane & 3;
               const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
               const int pr = q * 32 + rr;
-              const int yy = (r / p.tiles_x) * kHTH + pr / kHTW, xx = (r % p.tiles_x) * kHTW + pr % kHTW;
+              const int yy = ty0 + pr / kHTW, xx = tx0 + pr % kHTW;
               if (yy < p.H && xx < p.W)
                 *reinterpret_cast<uint4*>(epi.out + (((long)img * p.H + yy) * p.W + xx) * epi.ostride + epi.ooff + n + ch * 8) = val;
             }
@@ -601,18 +613,18 @@ __global__ void __launch_bounds__(kThreads, HCfg<BN>::kCtasPerSm) conv_tc_halo_k
   if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
-template <int BN, typename Epi>
+template <int BN, int MT, typename Epi>
 int launch_tc_halo(const TcParams& p, const Epi& epi, cudaStream_t s) {
-  using C = HCfg<BN>;
+  using C = HCfg<BN, MT>;
   static bool set = false;
   if (!set) {
-    if (cudaFuncSetAttribute(conv_tc_halo_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_halo_kernel<BN, MT, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) != cudaSuccess)
       return PVO_ERR_CUDA;
     set = true;
   }
   const int slots = PVO_SM_COUNT * C::kCtasPerSm;
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  conv_tc_halo_kernel<BN, Epi><<<grid, kThreads, C::kSmem, s>>>(p, epi);
+  conv_tc_halo_kernel<BN, MT, Epi><<<grid, kThreads, C::kSmem, s>>>(p, epi);
   return pvo_check_launch();
 }
 
@@ -621,10 +633,11 @@ int dispatch_bn(const TcParams& p0, const Epi& epi, int bn, cudaStream_t s) {
   TcParams p = p0;
   p.n_tiles = (p.Cout + bn - 1) / bn;
   p.total_tiles = p.nimg * p.tiles_x * p.tiles_y * p.n_tiles;
+  if (p.halo == 2) return launch_tc_halo<128, 2>(p, epi, s);
   if (p.halo) {
-    if (bn == 256) return launch_tc_halo<256>(p, epi, s);
-    if (bn == 128) return launch_tc_halo<128>(p, epi, s);
-    return launch_tc_halo<64>(p, epi, s);
+    if (bn == 256) return launch_tc_halo<256, 1>(p, epi, s);
+    if (bn == 128) return launch_tc_halo<128, 1>(p, epi, s);
+    return launch_tc_halo<64, 1>(p, epi, s);
   }
   if (bn == 256) return launch_tc<256>(p, epi, s);
   if (bn == 128) return launch_tc<128>(p, epi, s);
@@ -645,7 +658,8 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
   if (nseg < 1 || nseg > kMaxSeg || Cout < 1 || nimg < 0 || !(KH & 1) || !(KW & 1) || KH > 15 || KW > 15) return PVO_ERR_INVALID;
   if (nimg == 0) return PVO_OK;
   TcParams p;
-  static const bool no_halo = getenv("PVO_TC_NO_HALO") != nullptr;     // A/B switch for measurements
+  static const bool no_halo = getenv("PVO_TC_NO_HALO") != nullptr;     // A/B switches for measurements
+  static const bool no_m2 = getenv("PVO_TC_NO_M2") != nullptr;
   p.halo = (KH == 3 && KW == 3 && !no_halo) ? 1 : 0;
   p.nseg = nseg;
   p.blocks_per_tap = 0;
@@ -654,17 +668,11 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
     if (seg_channels[s] % 8 || (seg_stride[s] * 2) % 16 || ((uintptr_t)seg_ptr[s]) % 16) return PVO_ERR_INVALID;
     p.seg_blocks[s] = (seg_channels[s] + kBK - 1) / kBK;
     p.blocks_per_tap += p.seg_blocks[s];
-    const uint64_t dims[4] = {(uint64_t)seg_channels[s], (uint64_t)Wd, (uint64_t)H, (uint64_t)nimg};
-    const uint64_t strides[3] = {(uint64_t)seg_stride[s] * 2, (uint64_t)seg_stride[s] * 2 * Wd, (uint64_t)seg_stride[s] * 2 * Wd * H};
-    const uint32_t box[4] = {kBK, (uint32_t)(p.halo ? kPW : kTileW), (uint32_t)(p.halo ? kPH : kTileH), 1};
-    const int rc = make_tmap_f16(&p.tmA[s], seg_ptr[s], 4, dims, strides, box);
-    if (rc != PVO_OK) return rc;
   }
-  for (int s = nseg; s < kMaxSeg; s++) p.tmA[s] = p.tmA[0];
   p.taps = KH * KW; p.KW = KW; p.padH = KH / 2; p.padW = KW / 2;
   p.H = H; p.W = Wd; p.nimg = nimg;
   p.tiles_x = p.halo ? (Wd + kHTW - 1) / kHTW : (Wd + kTileW - 1) / kTileW;
-  p.tiles_y = p.halo ? (H + kHTH - 1) / kHTH : (H + kTileH - 1) / kTileH;
+  p.tiles_y = p.halo ? (H + 15) / 16 : (H + kTileH - 1) / kTileH;
   p.Cout = Cout;
   if (p.taps * p.blocks_per_tap > kMaxKb) return PVO_ERR_UNSUPPORTED;
   const long Ktot = (long)p.taps * p.blocks_per_tap * kBK;
@@ -674,6 +682,20 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
     const long mt = (long)nimg * p.tiles_x * p.tiles_y;
     while (bn > 64 && mt * ((Cout + bn - 1) / bn) < 2 * PVO_SM_COUNT) bn >>= 1;
   }
+  // N = 128 halo layers: stack two M tiles per CTA (they share the weight stream) when that still leaves >= 3 waves.
+  // (Measured: q conv 0.172 -> 0.156 ms; N = 64 layers are faster with two independent CTAs per SM and stay on MT = 1.)
+  if (p.halo && bn == 128 && !no_m2) {
+    const long t2 = (long)nimg * p.tiles_x * ((H + 31) / 32) * ((Cout + bn - 1) / bn);
+    if (t2 >= 3 * PVO_SM_COUNT) { p.halo = 2; p.tiles_y = (H + 31) / 32; }
+  }
+  for (int s = 0; s < nseg; s++) {
+    const uint64_t dims[4] = {(uint64_t)seg_channels[s], (uint64_t)Wd, (uint64_t)H, (uint64_t)nimg};
+    const uint64_t strides[3] = {(uint64_t)seg_stride[s] * 2, (uint64_t)seg_stride[s] * 2 * Wd, (uint64_t)seg_stride[s] * 2 * Wd * H};
+    const uint32_t box[4] = {kBK, (uint32_t)(p.halo ? kPW : kTileW), (uint32_t)(p.halo ? 16 * p.halo + 2 : kTileH), 1};
+    const int rc = make_tmap_f16(&p.tmA[s], seg_ptr[s], 4, dims, strides, box);
+    if (rc != PVO_OK) return rc;
+  }
+  for (int s = nseg; s < kMaxSeg; s++) p.tmA[s] = p.tmA[0];
   {
     const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Cout};
     const uint64_t strides[1] = {(uint64_t)Ktot * 2};

@@ -86,6 +86,9 @@ def _rand_conv_case(seed, nimg, H, W, segs, cout, kh, kw):
     dict(nimg=2, H=17, W=33, segs=[128], cout=64, kh=3, kw=3),
     dict(nimg=2, H=16, W=16, segs=[128], cout=640, kh=3, kw=3),
     dict(nimg=1, H=24, W=16, segs=[64], cout=128, kh=7, kw=1),
+    # enough tiles for the stacked-M-tile halo kernel (two 16x8 tiles share each weight tile), ragged in both directions
+    dict(nimg=16, H=72, W=116, segs=[128], cout=128, kh=3, kw=3),
+    dict(nimg=16, H=72, W=116, segs=[64, 64], cout=128, kh=3, kw=3),
 ])
 def test_conv_tensor_core_matches_cuda_core_and_torch(case):
     """pvo_conv2d_tc (TMA + tcgen05 + TMEM) vs pvo_conv2d (CUDA cores) vs F.conv2d on the same half inputs."""
