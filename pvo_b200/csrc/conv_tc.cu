@@ -683,7 +683,8 @@ extern "C" int pvo_conv2d_tc(const void* const* seg_ptr, const int* seg_channels
     while (bn > 64 && mt * ((Cout + bn - 1) / bn) < 2 * PVO_SM_COUNT) bn >>= 1;
   }
   // N = 128 halo layers: stack two M tiles per CTA (they share the weight stream) when that still leaves >= 3 waves.
-  // (Measured: q conv 0.172 -> 0.156 ms; N = 64 layers are faster with two independent CTAs per SM and stay on MT = 1.)
+  // (Measured: q conv 0.172 -> 0.156 ms; N = 64 layers are faster with two independent CTAs per SM and stay on MT = 1;
+  //  running the N = 256 z|r conv as 128-wide stacked tiles instead was slower, 0.244 -> 0.287 ms.)
   if (p.halo && bn == 128 && !no_m2) {
     const long t2 = (long)nimg * p.tiles_x * ((H + 31) / 32) * ((Cout + bn - 1) / bn);
     if (t2 >= 3 * PVO_SM_COUNT) { p.halo = 2; p.tiles_y = (H + 31) / 32; }
