@@ -131,8 +131,11 @@ class UpdateEngine:
         self.c_q = _Conv(g('gru.convq.weight'), g('gru.convq.bias'), tc=tc, segs=[128, 320])
         self.glo_W = torch.cat([g('gru.conv%s_glo.weight' % n).reshape(128, 128) for n in 'zrq'], 0).float().contiguous()
         self.glo_b = torch.cat([g('gru.conv%s_glo.bias' % n) for n in 'zrq'], 0).float().contiguous()
-        self.c_heads1 = _Conv(torch.cat([g(h + '.0.weight') for h in HEAD_NAMES] + [g('agg.conv1.weight')], 0),
-                              torch.cat([g(h + '.0.bias') for h in HEAD_NAMES] + [g('agg.conv1.bias')], 0), tc=tc)
+        # the four heads' first convs as one 128->512 conv; agg.conv1 (128->128) separately: 640 columns would leave the third
+        # 256-wide tensor-core tile half empty, 512 + 128 tile exactly (and the 128-wide launch shares weight tiles across M tiles)
+        self.c_heads1 = _Conv(torch.cat([g(h + '.0.weight') for h in HEAD_NAMES], 0),
+                              torch.cat([g(h + '.0.bias') for h in HEAD_NAMES], 0), tc=tc)
+        self.c_agg1 = _Conv(g('agg.conv1.weight'), g('agg.conv1.bias'), tc=tc)
         self.heads2_W = pack_small_weight([g(h + '.2.weight') for h in HEAD_NAMES])
         self.heads2_b = torch.cat([g(h + '.2.bias') for h in HEAD_NAMES], 0).float().contiguous()
         self.heads2_frag = pack_heads_mma([g(h + '.2.weight') for h in HEAD_NAMES]) if mode == 'fp16' else None
@@ -258,9 +261,11 @@ class UpdateEngine:
         with T('conv_q'):
             conv2d(self.c_q, [(self.rnet, 128, 128), (X.data_ptr() + 128 * esz, 320, 448)], E, H, W, dc, X, 448, 0, 4,
                    aux0=self.z, aux1=self.glo3, use_tc=tc)
-        # 4 heads' first conv + agg.conv1 as one 128->640 conv + ReLU
+        # 4 heads' first convs (128->512) and agg.conv1 (128->128), + ReLU, into Hb[:, :512] / Hb[:, 512:]
         with T('conv_heads1'):
             conv2d(self.c_heads1, [(X, 128, 448)], E, H, W, dc, self.Hb, 640, 0, 1, use_tc=tc)
+            if with_agg:
+                conv2d(self.c_agg1, [(X, 128, 448)], E, H, W, dc, self.Hb, 640, 512, 1, use_tc=tc)
         with T('heads2'):
             if self.c_heads2t is not None:
                 hb = self.Hb.data_ptr()
