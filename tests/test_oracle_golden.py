@@ -82,3 +82,26 @@ def test_encoder_oracle_matches_reference_droidnet_features():
     assert torch.allclose(fm[:, :, ::8], gold['fmaps'], atol=1e-5)
     assert torch.allclose(net[:, :, ::8], gold['net'], atol=1e-5)
     assert torch.allclose(inp[:, :, ::8], gold['inp'], atol=1e-5)
+
+
+def test_oracle_lowmem_matches_reference_golden():
+    """oracle.step.graph_update_lowmem vs the reference's FactorGraph.update_lowmem run on CPU (tests/golden/make_golden_lowmem.py):
+    the global-BA control flow (chunks of source frames, per-chunk state updates, one BA per step with lm=1e-5, ep=1e-2)."""
+    import os
+    import numpy as np
+    from oracle import step as ostep, update_op as oupd
+    from tests.golden import cases
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'lowmem.npz'))
+    c = cases.graph_case(F=12, radius=2, h=16, w=24, seed=12)
+    st = ostep.make_state(c)
+    with torch.no_grad():
+        ostep.graph_update_lowmem(oupd.init_params(0), st, c['fmaps'], c['inps'], 12, itrs=2, steps=2)
+    T = lambda k: torch.from_numpy(z[k])
+    assert (st['poses'][:12] - T('poses')).abs().max() < 1e-5
+    assert ((st['disps'][:12] - T('disps')).abs() / T('disps').abs().clamp(min=1e-3)).max() < 1e-4
+    assert (st['target_cam'] - T('target')).abs().max() < 1e-3
+    assert (st['weight'] - T('weight')).abs().max() < 1e-4
+    assert (st['delta_dy'] - T('delta_dy')).abs().max() < 1e-3
+    assert (st['raw_mask'] - T('raw_mask')).abs().max() < 1e-3
+    assert (st['net'].float()[:, :, ::8] - T('net')).abs().max() < 2e-3
+    assert (st['damping'][:12] - T('damping')).abs().max() < 1e-5
