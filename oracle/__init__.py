@@ -5,20 +5,24 @@ Everything under ``oracle/`` is a CPU restatement of the reference's algorithm
 path in ``pvo_b200/``; it is never the thing that is shipped or measured.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
-``--impl reference`` legs may import from here.  Nothing in ``pvo_b200/`` imports
-``oracle`` (enforced by ``tests/test_no_oracle_in_product.py``).
+``--impl reference`` / reference-GPU-path legs may import from here.  Nothing in ``pvo_b200/``
+imports ``oracle`` (enforced by ``tests/test_cabi_cpu.py``).
 
-Pinning status (see DESIGN.md section "Oracle"):
+Pinning status:
   * SE3 ops ............ pinned by lietorch's own property tests
                           (thirdparty/lietorch/lietorch/run_tests.py:16-52), restated
-                          in tests/test_oracle_se3.py, and against the reference's
+                          in tests/test_host_logic_cpu.py, and against the reference's
                           Python geometry (geom/projective_ops.py, geom/ba.py) imported
-                          from /root/reference in this container -> tests/golden/.
+                          from /root/reference in this container -> tests/golden/geom.npz.
   * update operator ..... pinned against the reference's own DynamicUpdateModule /
                           ConvGRU / GraphAgg classes imported from /root/reference
-                          (tests/golden/make_golden.py) -> tests/golden/update_op.npz.
+                          (tests/golden/make_golden.py) -> tests/golden/update_op.npz;
+                          BasicEncoder / DroidNet.forward -> droid_net.npz.
   * Python BA ........... pinned against reference geom/ba.py BA()/MoBA() run here
-                          on the shimmed lietorch -> tests/golden/ba_python.npz.
+                          on the shimmed lietorch -> tests/golden/geom.npz.
+  * graph step .......... pinned against the reference's FactorGraph.update (segment filter on),
+                          FactorGraph.update_lowmem and add_proximity_factors run on CPU
+                          -> graph_step.npz, lowmem.npz, proximity.npz.
   * corr_index lookup ... the reference has no CPU kernel and no test vectors; the
                           restatement (oracle/corr_ref.c) is validated on the GPU box
                           against the reference's own correlation_kernels.cu compiled
@@ -28,4 +32,9 @@ Pinning status (see DESIGN.md section "Oracle"):
                           restatement is cross-checked against the reference's *Python*
                           BA where the two semantics coincide.  PARITY UNPINNED against
                           the CUDA kernel itself.
+  * Panoptic-FPN ........ post-processing half (box decode, proposals + NMS, level assignment,
+                          detections, mask pasting, panoptic merge + id maps) pinned bit for bit
+                          against the reference's own files executed on CPU -> fpn_parts.npz;
+                          ROIAlign / anchors / box deltas by Detectron2's known-answer tests;
+                          the convolutional half: PARITY UNPINNED (detectron2 cannot be imported).
 """

@@ -1,11 +1,19 @@
 """Plain-torch CPU restatement of PVO's Panoptic-FPN *inference* path -- oracle, test infrastructure only.
 
-PARITY UNPINNED against the reference as a whole: ``import detectron2`` fails in this container (fvcore / iopath /
-pycocotools absent), so the reference classes cannot be run to make golden vectors.  Pinned
-pieces: ROIAlign (torchvision, the reference's own dependency, checked against Detectron2's hand-computed 4x4
-known-answer test, VPS_Module/tests/layers/test_roi_align.py:14-45), the default anchor grid
-(tests/modeling/test_anchor_generator.py:14-42) and the Box2Box delta round trip
-(tests/modeling/test_box2box_transform.py:17-31) -- restated in tests/test_fpn_oracle_cpu.py.
+Pinning status.  ``import detectron2`` fails in this container (fvcore / iopath / pycocotools / the compiled _C are absent,
+SURVEY.md section 8(c)), so the model as a whole cannot be run to make golden vectors.  But the post-processing half of the
+path CAN be executed from the reference tree file by file (tests/golden/make_golden_fpn_parts.py loads mask_ops.py,
+boxes.py, instances.py, nms.py, box_regression.py, proposal_utils.py whole, and compiles assign_boxes_to_levels,
+fast_rcnn_inference_single_image and combine_semantic_and_instance_outputs + its VKITTI id maps from their source text):
+  PINNED, bit for bit, against the reference's own code (tests/golden/fpn_parts.npz, tests/test_fpn_oracle_cpu.py):
+      apply_deltas, rpn_proposals (top-k / clip / NMS / order), assign_levels, fast_rcnn_inference_single, paste_masks,
+      combine_semantic_and_instance and the id maps.
+  PINNED by Detectron2's own known-answer tests: ROIAlign (torchvision, hand-computed 4x4 expectations,
+      VPS_Module/tests/layers/test_roi_align.py:14-45), the default anchor grid (tests/modeling/test_anchor_generator.py:14-42),
+      the Box2Box delta round trip (tests/modeling/test_box2box_transform.py:17-31).
+  PARITY UNPINNED: the convolutional half (ResNet-50 / FPN / SemSegFPNHead / RPN head / box and mask heads) -- standard
+      layer arithmetic (conv, FrozenBN, GroupNorm, bilinear / nearest resampling) restated from the files below; Detectron2's
+      layer classes need fvcore to import.
 
 Follows (file:line under VPS_Module/detectron2/):
   modeling/meta_arch/rcnn.py:224-231          preprocess: (x - pixel_mean) / pixel_std, pad to a multiple of 32

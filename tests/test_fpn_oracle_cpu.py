@@ -81,3 +81,57 @@ def test_restated_inference_runs_and_is_consistent():
         for s in segs:
             assert s['category_id'] == s['id'] // 10000
         assert r['instances']['pred_masks'].shape[1:] == (h, w)
+
+
+# ---- pieces pinned against the reference's OWN code, executed on CPU by tests/golden/make_golden_fpn_parts.py ---------------
+def _parts():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fpn_parts.npz'))
+
+
+def test_apply_deltas_matches_reference_box2box_transform():
+    z = _parts()
+    src = torch.from_numpy(z['d_boxes'])
+    for name, wts in (('d1', (1.0, 1.0, 1.0, 1.0)), ('d3', (10.0, 10.0, 5.0, 5.0))):
+        got = ofpn.apply_deltas(torch.from_numpy(z[name + '_in']), src, wts)
+        assert torch.equal(got, torch.from_numpy(z[name + '_out'])), name
+
+
+def test_rpn_proposals_match_reference_find_top_rpn_proposals():
+    z = _parts()
+    logits = [torch.from_numpy(z['rpn_logits%d' % i]) for i in range(3)]
+    deltas = [torch.from_numpy(z['rpn_deltas%d' % i]) for i in range(3)]
+    got = ofpn.rpn_proposals(logits, deltas, [(96, 160), (90, 150)], pre_nms_topk=300, post_nms_topk=200, nms_thresh=0.7)
+    for n, (b, s_) in enumerate(got):
+        assert torch.equal(s_, torch.from_numpy(z['rpn_scores%d' % n])), n
+        assert torch.equal(b, torch.from_numpy(z['rpn_boxes%d' % n])), n
+
+
+def test_level_assignment_matches_reference_poolers():
+    z = _parts()
+    assert torch.equal(ofpn.assign_levels(torch.from_numpy(z['lvl_boxes'])), torch.from_numpy(z['lvl_out']))
+
+
+def test_detections_match_reference_fast_rcnn_inference():
+    z = _parts()
+    b, s_, c = ofpn.fast_rcnn_inference_single(torch.from_numpy(z['det_boxes_in']), torch.from_numpy(z['det_scores_in']), (200, 320))
+    assert torch.equal(b, torch.from_numpy(z['det_boxes']))
+    assert torch.equal(s_, torch.from_numpy(z['det_scores']))
+    assert torch.equal(c, torch.from_numpy(z['det_classes']))
+
+
+def test_paste_masks_matches_reference_mask_ops():
+    z = _parts()
+    got = ofpn.paste_masks(torch.from_numpy(z['paste_probs'])[:, None], torch.from_numpy(z['paste_boxes']), 96, 160)
+    assert torch.equal(got, torch.from_numpy(z['paste_out']))
+
+
+def test_panoptic_merge_matches_reference_combine():
+    z = _parts()
+    assert dict(z['thing_id2cat'].tolist()) == ofpn.THING_ID2CAT and dict(z['stuff_id2cat'].tolist()) == ofpn.STUFF_ID2CAT
+    masks = torch.from_numpy(z['paste_out'])
+    pan, segs = ofpn.combine_semantic_and_instance((None, torch.from_numpy(z['cmb_scores']), torch.from_numpy(z['cmb_classes']), masks),
+                                                   torch.from_numpy(z['cmb_sem']), stuff_area_thresh=1024)
+    assert torch.equal(pan, torch.from_numpy(z['cmb_pan']))
+    assert [s['id'] for s in segs] == z['cmb_seg_ids'].tolist()
+    assert [s.get('instance_id', -1) for s in segs] == z['cmb_seg_inst'].tolist()
