@@ -36,5 +36,7 @@ Pinning status:
                           detections, mask pasting, panoptic merge + id maps) pinned bit for bit
                           against the reference's own files executed on CPU -> fpn_parts.npz;
                           ROIAlign / anchors / box deltas by Detectron2's known-answer tests;
-                          the convolutional half: PARITY UNPINNED (detectron2 cannot be imported).
+                          the convolutional half (ResNet-50, FPN, sem-seg / RPN / box / mask heads) pinned
+                          against the reference's own module classes loaded file by file with the
+                          missing third-party names stubbed -> fpn_net.npz (strict state-dict load).
 """

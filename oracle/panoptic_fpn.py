@@ -11,9 +11,13 @@ fast_rcnn_inference_single_image and combine_semantic_and_instance_outputs + its
   PINNED by Detectron2's own known-answer tests: ROIAlign (torchvision, hand-computed 4x4 expectations,
       VPS_Module/tests/layers/test_roi_align.py:14-45), the default anchor grid (tests/modeling/test_anchor_generator.py:14-42),
       the Box2Box delta round trip (tests/modeling/test_box2box_transform.py:17-31).
-  PARITY UNPINNED: the convolutional half (ResNet-50 / FPN / SemSegFPNHead / RPN head / box and mask heads) -- standard
-      layer arithmetic (conv, FrozenBN, GroupNorm, bilinear / nearest resampling) restated from the files below; Detectron2's
-      layer classes need fvcore to import.
+  PINNED against the reference's own module classes (tests/golden/make_golden_fpn_net.py stubs only the missing third-party
+      names and loads resnet.py, fpn.py, box_head.py, mask_head.py whole + SemSegFPNHead, StandardRPNHead,
+      FastRCNNOutputLayers from source; strict load_state_dict of init_params(), so the parameter inventory is the
+      reference's): ResNet-50 + FPN features p2..p6, sem-seg logits, RPN logits / deltas, box head, mask head
+      -> tests/golden/fpn_net.npz, agreement 2e-4 relative (float32 summation order).
+  Not executed from the reference: the glue of PanopticFPN.inference itself (preprocess / pad, the order of the calls,
+      detector_postprocess / sem_seg_postprocess at output size == image size), restated from the lines cited below.
 
 Follows (file:line under VPS_Module/detectron2/):
   modeling/meta_arch/rcnn.py:224-231          preprocess: (x - pixel_mean) / pixel_std, pad to a multiple of 32

@@ -135,3 +135,35 @@ def test_panoptic_merge_matches_reference_combine():
     assert torch.equal(pan, torch.from_numpy(z['cmb_pan']))
     assert [s['id'] for s in segs] == z['cmb_seg_ids'].tolist()
     assert [s.get('instance_id', -1) for s in segs] == z['cmb_seg_inst'].tolist()
+
+
+def test_convolutional_half_matches_reference_modules():
+    """oracle backbone / FPN / sem-seg head / RPN head / box head / mask head vs the reference's OWN module classes
+    (resnet.py, fpn.py, semantic_seg.py, rpn.py, box_head.py, mask_head.py, fast_rcnn.py) loaded from the reference tree and run
+    on CPU with the oracle's seeded parameters -- strict state-dict load, so the parameter inventory is pinned too
+    (tests/golden/make_golden_fpn_net.py)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fpn_net.npz'))
+    sd = ofpn.init_params(0)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 3, 64, 96, generator=g) * 40
+    pooled = torch.randn(6, 256, 7, 7, generator=g)
+    mp = torch.randn(4, 256, 14, 14, generator=g)
+
+    def close(a, b, name):
+        b = torch.from_numpy(b)
+        assert a.shape == b.shape, name
+        assert (a - b).abs().max() <= 2e-4 * b.abs().max() + 1e-5, (name, (a - b).abs().max().item(), b.abs().max().item())
+    with torch.no_grad():
+        feats = ofpn.backbone(sd, x)
+        for k in ('p2', 'p3', 'p4', 'p5', 'p6'):
+            close(feats[k], z['feat_' + k], k)
+        close(ofpn.sem_seg_head(sd, feats)[:, :, ::2, ::2], z['sem'], 'sem')
+        lg, dl = ofpn.rpn_head(sd, feats)
+        for i in range(5):
+            close(lg[i], z['rpn_logits%d' % i], 'rpn_logits%d' % i)
+            close(dl[i], z['rpn_deltas%d' % i], 'rpn_deltas%d' % i)
+        cls, reg = ofpn.box_head(sd, pooled)
+        close(cls, z['box_cls'], 'box_cls')
+        close(reg, z['box_reg'], 'box_reg')
+        close(ofpn.mask_head(sd, mp), z['mask_logits'], 'mask_logits')
