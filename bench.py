@@ -384,7 +384,8 @@ def gpu_reference_sample(fg, c, dev):
     Baseline only: nothing here is on the product path."""
     import torch
     out = {'lookup_ms': None, 'update_operator_ms': None, 'ba_ms': None,
-           'note': 'reference BA (droid_kernels.cu) is unbuildable as shipped: vendored Eigen lacks Eigen/Core'}
+           'note': 'reference BA = droid_kernels.cu with its Eigen sparse LLT replaced by a dense float64 Cholesky (the vendored Eigen is '
+                   'incomplete; patch documented in oracle/build_ref.py), host round trips as in the reference'}
 
     def timed(fn, reps=5):
         for _ in range(2):
@@ -417,6 +418,24 @@ def gpu_reference_sample(fg, c, dev):
             out['note'] += '; oracle/_ref/droid_corr_ref.so absent (built only where the reference tree is mounted)'
     except Exception as ex:
         out['note'] += '; reference lookup failed: %r' % (ex,)
+    try:
+        from oracle import build_ref
+        refba = build_ref.load_ba()
+        if refba is not None:
+            v_ = fg.video
+            nf_ = v_.counter.value
+            ii_, jj_ = fg.ii, fg.jj
+            tgt = fg.target_cam[0].permute(0, 3, 1, 2).contiguous()        # (E,2,h,w) as factor_graph.py:297-300 passes them
+            wgt = fg.weight[0].permute(0, 3, 1, 2).contiguous()
+            kx_ = torch.unique(torch.cat([torch.arange(1, nf_, device=dev), ii_]))
+            eta_ = (0.2 * fg.damping[kx_] + 1e-7).contiguous()
+            intr_ = v_.intrinsics[0].contiguous()
+            out['ba_ms'] = round(timed(lambda: refba.ba(v_.poses.clone(), v_.disps.clone(), intr_, tgt, wgt, eta_, ii_, jj_, 1, nf_, 2,
+                                                         1e-4, 0.1, False)), 4)
+        else:
+            out['note'] += '; oracle/_ref/droid_ba_ref.so absent'
+    except Exception as ex:
+        out['note'] += '; reference BA failed: %r' % (ex,)
     try:
         from oracle import update_op as oupd
         sd = {k: v.to(dev).half() for k, v in oupd.init_params(0).items()}

@@ -28,10 +28,13 @@ Pinning status:
                           against the reference's own correlation_kernels.cu compiled
                           into oracle/_ref/ (tests/test_corr_gpu.py).  Without a GPU:
                           PARITY UNPINNED.
-  * droid_backends.ba ... reference cannot be built (vendored Eigen lacks Eigen/Core);
-                          restatement is cross-checked against the reference's *Python*
-                          BA where the two semantics coincide.  PARITY UNPINNED against
-                          the CUDA kernel itself.
+  * droid_backends.ba ... the pristine reference cannot be built (vendored Eigen lacks Eigen/Core).  oracle/build_ref.py
+                          builds droid_kernels.cu with three documented patches (Eigen sparse LLT -> dense float64
+                          Cholesky with the same damping / failure semantics, xi[45] -> xi[5], no Eigen includes) into
+                          oracle/_ref/droid_ba_ref.so; on the GPU box tests/test_geom_gpu.py checks the reference's
+                          BA kernels == this restatement == pvo_ba (poses, depth, motion-only) and its
+                          frame_distance == ours.  Also cross-checked against the reference's *Python* BA where the
+                          two semantics coincide.  Without a GPU: PARITY UNPINNED.
   * Panoptic-FPN ........ post-processing half (box decode, proposals + NMS, level assignment,
                           detections, mask pasting, panoptic merge + id maps) pinned bit for bit
                           against the reference's own files executed on CPU -> fpn_parts.npz;

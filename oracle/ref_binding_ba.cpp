@@ -1,0 +1,16 @@
+// Binding for the reference's droid_kernels.cu compiled into oracle/_ref/droid_ba_ref.so (see oracle/build_ref.py).
+// Our own file: it only declares three host wrappers the reference defines (VO_Module/src/droid_kernels.cu: ba_cuda
+// :1293-1410, frame_distance_cuda :1413-1446, projective_transform_cuda) with the signatures of VO_Module/src/droid.cpp:5-56.
+#include <torch/extension.h>
+#include <vector>
+
+std::vector<torch::Tensor> ba_cuda(torch::Tensor poses, torch::Tensor disps, torch::Tensor intrinsics, torch::Tensor targets,
+                                   torch::Tensor weights, torch::Tensor eta, torch::Tensor ii, torch::Tensor jj, const int t0,
+                                   const int t1, const int iterations, const float lm, const float ep, const bool motion_only);
+torch::Tensor frame_distance_cuda(torch::Tensor poses, torch::Tensor disps, torch::Tensor intrinsics, torch::Tensor ii,
+                                  torch::Tensor jj, const float beta);
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("ba", &ba_cuda, "reference ba_cuda (Eigen sparse solve replaced by a dense float64 Cholesky, see build_ref.py)");
+  m.def("frame_distance", &frame_distance_cuda, "reference frame_distance_cuda");
+}
