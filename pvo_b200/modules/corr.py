@@ -11,21 +11,20 @@ from .._lib import check, ptr, stream
 
 
 class CorrSampler(torch.autograd.Function):
-    """corr.py:6-20"""
+    """Differentiable window lookup of ONE pyramid level (reference interface: corr.py:6-20): forward and backward are the
+    pvo_corr_index_forward / _backward kernels."""
 
     @staticmethod
     def forward(ctx, volume, coords, radius):
-        ctx.save_for_backward(volume, coords)
+        out = droid_backends.corr_index_forward(volume, coords, radius)[0]
         ctx.radius = radius
-        corr, = droid_backends.corr_index_forward(volume, coords, radius)
-        return corr
+        ctx.save_for_backward(volume, coords)
+        return out
 
     @staticmethod
-    def backward(ctx, grad_output):
-        volume, coords = ctx.saved_tensors
-        grad_output = grad_output.contiguous()
-        grad_volume, = droid_backends.corr_index_backward(volume, coords, grad_output, ctx.radius)
-        return grad_volume, None, None
+    def backward(ctx, grad_out):
+        vol, xy = ctx.saved_tensors
+        return droid_backends.corr_index_backward(vol, xy, grad_out.contiguous(), ctx.radius)[0], None, None
 
 
 def to_pixel_major(x):
@@ -116,57 +115,48 @@ class CorrBlock:
 
 
 class CorrLayer(torch.autograd.Function):
-    """corr.py:74-88"""
+    """On-the-fly correlation of one pyramid level (reference: corr.py:74-88 over altcorr_kernel.cu); gradients are the
+    training path, which this package does not provide -- droid_backends.altcorr_backward says so when called."""
 
     @staticmethod
     def forward(ctx, fmap1, fmap2, coords, r):
-        ctx.r = r
+        out = droid_backends.altcorr_forward(fmap1, fmap2, coords, r)[0]
         ctx.save_for_backward(fmap1, fmap2, coords)
-        corr, = droid_backends.altcorr_forward(fmap1, fmap2, coords, ctx.r)
-        return corr
+        ctx.r = r
+        return out
 
     @staticmethod
     def backward(ctx, grad_corr):
-        fmap1, fmap2, coords = ctx.saved_tensors
-        g1, g2, gc = droid_backends.altcorr_backward(fmap1, fmap2, coords, grad_corr.contiguous(), ctx.r)
-        return g1, g2, gc, None
+        grads = droid_backends.altcorr_backward(*ctx.saved_tensors, grad_corr.contiguous(), ctx.r)
+        return (*grads, None)
 
 
 class AltCorrBlock:
-    """corr.py:91-139: correlation computed on the fly from the feature pyramid (global-BA path)."""
+    """Correlation features without a materialised volume (global-BA path; reference interface corr.py:91-139):
+    ``AltCorrBlock(fmaps)(coords, ii, jj)`` with fmaps (B,N,C,H,W), coords (B,E,H,W,2) or (B,E,H,W,S,2) -> (B,E,L*49,H,W[,S])."""
 
     def __init__(self, fmaps, num_levels=4, radius=3):
-        self.num_levels = num_levels
-        self.radius = radius
+        self.num_levels, self.radius = num_levels, radius
         B, N, C, H, W = fmaps.shape
-        fmaps = fmaps.view(B * N, C, H, W) / 4.0
-        self.pyramid = []
-        for i in range(self.num_levels):
-            sz = (B, N, H // 2 ** i, W // 2 ** i, C)
-            self.pyramid.append(fmaps.permute(0, 2, 3, 1).contiguous().view(*sz))
-            fmaps = torch.nn.functional.avg_pool2d(fmaps, 2, stride=2)
+        level = fmaps.reshape(B * N, C, H, W) / 4.0                     # the same pre-scaling as the volume path
+        self.pyramid = []                                              # channels-last float maps, one per level
+        for _ in range(num_levels):
+            self.pyramid.append(level.permute(0, 2, 3, 1).contiguous().view(B, N, level.shape[2], level.shape[3], C))
+            level = torch.nn.functional.avg_pool2d(level, 2, stride=2)
+
+    def _level(self, lvl, src, dst, xy):
+        """xy (B,E,S,H,W,2) in level-0 pixels -> (B,E,49,H,W,S) correlation window of pyramid level `lvl`"""
+        B, E, S, H, W, _ = xy.shape
+        flat = lambda t: t.reshape((B * E,) + tuple(t.shape[2:])).float().contiguous()
+        win = CorrLayer.apply(flat(self.pyramid[0][:, src]), flat(self.pyramid[lvl][:, dst]),
+                              (xy / float(1 << lvl)).reshape(B * E, S, H, W, 2).contiguous(), self.radius)
+        return win.view(B, E, S, -1, H, W).permute(0, 1, 3, 4, 5, 2)
 
     def corr_fn(self, coords, ii, jj):
-        B, N, H, W, S, _ = coords.shape
-        coords = coords.permute(0, 1, 4, 2, 3, 5)
-        corr_list = []
-        for i in range(self.num_levels):
-            fmap1_i = self.pyramid[0][:, ii]
-            fmap2_i = self.pyramid[i][:, jj]
-            coords_i = (coords / 2 ** i).reshape(B * N, S, H, W, 2).contiguous()
-            fmap1_i = fmap1_i.reshape((B * N,) + fmap1_i.shape[2:])
-            fmap2_i = fmap2_i.reshape((B * N,) + fmap2_i.shape[2:])
-            corr = CorrLayer.apply(fmap1_i.float().contiguous(), fmap2_i.float().contiguous(), coords_i, self.radius)
-            corr = corr.view(B, N, S, -1, H, W).permute(0, 1, 3, 4, 5, 2)
-            corr_list.append(corr)
-        return torch.cat(corr_list, dim=2)
+        xy = coords.permute(0, 1, 4, 2, 3, 5)                           # (B,E,H,W,S,2) -> (B,E,S,H,W,2)
+        return torch.cat([self._level(l, ii, jj, xy) for l in range(self.num_levels)], dim=2)
 
     def __call__(self, coords, ii, jj):
-        squeeze_output = False
-        if len(coords.shape) == 5:
-            coords = coords.unsqueeze(dim=-2)
-            squeeze_output = True
-        corr = self.corr_fn(coords, ii, jj)
-        if squeeze_output:
-            corr = corr.squeeze(dim=-1)
-        return corr.contiguous()
+        single = coords.dim() == 5                                     # one sample per pixel: add / drop the S axis
+        out = self.corr_fn(coords.unsqueeze(-2) if single else coords, ii, jj)
+        return (out.squeeze(-1) if single else out).contiguous()
