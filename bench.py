@@ -12,9 +12,13 @@ not per iteration) is reported separately as ``edge_add_ms``.  At N>1 each rank 
 one 8N-keyframe graph (weak scaling) and the reduced camera system is all-reduced over NCCL once per BA iteration.
 
 JSON keys follow the driver contract: value = whole-job steps/s with the state resident in HBM; e2e = the same step
-driven through the public API with the mutable graph state arriving from / returning to pinned HOST buffers inside
-the timed region; roofline = the dominant kernel (tensor-core 448->256 GRU gate convolution) vs the measured bf16
-peak in MEASURED_PEAKS.json; cpu_baseline = the CPU oracle (a port of the reference's Python path) on the host cores.
+driven through the public API with the mutable graph state arriving from / returning to pinned HOST buffers every step
+(copies of neighbouring steps overlap the compute on separate streams); roofline = the dominant kernel (tensor-core
+448->256 GRU gate convolution) vs the measured bf16 peak in MEASURED_PEAKS.json, with its DRAM traffic from the committed ncu
+capture (profiles/ncu_traffic.json); cpu_baseline = the CPU oracle (a port of the reference's Python path) on the host
+cores; reference_gpu_path = the reference's own GPU code for the stages that can be had on this box, timed on the same GPU
+(its correlation kernel and its BA kernels compiled into oracle/_ref/, its update operator's module structure on cuDNN).
+--workload vkitti / fpn run BASELINE configs[2] shape / configs[3]; --impl reference = the reference's CPU path.
 """
 import argparse
 import json
