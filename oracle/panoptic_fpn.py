@@ -1,23 +1,24 @@
 """Plain-torch CPU restatement of PVO's Panoptic-FPN *inference* path -- oracle, test infrastructure only.
 
 Pinning status.  ``import detectron2`` fails in this container (fvcore / iopath / pycocotools / the compiled _C are absent,
-SURVEY.md section 8(c)), so the model as a whole cannot be run to make golden vectors.  But the post-processing half of the
-path CAN be executed from the reference tree file by file (tests/golden/make_golden_fpn_parts.py loads mask_ops.py,
-boxes.py, instances.py, nms.py, box_regression.py, proposal_utils.py whole, and compiles assign_boxes_to_levels,
-fast_rcnn_inference_single_image and combine_semantic_and_instance_outputs + its VKITTI id maps from their source text):
-  PINNED, bit for bit, against the reference's own code (tests/golden/fpn_parts.npz, tests/test_fpn_oracle_cpu.py):
-      apply_deltas, rpn_proposals (top-k / clip / NMS / order), assign_levels, fast_rcnn_inference_single, paste_masks,
-      combine_semantic_and_instance and the id maps.
-  PINNED by Detectron2's own known-answer tests: ROIAlign (torchvision, hand-computed 4x4 expectations,
-      VPS_Module/tests/layers/test_roi_align.py:14-45), the default anchor grid (tests/modeling/test_anchor_generator.py:14-42),
-      the Box2Box delta round trip (tests/modeling/test_box2box_transform.py:17-31).
-  PINNED against the reference's own module classes (tests/golden/make_golden_fpn_net.py stubs only the missing third-party
-      names and loads resnet.py, fpn.py, box_head.py, mask_head.py whole + SemSegFPNHead, StandardRPNHead,
-      FastRCNNOutputLayers from source; strict load_state_dict of init_params(), so the parameter inventory is the
-      reference's): ResNet-50 + FPN features p2..p6, sem-seg logits, RPN logits / deltas, box head, mask head
-      -> tests/golden/fpn_net.npz, agreement 2e-4 relative (float32 summation order).
-  Not executed from the reference: the glue of PanopticFPN.inference itself (preprocess / pad, the order of the calls,
-      detector_postprocess / sem_seg_postprocess at output size == image size), restated from the lines cited below.
+SURVEY.md section 8(c)), but every FILE the inference path needs loads from the reference tree once those third-party names are
+stubbed, so the reference model itself was run here, three ways (generators under tests/golden/, tests in
+tests/test_fpn_oracle_cpu.py):
+  WHOLE MODEL (make_golden_fpn_e2e.py -> fpn_e2e.npz): the reference's own PanopticFPN.inference -- GeneralizedRCNN.preprocess_image,
+      ImageList padding, ResNet-50 + FPN, SemSegFPNHead, RPN (DefaultAnchorGenerator, find_top_rpn_proposals), StandardROIHeads
+      (ROIPooler, FastRCNNOutputLayers.inference, mask head + mask_rcnn_inference), sem_seg_postprocess, detector_postprocess,
+      combine_semantic_and_instance_outputs -- built with the VKITTI config's arguments, strict load_state_dict of init_params(),
+      two images of different size.  This file's `inference` gives the same 100 detections per image (boxes to 5e-4 px, scores
+      to 5e-6), the same segment list, the same panoptic ids on all but 6 of 65 840 pixels and the same masks on all but 18 of
+      6.6 M (float32 summation order at the 0.5 threshold).
+  PIECES, bit for bit (make_golden_fpn_parts.py -> fpn_parts.npz): apply_deltas, rpn_proposals (top-k / clip / NMS / order),
+      assign_levels, fast_rcnn_inference_single, paste_masks, combine_semantic_and_instance and the id maps, on inputs chosen
+      to hit ties, clipping, empty classes and the area / overlap thresholds.
+  CONVOLUTIONAL HALF at full output (make_golden_fpn_net.py -> fpn_net.npz): features p2..p6, sem-seg logits, RPN logits /
+      deltas, box head, mask head, 2e-4 relative; strict load_state_dict pins the parameter inventory to the reference's.
+  Detectron2's own known-answer tests: ROIAlign (VPS_Module/tests/layers/test_roi_align.py:14-45), the default anchor grid
+      (tests/modeling/test_anchor_generator.py:14-42), the Box2Box delta round trip (tests/modeling/test_box2box_transform.py:17-31).
+  Not covered: the video "fusion" branch (inference_fusion; FUSION = False here) and training.
 
 Follows (file:line under VPS_Module/detectron2/):
   modeling/meta_arch/rcnn.py:224-231          preprocess: (x - pixel_mean) / pixel_std, pad to a multiple of 32

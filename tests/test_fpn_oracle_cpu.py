@@ -1,6 +1,8 @@
 """Known-answer tests lifted from Detectron2's own suite (the literal expectations, VPS_Module/tests/...) that pin the
 pieces of the Panoptic-FPN oracle that CAN be pinned without importing detectron2, plus a
 smoke run of the whole restated inference path."""
+import os
+
 import numpy as np
 import torch
 import torchvision
@@ -85,7 +87,6 @@ def test_restated_inference_runs_and_is_consistent():
 
 # ---- pieces pinned against the reference's OWN code, executed on CPU by tests/golden/make_golden_fpn_parts.py ---------------
 def _parts():
-    import os
     return np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fpn_parts.npz'))
 
 
@@ -142,7 +143,6 @@ def test_convolutional_half_matches_reference_modules():
     (resnet.py, fpn.py, semantic_seg.py, rpn.py, box_head.py, mask_head.py, fast_rcnn.py) loaded from the reference tree and run
     on CPU with the oracle's seeded parameters -- strict state-dict load, so the parameter inventory is pinned too
     (tests/golden/make_golden_fpn_net.py)."""
-    import os
     z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fpn_net.npz'))
     sd = ofpn.init_params(0)
     g = torch.Generator().manual_seed(21)
@@ -167,3 +167,32 @@ def test_convolutional_half_matches_reference_modules():
         close(cls, z['box_cls'], 'box_cls')
         close(reg, z['box_reg'], 'box_reg')
         close(ofpn.mask_head(sd, mp), z['mask_logits'], 'mask_logits')
+
+
+def test_whole_model_matches_reference_panoptic_fpn_inference():
+    """the reference's own PanopticFPN.inference (every module class + preprocess_image / ImageList padding / RPN /
+    StandardROIHeads / sem_seg_postprocess / detector_postprocess / combine, tests/golden/make_golden_fpn_e2e.py) on two
+    images of different size against the restated whole-model inference.  float32 summation order differs between the two
+    (folded norms, fused loops), so boxes agree to ~5e-4 px and a handful of mask / id pixels sit on the 0.5 threshold."""
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fpn_e2e.npz'))
+    g = torch.Generator().manual_seed(31)
+    ims = [torch.randint(0, 256, s, generator=g).float() for s in ((3, 160, 224), (3, 150, 200))]
+    with torch.no_grad():
+        res = ofpn.inference(ofpn.init_params(0), ims)
+    for n, r in enumerate(res):
+        pan, segs = r['panoptic_seg']
+        inst = r['instances']
+        assert [s['id'] for s in segs] == z['seg_ids%d' % n].tolist()
+        assert [s['category_id'] for s in segs] == z['seg_cat%d' % n].tolist()
+        assert [bool(s['isthing']) for s in segs] == z['seg_isthing%d' % n].tolist()
+        assert [s.get('instance_id', -1) for s in segs] == z['seg_inst%d' % n].tolist()
+        assert inst['pred_boxes'].shape[0] == z['boxes%d' % n].shape[0] == 100
+        assert (inst['pred_boxes'] - torch.from_numpy(z['boxes%d' % n])).abs().max() < 5e-3
+        assert (inst['scores'] - torch.from_numpy(z['scores%d' % n])).abs().max() < 1e-4
+        assert np.array_equal(inst['pred_classes'].numpy(), z['classes%d' % n])
+        masks = np.unpackbits(z['masks%d' % n], axis=-1)[..., :pan.shape[1]].astype(bool)
+        assert (inst['pred_masks'].numpy() != masks).mean() < 2e-5
+        assert (pan.numpy() != z['pan%d' % n]).mean() < 1e-3
+        assert (r['sem_seg'].argmax(0).numpy() != z['sem_label%d' % n]).mean() < 1e-3
+        want = torch.from_numpy(z['sem_logits%d' % n])
+        assert (r['sem_seg'][:, ::4, ::4] - want).abs().max() < 1e-4 * want.abs().max()
