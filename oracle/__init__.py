@@ -41,5 +41,7 @@ Pinning status:
                           ROIAlign / anchors / box deltas by Detectron2's known-answer tests;
                           the convolutional half (ResNet-50, FPN, sem-seg / RPN / box / mask heads) pinned
                           against the reference's own module classes loaded file by file with the
-                          missing third-party names stubbed -> fpn_net.npz (strict state-dict load).
+                          missing third-party names stubbed -> fpn_net.npz (strict state-dict load); the WHOLE model
+                          -- the reference's own PanopticFPN.inference, every class from the tree -- run on
+                          two images -> fpn_e2e.npz: same detections, segments and panoptic ids.
 """
