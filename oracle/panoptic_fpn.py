@@ -51,7 +51,7 @@ RES_STAGES = ((3, 64, 256), (4, 128, 512), (6, 256, 1024), (3, 512, 2048))   # b
 
 
 # ------------------------------------------------------------------------------------------------ parameters
-def param_shapes():
+def param_shapes(fusion=False):
     s = {}
 
     def conv(name, co, ci, k, bias=True, bn=False):
@@ -99,10 +99,12 @@ def param_shapes():
     s['roi_heads.mask_head.deconv.weight'] = (256, 256, 2, 2)        # ConvTranspose2d: (in, out, kh, kw)
     s['roi_heads.mask_head.deconv.bias'] = (256,)
     conv('roi_heads.mask_head.predictor', NUM_THING, 256, 1)
+    if fusion:                                                       # panoptic_fpn.py:81: the video-fusion conv (last: the other
+        conv('fusion_conv1', 256, 512, 3)                            # seeded parameters do not move)
     return s
 
 
-def init_params(seed=0):
+def init_params(seed=0, fusion=False):
     """Seeded random weights with per-layer gains chosen so that activations stay O(1) through all ~55 layers (raw pixel
     input has std ~60: the stem is scaled down by 64; bottleneck tails and un-rectified convs use smaller gains so the
     residual stream does not grow) -- the fp16 path must not overflow where a trained checkpoint would not -- and so that
@@ -110,7 +112,7 @@ def init_params(seed=0):
     gamma 1, beta 0, each perturbed by N(0, 0.1)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
-    for name, shape in param_shapes().items():
+    for name, shape in param_shapes(fusion).items():
         if name.endswith('running_var'):
             sd[name] = (1.0 + 0.1 * torch.randn(shape, generator=g)).clamp(min=0.5)
         elif '.norm.' in name and name.endswith('weight'):
@@ -124,7 +126,7 @@ def init_params(seed=0):
                 gain = 2.0 ** 0.5 / 64.0
             elif 'bottom_up' in name and 'conv3' in name:
                 gain = 0.5
-            elif 'shortcut' in name or 'fpn_' in name:
+            elif 'shortcut' in name or 'fpn_' in name or 'fusion' in name:
                 gain = 1.0
             elif 'objectness' in name or 'predictor.weight' in name:
                 gain = 2.0
@@ -405,12 +407,8 @@ def combine_semantic_and_instance(boxes_scores_classes_masks, semantic, overlap_
 
 
 # ------------------------------------------------------------------------------------------------ whole model
-def inference(sd, images, debug=None):
-    """PanopticFPN.inference for a list of (3,H,W) BGR images.  Returns per image dict(sem_seg, instances, panoptic_seg)."""
-    x, sizes = preprocess(images)
-    feats = backbone(sd, x)
-    sem = sem_seg_head(sd, feats)
-    logits, deltas = rpn_head(sd, feats)
+def _roi_heads_and_merge(sd, feats, sem, logits, deltas, sizes, debug=None):
+    """RPN proposals -> StandardROIHeads -> post-processing -> merge, for features of len(sizes) images"""
     props = rpn_proposals(logits, deltas, sizes)
     pooled = roi_pool(feats, [p[0] for p in props], 7)
     cls, reg = box_head(sd, pooled)
@@ -440,3 +438,52 @@ def inference(sd, images, debug=None):
         debug.update(feats=feats, sem=sem, rpn_logits=logits, rpn_deltas=deltas, proposals=props, box_cls=cls, box_reg=reg,
                      detections=dets, mask_logits=ml)
     return results
+
+
+def inference(sd, images, debug=None):
+    """PanopticFPN.inference for a list of (3,H,W) BGR images.  Returns per image dict(sem_seg, instances, panoptic_seg)."""
+    x, sizes = preprocess(images)
+    feats = backbone(sd, x)
+    sem = sem_seg_head(sd, feats)
+    logits, deltas = rpn_head(sd, feats)
+    return _roi_heads_and_merge(sd, feats, sem, logits, deltas, sizes, debug)
+
+
+# ------------------------------------------------------------------------------------------------ video fusion branch
+def flow_transport(feat_ref, flow):
+    """PanopticFPN.flow_transport_feature (panoptic_fpn.py:310-344) for one level: feat_ref (C,h,w) features of the previous
+    frame, flow (2,H,W) its forward optical flow (x, y) in full-resolution pixels -> (C,h,w) features carried to where the
+    flow points, zero where nothing lands.  Exactly as the reference does it, oddities included: the flow is resized to
+    (h,w) (bilinear, align_corners=True, :433-438) but NOT rescaled to feature pixels; it is cast float -> uint16 (:314), i.e.
+    truncated toward zero and wrapped mod 2^16, so any flow component <= -1 lands out of range and the pixel is dropped
+    (:330-335); several sources landing on one target: the last one in raster order stays (numpy-ordered index assignment,
+    :337)."""
+    import numpy as np
+    C, h, w = feat_ref.shape
+    f = F.interpolate(flow[None, :2].float(), size=(h, w), mode='bilinear', align_corners=True)[0]
+    f = f.to(torch.int32).numpy().astype(np.int64) & 0xFFFF       # trunc toward zero, wrap to uint16
+    v, u = np.mgrid[0:h, 0:w]
+    u1, v1 = (u + f[0]).astype(np.int32), (v + f[1]).astype(np.int32)
+    ok = (0 <= u1) & (u1 < w) & (0 <= v1) & (v1 < h)
+    out = np.zeros((C, h, w), dtype=np.float32)
+    src = feat_ref.numpy()
+    out[:, v1[ok], u1[ok]] = src[:, v[ok], u[ok]]                  # numpy: repeated targets keep the last assignment
+    return torch.from_numpy(out)
+
+
+def inference_fusion(sd, ref_image, ref_flow, cur_image, debug=None, alpha=1.0):
+    """PanopticFPN.inference_fusion for the second and later frames of a video (panoptic_fpn.py:254-308 -> wrap_in_stage2
+    :193-240, flow_transport on, depth transport off): backbone on (ref, cur) together, per level cat(cur features,
+    alpha * transported ref features) -> fusion_conv1 (512 -> 256, 3x3, :410-414), then the ordinary heads on the fused
+    pyramid for the current image.  The first frame of a video runs `inference` (:256-264).  Needs init_params(fusion=True)."""
+    x, sizes = preprocess([ref_image, cur_image])
+    feats = backbone(sd, x)
+    fused = {}
+    for k, f in feats.items():
+        warped = flow_transport(f[0], ref_flow)
+        fused[k] = conv(sd, 'fusion_conv1', torch.cat([f[1], alpha * warped], dim=0)[None], pad=1)
+    sem = sem_seg_head(sd, fused)
+    logits, deltas = rpn_head(sd, fused)
+    if debug is not None:
+        debug['pair_feats'] = feats
+    return _roi_heads_and_merge(sd, fused, sem, logits, deltas, sizes[1:], debug)

@@ -124,6 +124,33 @@ def _cat_rows(ts):
     return torch.cat(ts).contiguous()
 
 
+def flow_transport_index(flow, h, w):
+    """Index form of PanopticFPN.flow_transport_feature (panoptic_fpn.py:310-344) for one pyramid level: flow (2+,H,W)
+    forward flow (x, y) of the previous frame -> (h*w,) int64, for every pixel of the level the raster index of the
+    previous-frame pixel whose features land on it, -1 where nothing lands.  The reference's rules, oddities included: the
+    flow is resized to (h,w) (bilinear, align_corners=True, :433-438) but not rescaled; float -> uint16 cast (:314) =
+    truncate toward zero and wrap mod 2^16, so a component <= -1 lands out of range and is dropped (:330-335); when
+    several sources land on one target the last in raster order stays (:337, serial index assignment) -- here a
+    scatter-max over source indices, deterministic on the GPU.  Tensor ops only: runs on whatever device `flow` is on."""
+    dev = flow.device
+    f = F.interpolate(flow[None, :2].float(), size=(h, w), mode='bilinear', align_corners=True)[0]
+    f = f.to(torch.int32).to(torch.int64) & 0xFFFF
+    u1 = torch.arange(w, device=dev)[None, :] + f[0]
+    v1 = torch.arange(h, device=dev)[:, None] + f[1]
+    n = h * w
+    tgt = torch.where((u1 < w) & (v1 < h), v1 * w + u1, torch.full_like(u1, n)).reshape(-1)     # slot n collects the dropped ones
+    win = torch.full((n + 1,), -1, dtype=torch.int64, device=dev)
+    win.scatter_reduce_(0, tgt, torch.arange(n, device=dev), 'amax', include_self=True)
+    return win[:n]
+
+
+def flow_transport(feat_ref, win):
+    """feat_ref (h*w, C) pixel-major features of the previous frame, win from flow_transport_index -> (h*w, C) carried
+    features, zero where nothing lands"""
+    got = feat_ref[win.clamp(min=0)]
+    return torch.where((win >= 0)[:, None], got, torch.zeros_like(got))
+
+
 class PanopticFPN:
     def __init__(self, state_dict, device='cuda', use_cuda_graph=True):
         self.device = torch.device(device)
@@ -176,6 +203,11 @@ class PanopticFPN:
         self.cv['deconv'] = tc(dw.permute(2, 3, 1, 0).reshape(4 * 256, 256)[:, :, None, None].contiguous(),
                                sd['roi_heads.mask_head.deconv.bias'].repeat(4))
         self.cv['mask_pred'] = tc(sd['roi_heads.mask_head.predictor.weight'], sd['roi_heads.mask_head.predictor.bias'])
+        self.fusion = 'fusion_conv1.weight' in sd          # the video branch's 512 -> 256 conv (panoptic_fpn.py:81, :410-414)
+        if self.fusion:
+            self.cv['fusion_conv1'] = tc(sd['fusion_conv1.weight'], sd['fusion_conv1.bias'])
+        self.alpha = 1.0                                   # panoptic_fpn.py:70
+        self.vid = self.ref_flow = self.ref_image = self.ref_id = None
         self.mean = torch.tensor(PIXEL_MEAN, device=self.device).view(1, 1, 1, 3)
         self._scratch = None
 
@@ -480,6 +512,10 @@ class PanopticFPN:
         images = [im['image'] if isinstance(im, dict) else im for im in images]
         x, sizes = self.preprocess(images)
         feats, sem, rpn = self.dense(x)
+        return self._roi_heads_and_merge(feats, sem, rpn, sizes, debug)
+
+    def _roi_heads_and_merge(self, feats, sem, rpn, sizes, debug=None):
+        """proposals -> box head -> detections -> mask head -> paste -> merge for the len(sizes) images the pyramid holds"""
         props = self.proposals(rpn, sizes)
         cls, reg = self.box_head(self.roi_pool(feats, [p[0] for p in props], 7))
         dets = self.detections(cls, reg, props, sizes)
@@ -513,5 +549,44 @@ class PanopticFPN:
         if debug is not None:
             debug.update(feats=feats, sem=sem, rpn=rpn, proposals=props, box_cls=cls, box_reg=reg, detections=dets, mask_logits=ml)
         return results
+
+    # ------------------------------------------------------------------------------------------ video fusion branch
+    def fuse_pair(self, ref_image, ref_flow, cur_image):
+        """wrap_in_stage2 up to the heads (panoptic_fpn.py:193-212): backbone on (ref, cur) as one batch of two; per level
+        cat(cur features, alpha * ref features carried along the flow) -> fusion_conv1 on the tensor cores.
+        -> fused pyramid of ONE image ({'p2'..'p6': ((h*w, 256) half, h, w)}), its sizes list"""
+        if not self.fusion:
+            raise RuntimeError('the state dict holds no fusion_conv1: build PanopticFPN from a FUSION checkpoint')
+        x, sizes = self.preprocess([ref_image, cur_image])
+        feats = self.backbone(x)
+        flow = ref_flow.to(self.device)
+        fused = {}
+        for k, (f, h, w) in feats.items():
+            f = f.view(2, h * w, 256)
+            carried = flow_transport(f[0], flow_transport_index(flow, h, w))
+            if self.alpha != 1.0:
+                carried = carried * self.alpha
+            pair = torch.cat([f[1], carried], dim=1).contiguous()               # (h*w, 512): current | carried
+            fused[k] = (self._conv('fusion_conv1', pair, 1, h, w), h, w)
+        self.N = 1
+        return fused, sizes[1:]
+
+    @torch.no_grad()
+    def inference_fusion(self, batched_inputs, debug=None):
+        """PanopticFPN.inference_fusion (panoptic_fpn.py:254-308), FUSION = True, flow transport on, depth transport off (the
+        shipped settings, :71-73).  batched_inputs: [{'image': (3,H,W) BGR, 'image_id': str, optional 'flow': (2,H,W)}] -- one
+        frame.  The first frame of a video (image_id[:4] changes) takes the single-image path; later frames are fused with
+        the previous frame's features carried along its flow.  The frame's own image / flow are kept for the next call."""
+        inp = batched_inputs[0]
+        vid = inp['image_id'][:4]
+        if vid != self.vid:
+            self.vid = vid
+            res = self.inference([inp['image']], debug)
+        else:
+            fused, sizes = self.fuse_pair(self.ref_image, self.ref_flow, inp['image'])
+            res = self._roi_heads_and_merge(fused, self.sem_seg(fused), self.rpn_head(fused), sizes, debug)
+        if 'flow' in inp:
+            self.ref_flow, self.ref_image, self.ref_id = inp['flow'], inp['image'], inp['image_id']
+        return res
 
     __call__ = inference

@@ -41,7 +41,7 @@ def images():
     return [torch.randint(0, 256, s, generator=g).float() for s in SIZES]
 
 
-def build():
+def build(fusion=False):
     backbone, sem, rpn_head, bh, pred_unused, mh = net.build()
     stub, load_file, Registry = net.stub, net.load_file, net.Registry
     noop = lambda *a, **k: None
@@ -115,9 +115,71 @@ def build():
         mask_in_features=['p2', 'p3', 'p4', 'p5'], mask_pooler=poolers.ROIPooler(14, scales, 0, 'ROIAlignV2'), mask_head=mh,
         num_classes=3, batch_size_per_image=512, positive_fraction=0.25, proposal_matcher=matcher.Matcher([0.5], [0, 1], allow_low_quality_matches=False))
     model = ns['PanopticFPN'](sem_seg_head=sem, combine_overlap_thresh=0.5, combine_stuff_area_thresh=4096, combine_instances_score_thresh=0.5,
-                              fusion=False, backbone=backbone, proposal_generator=proposal_generator, roi_heads=roi_heads,
+                              fusion=fusion, backbone=backbone, proposal_generator=proposal_generator, roi_heads=roi_heads,
                               pixel_mean=(103.530, 116.280, 123.675), pixel_std=(1.0, 1.0, 1.0), input_format='BGR')
     return model
+
+
+def pack(res, out, tag=''):
+    for n, r in enumerate(res):
+        pan, segs = r['panoptic_seg']
+        inst = r['instances']
+        k = '%s%d' % (tag, n)
+        out['pan' + k] = pan.numpy().astype(np.int32)
+        out['seg_ids' + k] = np.array([s['id'] for s in segs], dtype=np.int64)
+        out['seg_cat' + k] = np.array([s['category_id'] for s in segs], dtype=np.int64)
+        out['seg_isthing' + k] = np.array([bool(s['isthing']) for s in segs])
+        out['seg_inst' + k] = np.array([s.get('instance_id', -1) for s in segs], dtype=np.int64)
+        out['boxes' + k] = inst.pred_boxes.tensor.numpy()
+        out['scores' + k] = inst.scores.numpy()
+        out['classes' + k] = inst.pred_classes.numpy()
+        out['masks' + k] = np.packbits(inst.pred_masks.numpy(), axis=-1)
+        out['sem_label' + k] = r['sem_seg'].argmax(dim=0).numpy().astype(np.uint8)
+        out['sem_logits' + k] = r['sem_seg'][:, ::4, ::4].numpy()
+        print(k, 'detections', len(inst), 'kept (score >= 0.5)', int((inst.scores >= 0.5).sum()), 'segments', len(segs))
+
+
+FUSION_SIZE, FUSION_SEED = (3, 128, 192), 41
+
+
+def fusion_inputs():
+    """two frames of one 'video' + the forward flow of the first: a smooth field of a few pixels with a patch of negative
+    flow (dropped by the reference's uint16 cast) and a patch that leaves the image"""
+    g = torch.Generator().manual_seed(FUSION_SEED)
+    a = torch.randint(0, 256, FUSION_SIZE, generator=g).float()
+    b = torch.randint(0, 256, FUSION_SIZE, generator=g).float()
+    _, H, W = FUSION_SIZE
+    coarse = torch.rand(1, 2, 5, 7, generator=g) * 6.0
+    flow = F.interpolate(coarse, size=(H, W), mode='bilinear', align_corners=True)[0]
+    flow[:, 20:50, 30:70] -= 7.5
+    flow[0, 80:110, 150:] += 60.0
+    return a, b, flow
+
+
+def main_fusion(out):
+    """the video branch: frame 1 goes through the plain path and leaves (image, flow) behind; frame 2 of the same video id
+    goes through wrap_in_stage2: backbone on (ref, cur), flow_transport_feature, fusion_conv1, heads"""
+    # index assignment with repeated targets (`mask[:, v1, u1] = ...`, :337): serial execution keeps the last source in raster
+    # order; with several intra-op threads torch's CPU index_put races at chunk boundaries (single channels keep an earlier
+    # source).  The serial result is the one pinned.
+    torch.set_num_threads(1)
+    model = build(fusion=True)
+    sd = ofpn.init_params(0, fusion=True)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    a, b, flow = fusion_inputs()
+    r1 = model([{'image': a, 'image_id': '0001_00000', 'flow': flow}])
+    r2 = model([{'image': b, 'image_id': '0001_00001', 'flow': flow}])
+    pack(r1, out, 'f1_')
+    pack(r2, out, 'f2_')
+    # the transport alone, every level shape of a 128 x 192 frame, random features
+    g = torch.Generator().manual_seed(FUSION_SEED + 1)
+    for k, (h, w) in {'p2': (32, 48), 'p4': (8, 12), 'p6': (2, 3)}.items():
+        feat = torch.randn(2, 16, h, w, generator=g)
+        res = model.flow_transport_feature({k: feat.clone()}, flow)[k]
+        assert torch.equal(res[0, :16], feat[1])
+        out['transport_' + k] = res[0, 16:].numpy()
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
 
 
 def main():
@@ -132,21 +194,8 @@ def main():
     model.eval()
     res = model.inference([{'image': im} for im in images()])
     out = {}
-    for n, r in enumerate(res):
-        pan, segs = r['panoptic_seg']
-        inst = r['instances']
-        out['pan%d' % n] = pan.numpy().astype(np.int32)
-        out['seg_ids%d' % n] = np.array([s['id'] for s in segs], dtype=np.int64)
-        out['seg_cat%d' % n] = np.array([s['category_id'] for s in segs], dtype=np.int64)
-        out['seg_isthing%d' % n] = np.array([bool(s['isthing']) for s in segs])
-        out['seg_inst%d' % n] = np.array([s.get('instance_id', -1) for s in segs], dtype=np.int64)
-        out['boxes%d' % n] = inst.pred_boxes.tensor.numpy()
-        out['scores%d' % n] = inst.scores.numpy()
-        out['classes%d' % n] = inst.pred_classes.numpy()
-        out['masks%d' % n] = np.packbits(inst.pred_masks.numpy(), axis=-1)
-        out['sem_label%d' % n] = r['sem_seg'].argmax(dim=0).numpy().astype(np.uint8)
-        out['sem_logits%d' % n] = r['sem_seg'][:, ::4, ::4].numpy()
-        print(n, 'detections', len(inst), 'kept (score >= 0.5)', int((inst.scores >= 0.5).sum()), 'segments', [s['id'] for s in segs])
+    pack(res, out)
+    main_fusion(out)
     np.savez_compressed(os.path.join(HERE, 'fpn_e2e.npz'), **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -196,3 +196,53 @@ def test_whole_model_matches_reference_panoptic_fpn_inference():
         assert (r['sem_seg'].argmax(0).numpy() != z['sem_label%d' % n]).mean() < 1e-3
         want = torch.from_numpy(z['sem_logits%d' % n])
         assert (r['sem_seg'][:, ::4, ::4] - want).abs().max() < 1e-4 * want.abs().max()
+
+
+def _fusion_inputs():
+    """the inputs of tests/golden/make_golden_fpn_e2e.py fusion_inputs()"""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(41)
+    a = torch.randint(0, 256, (3, 128, 192), generator=g).float()
+    b = torch.randint(0, 256, (3, 128, 192), generator=g).float()
+    coarse = torch.rand(1, 2, 5, 7, generator=g) * 6.0
+    flow = F.interpolate(coarse, size=(128, 192), mode='bilinear', align_corners=True)[0]
+    flow[:, 20:50, 30:70] -= 7.5
+    flow[0, 80:110, 150:] += 60.0
+    return a, b, flow
+
+
+def test_flow_transport_matches_reference_bit_for_bit():
+    """PanopticFPN.flow_transport_feature executed from the reference (numpy uint16 cast, serial index assignment) on three
+    level shapes, with negative flow (dropped), flow leaving the image and repeated targets"""
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fpn_e2e.npz'))
+    flow = _fusion_inputs()[2]
+    g = torch.Generator().manual_seed(42)
+    for k, (h, w) in {'p2': (32, 48), 'p4': (8, 12), 'p6': (2, 3)}.items():
+        feat = torch.randn(2, 16, h, w, generator=g)
+        assert np.array_equal(ofpn.flow_transport(feat[0], flow).numpy(), z['transport_' + k]), k
+    assert (z['transport_p2'] != 0).mean() > 0.5 and (z['transport_p2'] == 0).mean() > 0.2
+
+
+def test_video_fusion_matches_reference_inference_fusion():
+    """two frames of one video through the reference's own PanopticFPN (FUSION = True): frame 1 = single-image path, frame 2 =
+    wrap_in_stage2 (pair backbone, flow transport, fusion_conv1, heads)"""
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fpn_e2e.npz'))
+    a, b, flow = _fusion_inputs()
+    sd = ofpn.init_params(0, fusion=True)
+    with torch.no_grad():
+        runs = (('f1_0', ofpn.inference(sd, [a])[0]), ('f2_0', ofpn.inference_fusion(sd, a, flow, b)[0]))
+    for tag, r in runs:
+        pan, segs = r['panoptic_seg']
+        inst = r['instances']
+        assert [s['id'] for s in segs] == z['seg_ids' + tag].tolist(), tag
+        assert [s.get('instance_id', -1) for s in segs] == z['seg_inst' + tag].tolist(), tag
+        assert inst['pred_boxes'].shape[0] == z['boxes' + tag].shape[0]
+        assert (inst['pred_boxes'] - torch.from_numpy(z['boxes' + tag])).abs().max() < 5e-3
+        assert (inst['scores'] - torch.from_numpy(z['scores' + tag])).abs().max() < 1e-4
+        assert np.array_equal(inst['pred_classes'].numpy(), z['classes' + tag])
+        masks = np.unpackbits(z['masks' + tag], axis=-1)[..., :pan.shape[1]].astype(bool)
+        assert (inst['pred_masks'].numpy() != masks).mean() < 2e-5
+        assert (pan.numpy() != z['pan' + tag]).mean() < 1e-3
+        want = torch.from_numpy(z['sem_logits' + tag])
+        assert (r['sem_seg'][:, ::4, ::4] - want).abs().max() < 1e-4 * want.abs().max()
+    assert z['seg_idsf1_0'].tolist() != z['seg_idsf2_0'].tolist()       # the fused frame is a different result, not a replay

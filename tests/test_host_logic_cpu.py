@@ -171,3 +171,63 @@ def test_segments_for_vo_matches_the_reference_resize_chain():
         want = F.interpolate(segm, scale_factor=1 / 8, recompute_scale_factor=True).int()
         got = segments_for_vo(pan, size)
         assert got.shape == want.shape and torch.equal(got, want), (H, W, size)
+
+
+def test_flow_transport_index_matches_the_reference_on_cpu_tensors():
+    """pvo_b200.panoptic_fpn.flow_transport_index / flow_transport are plain tensor ops: run them on CPU tensors against the
+    golden output of the reference's flow_transport_feature (tests/golden/make_golden_fpn_e2e.py), bit for bit"""
+    import os
+    import numpy as np
+    import torch.nn.functional as F
+    from pvo_b200.panoptic_fpn import flow_transport, flow_transport_index
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fpn_e2e.npz'))
+    g = torch.Generator().manual_seed(41)
+    torch.randint(0, 256, (3, 128, 192), generator=g), torch.randint(0, 256, (3, 128, 192), generator=g)    # the two frames
+    coarse = torch.rand(1, 2, 5, 7, generator=g) * 6.0
+    flow = F.interpolate(coarse, size=(128, 192), mode='bilinear', align_corners=True)[0]
+    flow[:, 20:50, 30:70] -= 7.5
+    flow[0, 80:110, 150:] += 60.0
+    g = torch.Generator().manual_seed(42)
+    for k, (h, w) in {'p2': (32, 48), 'p4': (8, 12), 'p6': (2, 3)}.items():
+        feat = torch.randn(2, 16, h, w, generator=g)
+        win = flow_transport_index(flow, h, w)
+        assert win.shape == (h * w,) and win.dtype == torch.int64 and int(win.max()) < h * w
+        got = flow_transport(feat[0].permute(1, 2, 0).reshape(h * w, 16), win)             # pixel-major, as on the GPU
+        assert np.array_equal(got.view(h, w, 16).permute(2, 0, 1).numpy(), z['transport_' + k]), k
+    # nothing lands anywhere: flow entirely negative
+    assert int(flow_transport_index(torch.full((2, 16, 16), -3.0), 4, 4).max()) == -1
+
+
+def test_fuse_pair_glue_with_stand_in_kernels():
+    """PanopticFPN.fuse_pair's tensor plumbing (pair order, pixel-major views, channel order of the 512-channel fused input,
+    per-level flow resize) with the two CUDA stages replaced by fp32 torch stand-ins IN THIS TEST ONLY: the fused pyramid
+    must equal the oracle's.  (The real kernels are checked on the GPU in tests/test_video_fusion_gpu.py.)"""
+    import torch.nn.functional as F
+    from oracle import panoptic_fpn as ofpn
+    from pvo_b200.panoptic_fpn import PanopticFPN
+    sd = ofpn.init_params(0, fusion=True)
+    g = torch.Generator().manual_seed(9)
+    a, b = (torch.randint(0, 256, (3, 64, 96), generator=g).float() for _ in range(2))
+    flow = torch.rand(2, 64, 96, generator=g) * 5 - 1
+    m = PanopticFPN.__new__(PanopticFPN)
+    m.device, m.fusion, m.alpha = torch.device('cpu'), True, 1.0
+    m.mean = torch.tensor(ofpn.PIXEL_MEAN).view(1, 1, 1, 3)
+
+    def backbone(x):                                        # stand-in: the oracle's backbone, handed over pixel-major
+        feats = ofpn.backbone(sd, x.float().permute(0, 3, 1, 2))
+        return {k: (v.permute(0, 2, 3, 1).reshape(-1, 256), v.shape[2], v.shape[3]) for k, v in feats.items()}
+
+    def conv(name, src, N, H, W, **kw):                     # stand-in for the tensor-core conv: pixel-major in and out
+        x = src.view(N, H, W, -1).permute(0, 3, 1, 2)
+        return F.conv2d(x, sd[name + '.weight'], sd[name + '.bias'], padding=1).permute(0, 2, 3, 1).reshape(N * H * W, -1)
+    m.backbone, m._conv = backbone, conv
+    with torch.no_grad():
+        fused, sizes = m.fuse_pair(a, flow, b)
+        dbg = {}
+        ofpn.inference_fusion(sd, a, flow, b, debug=dbg)
+    assert sizes == [(64, 96)] and m.N == 1
+    for k, (t, h, w) in fused.items():
+        want = dbg['feats'][k]
+        assert (h, w) == tuple(want.shape[-2:])
+        got = t.view(1, h, w, 256).permute(0, 3, 1, 2)
+        assert (got - want).abs().max() <= 2e-3 * want.abs().max(), k      # half rounding of the normalised image only
