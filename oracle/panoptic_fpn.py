@@ -18,7 +18,11 @@ tests/test_fpn_oracle_cpu.py):
       deltas, box head, mask head, 2e-4 relative; strict load_state_dict pins the parameter inventory to the reference's.
   Detectron2's own known-answer tests: ROIAlign (VPS_Module/tests/layers/test_roi_align.py:14-45), the default anchor grid
       (tests/modeling/test_anchor_generator.py:14-42), the Box2Box delta round trip (tests/modeling/test_box2box_transform.py:17-31).
-  Not covered: the video "fusion" branch (inference_fusion; FUSION = False here) and training.
+  VIDEO-FUSION BRANCH (same generator, model built with fusion=True; `f1_*`, `f2_*`, `transport_*` in fpn_e2e.npz): the reference's
+      inference_fusion on two frames of one video -- `inference_fusion` below gives the same detections / segment list /
+      panoptic ids (<= 1 pixel differs) -- and its flow_transport_feature alone on three level shapes with negative,
+      out-of-image and colliding flow vectors: `flow_transport` below is bit-for-bit equal.
+  Not covered: training; the depth-filtered transport (flow_depth_transport, off in the shipped settings, panoptic_fpn.py:72).
 
 Follows (file:line under VPS_Module/detectron2/):
   modeling/meta_arch/rcnn.py:224-231          preprocess: (x - pixel_mean) / pixel_std, pad to a multiple of 32
