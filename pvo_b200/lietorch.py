@@ -3,8 +3,10 @@
 
 The per-pixel group actions of the hot path (Gij * X, adjT for the Jacobians, retraction) live inside the fused CUDA
 kernels (csrc/reproject.cu, csrc/ba.cu); this class only has to carry pose tensors through the reference's call
-signatures (``lietorch.SE3(video.poses[None])``, ``Gs[:, ii]``, ``.inv()``, ``*``, ``.retr``, ``.data``) and do the
-handful of O(#frames) operations the callers perform on them.
+signatures (``lietorch.SE3(video.poses[None])``, ``Gs[:, ii]``, ``.inv()``, ``*``, ``.retr``, ``.log``, ``.adjT``,
+``.data``, ``lietorch.cat``) and do the handful of O(#frames) operations the callers perform on them (pose interpolation in
+the trajectory filler, the initial pose of a new keyframe).  Checked against lietorch's own property tests
+(run_tests.py:16-52) in tests/test_host_logic_cpu.py.
 """
 import torch
 
@@ -85,6 +87,55 @@ class SE3:
 
     def retr(self, a):
         return SE3.exp(a).mul(self)
+
+    def log(self):
+        """Lie-algebra coordinates [tau, phi] (include/se3.h:124-131, so3.h:123-150): phi from the atan form of the
+        quaternion log, tau = V^-1 t with V^-1 = I - 1/2 [phi]x + c [phi]x^2, c = (1 - th/2 cot(th/2)) / th^2"""
+        t, q = self.data[..., :3], _qnorm(self.data[..., 3:])
+        v, w = q[..., :3], q[..., 3:]
+        n2 = (v * v).sum(-1, keepdim=True)
+        n = n2.sqrt()
+        small = n < 1e-6
+        ns = torch.where(small, torch.ones_like(n), n)
+        # 2 atan(n / w) / n, continued through w < 0 with atan2; series 2/w - 2 n^2 / (3 w^3) near n = 0
+        k = torch.where(small, 2.0 / w - 2.0 * n2 / (3.0 * w * w * w), 2.0 * torch.atan2(ns * torch.sign(w), w.abs()) / ns)
+        phi = k * v
+        th2 = (phi * phi).sum(-1, keepdim=True)
+        th = th2.sqrt()
+        tiny = th < 1e-6
+        ths = torch.where(tiny, torch.ones_like(th), th)
+        c = torch.where(tiny, torch.full_like(th, 1.0 / 12) + th2 / 720, (1 - 0.5 * ths * torch.cos(0.5 * ths) / torch.sin(0.5 * ths)) / (ths * ths))
+        a = torch.linalg.cross(phi, t, dim=-1)
+        tau = t - 0.5 * a + c * torch.linalg.cross(phi, a, dim=-1)
+        return torch.cat([tau, phi], -1)
+
+    def adj(self, a):
+        """Ad_X a for a = [tau, phi] (include/se3.h:58-70): [R tau + t x (R phi), R phi]"""
+        d, a = self.data, a
+        shp = torch.broadcast_shapes(d.shape[:-1], a.shape[:-1])
+        d, a = d.expand(shp + (7,)), a.expand(shp + (6,))
+        q, t = _qnorm(d[..., 3:]), d[..., :3]
+        rphi = _qrot(q, a[..., 3:])
+        return torch.cat([_qrot(q, a[..., :3]) + torch.linalg.cross(t, rphi, dim=-1), rphi], -1)
+
+    def adjT(self, a):
+        """Ad_X^T a (include/se3.h:72-86, groups.py:159-164): [R^T tau, R^T (phi - t x tau)]"""
+        d, a = self.data, a
+        shp = torch.broadcast_shapes(d.shape[:-1], a.shape[:-1])
+        d, a = d.expand(shp + (7,)), a.expand(shp + (6,))
+        q, t = _qnorm(d[..., 3:]), d[..., :3]
+        qi = torch.cat([-q[..., :3], q[..., 3:]], -1)
+        return torch.cat([_qrot(qi, a[..., :3]), _qrot(qi, a[..., 3:] - torch.linalg.cross(t, a[..., :3], dim=-1))], -1)
+
+    def matrix(self):
+        """(..., 4, 4) homogeneous transform (groups.py:122-127)"""
+        d = self.data
+        eye = torch.eye(3, dtype=d.dtype, device=d.device).expand(d.shape[:-1] + (3, 3))
+        R = _qrot(_qnorm(d[..., 3:])[..., None, :], eye)                       # rows = R e_k  ->  R^T
+        top = torch.cat([R.transpose(-1, -2), d[..., :3, None]], -1)
+        bottom = torch.zeros(d.shape[:-1] + (1, 4), dtype=d.dtype, device=d.device)
+        bottom[..., 0, 3] = 1
+        return torch.cat([top, bottom], -2)
 
     def __mul__(self, other):
         return self.mul(other) if isinstance(other, SE3) else self.act(other)

@@ -231,3 +231,31 @@ def test_fuse_pair_glue_with_stand_in_kernels():
         assert (h, w) == tuple(want.shape[-2:])
         got = t.view(1, h, w, 256).permute(0, 3, 1, 2)
         assert (got - want).abs().max() <= 2e-3 * want.abs().max(), k      # half rounding of the normalised image only
+
+
+def test_product_se3_passes_lietorch_property_tests():
+    """thirdparty/lietorch/run_tests.py:16-52 (exp-log, inverse, adjoint, action vs matrix; float64, atol 1e-8) on the SE3
+    class the package ships (pvo_b200.lietorch), plus agreement with the oracle's SE3"""
+    from pvo_b200.lietorch import SE3
+    g = torch.Generator().manual_seed(0)
+    a = .2 * torch.randn(2, 3, 4, 6, dtype=torch.float64, generator=g)
+    assert torch.allclose(SE3.exp(a).log(), a, atol=1e-8)
+    big = torch.randn(64, 6, dtype=torch.float64, generator=g) * torch.tensor([1, 1, 1, 1.7, 1.7, 1.7], dtype=torch.float64)
+    keep = big[:, 3:].norm(dim=-1) < 3.0                                    # principal branch
+    assert torch.allclose(SE3.exp(big[keep]).log(), big[keep], atol=1e-8)
+    tiny = 1e-9 * torch.randn(8, 6, dtype=torch.float64, generator=g)
+    assert torch.allclose(SE3.exp(tiny).log(), tiny, atol=1e-12)
+    X = SE3.exp(.1 * torch.randn(2, 3, 6, dtype=torch.float64, generator=g))
+    assert torch.allclose((X * X.inv()).log(), torch.zeros(2, 3, 6, dtype=torch.float64), atol=1e-8)
+    X = SE3.exp(torch.randn(2, 3, 6, dtype=torch.float64, generator=g))
+    a = torch.randn(2, 3, 6, dtype=torch.float64, generator=g)
+    Y1, Y2 = X * SE3.exp(a), SE3.exp(X.adj(a)) * X
+    assert torch.allclose((Y1 * Y2.inv()).log(), torch.zeros_like(a), atol=1e-8)
+    b = torch.randn(2, 3, 6, dtype=torch.float64, generator=g)
+    assert torch.allclose((X.adj(a) * b).sum(-1), (a * X.adjT(b)).sum(-1), atol=1e-8)
+    p = torch.randn(2, 3, 3, dtype=torch.float64, generator=g)
+    ph = torch.cat([p, torch.ones(2, 3, 1, dtype=torch.float64)], -1)
+    assert torch.allclose(X * p, (X.matrix() @ ph[..., None])[..., :3, 0], atol=1e-8)
+    assert torch.allclose((X * ph)[..., :3], X * p, atol=1e-12)
+    assert torch.allclose(X.log(), se3.se3_log(X.data), atol=1e-10) and torch.allclose(X.adjT(b), se3.se3_adjT(X.data, b), atol=1e-10)
+    assert torch.allclose(X.retr(a).data, se3.se3_retr(X.data, a), atol=1e-10)
