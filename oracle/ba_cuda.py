@@ -262,3 +262,31 @@ def depth_video_ba(poses, disps, intrinsics0, target, weight, eta, ii, jj, t0=1,
     out = ba(poses, disps, intrinsics0, target, weight, eta, ii, jj, t0, t1, itrs, lm, ep, motion_only)
     disps.clamp_(min=0.001)
     return out
+
+
+def frame_distance(poses, disps, intrinsics, ii, jj, beta):
+    """droid_backends.frame_distance (droid_kernels.cu:497-636, wrapper :1413-1436): per pair (i, j) the mean induced flow
+    magnitude of frame i's pixels, beta * (flow of the full motion) + (1 - beta) * (flow of the translation alone), over
+    the pixels that stay in front of camera j (Z > MIN_DEPTH); 1000 when fewer than 75 % do.  Vectorised form of the
+    per-pair restatement in tests/test_geom_gpu.py (_frame_distance_ref), which the GPU tests hold against the reference's
+    own kernel (oracle/_ref/droid_ba_ref.so)."""
+    ii, jj = ii.reshape(-1).long(), jj.reshape(-1).long()
+    ht, wd = disps.shape[1:]
+    fx, fy, cx, cy = intrinsics.reshape(-1)[:4].unbind(0)
+    v, u = torch.meshgrid(torch.arange(ht, dtype=torch.float32), torch.arange(wd, dtype=torch.float32), indexing='ij')
+    X0 = torch.stack([(u - cx) / fx, (v - cy) / fy, torch.ones_like(u)], -1)[None]           # (1,h,w,3)
+    tij, qij = _rel_se3(poses[ii, :3], poses[ii, 3:], poses[jj, :3], poses[jj, 3:])
+    d = disps[ii][..., None]                                                                   # (n,h,w,1)
+    acc = torch.zeros(ii.shape[0], dtype=torch.float64)
+    val = torch.zeros(ii.shape[0], dtype=torch.float64)
+    tot = 0.0
+    for full, wgt in ((True, beta), (False, 1.0 - beta)):
+        X = (_act_so3(qij[:, None, None], X0) if full else X0) + d * tij[:, None, None]
+        du = fx * X[..., 0] / X[..., 2] + cx - u
+        dv = fy * X[..., 1] / X[..., 2] + cy - v
+        m = X[..., 2] > MIN_DEPTH
+        acc += wgt * torch.where(m, torch.sqrt(du * du + dv * dv), torch.zeros_like(du)).double().sum(dim=(1, 2))
+        val += wgt * m.double().sum(dim=(1, 2))
+        tot += wgt * ht * wd
+    out = torch.where(val / (tot + 1e-8) < 0.75, torch.full_like(acc, 1000.0), acc / val.clamp(min=1e-12))
+    return out.float()

@@ -8,7 +8,7 @@ The reference's native dependencies cannot be built here, 
 shimmed in ``sys.modules`` before import:
   * ``lietorch``       -> oracle.se3 (SE3 only; PVO instantiates no other group, projective_ops.py:81)
   * ``torch_scatter``  -> oracle.geom.scatter_sum / scatter_mean (call sites droid_net.py:87, geom/ba.py:14-28)
-  * ``droid_backends`` -> oracle CPU restatements (corr_index_forward, altcorr_forward, ba)
+  * ``droid_backends`` -> oracle CPU restatements (corr_index_forward, altcorr_forward, ba, frame_distance)
 plus ``numpy.range = numpy.arange`` for the dead-code bug at droid_net.py:295 and a stub ``matplotlib``.
 """
 import os
@@ -69,6 +69,7 @@ def _make_backends():
         return list(ba_cuda.ba(poses, disps, intrinsics, targets, weights, eta, ii, jj,
                                t0, t1, itrs, lm, ep, motion_only))
     m.ba = ba
+    m.frame_distance = lambda poses, disps, intrinsics, ii, jj, beta: ba_cuda.frame_distance(poses, disps, intrinsics, ii, jj, beta)
     return m
 
 

@@ -259,3 +259,28 @@ def test_product_se3_passes_lietorch_property_tests():
     assert torch.allclose((X * ph)[..., :3], X * p, atol=1e-12)
     assert torch.allclose(X.log(), se3.se3_log(X.data), atol=1e-10) and torch.allclose(X.adjT(b), se3.se3_adjT(X.data, b), atol=1e-10)
     assert torch.allclose(X.retr(a).data, se3.se3_retr(X.data, a), atol=1e-10)
+
+
+def test_trajectory_filler_interpolation_on_cpu_tensors():
+    """PoseTrajectoryFiller.interpolate (constant velocity between the enclosing keyframes, trajectory_filler.py:42-57) is
+    tensor code: run it on a CPU video stub against the same formulas written with the oracle's SE3, frame by frame"""
+    import types
+    from pvo_b200.trajectory_filler import PoseTrajectoryFiller
+    g = torch.Generator().manual_seed(3)
+    N = 5
+    poses = se3.se3_exp(0.3 * torch.randn(N, 6, generator=g))
+    ts = torch.tensor([0.0, 2.0, 3.0, 7.0, 8.0])
+    video = types.SimpleNamespace(counter=types.SimpleNamespace(value=N), tstamp=torch.cat([ts, torch.zeros(3)]),
+                                  poses=torch.cat([poses, torch.zeros(3, 7)]))
+    f = PoseTrajectoryFiller.__new__(PoseTrajectoryFiller)
+    f.video, f.device = video, 'cpu'
+    tstamps = [0.0, 1.0, 2.0, 2.5, 6.0, 7.0, 7.9, 8.0, 9.5]
+    Gs, t0, t1 = f.interpolate(tstamps)
+    assert t0.tolist() == [0, 0, 1, 1, 2, 3, 3, 4, 4] and t1.tolist() == [1, 1, 2, 2, 3, 4, 4, 4, 4]
+    for k, t in enumerate(tstamps):
+        a, b = int(t0[k]), int(t1[k])
+        dP = se3.se3_mul(poses[b], se3.se3_inv(poses[a]))
+        v = se3.se3_log(dP) / (ts[b] - ts[a] + 1e-3)
+        want = se3.se3_mul(se3.se3_exp(v * (t - ts[a])), poses[a])
+        assert torch.allclose(Gs.data[k], want, atol=1e-5), k
+    assert torch.allclose(Gs.data[0], poses[0], atol=1e-6) and torch.allclose(Gs.data[8], poses[4], atol=1e-6)   # at / past the ends

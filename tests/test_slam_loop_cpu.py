@@ -1,0 +1,75 @@
+"""The orchestration layer (pvo_b200.motion_filter / droid_frontend / droid_backend / trajectory_filler) against the reference's
+own, on CPU.  tests/golden/slam_loop.npz was produced by the reference's MotionFilter, DroidFrontend, DroidBackend and
+PoseTrajectoryFiller driving the reference's FactorGraph / DepthVideo / CorrBlock (oracle shims for the native extensions).
+Here the SAME lower layer (reference FactorGraph etc., imported from /root/reference -- build container only, the test is
+skipped elsewhere) is driven by THIS package's orchestration classes: every decision (frames kept, keyframes removed, edges
+after every frame) must be identical and the state equal to float rounding.  The full stack on the B200 kernels is compared
+with the same golden file in tests/test_slam_loop_gpu.py."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_import
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason='/root/reference is only mounted in the build container')
+
+
+def test_orchestration_reproduces_the_reference_loop(monkeypatch):
+    from tests.golden.make_golden import droid_net_state
+    from tests.golden.make_golden_slam_loop import loop_args, video_frames
+    import tests.golden.make_golden_slam_loop as gen
+    import pvo_b200.droid_backend as pb
+    import pvo_b200.droid_frontend as pf
+    import pvo_b200.motion_filter as pm
+    import pvo_b200.trajectory_filler as pt
+    gold = np.load(os.path.join(G, 'slam_loop.npz'))
+    torch.manual_seed(0)
+    ref = ref_import.load()
+    for mod in (pf, pb, pt):
+        monkeypatch.setattr(mod, 'FactorGraph', ref.factor_graph.FactorGraph)
+    monkeypatch.setattr(pm, 'CorrBlock', ref.corr.CorrBlock)
+    monkeypatch.setattr(gen, 'FILTER_THRESH', float(gold['filter_thresh']))
+    monkeypatch.setattr(gen, 'KEYFRAME_THRESH', float(gold['keyframe_thresh']))
+    m = ref.droid_net.DroidNet()
+    m.load_state_dict(droid_net_state(), strict=True)
+    m.eval()
+
+    def update(net, inp, corr, *a, **k):
+        r = m.update(net.float(), inp.float(), corr.float(), *a, **k)
+        return ((r[0].half(),) + tuple(r[1:])) if update.half_state else r
+    update.half_state = False
+    net = types.SimpleNamespace(cnet=m.cnet, fnet=m.fnet, update=update)
+    args = loop_args()
+    frames = video_frames()
+    with torch.no_grad():
+        video = ref.depth_video.DepthVideo(args.image_size, args.buffer, args.device, args.segm_filter, args.thresh)
+        filt = pm.MotionFilter(net, video, thresh=args.filter_thresh, device='cpu', autocast=False)
+        front = pf.DroidFrontend(net, video, args)
+        kept = []
+        for n, (t, img, intr, seg) in enumerate(frames):
+            kept.append(filt.track(t, img, None, intr, seg))
+            front()
+            assert video.counter.value == int(gold['count%d' % n]), n
+            assert front.t1 == int(gold['t1_%d' % n]), n
+            es = np.array(sorted(zip(front.graph.ii.tolist(), front.graph.jj.tolist())), dtype=np.int64).reshape(-1, 2)
+            assert np.array_equal(es, gold['edges%d' % n]), n
+            ia = np.array(sorted(zip(front.graph.ii_inac.tolist(), front.graph.jj_inac.tolist())), dtype=np.int64).reshape(-1, 2)
+            assert np.array_equal(ia, gold['inactive%d' % n]), n
+        n = video.counter.value
+        assert kept == [True] * 8 + [False] * 6 and n == 7                     # 8 kept, one removed by the frontend
+        assert np.array_equal(video.tstamp[:n].numpy(), gold['tstamp'])
+        assert np.abs(video.poses[:n + 1].numpy() - gold['front_poses']).max() < 1e-5
+        assert np.abs(video.disps[:n + 1].numpy() - gold['front_disps']).max() < 1e-5
+        update.half_state = True
+        pb.DroidBackend(net, video, args)(2)
+        update.half_state = False
+        assert np.abs(video.poses[:n].numpy() - gold['back_poses']).max() < 1e-5
+        assert np.abs(video.disps[:n].numpy() - gold['back_disps']).max() < 1e-5
+        traj = pt.PoseTrajectoryFiller(net, video, device='cpu', autocast=False)(frames)
+        assert traj.data.shape == (len(frames), 7)
+        assert np.abs(traj.data.numpy() - gold['trajectory']).max() < 1e-4
+        assert video.counter.value == n                                           # the temporary frames are gone again
