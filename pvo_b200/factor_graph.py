@@ -97,11 +97,11 @@ class FactorGraph:
 
     # ------------------------------------------------------------------ edge bookkeeping (factor_graph.py:60-225)
     def __filter_repeated_edges(self, ii, jj):
-        keep = torch.zeros(ii.shape[0], dtype=torch.bool, device=ii.device)
-        eset = set([(i.item(), j.item()) for i, j in zip(self.ii, self.jj)] +
-                   [(i.item(), j.item()) for i, j in zip(self.ii_inac, self.jj_inac)])
-        for k, (i, j) in enumerate(zip(ii, jj)):
-            keep[k] = (i.item(), j.item()) not in eset
+        """drop the candidate edges that are already active or inactive (factor_graph.py:60-70).  The reference walks a
+        Python set with one `.item()` per element; here one `isin` over packed (i, j) keys -- no host synchronisation."""
+        big = self.video.poses.shape[0] + 1
+        have = torch.cat([self.ii * big + self.jj, self.ii_inac * big + self.jj_inac])
+        keep = ~torch.isin(ii * big + jj, have)
         return ii[keep], jj[keep]
 
     def clear_edges(self):

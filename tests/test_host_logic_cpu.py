@@ -284,3 +284,25 @@ def test_trajectory_filler_interpolation_on_cpu_tensors():
         want = se3.se3_mul(se3.se3_exp(v * (t - ts[a])), poses[a])
         assert torch.allclose(Gs.data[k], want, atol=1e-5), k
     assert torch.allclose(Gs.data[0], poses[0], atol=1e-6) and torch.allclose(Gs.data[8], poses[4], atol=1e-6)   # at / past the ends
+
+
+def test_repeated_edge_filter_equals_the_reference_set_walk():
+    """FactorGraph's duplicate-edge filter (one isin over packed keys) == the reference's per-element set walk
+    (factor_graph.py:60-70): candidates already active or inactive go, repeats inside the candidate list stay"""
+    import types
+    from pvo_b200.factor_graph import FactorGraph
+    g = torch.Generator().manual_seed(0)
+    fg = FactorGraph.__new__(FactorGraph)
+    fg.video = types.SimpleNamespace(poses=torch.zeros(40, 7))
+    for trial in range(20):
+        n = 12 + trial
+        fg.ii, fg.jj = torch.randint(0, n, (30,), generator=g), torch.randint(0, n, (30,), generator=g)
+        fg.ii_inac, fg.jj_inac = torch.randint(0, n, (10,), generator=g), torch.randint(0, n, (10,), generator=g)
+        ii, jj = torch.randint(0, n, (50,), generator=g), torch.randint(0, n, (50,), generator=g)
+        eset = set(zip(fg.ii.tolist(), fg.jj.tolist())) | set(zip(fg.ii_inac.tolist(), fg.jj_inac.tolist()))
+        want = [(i, j) for i, j in zip(ii.tolist(), jj.tolist()) if (i, j) not in eset]
+        a, b = fg._FactorGraph__filter_repeated_edges(ii, jj)
+        assert list(zip(a.tolist(), b.tolist())) == want
+    fg.ii = fg.jj = fg.ii_inac = fg.jj_inac = torch.zeros(0, dtype=torch.long)
+    a, b = fg._FactorGraph__filter_repeated_edges(torch.tensor([1, 1]), torch.tensor([2, 2]))
+    assert a.tolist() == [1, 1] and b.tolist() == [2, 2]
