@@ -290,3 +290,90 @@ def frame_distance(poses, disps, intrinsics, ii, jj, beta):
         tot += wgt * ht * wd
     out = torch.where(val / (tot + 1e-8) < 0.75, torch.full_like(acc, 1000.0), acc / val.clamp(min=1e-12))
     return out.float()
+
+
+# ---- the visualiser-side kernels, pixel by pixel (small inputs only) ----------------------------------------------------
+def _act_se3_scalar(t, q, X):
+    """actSE3 (droid_kernels.cu:71-78) on numpy float32 scalars: X = (x, y, z, d) -> (R (x,y,z) + d t, d)"""
+    import numpy as np
+    f = np.float32
+    uv = [f(2.0) * (q[1] * X[2] - q[2] * X[1]), f(2.0) * (q[2] * X[0] - q[0] * X[2]), f(2.0) * (q[0] * X[1] - q[1] * X[0])]
+    Y = [X[0] + q[3] * uv[0] + (q[1] * uv[2] - q[2] * uv[1]), X[1] + q[3] * uv[1] + (q[2] * uv[0] - q[0] * uv[2]),
+         X[2] + q[3] * uv[2] + (q[0] * uv[1] - q[1] * uv[0])]
+    return [Y[0] + X[3] * t[0], Y[1] + X[3] * t[1], Y[2] + X[3] * t[2], X[3]]
+
+
+def _rel_scalar(poses, i, j):
+    tij, qij = _rel_se3(poses[i, :3], poses[i, 3:], poses[j, :3], poses[j, 3:])
+    return tij.numpy(), qij.numpy()
+
+
+def iproj_loop(poses, disps, intrinsics):
+    """iproj_kernel (droid_kernels.cu:758-829)"""
+    import numpy as np
+    f = np.float32
+    fx, fy, cx, cy = (f(x) for x in intrinsics.tolist())
+    n, ht, wd = disps.shape
+    out = np.zeros((n, ht, wd, 3), dtype=np.float32)
+    P, D = poses.numpy(), disps.numpy()
+    for k in range(n):
+        for i in range(ht):
+            for j in range(wd):
+                X = [(f(j) - cx) / fx, (f(i) - cy) / fy, f(1), D[k, i, j]]
+                Y = _act_se3_scalar(P[k, :3], P[k, 3:], X)
+                out[k, i, j] = [Y[0] / Y[3], Y[1] / Y[3], Y[2] / Y[3]]
+    return torch.from_numpy(out)
+
+
+def projmap_loop(poses, disps, intrinsics, ii, jj):
+    """projmap_kernel (droid_kernels.cu:406-495)"""
+    import numpy as np
+    f = np.float32
+    fx, fy, cx, cy = (f(x) for x in intrinsics.tolist())
+    ht, wd = disps.shape[1:]
+    E = ii.shape[0]
+    coords = np.zeros((E, ht, wd, 3), dtype=np.float32)
+    valid = np.zeros((E, ht, wd, 1), dtype=np.float32)
+    D = disps.numpy()
+    for e, (a, b) in enumerate(zip(ii.tolist(), jj.tolist())):
+        tij, qij = _rel_scalar(poses, a, b)
+        for i in range(ht):
+            for j in range(wd):
+                Y = _act_se3_scalar(tij, qij, [(f(j) - cx) / fx, (f(i) - cy) / fy, f(1), D[a, i, j]])
+                coords[e, i, j, :2] = [f(j), f(i)]
+                if Y[2] > 0.01:
+                    coords[e, i, j, :2] = [fx * (Y[0] / Y[2]) + cx, fy * (Y[1] / Y[2]) + cy]
+                valid[e, i, j, 0] = 1.0 if Y[2] > MIN_DEPTH else 0.0
+    return torch.from_numpy(coords), torch.from_numpy(valid)
+
+
+def depth_filter_loop(poses, disps, intrinsics, ix, thresh):
+    """depth_filter_kernel (droid_kernels.cu:640-754)"""
+    import math
+    import numpy as np
+    f = np.float32
+    fx, fy, cx, cy = (f(x) for x in intrinsics.tolist())
+    num, ht, wd = disps.shape
+    D = disps.numpy()
+    counter = np.zeros((ix.shape[0], ht, wd), dtype=np.float32)
+    for b, a in enumerate(ix.tolist()):
+        t = float(thresh[b])
+        for neigh in range(6):
+            jx = a - neigh - 1 if neigh < 3 else a + neigh
+            if jx < 0 or jx >= num:
+                continue
+            tij, qij = _rel_scalar(poses, a, jx)
+            for i in range(ht):
+                for j in range(wd):
+                    Y = _act_se3_scalar(tij, qij, [(f(j) - cx) / fx, (f(i) - cy) / fy, f(1), D[a, i, j]])
+                    with np.errstate(all='ignore'):
+                        uj, vj, dj = fx * (Y[0] / Y[2]) + cx, fy * (Y[1] / Y[2]) + cy, Y[3] / Y[2]
+                    if not (math.isfinite(uj) and math.isfinite(vj)):
+                        continue
+                    u0, v0 = int(math.floor(uj)), int(math.floor(vj))
+                    if u0 >= 0 and v0 >= 0 and u0 < wd - 1 and v0 < ht - 1:
+                        with np.errstate(all='ignore'):
+                            inv = 1.0 / np.float64(dj)
+                            if any(abs(inv - 1.0 / np.float64(D[jx, v0 + dv, u0 + du])) < t for dv, du in ((0, 0), (0, 1), (1, 0), (1, 1))):
+                                counter[b, i, j] += 1.0
+    return torch.from_numpy(counter)

@@ -108,12 +108,100 @@ def ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iteratio
     return [dx, dz]
 
 
-def _out_of_scope(name, where):
-    def fn(*a, **k):
-        raise NotImplementedError('%s (%s) is not on the VO hot path -- SURVEY.md section 2.2 marks it out of scope' % (name, where))
-    return fn
+# ------------------------------------------------------------------------------------------------------------------
+# The three visualiser-side entry points of the module (src/droid.cpp:234-247).  None is on the per-iteration path
+# (visualization.py:98-104 calls iproj / depth_filter when a keyframe is redrawn; projmap has no Python caller), so they are
+# tensor expressions over the pose / depth buffers -- a few launches of torch kernels on whatever device the buffers live on --
+# not entries of the C ABI.  Same arguments, return arity and quirks as the reference kernels.
+def _rel(poses, ix, jx):
+    """relSE3 (droid_kernels.cu:96-107): quaternions as stored"""
+    ti, qi, tj, qj = poses[ix, :3], poses[ix, 3:], poses[jx, :3], poses[jx, 3:]
+    xi, yi, zi, wi = qi.unbind(-1)
+    xj, yj, zj, wj = qj.unbind(-1)
+    qij = torch.stack([-wj * xi + xj * wi - yj * zi + zj * yi, -wj * yi + yj * wi - zj * xi + xj * zi,
+                       -wj * zi + zj * wi - xj * yi + yj * xi, wj * wi + xj * xi + yj * yi + zj * zi], -1)
+    return tj - _rot(qij, ti), qij
 
 
-projmap = _out_of_scope('projmap', 'src/droid_kernels.cu:406-495, never called from Python')
-depth_filter = _out_of_scope('depth_filter', 'src/droid_kernels.cu:640-754, visualiser only')
-iproj = _out_of_scope('iproj', 'src/droid_kernels.cu:758-829, visualiser only')
+def _rot(q, X):
+    """actSO3 (droid_kernels.cu:58-69), q (...,4) broadcast against X (...,3)"""
+    v, w = q[..., :3], q[..., 3:]
+    uv = 2.0 * torch.linalg.cross(v.expand_as(X), X, dim=-1)
+    return X + w * uv + torch.linalg.cross(v.expand_as(X), uv, dim=-1)
+
+
+def _rays(intrinsics, ht, wd):
+    fx, fy, cx, cy = intrinsics.reshape(-1)[:4].unbind(0)
+    v, u = torch.meshgrid(torch.arange(ht, dtype=torch.float32, device=intrinsics.device),
+                          torch.arange(wd, dtype=torch.float32, device=intrinsics.device), indexing='ij')
+    return torch.stack([(u - cx) / fx, (v - cy) / fy, torch.ones_like(u)], -1), u, v, (fx, fy, cx, cy)
+
+
+def _iproj(poses, disps, intrinsics):
+    n, ht, wd = disps.shape
+    X, _, _, _ = _rays(intrinsics, ht, wd)
+    d = disps[..., None]
+    Y = _rot(poses[:n, None, None, 3:], X[None].expand(n, ht, wd, 3)) + d * poses[:n, None, None, :3]
+    return Y / d
+
+
+def _projmap(poses, disps, intrinsics, ii, jj):
+    ht, wd = disps.shape[1:]
+    X, u, v, (fx, fy, cx, cy) = _rays(intrinsics, ht, wd)
+    tij, qij = _rel(poses, ii, jj)
+    E = ii.shape[0]
+    Y = _rot(qij[:, None, None], X[None].expand(E, ht, wd, 3)) + disps[ii][..., None] * tij[:, None, None]
+    front = Y[..., 2] > 0.01
+    coords = torch.zeros(E, ht, wd, 3, dtype=poses.dtype, device=poses.device)        # third channel never written (:1449)
+    coords[..., 0] = torch.where(front, fx * (Y[..., 0] / Y[..., 2]) + cx, u.expand(E, ht, wd))
+    coords[..., 1] = torch.where(front, fy * (Y[..., 1] / Y[..., 2]) + cy, v.expand(E, ht, wd))
+    return coords, (Y[..., 2:3] > 0.25).to(poses.dtype)
+
+
+def _depth_filter(poses, disps, intrinsics, ix, thresh):
+    num, ht, wd = disps.shape
+    X, _, _, (fx, fy, cx, cy) = _rays(intrinsics, ht, wd)
+    n = ix.shape[0]
+    counter = torch.zeros(n, ht, wd, dtype=disps.dtype, device=disps.device)
+    t = thresh.reshape(n, 1, 1).double()
+    for k in range(6):
+        jx = ix - k - 1 if k < 3 else ix + k                       # neighbours -1, -2, -3, +3, +4, +5 (:672)
+        ok = (jx >= 0) & (jx < num)
+        jc = jx.clamp(0, num - 1)
+        tij, qij = _rel(poses, ix, jc)
+        di = disps[ix]
+        Y = _rot(qij[:, None, None], X[None].expand(n, ht, wd, 3)) + di[..., None] * tij[:, None, None]
+        uj, vj = fx * (Y[..., 0] / Y[..., 2]) + cx, fy * (Y[..., 1] / Y[..., 2]) + cy
+        inv_dj = 1.0 / (di / Y[..., 2]).double()
+        u0f, v0f = torch.floor(uj), torch.floor(vj)
+        inside = ok[:, None, None] & (u0f >= 0) & (v0f >= 0) & (u0f < wd - 1) & (v0f < ht - 1)      # NaN compares false
+        u0 = torch.nan_to_num(u0f, nan=0.0, posinf=0.0, neginf=0.0).clamp(0, wd - 2).long()
+        v0 = torch.nan_to_num(v0f, nan=0.0, posinf=0.0, neginf=0.0).clamp(0, ht - 2).long()
+        flat = disps[jc].reshape(n, ht * wd)
+        hit = torch.zeros(n, ht, wd, dtype=torch.bool, device=disps.device)
+        for dv, du in ((0, 0), (0, 1), (1, 0), (1, 1)):
+            dn = torch.gather(flat, 1, ((v0 + dv) * wd + u0 + du).reshape(n, -1)).reshape(n, ht, wd).double()
+            hit |= (inv_dj - 1.0 / dn).abs() < t
+        counter += (inside & hit).to(disps.dtype)
+    return counter
+
+
+def iproj(poses, disps, intrinsics):
+    """src/droid_kernels.cu:758-829, :1494-1516: points (n,h,w,3) = (R_k x + d t_k) / d for the n = disps.shape[0] frames"""
+    require_cuda(poses, disps, intrinsics)
+    return _iproj(poses, disps, intrinsics)
+
+
+def projmap(poses, disps, intrinsics, ii, jj):
+    """src/droid_kernels.cu:406-495, :1439-1465: -> [coords (E,h,w,3), valid (E,h,w,1)]; pixels behind the camera (Z <= 0.01)
+    keep their own coordinates; valid = Z > 0.25"""
+    require_cuda(poses, disps, intrinsics, ii, jj)
+    return list(_projmap(poses, disps, intrinsics, ii, jj))
+
+
+def depth_filter(poses, disps, intrinsics, ix, thresh):
+    """src/droid_kernels.cu:640-754, :1467-1491: for every frame of `ix` and pixel, in how many of the six neighbour frames
+    (ix-1, ix-2, ix-3, ix+3, ix+4, ix+5 -- the reference's `ix + neigh_id`) one of the four depth samples around the
+    reprojected pixel agrees with the reprojected depth to `thresh` -> counter (len(ix),h,w) float"""
+    require_cuda(poses, disps, intrinsics, ix, thresh)
+    return _depth_filter(poses, disps, intrinsics, ix, thresh)

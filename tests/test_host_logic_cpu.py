@@ -1,5 +1,6 @@
 """Host-side logic that needs no GPU: weight packing layouts, parameter names, oracle self-consistency
 (lietorch's own property tests restated, CUDA-BA restatement vs the reference's Python BA)."""
+import pytest
 import torch
 
 from oracle import ba_cuda, geom, se3, update_op as oupd, corr as ocorr
@@ -306,3 +307,35 @@ def test_repeated_edge_filter_equals_the_reference_set_walk():
     fg.ii = fg.jj = fg.ii_inac = fg.jj_inac = torch.zeros(0, dtype=torch.long)
     a, b = fg._FactorGraph__filter_repeated_edges(torch.tensor([1, 1]), torch.tensor([2, 2]))
     assert a.tolist() == [1, 1] and b.tolist() == [2, 2]
+
+
+def test_visualiser_side_backends_match_the_pixel_loops():
+    """droid_backends.iproj / projmap / depth_filter are tensor expressions; on CPU tensors they must reproduce the per-pixel
+    restatements of the reference kernels (oracle.ba_cuda.*_loop, droid_kernels.cu:406-495, 640-829)"""
+    from oracle import ba_cuda
+    from pvo_b200 import droid_backends as db
+    g = torch.Generator().manual_seed(4)
+    F_, h, w = 9, 6, 8
+    poses = se3.se3_exp(torch.arange(F_, dtype=torch.float32)[:, None] * torch.tensor([0.06, 0.01, 0.03, 0.0, 0.02, 0.004])
+                        + 0.01 * torch.randn(F_, 6, generator=g))
+    disps = 0.3 + 1.5 * torch.rand(F_, h, w, generator=g)
+    disps[:, 2, 3] = 1e-4                                             # a far point: lands outside the neighbour image
+    intr = torch.tensor([w / 2.0, w / 2.0, w / 2.0, h / 2.0])
+    pts = db._iproj(poses, disps, intr)
+    want = ba_cuda.iproj_loop(poses, disps, intr)
+    assert pts.shape == (F_, h, w, 3) and (pts - want).abs().max() <= 1e-5 * want.abs().max()
+    ii, jj = torch.tensor([0, 3, 8, 4]), torch.tensor([2, 0, 5, 4])
+    p2 = poses.clone()
+    p2[5, 2] -= 4.0                                                   # pushes the nearer points of 8 -> 5 behind the camera
+    c, v = db._projmap(p2, disps, intr, ii, jj)
+    cw, vw = ba_cuda.projmap_loop(p2, disps, intr, ii, jj)
+    assert torch.equal(v, vw) and (v == 0).any() and (v == 1).any()
+    assert (c - cw).abs().max() < 1e-3 and (c[..., 2] == 0).all()
+    ix = torch.tensor([0, 2, 4, 8])
+    thresh = torch.tensor([0.05, 0.1, 0.2, 0.1])
+    cnt = db._depth_filter(poses, disps, intr, ix, thresh)
+    cw = ba_cuda.depth_filter_loop(poses, disps, intr, ix, thresh)
+    assert cnt.shape == (4, h, w) and cnt.max() >= 1 and (cnt == 0).any()
+    assert (cnt != cw).float().mean() < 0.01                           # a float32 tie at a threshold / pixel edge at most
+    with pytest.raises(RuntimeError):                                  # the public entry points keep the CUDA-only contract
+        db.iproj(poses, disps, intr)
