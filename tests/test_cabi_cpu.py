@@ -58,9 +58,10 @@ def test_ops_fail_loudly_without_cuda():
 
 def test_out_of_scope_entry_points_say_so():
     from pvo_b200 import droid_backends
-    for name in ('projmap', 'depth_filter', 'iproj'):
-        with pytest.raises(NotImplementedError):
-            getattr(droid_backends, name)()
+    for name in ('projmap', 'depth_filter', 'iproj'):           # provided (tensor expressions), CUDA tensors only like the rest
+        assert callable(getattr(droid_backends, name))
+    with pytest.raises(RuntimeError):
+        droid_backends.iproj(torch.zeros(2, 7), torch.ones(2, 4, 4), torch.ones(4))
     with pytest.raises(NotImplementedError):
         droid_backends.altcorr_backward(None, None, None, None, 3)
 
