@@ -57,6 +57,7 @@ def test_ops_fail_loudly_without_cuda():
 
 
 def test_out_of_scope_entry_points_say_so():
+    import torch
     from pvo_b200 import droid_backends
     for name in ('projmap', 'depth_filter', 'iproj'):           # provided (tensor expressions), CUDA tensors only like the rest
         assert callable(getattr(droid_backends, name))
