@@ -76,16 +76,28 @@ class DynamicUpdateModule(nn.Module):
         self.agg = GraphAgg()
         self._engine = None
         self._engine_key = None
+        self._forks = None
         self.register_load_state_dict_post_hook(lambda m, k: setattr(m, '_engine', None))
 
     # -------------------------------------------------------------------------------------------
-    def engine(self, mode, device):
+    def engine(self, mode, device, owner=None):
+        """The fused-kernel engine for (mode, device): weights packed once per load_state_dict.  owner=None -> the engine
+        forward() runs on; owner=<a FactorGraph> -> that graph's private fork (same weights, own buffers and hidden state),
+        dropped with the graph."""
         key = (mode, str(device))
         if self._engine is None or self._engine_key != key:
             sd = {k: v for k, v in self.state_dict().items()}
             self._engine = pnn.UpdateEngine(sd, mode=mode, device=device)
             self._engine_key = key
-        return self._engine
+        if owner is None:
+            return self._engine
+        if self._forks is None:
+            import weakref
+            self._forks = weakref.WeakKeyDictionary()
+        e = self._forks.get(owner)
+        if e is None or e.base is not self._engine:
+            e = self._forks[owner] = self._engine.fork()
+        return e
 
     def _mode(self, net):
         if self.precision in ('fp32', 'fp16'):

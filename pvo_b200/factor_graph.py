@@ -64,7 +64,7 @@ class FactorGraph:
             raise RuntimeError('FactorGraph: update_op must be a pvo_b200.droid_net.DynamicUpdateModule')
         prec = self.precision if self.precision != 'auto' else self.update_op.precision
         mode = prec if prec in ('fp32', 'fp16') else 'fp16'       # the reference's update() is autocast (:227)
-        return self.update_op.engine(mode, self.device)
+        return self.update_op.engine(mode, self.device, owner=self)
 
     def _pull_state(self):
         """engine (pixel-major) -> reference layout; called before the edge set is edited."""

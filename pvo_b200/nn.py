@@ -155,6 +155,17 @@ class UpdateEngine:
         self.E = self.K = self.H = self.W = 0
         self.timers = None            # dict -> per-launch CUDA events (bench.py)
 
+    def fork(self):
+        """An engine that shares the packed weights of this one but owns its activation buffers and hidden state.  Every
+        FactorGraph keeps its edges' hidden state resident in its engine between iterations, and the module's own forward()
+        (MotionFilter's one-step flow estimate) runs between those iterations: they must not share buffers."""
+        import copy
+        e = copy.copy(self)
+        e.E = e.K = e.H = e.W = 0          # the first reserve() allocates fresh buffers
+        e.timers = None
+        e.base = self
+        return e
+
     # ------------------------------------------------------------------ buffers
     def reserve(self, E, K, H, W, nframes=None):
         """(Re)allocate the activation buffers for E edges, K source frames, HxW grid."""

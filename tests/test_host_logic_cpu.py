@@ -339,3 +339,33 @@ def test_visualiser_side_backends_match_the_pixel_loops():
     assert (cnt != cw).float().mean() < 0.01                           # a float32 tie at a threshold / pixel edge at most
     with pytest.raises(RuntimeError):                                  # the public entry points keep the CUDA-only contract
         db.iproj(poses, disps, intr)
+
+
+def test_every_factor_graph_gets_its_own_engine_state():
+    """The update operator's fused engine keeps a graph's hidden state resident between iterations; MotionFilter's forward()
+    call and other graphs (backend, trajectory filler) run in between.  Each owner must get a private fork: same packed
+    weights, separate buffers; a weight reload invalidates the forks; a dead owner releases its fork."""
+    import gc
+    m = DynamicUpdateModule(precision='fp32')
+    base = m.engine('fp32', 'cpu')
+
+    class Owner:
+        pass
+    a, b = Owner(), Owner()
+    ea, eb = m.engine('fp32', 'cpu', owner=a), m.engine('fp32', 'cpu', owner=b)
+    assert ea is not eb and ea is not base and m.engine('fp32', 'cpu', owner=a) is ea and m.engine('fp32', 'cpu') is base
+    assert ea.c_zr is base.c_zr and eb.glo_W is base.glo_W                  # weights shared
+    ea.reserve(3, 2, 4, 6)
+    eb.reserve(1, 1, 4, 6)
+    base.reserve(1, 1, 4, 6)
+    assert ea.X.shape[0] == 3 * 24 and eb.X.shape[0] == 24
+    assert ea.X.data_ptr() != eb.X.data_ptr() != base.X.data_ptr()
+    ea.X.fill_(1.0)
+    base.reserve(2, 1, 4, 6)                                                # forward() with another edge count: a's state survives
+    assert float(ea.X.min()) == 1.0
+    m.load_state_dict(m.state_dict())                                       # weights reloaded -> new base, new forks
+    assert m.engine('fp32', 'cpu', owner=a) is not ea
+    n = len(m._forks)
+    del a, ea
+    gc.collect()
+    assert len(m._forks) == n - 1
