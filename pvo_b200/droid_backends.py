@@ -10,6 +10,17 @@ from . import _lib
 from ._lib import check, ptr, stream, require_cuda
 
 _ba_ws = {}
+_ba_plan = [None]           # who wrote the schedule ("plan") that currently sits in the shared BA workspace
+
+
+def ba_plan_owner():
+    return _ba_plan[0]
+
+
+def set_ba_plan_owner(token):
+    """A caller that wants `reuse_plan=True` on its next call records a token after its call and compares it before the next:
+    any other BA call in between (another graph, another window) rewrites the workspace and clears the token."""
+    _ba_plan[0] = token
 
 
 def corr_index_forward(volume, coords, radius):
@@ -91,6 +102,8 @@ def ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iteratio
     max_span: optional max |ii - jj| over the WHOLE graph (all shards): the pose system then has block bandwidth <= 2 max_span
     and the solver skips its own sparsity scan."""
     require_cuda(poses, disps, intrinsics, targets, weights, eta, ii, jj)
+    if not reuse_plan:
+        _ba_plan[0] = None
     if ii.dtype != torch.long or jj.dtype != torch.long:
         raise RuntimeError('ba: ii/jj must be int64')
     E = ii.shape[0]

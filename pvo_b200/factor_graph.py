@@ -10,14 +10,19 @@ update() does, with no host synchronisation and ~30 kernel launches (CUDA-graph 
 State that the reference keeps as (1,E,C,h,w) tensors (net, inp) lives pixel-major inside the update engine between
 iterations; the reference-layout views are materialised only when the edge set changes (add/rm factors).
 """
+import itertools
+
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, droid_backends
 from . import nn as pnn
 from ._lib import check, ptr, stream
 from .droid_net import DynamicUpdateModule
 from .modules.corr import CorrBlock, AltCorrBlock
+
+
+_SERIAL = itertools.count()         # one number per prepared edge set, process wide
 
 
 def coords_grid(ht, wd, device):
@@ -221,7 +226,7 @@ class FactorGraph:
         L = _lib.lib()
         c = dict(E=E, K=K, kx=kx, t0_default=max(1, int(self.ii.min().item()) + 1),
                  t1_default=int(max(self.ii.max().item(), self.jj.max().item())) + 1,
-                 ba_key=None, ba_kx={}, graphs={},
+                 serial=next(_SERIAL), ba_kx={}, graphs={},
                  max_degree=int(torch.bincount(self.ii).max().item()),
                  max_span=int((self.ii - self.jj).abs().max().item()))
         c['coords1'] = torch.empty(1, E, self.ht, self.wd, 2, device=self.device)
@@ -309,13 +314,16 @@ class FactorGraph:
                 kx_ba = torch.unique(torch.cat([torch.arange(t0, t1, device=self.device), ii]))
                 c['ba_kx'][(t0, t1)] = kx_ba
             damping = .2 * self.damping.index_select(0, kx_ba) + EP
-            reuse = c['ba_key'] == (t0, t1, ii.shape[0])
-            c['ba_key'] = (t0, t1, ii.shape[0])
+            # the BA schedule in the (shared) workspace can be reused iff the last BA call anywhere was this graph's, on this edge
+            # set and window
+            token = (id(self), c['serial'], t0, t1, ii.shape[0])
+            reuse = droid_backends.ba_plan_owner() == token
         # (5) dense bundle adjustment, in place on video.poses / video.disps
         with T('ba_total'):
             v.ba(target_cam[0], weight[0], damping, ii, jj, t0, t1, itrs=itrs, lm=1e-4, ep=0.1, motion_only=motion_only,
                  interleaved=True, reuse_plan=reuse, max_degree=0 if use_inactive else c['max_degree'],
                  max_span=None if use_inactive else c['max_span'])
+        droid_backends.set_ba_plan_owner(None if use_inactive else token)
         self.age += 1
         self.launch_count = _lib.LAUNCHES[0] - n0
 
