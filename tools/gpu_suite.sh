@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs on the GPU box (via gpurun): parity tests in isolated processes (a trapping kernel poisons its CUDA context),
 # smoke, bench, and optional ncu captures.  Everything is logged under gpurun_out/.
-#   tools/gpu_suite.sh [tests] [bench] [launches] [ncufull] [multi]
+#   tools/gpu_suite.sh [tests] [bench] [launches] [ncufull] [fpn] [fusion] [loop] [dist] [multi]
 set +e
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -25,6 +25,9 @@ tests)
   run t_net 600 $PT tests/test_net_gpu.py
   run t_fpn 900 $PT tests/test_fpn_gpu.py
   run t_edge 600 $PT tests/test_edge_cases_gpu.py
+  run t_fusion 600 $PT tests/test_video_fusion_gpu.py
+  run t_visual 300 $PT tests/test_visual_ops_gpu.py
+  run t_loop 900 $PT -rxX tests/test_slam_loop_gpu.py
   run smoke 300 python __graft_entry__.py smoke ;;
 bench)
   run bench_fp16 900 python bench.py --steps 50 --warmup 5
@@ -36,6 +39,12 @@ ncufull)
   run ncu_full 1500 ncu --set full --clock-control none --import-source on -k regex:"corr_lookup_fused|conv_tc|heads_stencil|ba_pass|ba_solve|corr_volume_tc" -s 40 -c 30 -o $OUT/prof_r01 -f python bench.py --steps 2 --warmup 3 --no-graph --profile-only ;;
 fpn)
   run t_fpn 900 $PT tests/test_fpn_gpu.py ;;
+fusion)
+  run t_fusion 600 $PT tests/test_video_fusion_gpu.py
+  run bench_fusion 300 python tools/bench_fusion.py ;;
+loop)      # first hardware run of the whole per-frame loop: decisions vs the reference golden, then the config-3 bench
+  run t_loop 900 $PT -rxX --runxfail tests/test_slam_loop_gpu.py tests/test_visual_ops_gpu.py
+  run bench_loop 900 python tools/bench_loop.py ;;
 dist)
   run t_dist 600 $PT tests/test_dist_gpu.py ;;
 multi)
