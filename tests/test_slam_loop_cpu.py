@@ -4,7 +4,7 @@ PoseTrajectoryFiller driving the reference's FactorGraph / DepthVideo / CorrBloc
 Here the SAME lower layer (reference FactorGraph etc., imported from /root/reference -- build container only, the test is
 skipped elsewhere) is driven by THIS package's orchestration classes: every decision (frames kept, keyframes removed, edges
 after every frame) must be identical and the state equal to float rounding.  The full stack on the B200 kernels is compared
-with the same golden file in tests/test_slam_loop_gpu.py."""
+with the same golden file in tests/test_zz_slam_loop_gpu.py."""
 import os
 import types
 

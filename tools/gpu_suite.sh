@@ -27,7 +27,7 @@ tests)
   run t_edge 600 $PT tests/test_edge_cases_gpu.py
   run t_fusion 600 $PT tests/test_video_fusion_gpu.py
   run t_visual 300 $PT tests/test_visual_ops_gpu.py
-  run t_loop 900 $PT -rxX tests/test_slam_loop_gpu.py
+  run t_loop 900 $PT -rxX tests/test_zz_slam_loop_gpu.py
   run smoke 300 python __graft_entry__.py smoke ;;
 bench)
   run bench_fp16 900 python bench.py --steps 50 --warmup 5
@@ -43,7 +43,7 @@ fusion)
   run t_fusion 600 $PT tests/test_video_fusion_gpu.py
   run bench_fusion 300 python tools/bench_fusion.py ;;
 loop)      # first hardware run of the whole per-frame loop: decisions vs the reference golden, then the config-3 bench
-  run t_loop 900 $PT -rxX --runxfail tests/test_slam_loop_gpu.py tests/test_visual_ops_gpu.py
+  run t_loop 900 $PT -rxX --runxfail tests/test_zz_slam_loop_gpu.py tests/test_visual_ops_gpu.py
   run bench_loop 900 python tools/bench_loop.py ;;
 dist)
   run t_dist 600 $PT tests/test_dist_gpu.py ;;
