@@ -111,6 +111,9 @@ def main():
             record('t1_%d' % n, np.array(front.t1))
             record('edges%d' % n, np.array(es, dtype=np.int64).reshape(-1, 2))
             record('inactive%d' % n, np.array(sorted(zip(front.graph.ii_inac.tolist(), front.graph.jj_inac.tolist())), dtype=np.int64).reshape(-1, 2))
+            c = video.counter.value                      # state after this frame (triage aid for the GPU comparison)
+            record('poses%d' % n, video.poses[:c + 1].numpy().copy())
+            record('disps%d' % n, video.disps[:c + 1].numpy().copy())
         return args, video, front, mags, dists
 
     # The weights are random, so the predicted flow magnitude barely depends on the motion: place the two thresholds inside

@@ -59,6 +59,9 @@ def test_orchestration_reproduces_the_reference_loop(monkeypatch):
             assert np.array_equal(es, gold['edges%d' % n]), n
             ia = np.array(sorted(zip(front.graph.ii_inac.tolist(), front.graph.jj_inac.tolist())), dtype=np.int64).reshape(-1, 2)
             assert np.array_equal(ia, gold['inactive%d' % n]), n
+            c = video.counter.value
+            assert np.abs(video.poses[:c + 1].numpy() - gold['poses%d' % n]).max() < 1e-5, n
+            assert np.abs(video.disps[:c + 1].numpy() - gold['disps%d' % n]).max() < 1e-5, n
         n = video.counter.value
         assert kept == [True] * 8 + [False] * 6 and n == 7                     # 8 kept, one removed by the frontend
         assert np.array_equal(video.tstamp[:n].numpy(), gold['tstamp'])

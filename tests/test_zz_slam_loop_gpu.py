@@ -71,6 +71,9 @@ def test_frontend_decisions_and_state():
         g = droid.frontend.graph
         es = np.array(sorted(zip(g.ii.tolist(), g.jj.tolist())), dtype=np.int64).reshape(-1, 2)
         assert np.array_equal(es, gold['edges%d' % n]), n
+        c = droid.video.counter.value                # per-frame state: says at which frame a drift starts
+        perr = np.abs(droid.video.poses[:c + 1].cpu().numpy() - gold['poses%d' % n]).max()
+        assert perr < 2e-3, (n, perr)
     n = droid.video.counter.value
     assert np.array_equal(droid.video.tstamp[:n].cpu().numpy(), gold['tstamp'])
     assert np.abs(droid.video.poses[:n + 1].cpu().numpy() - gold['front_poses']).max() < 2e-3
