@@ -136,7 +136,9 @@ class FactorGraph:
         self.ii = torch.cat([self.ii, ii], 0)
         self.jj = torch.cat([self.jj, jj], 0)
         self.age = torch.cat([self.age, torch.zeros_like(ii)], 0)
-        self._net = net if self._net is None else torch.cat([self._net.to(net.dtype), net], 1)
+        # torch.cat promotes like the reference's cat of a float state with half features (factor_graph.py:147): the
+        # hidden state of the existing edges is never narrowed
+        self._net = net if self._net is None else torch.cat([self._net, net.to(torch.promote_types(self._net.dtype, net.dtype))], 1)
         self.target_cam = torch.cat([self.target_cam, target], 1)
         self.weight = torch.cat([self.weight, torch.zeros_like(target)], 1)
         self.raw_mask = torch.cat([self.raw_mask, torch.zeros_like(target)[..., 0:self.mask_num]], 1)
