@@ -43,5 +43,9 @@ Pinning status:
                           against the reference's own module classes loaded file by file with the
                           missing third-party names stubbed -> fpn_net.npz (strict state-dict load); the WHOLE model
                           -- the reference's own PanopticFPN.inference, every class from the tree -- run on
-                          two images -> fpn_e2e.npz: same detections, segments and panoptic ids.
+                          two images -> fpn_e2e.npz: same detections, segments and panoptic ids; likewise the
+                          video-fusion branch (inference_fusion, flow transport bit for bit).
+  * the per-frame loop .. no restatement needed: the reference's MotionFilter / DroidFrontend / DroidBackend /
+                          PoseTrajectoryFiller run unmodified on these shims -> slam_loop.npz; the package's own
+                          orchestration classes reproduce it decision for decision (tests/test_slam_loop_cpu.py).
 """
