@@ -12,79 +12,90 @@ from . import _lib, droid_backends
 from ._lib import check, ptr, stream
 
 
+# name -> (shape after the buffer dimension in units of (ht, wd, ht//8, wd//8), dtype, fill); depth_video.py:23-58
+def _buffer_table(ht, wd):
+    h8, w8 = ht // 8, wd // 8
+    return {'tstamp': ((), torch.float, 0), 'dirty': ((), torch.bool, 0), 'red': ((), torch.bool, 0), 'poses': ((7,), torch.float, 0),
+            'disps': ((h8, w8), torch.float, 1), 'intrinsics': ((4,), torch.float, 0), 'fmaps': ((128, h8, w8), torch.half, 0),
+            'nets': ((128, h8, w8), torch.half, 0), 'inps': ((128, h8, w8), torch.half, 0), 'segms': ((1, h8, w8), torch.int, 0),
+            'full_flow': ((h8, w8, 2), torch.float, 1)}
+
+
+# what a video item carries, by position (depth_video.py:66-93): (tstamp, image, pose, disp, intrinsics, fmap, net, inp, segm)
+_OPTIONAL = ((2, 'poses'), (3, 'disps'), (4, 'intrinsics'))        # None = leave as is
+_TRAILING = ((5, 'fmaps'), (6, 'nets'), (7, 'inps'))              # present only in longer items
+
+
 class DepthVideo:
     def __init__(self, image_size=(480, 640), buffer=1024, device='cuda:0', segm_filter=False, thresh=0.8,
                  store_images=True):
-        self.counter = Value('i', 0)
-        self.ready = Value('i', 0)
-        self.ht = ht = image_size[0]
-        self.wd = wd = image_size[1]
+        self.counter, self.ready = Value('i', 0), Value('i', 0)      # keyframes held / frontend initialised
+        self.ht, self.wd = int(image_size[0]), int(image_size[1])
         self.device = device
-        z = lambda *s, dtype=torch.float: torch.zeros(*s, device=device, dtype=dtype)
-        self.tstamp = z(buffer)
-        self.images = z(buffer, 3, ht, wd, dtype=torch.uint8) if store_images else None
-        self.dirty = z(buffer, dtype=torch.bool)
-        self.red = z(buffer, dtype=torch.bool)
-        self.poses = z(buffer, 7)
-        self.disps = torch.ones(buffer, ht // 8, wd // 8, device=device, dtype=torch.float)
-        self.disps_up = z(buffer, ht, wd) if store_images else None
-        self.intrinsics = z(buffer, 4)
-        self.fmaps = z(buffer, 128, ht // 8, wd // 8, dtype=torch.half)
-        self.nets = z(buffer, 128, ht // 8, wd // 8, dtype=torch.half)
-        self.inps = z(buffer, 128, ht // 8, wd // 8, dtype=torch.half)
-        self.poses[:] = torch.as_tensor([0, 0, 0, 0, 0, 0, 1], dtype=torch.float, device=device)
-        self.segms = z(buffer, 1, ht // 8, wd // 8, dtype=torch.int)
-        self.full_flow = torch.ones(buffer, ht // 8, wd // 8, 2, device=device, dtype=torch.float)
-        self.segm_filter = segm_filter
-        self.thresh = thresh
+        for name, (shape, dtype, fill) in _buffer_table(self.ht, self.wd).items():
+            setattr(self, name, torch.full((buffer,) + shape, fill, dtype=dtype, device=device))
+        self.poses[:, 6] = 1                                         # identity: t = 0, q = (0,0,0,1)
+        # full-resolution buffers: only the visualiser / upsampler read them; bench and tests switch them off
+        self.images = torch.zeros(buffer, 3, self.ht, self.wd, dtype=torch.uint8, device=device) if store_images else None
+        self.disps_up = torch.zeros(buffer, self.ht, self.wd, device=device) if store_images else None
+        self.segm_filter, self.thresh = segm_filter, thresh
 
     def get_lock(self):
         return self.counter.get_lock()
 
-    def __item_setter(self, index, item):
-        if isinstance(index, int) and index >= self.counter.value:
-            self.counter.value = index + 1
-        elif isinstance(index, torch.Tensor) and index.max().item() > self.counter.value:
-            self.counter.value = index.max().item() + 1
+    def _store(self, index, item):
+        n = self.counter.value
+        if isinstance(index, int):
+            if index >= n:
+                self.counter.value = index + 1
+        elif isinstance(index, torch.Tensor):
+            top = int(index.max().item())
+            if top > n:
+                self.counter.value = top + 1
         self.tstamp[index] = item[0]
         if self.images is not None:
             self.images[index] = item[1]
-        for k, buf in ((2, self.poses), (3, self.disps), (4, self.intrinsics)):
-            if item[k] is not None:
-                buf[index] = item[k]
-        for k, buf in ((5, self.fmaps), (6, self.nets), (7, self.inps)):
-            if len(item) > k:
-                buf[index] = item[k]
+        for pos, name in _OPTIONAL:
+            if item[pos] is not None:
+                getattr(self, name)[index] = item[pos]
+        for pos, name in _TRAILING:
+            if len(item) > pos:
+                getattr(self, name)[index] = item[pos]
         if self.segm_filter and len(item) > 8:
             self.segms[index] = item[8]
 
     def __setitem__(self, index, item):
         with self.get_lock():
-            self.__item_setter(index, item)
-
-    def __getitem__(self, index):
-        with self.get_lock():
-            if isinstance(index, int) and index < 0:
-                index = self.counter.value + index
-            return (self.poses[index], self.disps[index], self.intrinsics[index], self.fmaps[index],
-                    self.nets[index], self.inps[index])
+            self._store(index, item)
 
     def append(self, *item):
         with self.get_lock():
-            self.__item_setter(self.counter.value, item)
+            self._store(self.counter.value, item)
+
+    def __getitem__(self, index):
+        """(pose, disp, intrinsics, fmap, net, inp) of a keyframe; negative ints count from the newest"""
+        with self.get_lock():
+            if isinstance(index, int) and index < 0:
+                index += self.counter.value
+            return tuple(getattr(self, name)[index] for name in ('poses', 'disps', 'intrinsics', 'fmaps', 'nets', 'inps'))
 
     @staticmethod
     def format_indicies(ii, jj, device):
-        ii = torch.as_tensor(ii).to(device=device, dtype=torch.long).reshape(-1)
-        jj = torch.as_tensor(jj).to(device=device, dtype=torch.long).reshape(-1)
-        return ii, jj
+        as_long = lambda x: torch.as_tensor(x).to(device=device, dtype=torch.long).reshape(-1)
+        return as_long(ii), as_long(jj)
+
+    def upsample(self, ix, mask):
+        """convex 8x upsampling of the depth of keyframes ix into disps_up (depth_video.py:139-143)"""
+        from .droid_net import cvx_upsample
+        self.disps_up[ix] = cvx_upsample(self.disps[ix].unsqueeze(-1), mask).squeeze()
 
     def normalize(self):
+        """rescale the map so that the mean inverse depth is 1 (depth_video.py:145-152)"""
         with self.get_lock():
             n = self.counter.value
-            s = self.disps[:n].mean()
-            self.disps[:n] /= s
-            self.poses[:n, :3] *= s
+            scale = self.disps[:n].mean()
+            self.disps[:n] /= scale
+            self.poses[:n, :3] *= scale
             self.dirty[:n] = True
 
     # ---------------------------------------------------------------- geometry on the CUDA kernels

@@ -17,50 +17,63 @@ from .motion_filter import MotionFilter
 from .trajectory_filler import PoseTrajectoryFiller
 
 
+def _plain_state_dict(weights, device):
+    """checkpoint path or state dict -> keys without the DataParallel 'module.' prefix (droid.py:52-59)"""
+    sd = torch.load(weights, map_location=device) if isinstance(weights, str) else weights
+    return OrderedDict((k.replace('module.', ''), v) for k, v in sd.items())
+
+
 class Droid:
     def __init__(self, args):
         self.args = args
-        self.load_weights(args.weights, getattr(args, 'use_aff_bri', False))
         self.disable_vis = getattr(args, 'disable_vis', True)
         if not self.disable_vis:
             raise NotImplementedError('the Open3D visualiser process is outside this package: run with disable_vis=True')
-        self.video = DepthVideo(args.image_size, args.buffer, args.device, args.segm_filter, args.thresh)
+        self.load_weights(args.weights, getattr(args, 'use_aff_bri', False))
         autocast = getattr(args, 'autocast', True)       # False: float32 everywhere (parity runs against the CPU golden)
         if not autocast:
             self.net.update.precision = 'fp32'
-        self.filterx = MotionFilter(self.net, self.video, thresh=args.filter_thresh, device=args.device, autocast=autocast)
-        self.frontend = DroidFrontend(self.net, self.video, args)
-        self.backend = DroidBackend(self.net, self.video, args)
-        self.traj_filler = PoseTrajectoryFiller(self.net, self.video, args.device, autocast=autocast)
+        dev = args.device
+        self.video = DepthVideo(args.image_size, args.buffer, dev, args.segm_filter, args.thresh)      # the shared state
+        self.filterx = MotionFilter(self.net, self.video, thresh=args.filter_thresh, device=dev, autocast=autocast)
+        self.frontend = DroidFrontend(self.net, self.video, args)                                     # sliding window
+        self.backend = DroidBackend(self.net, self.video, args)                                       # global passes
+        self.traj_filler = PoseTrajectoryFiller(self.net, self.video, dev, autocast=autocast)          # non-keyframe poses
 
     def load_weights(self, weights, use_aff_bri=False):
-        """weights: checkpoint path or state dict; a DataParallel 'module.' prefix is stripped (droid.py:52-59)"""
         self.net = DroidNet(use_aff_bri)
-        sd = torch.load(weights, map_location=self.args.device) if isinstance(weights, str) else weights
-        self.net.load_state_dict(OrderedDict((k.replace('module.', ''), v) for k, v in sd.items()))
+        self.net.load_state_dict(_plain_state_dict(weights, self.args.device))
         self.net.to(self.args.device).eval()
 
     @torch.no_grad()
     def track(self, tstamp, image, depth=None, intrinsics=None, segments=None):
+        """one incoming frame: keyframe decision + features, then one step of the frontend (droid.py:61-72; the reference
+        leaves the per-frame backend call commented out)"""
         self.filterx.track(tstamp, image, depth, intrinsics, segments)
         self.frontend()
 
     def terminate(self, stream=None, need_inv=True):
-        """global BA (7 then 12 steps), then the poses of ALL frames of `stream` as (n,7) [t, q]; need_inv: camera-to-world"""
+        """global BA (7 then 12 steps), then the poses of ALL frames of `stream` as (n,7) [t, q] (droid.py:74-95);
+        need_inv: return camera-to-world"""
         del self.frontend
-        torch.cuda.empty_cache()
-        self.backend(7)
-        torch.cuda.empty_cache()
-        self.backend(12)
+        for steps in (7, 12):
+            torch.cuda.empty_cache()
+            self.backend(steps)
         traj = self.traj_filler(stream)
-        return (traj.inv() if need_inv else traj).data.cpu().numpy()
+        if need_inv:
+            traj = traj.inv()
+        return traj.data.cpu().numpy()
+
+    # ---- read-outs (droid.py:97-107)
+    def _keyframes(self):
+        return self.video.counter.value
 
     def get_traj(self):
-        return lietorch.cat([SE3(self.video.poses[:self.video.counter.value])], 0).data.cpu().numpy()
+        return lietorch.cat([SE3(self.video.poses[:self._keyframes()])], 0).data.cpu().numpy()
 
     def get_depth(self):
-        n = self.video.counter.value
-        return upsample_inter(self.video.disps[:n].unsqueeze(0).unsqueeze(4)).squeeze(4).squeeze(0)
+        d = self.video.disps[:self._keyframes()]
+        return upsample_inter(d[None, ..., None])[0, ..., 0]
 
     def get_flow(self):
-        return upsample_inter(self.video.full_flow[:self.video.counter.value].unsqueeze(0) * 8)
+        return upsample_inter(self.video.full_flow[:self._keyframes()][None] * 8)

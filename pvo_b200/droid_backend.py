@@ -1,25 +1,34 @@
 """DroidBackend: global bundle adjustment over all keyframes (VO_Module/droid_slam/droid_backend.py:9-41).
 
-A fresh FactorGraph over the whole video with the memory-lean correlation (`corr_impl='alt'`: no stored volumes), proximity
-edges between all keyframes, `steps` iterations of FactorGraph.update_lowmem, edges dropped again."""
+One call = one global pass: the map is rescaled to unit mean inverse depth, a throw-away FactorGraph over the WHOLE video is
+built with the memory-lean correlation (`corr_impl='alt'`: no stored volumes) and proximity edges between all keyframes,
+`steps` iterations of FactorGraph.update_lowmem run on it, and the edges are dropped again."""
 import torch
 
 from .factor_graph import FactorGraph
+
+EDGE_BUDGET = 100000                      # droid_backend.py:31: effectively unlimited
+_OPTIONS = ('beta', 'backend_thresh', 'backend_radius', 'backend_nms')
 
 
 class DroidBackend:
     def __init__(self, net, video, args):
         self.video, self.update_op, self.device = video, net.update, args.device
-        self.t0 = self.t1 = 0
-        self.beta = args.beta
-        self.backend_thresh, self.backend_radius, self.backend_nms = args.backend_thresh, args.backend_radius, args.backend_nms
+        self.t0 = self.t1 = 0             # kept for interface parity; the pass always covers [0, counter)
+        for name in _OPTIONS:
+            setattr(self, name, getattr(args, name))
+
+    def global_graph(self):
+        """all keyframes, proximity edges chosen with the backend's radius / NMS / distance threshold"""
+        g = FactorGraph(self.video, self.update_op, self.device, corr_impl='alt', max_factors=EDGE_BUDGET)
+        g.add_proximity_factors(rad=self.backend_radius, nms=self.backend_nms, thresh=self.backend_thresh, beta=self.beta)
+        return g
 
     @torch.no_grad()
     def __call__(self, steps=12):
-        t = self.video.counter.value
+        n = self.video.counter.value
         self.video.normalize()
-        graph = FactorGraph(self.video, self.update_op, self.device, corr_impl='alt', max_factors=100000)
-        graph.add_proximity_factors(rad=self.backend_radius, nms=self.backend_nms, thresh=self.backend_thresh, beta=self.beta)
-        graph.update_lowmem(steps=steps)
-        graph.clear_edges()
-        self.video.dirty[:t] = True
+        g = self.global_graph()
+        g.update_lowmem(steps=steps)
+        g.clear_edges()
+        self.video.dirty[:n] = True

@@ -13,41 +13,56 @@ import torch
 from .factor_graph import FactorGraph
 
 
+_OPTIONS = ('warmup', 'beta', 'frontend_nms', 'keyframe_thresh', 'frontend_window', 'frontend_thresh', 'frontend_radius')
+
+
 class DroidFrontend:
-    max_age = 25            # droid_frontend.py:24-26
-    iters1 = 4
-    iters2 = 2
+    max_age = 25            # iterations an edge stays active (droid_frontend.py:24)
+    iters1 = 4              # iterations after a new keyframe was linked in (:25)
+    iters2 = 2              # ... and more when it is kept (:26)
+    max_factors = 48        # active-edge budget of the window graph (:13-14)
 
     def __init__(self, net, video, args):
-        self.video = video
-        self.update_op = net.update
-        self.graph = FactorGraph(video, net.update, args.device, max_factors=48)
-        self.t0 = self.t1 = 0           # window of keyframes under optimisation
+        self.video, self.update_op = video, net.update
+        self.graph = FactorGraph(video, net.update, args.device, max_factors=self.max_factors)
+        self.t0 = self.t1 = 0           # window of keyframes under optimisation: [t0, t1)
         self.is_initialized = False
         self.count = 0
-        for k in ('warmup', 'beta', 'frontend_nms', 'keyframe_thresh', 'frontend_window', 'frontend_thresh', 'frontend_radius'):
-            setattr(self, k, getattr(args, k))
+        for name in _OPTIONS:
+            setattr(self, name, getattr(args, name))
 
+    # ---------------------------------------------------------------------------------------------
     def _iterate(self, n, t0=None):
         for _ in range(n):
             self.graph.update(t0, None, use_inactive=True)
 
     def _seed_next(self, disp):
-        """pose of the newest keyframe and a constant depth as the initial guess of the next one (:64-65, :89-90)"""
-        self.video.poses[self.t1] = self.video.poses[self.t1 - 1]
-        self.video.disps[self.t1] = disp
+        """the newest keyframe's pose and a constant depth are the initial guess of the keyframe that comes next (:64-65, :89-90)"""
+        k = self.t1
+        self.video.poses[k] = self.video.poses[k - 1]
+        self.video.disps[k] = disp
 
+    def _redundant(self, k):
+        """is keyframe k too close to keyframe k-1 (mean induced flow, both directions) to be worth keeping? (:53-56)"""
+        d = self.video.distance([k - 1], [k], beta=self.beta, bidirectional=True)
+        return d.item() < self.keyframe_thresh
+
+    def _link_newest(self):
+        """proximity edges between the newest keyframes and the window (:45-46)"""
+        lo = max(self.t1 - self.frontend_window, 0)
+        self.graph.add_proximity_factors(self.t1 - 5, lo, rad=self.frontend_radius, nms=self.frontend_nms, thresh=self.frontend_thresh,
+                                         beta=self.beta, remove=True)
+
+    # ---------------------------------------------------------------------------------------------
     def _update(self):
+        g, v = self.graph, self.video
         self.count += 1
         self.t1 += 1
-        g, v = self.graph, self.video
         if g.corr is not None:
             g.rm_factors(g.age > self.max_age, store=True)
-        g.add_proximity_factors(self.t1 - 5, max(self.t1 - self.frontend_window, 0), rad=self.frontend_radius,
-                                nms=self.frontend_nms, thresh=self.frontend_thresh, beta=self.beta, remove=True)
+        self._link_newest()
         self._iterate(self.iters1)
-        d = v.distance([self.t1 - 3], [self.t1 - 2], beta=self.beta, bidirectional=True)
-        if d.item() < self.keyframe_thresh:              # the second-newest keyframe adds nothing: drop it
+        if self._redundant(self.t1 - 2):                  # the second-newest keyframe adds nothing: drop it, shift the newest down
             g.rm_keyframe(self.t1 - 2)
             with v.get_lock():
                 v.counter.value -= 1
@@ -65,17 +80,18 @@ class DroidFrontend:
         g.add_proximity_factors(0, 0, rad=2, nms=2, thresh=self.frontend_thresh, remove=False)
         self._iterate(12, t0=1)
         self._seed_next(v.disps[self.t1 - 4:self.t1].mean())
+        last = self.t1 - 1
+        self.last_pose, self.last_disp, self.last_time = v.poses[last].clone(), v.disps[last].clone(), v.tstamp[last].clone()
         self.is_initialized = True
-        self.last_pose = v.poses[self.t1 - 1].clone()
-        self.last_disp = v.disps[self.t1 - 1].clone()
-        self.last_time = v.tstamp[self.t1 - 1].clone()
         with v.get_lock():
             v.ready.value = 1
             v.dirty[:self.t1] = True
 
     @torch.no_grad()
     def __call__(self):
-        if not self.is_initialized and self.video.counter.value == self.warmup:
+        held = self.video.counter.value
+        if self.is_initialized:
+            if self.t1 < held:
+                self._update()
+        elif held == self.warmup:
             self._initialize()
-        elif self.is_initialized and self.t1 < self.video.counter.value:
-            self._update()

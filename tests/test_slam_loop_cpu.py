@@ -76,3 +76,59 @@ def test_orchestration_reproduces_the_reference_loop(monkeypatch):
         assert traj.data.shape == (len(frames), 7)
         assert np.abs(traj.data.numpy() - gold['trajectory']).max() < 1e-4
         assert video.counter.value == n                                           # the temporary frames are gone again
+
+
+def test_depth_video_bookkeeping_equals_the_reference_class():
+    """DepthVideo's host side (buffers, append / item assignment with ints, tensors and slices, negative indexing, normalize,
+    counter rules) against the reference's DepthVideo on CPU tensors, operation by operation"""
+    from pvo_b200.depth_video import DepthVideo
+    ref = ref_import.load()
+    g = torch.Generator().manual_seed(1)
+    H, W, B = 64, 96, 12
+    mine = DepthVideo(image_size=[H, W], buffer=B, device='cpu', segm_filter=True, thresh=0.7)
+    theirs = ref.depth_video.DepthVideo(image_size=[H, W], buffer=B, device='cpu', segm_filter=True, thresh=0.7)
+    names = ('tstamp', 'images', 'dirty', 'red', 'poses', 'disps', 'disps_up', 'intrinsics', 'fmaps', 'nets', 'inps', 'segms', 'full_flow')
+
+    def same():
+        assert mine.counter.value == theirs.counter.value
+        for n in names:
+            a, b = getattr(mine, n), getattr(theirs, n)
+            assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b), n
+    same()
+
+    def item(k, full=True, batch=None):
+        lead = () if batch is None else (batch,)
+        r = lambda *s, **kw: torch.randn(*(lead + s), generator=g, **kw)
+        it = [float(k) if batch is None else torch.arange(batch).float() + k, torch.randint(0, 255, lead + (3, H, W), generator=g, dtype=torch.uint8),
+              r(7), r(H // 8, W // 8).abs() + 0.1, r(4).abs() + 1]
+        if full:
+            it += [r(128, H // 8, W // 8).half(), r(128, H // 8, W // 8).half(), r(128, H // 8, W // 8).half(),
+                   torch.randint(0, 9, lead + (1, H // 8, W // 8), generator=g, dtype=torch.int32)]
+        return tuple(it)
+    for k in range(4):
+        it = item(k)
+        mine.append(*it), theirs.append(*it)
+        same()
+    it = item(9)
+    it = it[:2] + (None, None) + it[4:]                    # pose / depth left alone, as the motion filter appends
+    mine.append(*it), theirs.append(*it)
+    same()
+    it = item(20, full=False)
+    mine[7] = it
+    theirs[7] = it                                         # int index beyond the counter moves it
+    same()
+    idx = torch.tensor([2, 9])
+    it = item(30, batch=2)
+    mine[idx] = it
+    theirs[idx] = it                                       # tensor index
+    same()
+    it = item(40, full=False, batch=3)
+    mine[3:6] = it
+    theirs[3:6] = it                                       # slice: counter untouched (trajectory filler)
+    same()
+    for i in (0, -1, 4):
+        for a, b in zip(mine[i], theirs[i]):
+            assert torch.equal(a, b)
+    mine.normalize(), theirs.normalize()
+    same()
+    assert DepthVideo.format_indicies([1, 2], torch.tensor([[3], [4]]), 'cpu')[1].tolist() == [3, 4]
