@@ -18,7 +18,8 @@ driven through the public API with the mutable graph state arriving from / retur
 capture (profiles/ncu_traffic.json); cpu_baseline = the CPU oracle (a port of the reference's Python path) on the host
 cores; reference_gpu_path = the reference's own GPU code for the stages that can be had on this box, timed on the same GPU
 (its correlation kernel and its BA kernels compiled into oracle/_ref/, its update operator's module structure on cuDNN).
---workload vkitti / fpn run BASELINE configs[2] shape / configs[3]; --impl reference = the reference's CPU path.
+--workload vkitti / fpn run BASELINE configs[2] shape / configs[3] (fusion / loop: the video branch of the segmenter, the whole
+per-frame loop); --impl reference = the reference's CPU path.
 """
 import argparse
 import json
@@ -497,15 +498,22 @@ def main():
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     ap.add_argument('--profile-only', action='store_true', help='skip the e2e and CPU legs (for ncu runs)')
-    ap.add_argument('--workload', default='vo', choices=['vo', 'vkitti', 'fpn'],
+    ap.add_argument('--workload', default='vo', choices=['vo', 'vkitti', 'fpn', 'fusion', 'loop'],
                     help='vo = BASELINE configs[1] (the contract line); vkitti = configs[2] shape: 240x808 frames (30x101 grid), 12 keyframes, '
-                         'radius 2, panoptic segment filter ON; fpn = configs[3] (delegates to tools/bench_fpn.py)')
+                         'radius 2, panoptic segment filter ON; fpn = configs[3] (delegates to tools/bench_fpn.py); fusion = Panoptic-FPN video branch '
+                         '(tools/bench_fusion.py); loop = the whole per-frame loop at the configs[2] shape (tools/bench_loop.py)')
     args, rest = ap.parse_known_args()
     if args.workload == 'fpn':
         sys.argv = [os.path.join(ROOT, 'tools', 'bench_fpn.py'), '--steps', str(min(args.steps, 10)), '--warmup', str(args.warmup)] + rest
         sys.path.insert(0, os.path.join(ROOT, 'tools'))
         import bench_fpn
         bench_fpn.main()
+        return
+    if args.workload in ('fusion', 'loop'):
+        name = 'bench_' + args.workload
+        sys.argv = [os.path.join(ROOT, 'tools', name + '.py')] + rest
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        __import__(name).main()
         return
     if args.workload == 'vkitti':
         global F_PER_GPU, RADIUS, HT, WD, METRIC
