@@ -132,3 +132,78 @@ def test_depth_video_bookkeeping_equals_the_reference_class():
     mine.normalize(), theirs.normalize()
     same()
     assert DepthVideo.format_indicies([1, 2], torch.tensor([[3], [4]]), 'cpu')[1].tolist() == [3, 4]
+
+
+def test_factor_graph_bookkeeping_equals_the_reference_class(monkeypatch):
+    """FactorGraph's edge bookkeeping -- add_factors (duplicate filter, eviction of the oldest edges at max_factors),
+    rm_factors with and without storing the removed edges as inactive, rm_keyframe (index shift of active and inactive edges,
+    video buffers moved down), clear_edges -- is tensor code: run it on CPU next to the reference's FactorGraph through the
+    same operation sequence.  Only the two device stages add_factors touches are replaced in this test (the volume by a
+    stand-in that counts edges, reprojection by the reference's)."""
+    import pvo_b200.factor_graph as pfg
+    from pvo_b200.depth_video import DepthVideo
+    ref = ref_import.load()
+    g = torch.Generator().manual_seed(2)
+    H, W, B, F_ = 128, 160, 16, 9
+    mine_v = DepthVideo(image_size=[H, W], buffer=B, device='cpu', segm_filter=True)
+    ref_v = ref.depth_video.DepthVideo(image_size=[H, W], buffer=B, device='cpu', segm_filter=True)
+    from oracle import se3 as ose3
+    for k in range(F_):
+        item = (float(k), torch.zeros(3, H, W, dtype=torch.uint8), ose3.se3_exp(0.05 * torch.randn(6, generator=g)),
+                0.5 + torch.rand(H // 8, W // 8, generator=g), torch.tensor([W / 16.0, W / 16.0, W / 16.0, H / 16.0]),
+                torch.randn(128, H // 8, W // 8, generator=g).half(), torch.randn(128, H // 8, W // 8, generator=g).half(),
+                torch.randn(128, H // 8, W // 8, generator=g).half(), torch.randint(0, 5, (1, H // 8, W // 8), generator=g, dtype=torch.int32))
+        mine_v.append(*item), ref_v.append(*item)
+
+    class CountingVolume:                      # stands in for CorrBlock: FactorGraph only cats and masks it
+        def __init__(self, f1, f2=None):
+            self.n = f1 if isinstance(f1, int) else f1.shape[1]
+
+        def cat(self, other):
+            return CountingVolume(self.n + other.n)
+
+        def __getitem__(self, keep):
+            return CountingVolume(int(keep.sum()))
+    monkeypatch.setattr(pfg, 'CorrBlock', CountingVolume)
+    mine_v.reproject = lambda ii, jj: ref_v.reproject(ii, jj)
+    mine = pfg.FactorGraph(mine_v, None, device='cpu', max_factors=14)
+    theirs = ref.factor_graph.FactorGraph(ref_v, None, device='cpu', max_factors=14)
+
+    def same(tag):
+        for n in ('ii', 'jj', 'age', 'ii_inac', 'jj_inac'):
+            assert torch.equal(getattr(mine, n), getattr(theirs, n)), (tag, n)
+        assert mine.corr.n == mine.ii.shape[0] == theirs.corr.corr_pyramid[0].shape[0], tag      # the volume follows the edges
+        for n in ('target_cam', 'weight', 'raw_mask', 'delta_dy', 'target_cam_inac', 'weight_inac', 'raw_mask_inac', 'delta_dy_inac'):
+            a, b = getattr(mine, n), getattr(theirs, n)
+            assert a.shape == b.shape and torch.equal(a, b), (tag, n)
+        for a, b in ((mine.net, theirs.net), (mine.inp, theirs.inp), (mine.segm, theirs.segm)):
+            assert (a is None) == (b is None), tag
+            if a is not None:
+                assert a.shape == b.shape and torch.equal(a.float(), b.float()), tag
+        for n in ('poses', 'disps', 'intrinsics', 'fmaps', 'nets', 'inps', 'segms'):
+            assert torch.equal(getattr(mine_v, n), getattr(ref_v, n)), (tag, n)
+
+    def both(fn):
+        fn(mine), fn(theirs)
+    both(lambda f: f.add_neighborhood_factors(0, 5, r=2))
+    same('neighbourhood')
+    both(lambda f: f.add_factors(torch.tensor([0, 1, 5, 5]), torch.tensor([1, 0, 3, 4])))          # two repeats, two new
+    same('repeats filtered')
+    for f in (mine, theirs):                                                                        # what update() leaves behind
+        f.age += torch.arange(f.age.shape[0]) % 7
+        f.weight = torch.rand(f.weight.shape, generator=torch.Generator().manual_seed(3))
+        f.target_cam = f.target_cam + 0.5
+    same('aged')
+    both(lambda f: f.rm_factors(f.age > 4, store=True))
+    same('stored as inactive')
+    both(lambda f: f.add_factors(torch.tensor([6, 7, 6, 5, 7]), torch.tensor([7, 6, 5, 6, 5]), remove=True))   # over budget -> evict oldest
+    same('evicted at max_factors')
+    assert mine.ii.shape[0] <= 14 and mine.ii_inac.shape[0] > 0
+    both(lambda f: f.rm_keyframe(5))
+    same('keyframe removed')
+    both(lambda f: f.add_factors(torch.tensor([0, 2]), torch.tensor([1, 0])))                       # inactive edges are repeats too
+    same('inactive are repeats')
+    both(lambda f: f.rm_factors(f.ii == 0, store=False))
+    same('dropped')
+    both(lambda f: f.clear_edges())
+    assert mine.ii.shape[0] == 0 and theirs.ii.shape[0] == 0
