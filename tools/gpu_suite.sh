@@ -43,6 +43,7 @@ fusion)
   run t_fusion 600 $PT tests/test_video_fusion_gpu.py
   run bench_fusion 300 python tools/bench_fusion.py ;;
 loop)      # first hardware run of the whole per-frame loop: decisions vs the reference golden, then the config-3 bench
+  run t_modes 600 $PT -rxX --runxfail tests/test_zy_graph_modes_gpu.py
   run t_loop 900 $PT -rxX --runxfail tests/test_zz_slam_loop_gpu.py tests/test_visual_ops_gpu.py
   run bench_loop 900 python tools/bench_loop.py ;;
 dist)
