@@ -207,3 +207,14 @@ def test_factor_graph_bookkeeping_equals_the_reference_class(monkeypatch):
     same('dropped')
     both(lambda f: f.clear_edges())
     assert mine.ii.shape[0] == 0 and theirs.ii.shape[0] == 0
+
+
+def test_gpu_test_restates_the_generator_frames_exactly():
+    """tests/test_zz_slam_loop_gpu.py cannot import the generator on the GPU box (it needs the reference tree), so it restates
+    the synthetic video: the two must be identical"""
+    import importlib
+    from tests.golden.make_golden_slam_loop import video_frames as generator_frames
+    restated = importlib.import_module('tests.test_zz_slam_loop_gpu').video_frames()
+    for a, b in zip(restated, generator_frames()):
+        assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert len(restated) == 14

@@ -52,16 +52,6 @@ def make_droid(gold):
     return Droid(args)
 
 
-def test_generator_frames_are_restated_exactly():
-    pytest.importorskip('oracle.ref_import')
-    from oracle import ref_import
-    if not ref_import.available():
-        pytest.skip('build container only')
-    from tests.golden.make_golden_slam_loop import video_frames as ref_frames
-    for a, b in zip(video_frames(), ref_frames()):
-        assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
-
-
 def test_frontend_decisions_and_state():
     gold = np.load(os.path.join(G, 'slam_loop.npz'))
     droid = make_droid(gold)
