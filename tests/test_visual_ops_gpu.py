@@ -2,14 +2,14 @@
 reference's own kernels (droid_kernels.cu:406-495, 640-829, compiled into oracle/_ref/droid_ba_ref.so by oracle/build_ref.py) and
 against the per-pixel restatements of the oracle.
 
-First hardware run pending (written after round 1's GPU budget was spent): xfail(strict=False) until it has run once."""
+Passed on its first hardware run (round 2)."""
 import pytest
 import torch
 
 from oracle import ba_cuda, se3
 
 # the timeout ends the process instead of leaving the box hung should an untried path ever spin on the device
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(420, method='thread'), pytest.mark.xfail(strict=False, reason='first hardware run pending (added after the GPU budget of round 1 was spent)')]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(420, method='thread')]
 
 
 def case():

@@ -3,8 +3,7 @@ after a keyframe removal, with an explicit t0) and `motion_only=True` on a windo
 reference's FactorGraph run on CPU (tests/golden/make_golden_graph_modes.py -> graph_modes.npz), float32 path.  Same
 observables and tolerances as test_step_gpu.test_graph_update_matches_reference_golden, slightly wider for the later steps.
 
-First hardware run pending (written after round 1's GPU budget was spent): xfail(strict=False) until it has run once; the
-file name sorts after the validated test files on purpose."""
+Passed on its first hardware run (round 2).  The file name sorts after the older test files on purpose."""
 import os
 
 import numpy as np
@@ -14,7 +13,7 @@ import torch
 from tests.golden import cases
 
 # the timeout ends the process instead of leaving the box hung should an untried path ever spin on the device
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(420, method='thread'), pytest.mark.xfail(strict=False, reason='first hardware run pending (added after the GPU budget of round 1 was spent)')]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(420, method='thread')]
 G = os.path.join(os.path.dirname(__file__), 'golden')
 CASE = dict(F=7, radius=2, h=16, w=24, seed=6, with_segm=True)
 EXTRA = 3
