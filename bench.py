@@ -78,6 +78,28 @@ class ClockSampler(threading.Thread):
                 'samples': len(s)}
 
 
+def pin_to_gpu_numa(index):
+    """Bind this process to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) so that the pinned staging
+    buffers of the end-to-end leg are first-touched on that NUMA node: 8 NUMA-blind ranks staging ~60 MB each way per step
+    made e2e regress from 4 to 8 GPUs in round 1.  Best effort; returns what it did for the bench line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        path = '/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(path).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            NUMA['cpus'] = len(cpus)
+    except Exception as ex:
+        NUMA['error'] = repr(ex)[:80]
+
+
+NUMA = {}
+
+
 # ------------------------------------------------------------------------------------------------ workloads
 def make_case(nf, seed=1):
     from tests.golden import cases
@@ -99,8 +121,8 @@ def run_ours(args, rank, world, local_rank):
     from pvo_b200.depth_video import DepthVideo
     from pvo_b200.droid_net import DynamicUpdateModule
     from pvo_b200.factor_graph import FactorGraph
-    from oracle import update_op as oupd      # weights only (seeded init shared with the parity tests)
 
+    pin_to_gpu_numa(local_rank)                 # before any pinned allocation: staging buffers become NUMA-local to the GPU
     torch.cuda.set_device(local_rank)
     dev = 'cuda:%d' % local_rank
     nf = F_PER_GPU * world
@@ -127,8 +149,8 @@ def run_ours(args, rank, world, local_rank):
     v.nets[:nf] = c['nets'].to(dev)
     v.inps[:nf] = c['inps'].to(dev)
     v.counter.value = nf
+    torch.manual_seed(0)                        # random-init weights of the reference architecture (PyTorch default init)
     m = DynamicUpdateModule(precision=args.precision).to(dev)
-    m.load_state_dict(oupd.init_params(0))
     fg = FactorGraph(v, m, device=dev, precision=args.precision, use_cuda_graph=not args.no_graph)
     if world > 1:
         from pvo_b200 import dist as pdist
@@ -162,6 +184,34 @@ def run_ours(args, rank, world, local_rank):
 
     # the per-step working set (volume 2.2 GB + activations ~0.9 GB) is far larger than L2, so consecutive steps
     # cannot hit in L2; the explicit flush below is belt and braces and sits OUTSIDE the timed events.
+    consistency = None
+    if world > 1:
+        # multi-GPU correctness, asserted in the bench itself: after the first warm-up step every rank must hold the same poses
+        # (bitwise: each rank sums the pushed systems in rank order), and they must equal a single-GPU solve of the WHOLE graph
+        step()
+        sync()
+        mine = v.poses[:nf].clone()
+        allp = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        same = all(torch.equal(allp[0], q) for q in allp)
+        assert same, 'sharded BA: pose replicas differ across ranks'
+        single = None
+        if rank == 0:
+            v1 = DepthVideo(image_size=(8 * HT, 8 * WD), buffer=max(nf + 8, 16), device=dev, store_images=False, segm_filter=False, thresh=0.8)
+            for name in ('poses', 'disps', 'fmaps', 'nets', 'inps'):
+                getattr(v1, name)[:nf] = c[name].to(dev)
+            v1.intrinsics[:] = c['intrinsics'][0].to(dev)
+            v1.counter.value = nf
+            fg1 = FactorGraph(v1, m, device=dev, precision=args.precision)
+            fg1.add_factors(c['ii'], c['jj'])
+            fg1.update(t0=1, t1=nf, itrs=2)
+            torch.cuda.synchronize()
+            single = float((v1.poses[:nf] - mine).abs().max().item())
+            del fg1, v1
+            torch.cuda.empty_cache()
+            assert single < 5e-3, 'sharded BA differs from the single-GPU solve: %g' % single
+        consistency = {'replicas_bitwise_equal': same, 'max_abs_pose_diff_vs_single_gpu': single}
+        reset_state()
     for _ in range(max(args.warmup, 3)):
         step()
     sync()
@@ -191,6 +241,51 @@ def run_ours(args, rank, world, local_rank):
     E_total = int(c['E']) if world > 1 else E
     units_per_step = E_total / 36.0 if world > 1 else 1.0
     value = units_per_step * 1000.0 / ms_per_step
+
+    # ---- the frontend's mode: use_inactive=True (droid_frontend.py:49,62,81,87) with stored edges in the BA, same timing recipe
+    inactive = None
+    if world == 1 and not args.profile_only:
+        far_i = torch.arange(0, nf - 4)
+        xi, xj = torch.cat([far_i, far_i + 4]), torch.cat([far_i + 4, far_i])           # the 2 (F - 4) edges at distance 4
+        fg.add_factors(xi.to(dev), xj.to(dev))
+        fg.rm_factors((fg.ii - fg.jj).abs() == 4, store=True)                          # ... retired into the inactive set
+        ts = []
+        for k in range(3 + min(args.steps, 10)):
+            flush.zero_()
+            if k % 10 == 0:
+                reset_state()
+            sync()
+            ev0.record()
+            fg.update(t0=1, t1=nf, itrs=2, use_inactive=True)
+            ev1.record()
+            sync()
+            if k >= 3:
+                ts.append(ev0.elapsed_time(ev1))
+        inactive = {'ms_per_step': round(sum(ts) / len(ts), 4), 'active_edges': int(fg.ii.shape[0]), 'inactive_edges_in_ba': int(fg._cache['inac']['n']),
+                    'path': 'CUDA graph replay' if not args.no_graph else 'launch plan', 'ratio_to_plain_step': round(sum(ts) / len(ts) / ms_per_step, 3)}
+        reset_state()
+
+    # ---- warm volume build (per NEW edge, not per iteration): all-pairs GEMM on tcgen05 + 4-level pyramid in the epilogue
+    volume = None
+    if world == 1 and not args.profile_only and args.precision == 'fp16':
+        from pvo_b200.modules.corr import build_pyramid_tiled
+        g1, g2 = v.fmaps[ii.to(dev)].contiguous(), v.fmaps[jj.to(dev)].contiguous()
+        ts = []
+        for k in range(5):
+            flush.zero_()
+            sync()
+            ev0.record()
+            lv = build_pyramid_tiled(g1, g2)
+            ev1.record()
+            sync()
+            if k >= 2:
+                ts.append(ev0.elapsed_time(ev1))
+            del lv
+        vb = E * HT * WD * sum((HT >> l_) * (WD >> l_) for l_ in range(4)) * 2 + 2 * E * 128 * HT * WD * 2
+        vms = sum(ts) / len(ts)
+        volume = {'bound': 'hbm', 'kernel': 'corr_volume_tc_kernel<80,tiled> (+ 2 layout kernels)', 'ms': round(vms, 3), 'ms_per_edge': round(vms / E, 4),
+                  'achieved': round(vb / vms / 1e6, 1), 'peak': peaks()['hbm'], 'unit': 'GB/s', 'frac': round(vb / vms / 1e6 / peaks()['hbm'], 4),
+                  'bytes': vb, 'what': 'warm build of all %d edges: pyramid written once (61 MB/edge) + features read' % E}
 
     # ---- instrumented pass: per-launch CUDA events on the launching stream
     eng = fg._engine()
@@ -303,7 +398,9 @@ def run_ours(args, rank, world, local_rank):
         lb = E * hw * (4 * 64 * 2 + 8 + 208 * 2)
         secondary['corr_lookup'] = {'bound': 'hbm', 'achieved': round(lb / (look_ms * 1e-3) / 1e9, 1), 'peak': pk['hbm'], 'unit': 'GB/s',
                                     'frac': round(lb / (look_ms * 1e-3) / 1e9 / pk['hbm'], 4), 'bytes_per_launch': lb,
-                                    'traffic': traffic.get('corr_lookup_fused_kernel')}
+                                    'traffic': traffic.get('corr_lookup_tiled_kernel'), 'kernel': 'corr_lookup_tiled_kernel<1> (4 levels, tiled volume, cp.async zero-fill staging)'}
+    if volume is not None:
+        secondary['corr_volume'] = volume
     ba_ms = sum(v_ for k_, v_ in kernel_ms.items() if k_.startswith('ba'))
     upd_ms = sum(v_ for k_, v_ in kernel_ms.items() if k_.startswith('conv') or k_ in ('colmean', 'glo_matvec', 'heads2', 'segment_mean', 'eta'))
     cpu = cpu_baseline_sample()
@@ -323,7 +420,8 @@ def run_ours(args, rank, world, local_rank):
                         'neighbouring steps overlap the compute on separate streams (double-buffered staging)'},
         'gpu_launches': launches,
         'clocks': clocks.result(),
-        'roofline': roof, 'roofline_other': secondary,
+        'roofline': roof, 'roofline_other': secondary, 'use_inactive_step': inactive, 'multi_gpu_consistency': consistency, 'numa': NUMA,
+        'parity_gate': parity_gate(args) if world == 1 else None,
         'kernel_ms': {k: round(x, 4) for k, x in sorted(kernel_ms.items())},
         'stage_ms': {'update_operator': round(upd_ms, 4), 'ba_2_iterations': round(ba_ms, 4), 'corr_lookup': look_ms,
                      'edge_add_ms': round(edge_add_ms, 3)},
@@ -332,6 +430,24 @@ def run_ours(args, rank, world, local_rank):
         'reference_gpu_path': gpu_ref,
     }
     print(json.dumps(line))
+
+
+def parity_gate(args):
+    """CHECKER leg (not timed, not on the product path; `--no-gate` skips it): how far the benchmarked half / tensor-core path is
+    from float32 after two update iterations at config 2, next to how far the REFERENCE's own inference mode is (its unmodified
+    FactorGraph + DynamicUpdateModule under torch.autocast on cuDNN, staged bytecode in oracle/_ref/py, same GPU, same inputs).
+    tests/test_config2_gpu.py asserts ours <= 2 x reference; the bench line prints both."""
+    if args.no_gate or args.precision != 'fp16' or args.workload != 'vo':
+        return None
+    try:
+        from tests import ref_harness
+        import torch
+        r = ref_harness.fp16_gate(steps=2)
+        torch.cuda.empty_cache()
+        r['ok'] = all(r['ours_fp16'][k] <= 2.0 * r['reference_autocast'][k] + 1e-3 for k in r['ours_fp16'])
+        return {k: ({a: float('%.3g' % b) for a, b in v.items()} if isinstance(v, dict) else v) for k, v in r.items()}
+    except Exception as ex:
+        return {'unavailable': repr(ex)[:160]}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -354,11 +470,12 @@ def _oracle_step_time(nf, steps=1, warm=0, threads=None):
 
 
 def best_threads(cores):
-    """oneDNN/OpenMP do not always scale to every hardware thread: time a small sub-graph at a few counts, keep the best."""
+    """oneDNN/OpenMP do not always scale to every hardware thread: time ONE step of the FULL config-2 graph (36 edges; a smaller
+    graph favours fewer threads than the real workload) at a few counts, keep the best."""
     cands = sorted(set([c for c in (16, 32, 64, cores) if c <= cores] or [cores]))
     best, best_t = cores, None
     for n in cands:
-        t, _ = _oracle_step_time(3, steps=1, warm=1, threads=n)
+        t, _ = _oracle_step_time(F_PER_GPU, steps=1, warm=0, threads=n)
         if best_t is None or t < best_t:
             best, best_t = n, t
     return best
@@ -498,6 +615,8 @@ def main():
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     ap.add_argument('--profile-only', action='store_true', help='skip the e2e and CPU legs (for ncu runs)')
+    ap.add_argument('--no-gate', action='store_true', help='skip the fp16 parity-gate leg (reference autocast run, oracle/_ref/py)')
+    ap.add_argument('--radius', type=int, default=None, help='neighbourhood radius of the frame graph (default 3; 8 = BASELINE configs[4] banded-8 graph)')
     ap.add_argument('--workload', default='vo', choices=['vo', 'vkitti', 'fpn', 'fusion', 'loop'],
                     help='vo = BASELINE configs[1] (the contract line); vkitti = configs[2] shape: 240x808 frames (30x101 grid), 12 keyframes, '
                          'radius 2, panoptic segment filter ON; fpn = configs[3] (delegates to tools/bench_fpn.py); fusion = Panoptic-FPN video branch '
@@ -515,8 +634,10 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, 'tools'))
         __import__(name).main()
         return
+    global F_PER_GPU, RADIUS, HT, WD, METRIC
+    if args.radius:
+        RADIUS = args.radius
     if args.workload == 'vkitti':
-        global F_PER_GPU, RADIUS, HT, WD, METRIC
         F_PER_GPU, RADIUS, HT, WD = 12, 2, 30, 101
         METRIC = 'VO update-op iters/sec (240x808 VKITTI2 shape, 12 KF, radius 2, segment filter on)'
     rank = int(os.environ.get('RANK', 0))

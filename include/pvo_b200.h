@@ -61,11 +61,48 @@ int pvo_corr_volume(const void* fmap1, const void* fmap2, void* const* levels_ou
 int pvo_corr_volume_f16(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w,
                         int num_levels, void* stream);
 
+/* The same volume + pyramid in the TILED private layout (what CorrBlock keeps on the production half path; the reference's
+ *   `corr_pyramid` attribute, droid_slam/modules/corr.py:29-38, is materialised from it on demand by pvo_corr_untile):
+ *   level l: (E, h*w, ceil((h>>l)/4), ceil((w>>l)/8), 4, 8) float16 -- each source pixel's (h>>l, w>>l) plane cut into tiles of
+ *   4 rows x 8 columns (64 bytes = one DRAM access), tile-row-major, zero padded to whole tiles.  The 8 rows of a lookup window
+ *   at any alignment lie in <= 2 tile columns: 16 (or 8) 16-byte pieces that share sectors, instead of 8 partially used rows. */
+int pvo_corr_volume_f16_tiled(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w,
+                              int num_levels, void* stream);
+
+/* CorrBlock.__call__ (droid_slam/modules/corr.py:40-50 -> src/correlation_kernels.cu:19-70) on the tiled layout: all four
+ *   levels in one launch, radius 3, float16; bit-identical to pvo_corr_lookup_pyramid / the reference kernel on the same volume
+ *   values.  levels / level_h / level_w: the tiled level tensors and the plane sizes (h>>l, w>>l); coords (E,h,w,2) float32;
+ *   layout / out / out_cstride as pvo_corr_lookup_pyramid.  The window rows are staged per pixel into shared memory with
+ *   zero-filling cp.async (out-of-plane pieces are not fetched), one code path for interior, border and outside windows. */
+int pvo_corr_lookup_tiled(const void* const* levels, const int* level_h, const int* level_w, int num_levels,
+                          const float* coords, void* out, int E, int h, int w, int radius, int layout, int out_cstride,
+                          void* stream);
+
+/* layout conversion of ONE level between (nplanes, h2, w2) and (nplanes, ceil(h2/4), ceil(w2/8), 4, 8), float16 */
+int pvo_corr_untile(const void* tiled, void* planar, long nplanes, int h2, int w2, void* stream);
+int pvo_corr_tile(const void* planar, void* tiled, long nplanes, int h2, int w2, void* stream);
+
 /* droid_backends.altcorr_forward(fmap1, fmap2, coords, radius) -> [corr]
  *   src/droid.cpp:240, src/altcorr_kernel.cu:27-149,290-319.
  *   fmap1 (B,H1,W1,C), fmap2 (B,H2,W2,C) float32, coords (B,S,H1,W1,2), out (B,S,(2r+1)^2,H1,W1). */
 int pvo_altcorr_forward(const float* fmap1, const float* fmap2, const float* coords, float* out, int B, int S, int H1,
                         int W1, int H2, int W2, int C, int radius, void* stream);
+
+/* droid_backends.altcorr_backward(fmap1, fmap2, coords, corr_grad, radius) -> [fmap1_grad, fmap2_grad, coords_grad]
+ *   src/droid.cpp:241, src/altcorr_kernel.cu:152-286,321-356 (training only).  corr_grad (B,S,49,H1,W1); fmap1_grad (B,H1,W1,C) is
+ *   written; fmap2_grad (B,H2,W2,C) must be zero-initialised (atomic accumulation); coords receive no gradient (the reference
+ *   returns zeros). */
+int pvo_altcorr_backward(const float* fmap1, const float* fmap2, const float* coords, const float* corr_grad,
+                         float* fmap1_grad, float* fmap2_grad, int B, int S, int H1, int W1, int H2, int W2, int C, int radius,
+                         void* stream);
+
+/* cvx_upsample(data, mask) (droid_slam/droid_net.py:23-37; DepthVideo.upsample depth_video.py:139-144): convex 8x upsampling,
+ *   softmax over the 9 logits of each of the 64 sub-pixels x 3x3 zero-padded neighbourhood.
+ *   data (N,ht,wd,dim) float32; mask (N,576,ht,wd) float32|float16 (channel = k*64 + sy*8 + sx); out (N,8ht,8wd,dim) float32. */
+int pvo_cvx_upsample(const float* data, const void* mask, float* out, int N, int ht, int wd, int dim, int mask_dtype, void* stream);
+/* upsample_inter (droid_net.py:54-61, droid.py:106-113, factor_graph.py:431-438): bilinear x8, align_corners=True, channels last.
+ *   in (N,ht,wd,dim) float32 -> out (N,8ht,8wd,dim) float32 */
+int pvo_upsample_inter(const float* in, float* out, int N, int ht, int wd, int dim, void* stream);
 
 /* ---- geometry ---------------------------------------------------------------------------------------------- */
 

@@ -7,8 +7,10 @@
 //   block b of rank r:  for each peer p: stage_p[parity][r][chunk b] = partial[chunk b];  fence;  flag_p[r][b] = epoch
 //                       wait until flag_local[q][b] == epoch for every rank q;  partial[chunk b] = sum_q stage_local[parity][q][chunk b]
 // One launch, no host involvement, capturable in a CUDA graph (the epoch lives in device memory and advances by itself).
-// Two staging parities suffice: a rank can be at most one all-reduce ahead of a peer, because finishing epoch e+1 needs
-// that peer's push for e+1, which the peer issues only after it has finished reading epoch e.
+// The epoch is ONE counter per rank, advanced once per launch by the last block to finish (not one per block: the block count
+// follows the message size, so per-block counters would drift apart when P changes between calls and with them the staging
+// parity).  Two staging parities suffice: a rank can be at most one all-reduce ahead of a peer, because finishing call c+1 needs
+// every block of that peer to have pushed for c+1, which the peer does only after its call c has completed (stream order).
 #include "common.cuh"
 
 namespace {
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(double* __restri
                                                                 int rank, int world, long n, long n_max) {
   __shared__ int s_epoch;
   const int b = blockIdx.x;
-  if (threadIdx.x == 0) s_epoch = epochs[b] + 1;
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile int*>(epochs) + 1;      // epochs[0]: calls completed, epochs[1]: blocks done
   __syncthreads();
   const int epoch = s_epoch;
   const int parity = epoch & 1;
@@ -61,7 +63,15 @@ __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(double* __restri
     for (int q = 0; q < world; q++) s += __ldcg(mine + (long)q * n_max + i);      // rank order: bitwise identical on every rank
     data[i] = s;
   }
-  if (threadIdx.x == 0) epochs[b] = epoch;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(epochs + 1, 1) == (int)gridDim.x - 1) {      // last block of this launch: every block has read epochs[0]
+      epochs[1] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile int*>(epochs) = epoch;
+    }
+  }
 }
 
 }  // namespace

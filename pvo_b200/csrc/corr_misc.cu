@@ -98,9 +98,64 @@ __global__ void __launch_bounds__(128) altcorr_fwd_kernel(const float* __restric
   for (int q = 0; q < 49; q++) o[(long)q * plane] = acc[q];
 }
 
+// altcorr backward (training path): one warp per (b, source pixel), lane <-> 4 channels.  For every sample n and tap (iy, ix) of the
+// 8x8 support: g = sum of the <= 4 output gradients the tap contributes to, each times its bilinear weight
+// (altcorr_kernel.cu:233-249; channel = y-offset + 7 * x-offset); fmap1_grad[pixel] += g * f2[tap] (kept in registers over all taps
+// and samples, written once), fmap2_grad[tap] += g * f1[pixel] (atomics, as the reference).  coords get no gradient (:340 zeros).
+__global__ void __launch_bounds__(128) altcorr_bwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+                                                          const float* __restrict__ coords, const float* __restrict__ cg,
+                                                          float* __restrict__ g1, float* __restrict__ g2, int B, int S, int H1, int W1,
+                                                          int H2, int W2, int C) {
+  const long plane = (long)H1 * W1;
+  const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long)B * plane) return;
+  const int b = (int)(wid / plane);
+  const long pix = wid - (long)b * plane;
+  const float* a = f1 + ((long)b * plane + pix) * C;
+  for (int c0 = lane * 4; c0 < C; c0 += 128) {
+    const float4 u = *reinterpret_cast<const float4*>(a + c0);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = 0; n < S; n++) {
+      const long t = ((long)b * S + n) * plane + pix;
+      const float x2 = coords[t * 2], y2 = coords[t * 2 + 1];
+      const float dx = x2 - floorf(x2), dy = y2 - floorf(y2);
+      const int fx = (int)fminf(fmaxf(floorf(x2), -16777216.f), 16777216.f), fy = (int)fminf(fmaxf(floorf(y2), -16777216.f), 16777216.f);
+      const float* gp = cg + ((long)b * S + n) * 49 * plane + pix;
+      for (int iy = 0; iy < 8; iy++)
+        for (int ix = 0; ix < 8; ix++) {
+          const int hh = fy - 3 + iy, ww = fx - 3 + ix;
+          if (!inb(hh, ww, H2, W2)) continue;          // the reference's f2 = 0 and no atomicAdd for such taps
+          float g = 0.0f;
+          if (iy > 0 && ix > 0) g += gp[(long)((iy - 1) + 7 * (ix - 1)) * plane] * dy * dx;
+          if (iy > 0 && ix < 7) g += gp[(long)((iy - 1) + 7 * ix) * plane] * dy * (1 - dx);
+          if (iy < 7 && ix > 0) g += gp[(long)(iy + 7 * (ix - 1)) * plane] * (1 - dy) * dx;
+          if (iy < 7 && ix < 7) g += gp[(long)(iy + 7 * ix) * plane] * (1 - dy) * (1 - dx);
+          const long off = (((long)b * H2 + hh) * W2 + ww) * C + c0;
+          const float4 v = *reinterpret_cast<const float4*>(f2 + off);
+          acc.x = fmaf(g, v.x, acc.x); acc.y = fmaf(g, v.y, acc.y); acc.z = fmaf(g, v.z, acc.z); acc.w = fmaf(g, v.w, acc.w);
+          atomicAdd(g2 + off, g * u.x); atomicAdd(g2 + off + 1, g * u.y); atomicAdd(g2 + off + 2, g * u.z); atomicAdd(g2 + off + 3, g * u.w);
+        }
+    }
+    *reinterpret_cast<float4*>(g1 + ((long)b * plane + pix) * C + c0) = acc;
+  }
+}
+
 }  // namespace
 
-extern "C" int pvo_version(void) { return 100; }
+extern "C" int pvo_version(void) { return 101; }
+
+extern "C" int pvo_altcorr_backward(const float* fmap1, const float* fmap2, const float* coords, const float* corr_grad,
+                                    float* fmap1_grad, float* fmap2_grad, int B, int S, int H1, int W1, int H2, int W2, int C,
+                                    int radius, void* stream) {
+  if (B < 0 || S < 0 || C % 4) return PVO_ERR_INVALID;
+  if (radius != 3) return PVO_ERR_UNSUPPORTED;
+  if (B == 0) return PVO_OK;
+  const long warps = (long)B * H1 * W1;
+  altcorr_bwd_kernel<<<ceil_div(warps * 32, 128), 128, 0, (cudaStream_t)stream>>>(fmap1, fmap2, coords, corr_grad, fmap1_grad, fmap2_grad, B,
+                                                                                   S, H1, W1, H2, W2, C);
+  return pvo_check_launch();
+}
 
 extern "C" int pvo_corr_index_backward(const float* coords, const void* corr_grad, void* volume_grad, int N, int h1,
                                        int w1, int h2, int w2, int radius, int dtype, void* stream) {

@@ -43,7 +43,10 @@ __device__ __forceinline__ __half pool4(__half a, __half b, __half c, __half d) 
   return __float2half_rn(s * 0.25f);
 }
 
-template <int W>
+// TILED: every (edge, source pixel) plane is written as tiles of 4 rows x 8 columns (64 B), tile-row-major, zero padded to whole
+// tiles -- the layout corr_lookup_tiled.cu gathers from: level l plane = [ceil(h_l/4)][ceil(w_l/8)][4][8] halves.  Level 0 leaves
+// the epilogue as whole 32-byte sectors (two rows of one tile per store pair).
+template <int W, bool TILED>
 __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __grid_constant__ VolParams p) {
   constexpr int N = 2 * W;                       // UMMA N = two rows of image 2
   constexpr int kA = 2 * 128 * 128;              // A: two K blocks of [128 rows][64 halves]
@@ -135,15 +138,17 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
     int as = 0;
     uint32_t aphase = 0;
     const int H = p.H, H1 = H / 2, H2 = H1 / 2, H3 = H2 / 2;
+    constexpr int TC0 = W / 8, TC1 = (W1 + 7) / 8, TC2 = (W2 + 7) / 8, TC3 = (W3 + 7) / 8;
+    const int TR0 = (H + 3) / 4, TR1 = (H1 + 3) / 4, TR2 = (H2 + 3) / 4, TR3 = (H3 + 3) / 4;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int e = item / p.mtiles, mt = item - e * p.mtiles;
       const int p1 = mt * 128 + q * 32 + lane;
       const bool ok = p1 < p.HW;
       const long rowi = (long)e * p.HW + p1;
-      __half* o0 = p.lvl[0] + rowi * ((long)H * W);
-      __half* o1 = p.lvl[1] + rowi * ((long)H1 * W1);
-      __half* o2 = p.lvl[2] + rowi * ((long)H2 * W2);
-      __half* o3 = p.lvl[3] + rowi * ((long)H3 * W3);
+      __half* o0 = p.lvl[0] + rowi * (TILED ? (long)TR0 * TC0 * 32 : (long)H * W);
+      __half* o1 = p.lvl[1] + rowi * (TILED ? (long)TR1 * TC1 * 32 : (long)H1 * W1);
+      __half* o2 = p.lvl[2] + rowi * (TILED ? (long)TR2 * TC2 * 32 : (long)H2 * W2);
+      __half* o3 = p.lvl[3] + rowi * (TILED ? (long)TR3 * TC3 * 32 : (long)H3 * W3);
       // pooled rows are kept packed (two halves per register); every loop below is fully unrolled so they stay in
       // registers.  pair x of a level-k row = columns (2x, 2x+1).
       __half2 l1prev[W1 / 2], l1cur[W1 / 2], l2prev[W2 / 2 + 1], l2cur[W2 / 2 + 1];
@@ -165,9 +170,15 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
             pb[t] = __floats2half2_rn(__uint_as_float(b[2 * t]), __uint_as_float(b[2 * t + 1]));
           }
           if (ok) {
-            *reinterpret_cast<uint4*>(o0 + (long)(2 * c) * W + j * 8) = make_uint4(h2u(pa[0]), h2u(pa[1]), h2u(pa[2]), h2u(pa[3]));
-            if (row1)
-              *reinterpret_cast<uint4*>(o0 + (long)(2 * c + 1) * W + j * 8) = make_uint4(h2u(pb[0]), h2u(pb[1]), h2u(pb[2]), h2u(pb[3]));
+            if (TILED) {     // rows 2c, 2c+1 = sub-rows (2(c&1), 2(c&1)+1) of tile (c>>1, j): 32 contiguous bytes = one sector
+              __half* t = o0 + ((long)(c >> 1) * TC0 + j) * 32 + (c & 1) * 16;
+              *reinterpret_cast<uint4*>(t) = make_uint4(h2u(pa[0]), h2u(pa[1]), h2u(pa[2]), h2u(pa[3]));
+              *reinterpret_cast<uint4*>(t + 8) = row1 ? make_uint4(h2u(pb[0]), h2u(pb[1]), h2u(pb[2]), h2u(pb[3])) : make_uint4(0u, 0u, 0u, 0u);
+            } else {
+              *reinterpret_cast<uint4*>(o0 + (long)(2 * c) * W + j * 8) = make_uint4(h2u(pa[0]), h2u(pa[1]), h2u(pa[2]), h2u(pa[3]));
+              if (row1)
+                *reinterpret_cast<uint4*>(o0 + (long)(2 * c + 1) * W + j * 8) = make_uint4(h2u(pb[0]), h2u(pb[1]), h2u(pb[2]), h2u(pb[3]));
+            }
           }
 #pragma unroll
           for (int t = 0; t < 2; t++)
@@ -180,9 +191,17 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
         if (lane == 0) mbar_arrive(&tempty[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
         if (ok && c < H1) {
+          if (TILED) {
 #pragma unroll
-          for (int x = 0; x < W1 / 4; x++)
-            *reinterpret_cast<uint2*>(o1 + (long)c * W1 + 4 * x) = make_uint2(h2u(l1cur[2 * x]), h2u(l1cur[2 * x + 1]));
+            for (int x = 0; x < TC1; x++)
+              *reinterpret_cast<uint4*>(o1 + ((long)(c >> 2) * TC1 + x) * 32 + (c & 3) * 8) =
+                  make_uint4(h2u(l1cur[4 * x]), (4 * x + 1 < W1 / 2) ? h2u(l1cur[4 * x + 1]) : 0u,
+                             (4 * x + 2 < W1 / 2) ? h2u(l1cur[4 * x + 2]) : 0u, (4 * x + 3 < W1 / 2) ? h2u(l1cur[4 * x + 3]) : 0u);
+          } else {
+#pragma unroll
+            for (int x = 0; x < W1 / 4; x++)
+              *reinterpret_cast<uint2*>(o1 + (long)c * W1 + 4 * x) = make_uint2(h2u(l1cur[2 * x]), h2u(l1cur[2 * x + 1]));
+          }
         }
         if (c & 1) {
           const int r2 = c >> 1;
@@ -191,15 +210,37 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
             l2cur[x] = __halves2half2(pool4(__low2half(l1prev[2 * x]), __high2half(l1prev[2 * x]), __low2half(l1cur[2 * x]), __high2half(l1cur[2 * x])),
                                       pool4(__low2half(l1prev[2 * x + 1]), __high2half(l1prev[2 * x + 1]), __low2half(l1cur[2 * x + 1]), __high2half(l1cur[2 * x + 1])));
           if (ok && r2 < H2) {
+            if (TILED) {
 #pragma unroll
-            for (int x = 0; x < W2 / 2; x++) *reinterpret_cast<uint32_t*>(o2 + (long)r2 * W2 + 2 * x) = h2u(l2cur[x]);
+              for (int t = 0; t < TC2; t++)
+                *reinterpret_cast<uint4*>(o2 + ((long)(r2 >> 2) * TC2 + t) * 32 + (r2 & 3) * 8) =
+                    make_uint4(h2u(l2cur[4 * t]), (4 * t + 1 < W2 / 2) ? h2u(l2cur[4 * t + 1]) : 0u,
+                               (4 * t + 2 < W2 / 2) ? h2u(l2cur[4 * t + 2]) : 0u, (4 * t + 3 < W2 / 2) ? h2u(l2cur[4 * t + 3]) : 0u);
+            } else {
+#pragma unroll
+              for (int x = 0; x < W2 / 2; x++) *reinterpret_cast<uint32_t*>(o2 + (long)r2 * W2 + 2 * x) = h2u(l2cur[x]);
+            }
           }
           if (r2 & 1) {
             const int r3 = r2 >> 1;
             if (ok && r3 < H3) {
+              if (TILED) {
+                __half v3[TC3 * 8];
 #pragma unroll
-              for (int x = 0; x < W3; x++)
-                o3[(long)r3 * W3 + x] = pool4(__low2half(l2prev[x]), __high2half(l2prev[x]), __low2half(l2cur[x]), __high2half(l2cur[x]));
+                for (int x = 0; x < TC3 * 8; x++)
+                  v3[x] = x < W3 ? pool4(__low2half(l2prev[x < W3 ? x : 0]), __high2half(l2prev[x < W3 ? x : 0]), __low2half(l2cur[x < W3 ? x : 0]),
+                                         __high2half(l2cur[x < W3 ? x : 0]))
+                                 : __float2half_rn(0.0f);
+#pragma unroll
+                for (int t = 0; t < TC3; t++)
+                  *reinterpret_cast<uint4*>(o3 + ((long)(r3 >> 2) * TC3 + t) * 32 + (r3 & 3) * 8) =
+                      make_uint4(h2u(__halves2half2(v3[8 * t], v3[8 * t + 1])), h2u(__halves2half2(v3[8 * t + 2], v3[8 * t + 3])),
+                                 h2u(__halves2half2(v3[8 * t + 4], v3[8 * t + 5])), h2u(__halves2half2(v3[8 * t + 6], v3[8 * t + 7])));
+              } else {
+#pragma unroll
+                for (int x = 0; x < W3; x++)
+                  o3[(long)r3 * W3 + x] = pool4(__low2half(l2prev[x]), __high2half(l2prev[x]), __low2half(l2cur[x]), __high2half(l2cur[x]));
+              }
             }
           } else {
 #pragma unroll
@@ -210,6 +251,17 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
           for (int x = 0; x < W1 / 2; x++) l1prev[x] = l1cur[x];
         }
       }
+      if (TILED && ok) {      // rows past the last written one, up to the end of the last tile row, are zeros in every level
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int r = 2 * p.nchunks; r < 4 * TR0; r++)
+          for (int t = 0; t < TC0; t++) *reinterpret_cast<uint4*>(o0 + ((long)(r >> 2) * TC0 + t) * 32 + (r & 3) * 8) = z4;
+        for (int r = H1; r < 4 * TR1; r++)
+          for (int t = 0; t < TC1; t++) *reinterpret_cast<uint4*>(o1 + ((long)(r >> 2) * TC1 + t) * 32 + (r & 3) * 8) = z4;
+        for (int r = H2; r < 4 * TR2; r++)
+          for (int t = 0; t < TC2; t++) *reinterpret_cast<uint4*>(o2 + ((long)(r >> 2) * TC2 + t) * 32 + (r & 3) * 8) = z4;
+        for (int r = H3; r < 4 * TR3; r++)
+          for (int t = 0; t < TC3; t++) *reinterpret_cast<uint4*>(o3 + ((long)(r >> 2) * TC3 + t) * 32 + (r & 3) * 8) = z4;
+      }
     }
   }
   fence_before_sync();
@@ -217,17 +269,17 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int W>
+template <int W, bool TILED>
 int launch_vol(const VolParams& p, cudaStream_t s) {
   constexpr int smem = 2 * 128 * 128 + kStagesB * 2 * (2 * W) * 128 + 1024 + 256;
   static bool set = false;
   if (!set) {
-    if (cudaFuncSetAttribute(corr_volume_tc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(corr_volume_tc_kernel<W, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return PVO_ERR_CUDA;
     set = true;
   }
   const int grid = p.items < PVO_SM_COUNT ? p.items : PVO_SM_COUNT;
-  corr_volume_tc_kernel<W><<<grid, kThreads, smem, s>>>(p);
+  corr_volume_tc_kernel<W, TILED><<<grid, kThreads, smem, s>>>(p);
   return pvo_check_launch();
 }
 
@@ -236,8 +288,8 @@ int launch_vol(const VolParams& p, cudaStream_t s) {
 // fmap1, fmap2: (E, h*w, 128) fp16 pixel-major, pre-divided by 4.  levels_out[l]: (E, h, w, h>>l, w>>l) fp16.
 // Supported: num_levels == 4, w in {40, 80} (N = 2w must be a legal UMMA N and pooling stays register resident);
 // anything else returns PVO_ERR_UNSUPPORTED and the caller uses pvo_corr_volume.
-extern "C" int pvo_corr_volume_f16(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w,
-                                   int num_levels, void* stream) {
+static int corr_volume_f16_impl(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w, int num_levels,
+                                bool tiled, void* stream) {
   if (E < 0 || h <= 0 || w <= 0) return PVO_ERR_INVALID;
   if (num_levels != 4 || (w != 80 && w != 40) || h < 8) return PVO_ERR_UNSUPPORTED;
   if (E == 0) return PVO_OK;
@@ -257,5 +309,17 @@ extern "C" int pvo_corr_volume_f16(const void* fmap1, const void* fmap2, void* c
   p.items = E * p.mtiles;
   p.nchunks = (h + 1) / 2;
   cudaStream_t s = (cudaStream_t)stream;
-  return w == 80 ? launch_vol<80>(p, s) : launch_vol<40>(p, s);
+  if (tiled) return w == 80 ? launch_vol<80, true>(p, s) : launch_vol<40, true>(p, s);
+  return w == 80 ? launch_vol<80, false>(p, s) : launch_vol<40, false>(p, s);
+}
+
+extern "C" int pvo_corr_volume_f16(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w,
+                                   int num_levels, void* stream) {
+  return corr_volume_f16_impl(fmap1, fmap2, levels_out, E, h, w, num_levels, false, stream);
+}
+
+// levels_out[l]: (E, h*w, ceil((h>>l)/4), ceil((w>>l)/8), 32) fp16 -- the tiled private layout of corr_lookup_tiled.cu
+extern "C" int pvo_corr_volume_f16_tiled(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w,
+                                         int num_levels, void* stream) {
+  return corr_volume_f16_impl(fmap1, fmap2, levels_out, E, h, w, num_levels, true, stream);
 }

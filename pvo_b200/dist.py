@@ -121,23 +121,26 @@ def attach(fg, rank, world, frames_per_rank, group=None):
     """Make a FactorGraph's BA go through ba_sharded.  The caller adds only this rank's edges (shard_edges)."""
     video = fg.video
     reducer = make_reducer(video.poses.device, group) if video.poses.is_cuda else None
-    span_cache = {}
     fg.allreduce_kind = 'one-shot push over NVLink peer memory (own kernel)' if reducer is not None else 'ncclAllReduce'
 
     def ba(target, weight, eta, ii, jj, t0=1, t1=None, itrs=2, lm=1e-4, ep=0.1, motion_only=False, interleaved=False,
            reuse_plan=False, max_degree=0, max_span=None):
-        if max_span is not None:                               # the bound must hold for the all-reduced system: max over ranks
-            if max_span not in span_cache:
-                t = torch.tensor([int(max_span)], device=video.poses.device)
-                if dist.is_initialized() and dist.get_world_size(group) > 1:
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-                span_cache[max_span] = int(t.item())
-            max_span = span_cache[max_span]
+        # max_span arrives already maximised over ranks (fg._span_reduce below, called by FactorGraph when the edge set changes)
         out = ba_sharded(video.poses, video.disps, video.intrinsics[0].contiguous(), target, weight, eta, ii, jj, t0, t1,
                          itrs, lm, ep, motion_only, interleaved=interleaved, group=group, max_degree=max_degree, reducer=reducer,
                          max_span=max_span)
         check(_lib.lib().pvo_clamp_min(ptr(video.disps), video.disps.numel(), 0.001, stream()), 'clamp_min')
         return out
+    def span_reduce(local_span):
+        """The bandwidth bound must hold for the all-reduced system: max over ranks.  Called by FactorGraph exactly once per
+        edge-set change (and once per inactive-slab build) on EVERY rank -- edge sets change in lockstep -- so the collective can
+        never be issued by a subset of the ranks (a per-value cache here could hit on one rank and miss on another)."""
+        if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+            return int(local_span)
+        t = torch.tensor([int(local_span)], device=video.poses.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return int(t.item())
     video.ba = ba
+    fg._span_reduce = span_reduce
     fg.rank, fg.world = rank, world
     return fg

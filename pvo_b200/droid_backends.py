@@ -4,6 +4,8 @@ Same function names, argument order, in-place behaviour and return arity (caller
 modules/corr.py:12,19,79), implemented as thin ctypes calls into libpvo_b200.so.  Outputs are allocated here with
 torch.empty (the kernels write every element; the reference's torch::zeros + read-modify-write is gone).
 """
+import os
+
 import torch
 
 from . import _lib
@@ -62,8 +64,18 @@ def altcorr_forward(fmap1, fmap2, coords, radius):
 
 
 def altcorr_backward(fmap1, fmap2, coords, corr_grad, radius):
-    raise NotImplementedError('altcorr_backward (training only, src/altcorr_kernel.cu:152-286) is outside the '
-                              'inference hot path -- SURVEY.md section 8(f) item 4')
+    """src/altcorr_kernel.cu:152-286, :321-356 (training path) -> [fmap1_grad, fmap2_grad, coords_grad (zeros, as the reference)]"""
+    require_cuda(fmap1, fmap2, coords, corr_grad)
+    if fmap1.dtype != torch.float32 or corr_grad.dtype != torch.float32:
+        raise RuntimeError('altcorr_backward: float32 only (the reference instantiates its kernel for float)')
+    B, H1, W1, C = fmap1.shape
+    _, H2, W2, _ = fmap2.shape
+    S = coords.shape[1]
+    g1 = torch.empty_like(fmap1)
+    g2 = torch.zeros_like(fmap2)
+    check(_lib.lib().pvo_altcorr_backward(ptr(fmap1.contiguous()), ptr(fmap2.contiguous()), ptr(coords.contiguous()), ptr(corr_grad.contiguous()),
+                                          ptr(g1), ptr(g2), B, S, H1, W1, H2, W2, C, radius, stream()), 'altcorr_backward')
+    return [g1, g2, torch.zeros_like(coords)]
 
 
 def frame_distance(poses, disps, intrinsics, ii, jj, beta):
@@ -86,6 +98,12 @@ def ba_workspace(E, nframes, P, K, HW, device):
         ws = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=device)
         _ba_ws[key] = ws
     return ws
+
+
+def current_workspace(device):
+    """the shared BA workspace of `device` (None before the first call): a captured CUDA graph keeps a reference to the buffer it
+    was captured on, so that growth elsewhere cannot free it under the graph"""
+    return _ba_ws.get((str(device),))
 
 
 def band_flag(max_span):
@@ -118,7 +136,25 @@ def ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iteratio
                             1 if motion_only else 0, 1 if interleaved else 0, ptr(dx), ptr(dz), ptr(ws), ws.numel(),
                             (1 if reuse_plan else 0) | ((int(max_degree) & 0xFFF) << 8) | band_flag(max_span), stream()), 'ba',
           launches=(0 if reuse_plan else 1) + int(iterations) * (3 if motion_only else 4))
+    if CHECK_BA:
+        check_ba_meta(ws, E, nframes, P, K, ht * wd)
     return [dx, dz]
+
+
+CHECK_BA = bool(int(os.environ.get('PVO_BA_CHECK', '0')))      # tests switch it on: read the device-side error flag after every call
+
+
+def check_ba_meta(ws, E, nframes, P, K, HW):
+    """The schedule kernel records what it could not honour: flag 1 = the number of depth frames unique(arange(t0,t1) U ii) differs
+    from eta's row count (the reference raises a shape error at `C + eta`, droid_kernels.cu:1374), flag 2 = a frame's Schur tile
+    did not fit in shared memory.  Reading it synchronises, so it is opt-in (PVO_BA_CHECK=1 / droid_backends.CHECK_BA = True)."""
+    import ctypes
+    meta = (ctypes.c_int * 3)()
+    check(_lib.lib().pvo_ba_read_meta(ptr(ws), E, nframes, P, K, HW, meta), 'ba_read_meta', launches=0)
+    if meta[1] == 1:
+        raise RuntimeError('ba: eta has %d rows but the window and edges span %d depth frames' % (K, meta[0]))
+    if meta[1] == 2:
+        raise RuntimeError('ba: out-degree %d of a keyframe exceeds the shared-memory Schur tile' % meta[2])
 
 
 # ------------------------------------------------------------------------------------------------------------------

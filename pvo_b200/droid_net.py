@@ -43,10 +43,15 @@ class LazyUpmask(dict):
     def __init__(self, module, shape):
         super().__init__(flow=None, dy_mask=None)
         self._m, self._shape = module, shape
+        self._eng = module._engine
+        self._gen = self._eng.generation          # the engine run whose GraphAgg features this mask belongs to
 
     def __getitem__(self, k):
         if k == 'disp' and not dict.__contains__(self, 'disp'):
-            eng = self._m._engine
+            eng = self._eng
+            if eng.generation != self._gen or self._m._engine is not eng:
+                raise RuntimeError('upmask["disp"] was read after another forward() of the same update module: its GraphAgg '
+                                   'features are gone -- read it before the next call (the reference returns a concrete tensor)')
             up = eng.run_upmask()
             B, K, H, W = self._shape
             nchw = eng.store_nchw(up, 576, 0, 576, K)
@@ -150,13 +155,19 @@ UpdateModule = DynamicUpdateModule     # the stale reference class (droid_net.py
 # DroidNet: encoders + update operator + (Python-semantics) BA, pairwise / training-style entry point
 # ------------------------------------------------------------------------------------------------------
 def cvx_upsample(data, mask):
-    """convex 8x upsampling with a softmax-9 mask (droid_net.py:23-37)"""
+    """convex 8x upsampling with a softmax-9 mask (droid_net.py:23-37): one kernel (csrc/upsample.cu) instead of the reference's
+    softmax + F.unfold + broadcast product + sum.  data (B,ht,wd,dim), mask (B,576,ht,wd) or anything that views to it."""
     batch, ht, wd, dim = data.shape
-    data = data.permute(0, 3, 1, 2)
-    mask = torch.softmax(mask.view(batch, 1, 9, 8, 8, ht, wd), dim=2)
-    up = torch.nn.functional.unfold(data, [3, 3], padding=1).view(batch, dim, 9, 1, 1, ht, wd)
-    up = torch.sum(mask * up, dim=2).permute(0, 4, 2, 5, 3, 1)
-    return up.reshape(batch, 8 * ht, 8 * wd, dim)
+    if not data.is_cuda:
+        raise RuntimeError('pvo_b200.cvx_upsample: CUDA tensors only (no CPU fallback)')
+    d = data.float().contiguous()
+    m = mask.reshape(batch, 576, ht, wd).contiguous()
+    if m.dtype not in (torch.float32, torch.float16):
+        m = m.float()
+    out = torch.empty(batch, 8 * ht, 8 * wd, dim, dtype=torch.float32, device=data.device)
+    _lib.check(_lib.lib().pvo_cvx_upsample(_lib.ptr(d), _lib.ptr(m), _lib.ptr(out), batch, ht, wd, dim, _lib.dtype_code(m), _lib.stream()),
+               'cvx_upsample')
+    return out.to(torch.promote_types(data.dtype, mask.dtype))
 
 
 def upsample_dim_1(disp, mask):
@@ -164,12 +175,21 @@ def upsample_dim_1(disp, mask):
     return cvx_upsample(disp.reshape(batch * num, ht, wd, 1), mask.reshape(batch * num, -1, ht, wd)).view(batch, num, 8 * ht, 8 * wd)
 
 
+def upsample_dim_x(flow, mask):
+    """droid_net.py:46-51"""
+    batch, num, ht, wd, dim = flow.shape
+    return cvx_upsample(flow.reshape(batch * num, ht, wd, dim), mask.reshape(batch * num, -1, ht, wd)).view(batch, num, 8 * ht, 8 * wd, dim)
+
+
 def upsample_inter(mask):
-    """bilinear x8, align_corners=True (droid_net.py:54-61)"""
+    """bilinear x8, align_corners=True (droid_net.py:54-61; also droid.py:106, factor_graph.py:431), one kernel"""
     batch, num, ht, wd, dim = mask.shape
-    m = mask.permute(0, 1, 4, 2, 3).reshape(batch * num, dim, ht, wd)
-    m = torch.nn.functional.interpolate(m, scale_factor=8, mode='bilinear', align_corners=True, recompute_scale_factor=True)
-    return m.permute(0, 2, 3, 1).reshape(batch, num, 8 * ht, 8 * wd, dim)
+    if not mask.is_cuda:
+        raise RuntimeError('pvo_b200.upsample_inter: CUDA tensors only (no CPU fallback)')
+    m = mask.float().contiguous()
+    out = torch.empty(batch, num, 8 * ht, 8 * wd, dim, dtype=torch.float32, device=mask.device)
+    _lib.check(_lib.lib().pvo_upsample_inter(_lib.ptr(m), _lib.ptr(out), batch * num, ht, wd, dim, _lib.stream()), 'upsample_inter')
+    return out.to(mask.dtype)
 
 
 class DroidNet(nn.Module):

@@ -41,6 +41,7 @@ class FactorGraph:
         self.corr_impl = corr_impl
         self.precision = precision
         self.use_cuda_graph = use_cuda_graph   # replay the whole iteration as one CUDA graph (no per-launch CPU cost)
+        self.use_launch_plan = True            # eager path: record the launches of an edge set once, re-issue them afterwards
         self.ht = ht = video.ht // 8
         self.wd = wd = video.wd // 8
         self.dy_thresh = 0.5
@@ -228,9 +229,11 @@ class FactorGraph:
         L = _lib.lib()
         c = dict(E=E, K=K, kx=kx, t0_default=max(1, int(self.ii.min().item()) + 1),
                  t1_default=int(max(self.ii.max().item(), self.jj.max().item())) + 1,
-                 serial=next(_SERIAL), ba_kx={}, graphs={},
+                 serial=next(_SERIAL), ba_kx={}, graphs={}, plans={},
                  max_degree=int(torch.bincount(self.ii).max().item()),
                  max_span=int((self.ii - self.jj).abs().max().item()))
+        if getattr(self, '_span_reduce', None) is not None:    # sharded graph: the bandwidth bound must hold for the summed system.
+            c['max_span'] = self._span_reduce(c['max_span'])   # One collective per edge-set change, issued by every rank (dist.attach)
         c['coords1'] = torch.empty(1, E, self.ht, self.wd, 2, device=self.device)
         c['seg_ws'] = torch.zeros(int(L.pvo_update_post_workspace_ints(E)), dtype=torch.int32, device=self.device)
         c['segm'] = self.segm[0, :, 0].contiguous() if self.segm is not None else None
@@ -243,12 +246,16 @@ class FactorGraph:
     @torch.no_grad()
     def update(self, t0=None, t1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
         """run update operator on factor graph (factor_graph.py:227-307)"""
-        if not (self.use_cuda_graph and self.timers is None and not use_inactive):
+        if not (self.use_cuda_graph and self.timers is None):
             return self._update(t0, t1, itrs, use_inactive, EP, motion_only)
-        # CUDA-graph path: 1st call with a given signature runs eagerly (lazy initialisation, attribute setup),
-        # 2nd call captures, later calls replay.  Every launch of the iteration is capture-safe (no host sync).
+        # CUDA-graph path: 1st call with a given signature runs eagerly (lazy initialisation, attribute setup; with
+        # use_inactive it also builds the inactive slab, the only step with a host synchronisation), 2nd call captures, later
+        # calls replay.  Every launch of the iteration is capture-safe.  The captured iteration always contains the BA
+        # schedule kernel and runs on a workspace this graph holds a reference to, so other BA calls on the device between
+        # replays (another FactorGraph, the backend, a different window) can neither leave a foreign schedule behind nor
+        # free the buffer the graph writes to.
         c = self._cache or self._prepare()
-        key = (t0, t1, itrs, EP, motion_only)
+        key = (t0, t1, itrs, EP, motion_only, use_inactive)
         entry = c['graphs'].get(key)
         if entry is None:
             c['graphs'][key] = 'warm'
@@ -260,12 +267,50 @@ class FactorGraph:
             # process group's watchdog thread from tripping the capture
             mode = 'thread_local' if getattr(self, 'world', 1) > 1 else 'global'
             with torch.cuda.graph(g, capture_error_mode=mode):
-                self._update(t0, t1, itrs, use_inactive, EP, motion_only)
+                self._update(t0, t1, itrs, use_inactive, EP, motion_only, capturing=True)
             c['graphs'][key] = g
+            c.setdefault('ws_refs', []).append(droid_backends.current_workspace(self.video.poses.device))
             entry = g
         entry.replay()
+        droid_backends.set_ba_plan_owner(None)          # the replay rewrote the shared schedule
 
-    def _update(self, t0=None, t1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False):
+    def _inactive_slab(self, c, t0, t1):
+        """`use_inactive=True` (every frontend call, droid_frontend.py:49,62,81,87): the BA also sees the stored edges whose
+        frames are still near the window (factor_graph.py:284-291).  The reference concatenates them with the active edges on
+        every iteration (4 torch.cat + torch.unique); here the selection is made ONCE per (edge set, window): one buffer holds
+        [selected inactive | active] targets and weights, and `self.target_cam` / `self.weight` BECOME views of its tail, so the
+        update operator's post-processing writes the active part in place and the BA reads the whole buffer -- no copies, no
+        host synchronisation per iteration.  The only syncs (selected-edge count, window end, degree / span bounds) are here."""
+        m = (self.ii_inac >= t0 - 3) & (self.jj_inac >= t0 - 3)
+        sel = torch.nonzero(m).flatten()
+        n, E = int(sel.shape[0]), c['E']
+        ii = torch.cat([self.ii_inac[sel], self.ii], 0)
+        jj = torch.cat([self.jj_inac[sel], self.jj], 0)
+        tw = torch.empty(2, 1, n + E, self.ht, self.wd, 2, device=self.device)
+        if n:
+            tw[0, :, :n] = self.target_cam_inac[:, sel]
+            tw[1, :, :n] = self.weight_inac[:, sel]
+        tw[0, :, n:] = self.target_cam
+        tw[1, :, n:] = self.weight
+        self.target_cam, self.weight = tw[0, :, n:], tw[1, :, n:]
+        t1_ = int(max(ii.max().item(), jj.max().item())) + 1 if t1 is None else t1        # depth_video.py:203-204
+        kx = torch.unique(torch.cat([torch.arange(t0, t1_, device=self.device), ii]))
+        # the reference indexes the damping by unique(ii) and its kernel by unique(arange(t0,t1) U ii) (droid_kernels.cu:1311-1319);
+        # when the two differ its `C + eta` raises a shape error -- so does this
+        if int(torch.unique(ii).shape[0]) != int(kx.shape[0]):
+            raise RuntimeError('FactorGraph.update: a frame of the BA window [%d, %d) has no out-edge (damping rows would misalign)'
+                               % (t0, t1_))
+        max_span = int((ii - jj).abs().max().item())
+        if getattr(self, '_span_reduce', None) is not None:
+            max_span = self._span_reduce(max_span)
+        ia = dict(key=(t0, t1), t1=t1_, n=n, ii=ii, jj=jj, tw=tw, kx=kx, serial=next(_SERIAL),
+                  max_degree=int(torch.bincount(ii).max().item()), max_span=max_span)
+        c['inac'] = ia
+        c['graphs'] = {k: g for k, g in c['graphs'].items() if not k[5]}      # graphs captured on the previous slab are stale
+        c['plans'] = {k: g for k, g in c['plans'].items() if not k[5]}
+        return ia
+
+    def _update(self, t0=None, t1=None, itrs=2, use_inactive=False, EP=1e-7, motion_only=False, capturing=False):
         c = self._cache or self._prepare()
         eng = self._engine()
         L = _lib.lib()
@@ -274,6 +319,40 @@ class FactorGraph:
         coords1 = c['coords1']
         T = lambda name: _lib.timed(self.timers, name)
         n0 = _lib.LAUNCHES[0]
+        if t0 is None:
+            t0 = c['t0_default']
+        ia = None
+        if use_inactive:
+            ia = c.get('inac')
+            if ia is None or ia['key'] != (t0, t1):
+                if capturing:
+                    raise RuntimeError('FactorGraph: the inactive slab must exist before capture')
+                ia = self._inactive_slab(c, t0, t1)
+        # Launch plan (_lib.LaunchPlan): the first iteration on an edge set records its launches, the following ones re-issue them
+        # without any Python argument marshalling.  Not with per-stage timers, the mixed-precision lookup (torch ops in between),
+        # a sharded graph (NCCL call in between) or while a CUDA graph is being captured.
+        key = (t0, t1, itrs, EP, motion_only, use_inactive)
+        plannable = (self.timers is None and not capturing and self.use_launch_plan and self.corr.dtype == eng.tdtype
+                     and getattr(self, 'world', 1) == 1)
+        plan = c['plans'].get(key) if plannable else None
+        if plan is not None:
+            plan.replay()
+            droid_backends.set_ba_plan_owner(None)            # the replay rewrote the shared schedule
+            self._state_in_engine = True
+            self.launch_count = plan.launches
+            return
+        with _lib.recording(plannable) as rec:
+            self._iteration(c, eng, ia, t0, t1, itrs, EP, motion_only, use_inactive, capturing or plannable)
+        if rec is not None and rec.calls is not None:
+            c['plans'][key] = rec
+        self.launch_count = _lib.LAUNCHES[0] - n0
+
+    def _iteration(self, c, eng, ia, t0, t1, itrs, EP, motion_only, use_inactive, fresh_schedule):
+        L = _lib.lib()
+        E, ht, wd = c['E'], self.ht, self.wd
+        v = self.video
+        coords1 = c['coords1']
+        T = lambda name: _lib.timed(self.timers, name)
         # (1) reprojection + motion features, written straight into the flow encoder's input buffer
         with T('reproject'):
             check(L.pvo_reproject(ptr(v.poses), ptr(v.disps), ptr(v.intrinsics), ptr(self.ii), ptr(self.jj), ptr(coords1),
@@ -281,7 +360,7 @@ class FactorGraph:
                                   eng.dcode, E, ht, wd, stream()), 'reproject')
         # (2) correlation features, pixel-major into the corr encoder's input buffer
         with T('corr_lookup'):
-            if self.corr.corr_pyramid[0].dtype == eng.tdtype:
+            if self.corr.dtype == eng.tdtype:
                 self.corr(coords1, out=eng.corr, layout=1, out_cstride=pnn.CORR_STRIDE)
             else:
                 self._lookup_mixed(coords1, eng)
@@ -289,23 +368,17 @@ class FactorGraph:
         eng.run(with_agg=True)
         self._state_in_engine = True
         # (4) target, masks, segment filter, weights (in place on the graph's state tensors)
-        if t0 is None:
-            t0 = c['t0_default']
         segm = c['segm'] if v.segm_filter else None
         with T('update_post'):
             check(L.pvo_update_post(ptr(coords1), ptr(eng.head_out), ptr(segm), float(v.thresh), ptr(self.target_cam),
                                     ptr(self.weight), ptr(self.raw_mask), ptr(self.delta_dy), ptr(self.full_flow),
                                     ptr(c['seg_ws']), c['seg_ws'].numel(), E, ht, wd, stream()), 'update_post',
                   launches=3 if segm is not None else 1)
-        self.damping.index_copy_(0, c['kx'], eng.eta)
+        kx, eta, dampall = c['kx'], eng.eta, self.damping
+        _lib.torch_op(lambda: dampall.index_copy_(0, kx, eta))
         if use_inactive:
-            m = (self.ii_inac >= t0 - 3) & (self.jj_inac >= t0 - 3)
-            ii = torch.cat([self.ii_inac[m], self.ii], 0)
-            jj = torch.cat([self.jj_inac[m], self.jj], 0)
-            target_cam = torch.cat([self.target_cam_inac[:, m], self.target_cam], 1).contiguous()
-            weight = torch.cat([self.weight_inac[:, m], self.weight], 1).contiguous()
-            damping = (.2 * self.damping[torch.unique(ii)] + EP).contiguous()
-            reuse = False
+            ii, jj, target_cam, weight, t1, kx_ba = ia['ii'], ia['jj'], ia['tw'][0], ia['tw'][1], ia['t1'], ia['kx']
+            max_degree, max_span, serial = ia['max_degree'], ia['max_span'], ia['serial']
         else:
             ii, jj, target_cam, weight = self.ii, self.jj, self.target_cam, self.weight
             if t1 is None:
@@ -315,19 +388,26 @@ class FactorGraph:
             if kx_ba is None:
                 kx_ba = torch.unique(torch.cat([torch.arange(t0, t1, device=self.device), ii]))
                 c['ba_kx'][(t0, t1)] = kx_ba
-            damping = .2 * self.damping.index_select(0, kx_ba) + EP
-            # the BA schedule in the (shared) workspace can be reused iff the last BA call anywhere was this graph's, on this edge
-            # set and window
-            token = (id(self), c['serial'], t0, t1, ii.shape[0])
-            reuse = droid_backends.ba_plan_owner() == token
+            max_degree, max_span, serial = c['max_degree'], c['max_span'], c['serial']
+        damping = c.get(('damp', kx_ba.shape[0]))
+        if damping is None:
+            damping = c[('damp', kx_ba.shape[0])] = torch.empty(kx_ba.shape[0], ht, wd, device=self.device)
+
+        def damp():
+            torch.index_select(dampall, 0, kx_ba, out=damping)
+            damping.mul_(.2).add_(EP)
+        _lib.torch_op(damp)
+        # the BA schedule in the (shared) workspace can be reused iff the last BA call anywhere was this graph's, on this edge set and
+        # window; a captured / recorded iteration always rebuilds it (see update())
+        token = (id(self), serial, t0, t1, ii.shape[0], motion_only)
+        reuse = (not fresh_schedule) and droid_backends.ba_plan_owner() == token
         # (5) dense bundle adjustment, in place on video.poses / video.disps
         with T('ba_total'):
             v.ba(target_cam[0], weight[0], damping, ii, jj, t0, t1, itrs=itrs, lm=1e-4, ep=0.1, motion_only=motion_only,
-                 interleaved=True, reuse_plan=reuse, max_degree=0 if use_inactive else c['max_degree'],
-                 max_span=None if use_inactive else c['max_span'])
-        droid_backends.set_ba_plan_owner(None if use_inactive else token)
-        self.age += 1
-        self.launch_count = _lib.LAUNCHES[0] - n0
+                 interleaved=True, reuse_plan=reuse, max_degree=max_degree, max_span=max_span)
+        droid_backends.set_ba_plan_owner(token)
+        age = self.age
+        _lib.torch_op(lambda: age.add_(1))
 
     @torch.no_grad()
     def update_lowmem(self, t0=None, t1=None, itrs=2, use_inactive=False, EP=1e-7, steps=8):
@@ -361,7 +441,9 @@ class FactorGraph:
                 self.delta_dy[:, m] = delta[..., 2:4].float() * (1 - bin_mask)
                 self.weight[:, m] = torch.sigmoid(weight.float() + (1 - bin_mask) * 10)
             self.net = net_all
-            damping = self.damping[torch.unique(self.ii)].contiguous() + EP
+            # rows = the BA's depth frames unique(arange(1,t) U ii) (droid_kernels.cu:1311-1319; the reference indexes unique(ii) and
+            # raises at `C + eta` when the two differ -- pvo_ba flags it, droid_backends.check_ba_meta)
+            damping = self.damping[torch.unique(torch.cat([torch.arange(1, t, device=self.device), self.ii]))].contiguous() + EP
             target_cam = self.target_cam.view(-1, ht, wd, 2).permute(0, 3, 1, 2).contiguous()
             weight = self.weight.view(-1, ht, wd, 2).permute(0, 3, 1, 2).contiguous()
             v.ba(target_cam, weight, damping, self.ii, self.jj, 1, t, itrs=itrs, lm=1e-5, ep=1e-2, motion_only=False)
@@ -371,6 +453,6 @@ class FactorGraph:
     def _lookup_mixed(self, coords1, eng):
         """volume dtype != engine dtype (e.g. half volume feeding the float32 parity engine)"""
         E = coords1.shape[1]
-        tmp = torch.empty(E * self.ht * self.wd, pnn.CORR_STRIDE, dtype=self.corr.corr_pyramid[0].dtype, device=self.device)
+        tmp = torch.empty(E * self.ht * self.wd, pnn.CORR_STRIDE, dtype=self.corr.dtype, device=self.device)
         self.corr(coords1, out=tmp, layout=1, out_cstride=pnn.CORR_STRIDE)
         eng.corr.copy_(tmp)

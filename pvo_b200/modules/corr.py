@@ -3,7 +3,9 @@
 
 Differences that are invisible to callers: the volume + pyramid of CorrBlock.__init__ is one fused launch
 (tcgen05 GEMM for half, CUDA cores for float32); __call__ looks up all four levels in one launch and writes the
-concatenated (B,E,196,h,w) tensor directly (no per-level zeros + cat)."""
+concatenated (B,E,196,h,w) tensor directly (no per-level zeros + cat).  On the production half path the pyramid is kept in
+a TILED private layout (tiles of 4 rows x 8 columns = one 64-byte DRAM access, csrc/corr_lookup_tiled.cu); the reference-layout
+`corr_pyramid` attribute is then materialised on demand (and assigning to it switches the block to the planar kernels)."""
 import torch
 
 from .. import _lib, droid_backends
@@ -36,6 +38,43 @@ def to_pixel_major(x):
     return out
 
 
+def tc_volume_supported(fmap, num_levels=4):
+    N, C, h, w = fmap.shape
+    return fmap.dtype == torch.float16 and C == 128 and w in (40, 80) and h >= 8 and num_levels == 4
+
+
+def tiled_shape(N, h, w, l):
+    """shape of level l of the tiled pyramid for N edges of an (h, w) grid"""
+    return (N, h * w, ((h >> l) + 3) // 4, ((w >> l) + 7) // 8, 32)
+
+
+def build_pyramid_tiled(fmap1, fmap2):
+    """fmap1, fmap2: (N,128,h,w) half -> 4 tiled levels (N, h*w, ceil(h_l/4), ceil(w_l/8), 32), one tcgen05 launch"""
+    _lib.require_cuda(fmap1, fmap2)
+    N, C, h, w = fmap1.shape
+    f1, f2 = to_pixel_major(fmap1 / 4.0), to_pixel_major(fmap2 / 4.0)
+    levels = [torch.empty(tiled_shape(N, h, w, l), dtype=torch.float16, device=fmap1.device) for l in range(4)]
+    check(_lib.lib().pvo_corr_volume_f16_tiled(ptr(f1), ptr(f2), _lib.ptr_array(levels), N, h, w, 4, stream()), 'corr_volume_f16_tiled')
+    return levels
+
+
+def untile(level, h2, w2):
+    """(N, HW, TR, TC, 32) -> (N, HW, h2, w2) planar"""
+    N, HW = level.shape[:2]
+    out = torch.empty(N, HW, h2, w2, dtype=level.dtype, device=level.device)
+    check(_lib.lib().pvo_corr_untile(ptr(level), ptr(out), N * HW, h2, w2, stream()), 'corr_untile')
+    return out
+
+
+def tile(level):
+    """(..., h2, w2) planar half -> (prod(...), ceil(h2/4), ceil(w2/8), 32) tiled, zero padded"""
+    h2, w2 = level.shape[-2:]
+    n = level.numel() // (h2 * w2)
+    out = torch.empty(n, (h2 + 3) // 4, (w2 + 7) // 8, 32, dtype=level.dtype, device=level.device)
+    check(_lib.lib().pvo_corr_tile(ptr(level.contiguous()), ptr(out), n, h2, w2, stream()), 'corr_tile')
+    return out
+
+
 def build_pyramid(fmap1, fmap2, num_levels=4, use_tc=None):
     """fmap1, fmap2: (N,C,h,w).  Returns [ (N,h,w,h>>l,w>>l) ] -- corr.py:23-38,63-71 in one call."""
     _lib.require_cuda(fmap1, fmap2)
@@ -59,20 +98,52 @@ def build_pyramid(fmap1, fmap2, num_levels=4, use_tc=None):
 class CorrBlock:
     """corr.py:23-71"""
 
-    def __init__(self, fmap1, fmap2, num_levels=4, radius=3, use_tc=None):
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=3, use_tc=None, tiled=None):
         self.num_levels = num_levels
         self.radius = radius
         batch, num, dim, ht, wd = fmap1.shape
         if fmap1.dtype not in (torch.float16, torch.float32):
             raise RuntimeError('CorrBlock: float16 / float32 feature maps only')
-        self.corr_pyramid = build_pyramid(fmap1.reshape(batch * num, dim, ht, wd).contiguous(),
-                                          fmap2.reshape(batch * num, dim, ht, wd).contiguous(), num_levels, use_tc)
+        f1 = fmap1.reshape(batch * num, dim, ht, wd).contiguous()
+        f2 = fmap2.reshape(batch * num, dim, ht, wd).contiguous()
+        self.ht, self.wd = ht, wd
+        can_tile = use_tc is not False and radius == 3 and tc_volume_supported(f1, num_levels)
+        if tiled is None:
+            tiled = can_tile
+        if tiled and not can_tile:
+            raise RuntimeError('CorrBlock: the tiled layout needs half features, 128 channels, w in (40, 80), 4 levels, radius 3')
+        self._tiled = build_pyramid_tiled(f1, f2) if tiled else None
+        self._planar = None if tiled else build_pyramid(f1, f2, num_levels, use_tc)
+
+    @property
+    def corr_pyramid(self):
+        """the reference's attribute (corr.py:29-38): [ (N, h, w, h>>l, w>>l) ]; converted from the tiled store when needed"""
+        if self._planar is None:
+            self._planar = [untile(t, self.ht >> l, self.wd >> l).view(t.shape[0], self.ht, self.wd, self.ht >> l, self.wd >> l)
+                            for l, t in enumerate(self._tiled)]
+        return self._planar
+
+    @corr_pyramid.setter
+    def corr_pyramid(self, levels):
+        self._planar = list(levels)
+        self._tiled = None               # a caller-supplied pyramid is used as is, through the planar kernels
+
+    def _lookup_tiled(self, coords, batch, num, ht, wd, out, layout, out_cstride):
+        t = self._tiled
+        if out is None:
+            out = torch.empty(batch, num, 196, ht, wd, dtype=torch.float16, device=coords.device)
+        check(_lib.lib().pvo_corr_lookup_tiled(_lib.ptr_array(t), _lib.int_array([ht >> l for l in range(4)]),
+                                               _lib.int_array([wd >> l for l in range(4)]), 4, ptr(coords), ptr(out), batch * num, ht, wd,
+                                               3, layout, out_cstride, stream()), 'corr_lookup_tiled')
+        return out
 
     def __call__(self, coords, out=None, layout=0, out_cstride=0):
         """coords (B,E,h,w,2) float32 -> (B,E,L*49,h,w) in the volume's dtype (corr.py:40-50).
         layout=1 writes pixel-major (B*E*h*w, out_cstride) into ``out`` for the fused update operator."""
         batch, num, ht, wd, _ = coords.shape
         coords = coords.contiguous().float()
+        if self._tiled is not None and not coords.requires_grad:
+            return self._lookup_tiled(coords, batch, num, ht, wd, out, layout, out_cstride)
         if self.radius != 3 or coords.requires_grad or any(p.requires_grad for p in self.corr_pyramid):
             return self._call_per_level(coords)
         pyr = self.corr_pyramid
@@ -95,14 +166,31 @@ class CorrBlock:
             out_pyramid.append(corr.view(batch, num, -1, ht, wd))
         return torch.cat(out_pyramid, dim=2)
 
+    @property
+    def dtype(self):
+        return (self._tiled or self._planar)[0].dtype
+
+    @property
+    def num_edges(self):
+        return (self._tiled or self._planar)[0].shape[0]
+
     def cat(self, other):
-        for i in range(self.num_levels):
-            self.corr_pyramid[i] = torch.cat([self.corr_pyramid[i], other.corr_pyramid[i]], 0)
+        if (self._tiled is None) != (other._tiled is None):          # mixed stores: fall back to the planar one
+            self.corr_pyramid = self.corr_pyramid
+            other = type('P', (), {'_tiled': None, '_planar': other.corr_pyramid})
+        if self._tiled is not None:
+            self._tiled = [torch.cat([a, b], 0) for a, b in zip(self._tiled, other._tiled)]
+            self._planar = None
+        else:
+            self._planar = [torch.cat([a, b], 0) for a, b in zip(self._planar, other._planar)]
         return self
 
     def __getitem__(self, index):
-        for i in range(self.num_levels):
-            self.corr_pyramid[i] = self.corr_pyramid[i][index].contiguous()
+        if self._tiled is not None:
+            self._tiled = [t[index].contiguous() for t in self._tiled]
+            self._planar = None
+        else:
+            self._planar = [t[index].contiguous() for t in self._planar]
         return self
 
     @staticmethod
@@ -115,8 +203,8 @@ class CorrBlock:
 
 
 class CorrLayer(torch.autograd.Function):
-    """On-the-fly correlation of one pyramid level (reference: corr.py:74-88 over altcorr_kernel.cu); gradients are the
-    training path, which this package does not provide -- droid_backends.altcorr_backward says so when called."""
+    """On-the-fly correlation of one pyramid level (reference: corr.py:74-88 over altcorr_kernel.cu), differentiable with respect to
+    both feature maps (coords get a zero gradient, as in the reference)."""
 
     @staticmethod
     def forward(ctx, fmap1, fmap2, coords, r):
@@ -127,8 +215,8 @@ class CorrLayer(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_corr):
-        grads = droid_backends.altcorr_backward(*ctx.saved_tensors, grad_corr.contiguous(), ctx.r)
-        return (*grads, None)
+        g1, g2, gc = droid_backends.altcorr_backward(*ctx.saved_tensors, grad_corr.contiguous(), ctx.r)
+        return g1, g2, gc, None
 
 
 class AltCorrBlock:

@@ -154,6 +154,7 @@ class UpdateEngine:
         self.c_upmask = _Conv(g('agg.upmask_disp.0.weight'), g('agg.upmask_disp.0.bias'), tc=tc)
         self.E = self.K = self.H = self.W = 0
         self.timers = None            # dict -> per-launch CUDA events (bench.py)
+        self.generation = 0           # bumped by every run(): lets lazily evaluated outputs notice that their inputs are gone
 
     def fork(self):
         """An engine that shares the packed weights of this one but owns its activation buffers and hidden state.  Every
@@ -228,6 +229,7 @@ class UpdateEngine:
         eta (when with_agg).  ~14 launches, no host sync."""
         L = _lib.lib()
         T = lambda name: _lib.timed(self.timers, name)
+        self.generation += 1
         E, K, H, W, dc, tc = self.E, self.K, self.H, self.W, self.dcode, self.use_tc
         HW = H * W
         X = self.X

@@ -63,8 +63,8 @@ def test_out_of_scope_entry_points_say_so():
         assert callable(getattr(droid_backends, name))
     with pytest.raises(RuntimeError):
         droid_backends.iproj(torch.zeros(2, 7), torch.ones(2, 4, 4), torch.ones(4))
-    with pytest.raises(NotImplementedError):
-        droid_backends.altcorr_backward(None, None, None, None, 3)
+    with pytest.raises(RuntimeError):                           # provided since round 2; CUDA tensors only
+        droid_backends.altcorr_backward(torch.zeros(1, 4, 4, 8), torch.zeros(1, 4, 4, 8), torch.zeros(1, 1, 4, 4, 2), torch.zeros(1, 1, 49, 4, 4), 3)
 
 
 def test_ba_workspace_size_is_monotone():

@@ -218,3 +218,67 @@ def test_reference_altcorr_matches_ours():
     c = ocorr.altcorr_forward(f1.cpu(), f2.cpu(), coords.cpu(), 3)
     assert torch.allclose(r, o, atol=2e-4, rtol=1e-4)
     assert torch.allclose(r.cpu(), c, atol=2e-4, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tiled private layout (production half path): csrc/corr_lookup_tiled.cu + the TILED epilogue of csrc/corr_volume_tc.cu
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('hw', [(60, 80), (30, 40), (16, 40), (9, 80), (13, 40)])
+def test_tiled_volume_build_equals_planar_build_bit_for_bit(hw):
+    """the tiled epilogue writes the same values as the planar one (same TMEM accumulators, same rounding cascade), zero pads
+    included: tile(planar) == tiled and untile(tiled) == planar, every level"""
+    from pvo_b200.modules.corr import build_pyramid, build_pyramid_tiled, tile, untile
+    h, w = hw
+    g = torch.Generator().manual_seed(14)
+    E = 3
+    f1 = torch.randn(E, 128, h, w, generator=g).half().cuda()
+    f2 = torch.randn(E, 128, h, w, generator=g).half().cuda()
+    planar = build_pyramid(f1, f2, 4, use_tc=True)
+    # poison the allocator's next blocks so that unwritten pad elements cannot pass as zeros by luck
+    junk = [torch.full((E * h * w * (((h >> l) + 3) // 4) * (((w >> l) + 7) // 8) * 32,), 7.0, dtype=torch.float16, device='cuda') for l in range(4)]
+    del junk
+    tiled = build_pyramid_tiled(f1, f2)
+    for l in range(4):
+        h2, w2 = h >> l, w >> l
+        assert tiled[l].shape == (E, h * w, (h2 + 3) // 4, (w2 + 7) // 8, 32)
+        assert torch.equal(untile(tiled[l], h2, w2).view(planar[l].shape).view(torch.int16), planar[l].view(torch.int16)), l
+        assert torch.equal(tile(planar[l]).view(tiled[l].shape).view(torch.int16), tiled[l].view(torch.int16)), l
+
+
+@pytest.mark.parametrize('hw', [(16, 40), (30, 40), (20, 80)])
+def test_tiled_lookup_equals_planar_lookup_bit_for_bit(hw):
+    """one code path for interior, border-straddling and fully outside windows (zero-filled tiles == skipped taps), both output
+    layouts; coordinates include exact integers, far-out values, NaN and inf"""
+    from pvo_b200.modules.corr import CorrBlock
+    h, w = hw
+    g = torch.Generator().manual_seed(15)
+    E = 5
+    f1 = torch.randn(1, E, 128, h, w, generator=g).half().cuda()
+    f2 = torch.randn(1, E, 128, h, w, generator=g).half().cuda()
+    tb = CorrBlock(f1, f2)
+    assert tb._tiled is not None
+    pb = CorrBlock(f1, f2, tiled=False)
+    assert pb._tiled is None
+    coords = _coords(E, h, w, 33, spread=7.0, far=True).permute(0, 2, 3, 1)[None].contiguous()
+    coords[0, 0, 4, :4, 0] = float('nan')
+    coords[0, 1, 4, :4, 1] = float('inf')
+    coords[0, 2, 4, :4, 0] = -float('inf')
+    coords[0, 3, 4, :4] = 3.0e9
+    coords[0, 4, 5] = coords[0, 4, 5] * 0 - 0.5
+    coords = coords.cuda()
+    a, b = tb(coords), pb(coords)
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    pa = torch.full((E * h * w, 208), 7.0, dtype=torch.float16, device='cuda')
+    pb_ = torch.full((E * h * w, 208), 7.0, dtype=torch.float16, device='cuda')
+    tb(coords, out=pa, layout=1, out_cstride=208)
+    pb(coords, out=pb_, layout=1, out_cstride=208)
+    assert torch.equal(pa.view(torch.int16), pb_.view(torch.int16))
+    # the reference-layout attribute, materialised from the tiled store, equals the planar build
+    for x, y in zip(tb.corr_pyramid, pb.corr_pyramid):
+        assert torch.equal(x.view(torch.int16), y.view(torch.int16))
+    # edge bookkeeping on the tiled store
+    keep = torch.tensor([True, False, True, True, False], device='cuda')
+    tb2 = CorrBlock(f1, f2)[keep]
+    assert tb2.num_edges == 3 and torch.equal(tb2(coords[:, keep]).view(torch.int16), a[:, keep].contiguous().view(torch.int16))
+    tb3 = CorrBlock(f1[:, :2], f2[:, :2]).cat(CorrBlock(f1[:, 2:], f2[:, 2:]))
+    assert torch.equal(tb3(coords).view(torch.int16), a.view(torch.int16))

@@ -118,7 +118,7 @@ def test_edge_bookkeeping_round_trip():
     mask = torch.zeros(E, dtype=torch.bool, device='cuda')
     mask[::3] = True
     fg.rm_factors(mask, store=True)
-    assert fg.net.shape[1] == E - int(mask.sum()) and fg.corr.corr_pyramid[0].shape[0] == E - int(mask.sum())
+    assert fg.net.shape[1] == E - int(mask.sum()) and fg.corr.num_edges == E - int(mask.sum())
     assert torch.equal(fg.net, net_before[:, ~mask])
     assert fg.ii_inac.shape[0] == int(mask.sum())
     fg.update(itrs=1)
@@ -142,7 +142,7 @@ def test_add_proximity_factors_selects_the_reference_edges():
     fg.add_proximity_factors(t0=0, t1=0, rad=2, nms=2, beta=0.25, thresh=1e3)
     have = set(map(tuple, torch.stack([fg.ii, fg.jj], 1).cpu().tolist()))
     assert have == set(map(tuple, before)) | set(want)
-    assert fg.corr.corr_pyramid[0].shape[0] == fg.ii.shape[0] == fg.net.shape[1]
+    assert fg.corr.num_edges == fg.ii.shape[0] == fg.net.shape[1]
     fg.update(itrs=1)
     assert torch.isfinite(v.poses).all()
 
