@@ -369,3 +369,39 @@ def test_every_factor_graph_gets_its_own_engine_state():
     del a, ea
     gc.collect()
     assert len(m._forks) == n - 1
+
+
+def test_geom_chol_matches_dense_algebra_and_its_gradient():
+    """pvo_b200.geom.chol (reference interface geom/chol.py:5-73): solutions against torch.linalg.solve on the assembled system,
+    CholeskySolver.backward against autograd through torch.linalg.solve, and the failed-factorisation contract"""
+    import torch
+    from pvo_b200.geom import chol
+    g = torch.Generator().manual_seed(2)
+    B, P, M, D, HW = 1, 3, 2, 6, 5
+    J = torch.randn(B, P * D, P * D + 4, generator=g, dtype=torch.float64)
+    Hfull = (J @ J.transpose(1, 2)) + 0.5 * torch.eye(P * D, dtype=torch.float64)
+    H = Hfull.view(B, P, D, P, D).permute(0, 1, 3, 2, 4).contiguous()
+    b = torch.randn(B, P, D, generator=g, dtype=torch.float64)
+    x = chol.block_solve(H, b, ep=0.1, lm=1e-4)
+    Hd = Hfull + (0.1 + 1e-4 * Hfull) * torch.eye(P * D, dtype=torch.float64)
+    assert torch.allclose(x.reshape(B, -1, 1), torch.linalg.solve(Hd, b.reshape(B, -1, 1)), atol=1e-10)
+    E = 0.3 * torch.randn(B, P, M, D, HW, generator=g, dtype=torch.float64)
+    C = 2.0 + torch.rand(B, M, HW, generator=g, dtype=torch.float64)
+    w = torch.randn(B, M, HW, generator=g, dtype=torch.float64)
+    dx, dz = chol.schur_solve(H, E, C, b, w)
+    Em = E.permute(0, 1, 3, 2, 4).reshape(B, P * D, M * HW)
+    full = torch.cat([torch.cat([Hd, Em], 2), torch.cat([Em.transpose(1, 2), torch.diag_embed(C.view(B, -1))], 2)], 1)
+    sol = torch.linalg.solve(full, torch.cat([b.reshape(B, -1, 1), w.reshape(B, -1, 1)], 1))
+    assert torch.allclose(dx.reshape(B, -1, 1), sol[:, :P * D], atol=1e-9) and torch.allclose(dz.reshape(B, -1, 1), sol[:, P * D:], atol=1e-9)
+    assert torch.equal(chol.schur_solve(H, E, C, b, w, sless=True), dx)
+    Hr, br = Hd.clone().requires_grad_(True), b.reshape(B, -1, 1).clone().requires_grad_(True)
+    gx = torch.randn(B, P * D, 1, generator=g, dtype=torch.float64)
+    chol.CholeskySolver.apply(Hr, br).backward(gx)
+    Ha, ba_ = Hd.clone().requires_grad_(True), b.reshape(B, -1, 1).clone().requires_grad_(True)
+    torch.linalg.solve(Ha, ba_).backward(gx)
+    # the reference returns dH = -x u^T, the transpose of autograd's -u x^T: identical for every symmetric H(theta), which is all BA builds
+    sym = lambda t: t + t.transpose(-1, -2)
+    assert torch.allclose(sym(Hr.grad), sym(Ha.grad), atol=1e-9) and torch.allclose(Hr.grad, Ha.grad.transpose(-1, -2), atol=1e-9)
+    assert torch.allclose(br.grad, ba_.grad, atol=1e-9)
+    bad = -torch.eye(4, dtype=torch.float64)[None]
+    assert float(chol.CholeskySolver.apply(bad, torch.ones(1, 4, 1, dtype=torch.float64)).abs().max()) == 0.0
