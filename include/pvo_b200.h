@@ -66,21 +66,24 @@ int pvo_corr_volume_f16(const void* fmap1, const void* fmap2, void* const* level
  *   level l: (E, h*w, ceil((h>>l)/4), ceil((w>>l)/8), 4, 8) float16 -- each source pixel's (h>>l, w>>l) plane cut into tiles of
  *   4 rows x 8 columns (64 bytes = one DRAM access), tile-row-major, zero padded to whole tiles.  The 8 rows of a lookup window
  *   at any alignment lie in <= 2 tile columns: 16 (or 8) 16-byte pieces that share sectors, instead of 8 partially used rows. */
-int pvo_corr_volume_f16_tiled(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w,
-                              int num_levels, void* stream);
+/*   fmap1 (E, h*w, 128); fmap2 (E, h*wpad, 128), image 2 zero padded to wpad in {40, 80, 104, 128} columns (the tensor-core tile
+ *   width); level tensors are sized with wpad: (capacity, h*w, ceil((h>>l)/4), ceil((wpad>>l)/8), 4, 8).  slots (E int32, or NULL):
+ *   edge e is written to plane block slots[e] -- FactorGraph keeps volumes in a pool, edges come and go without copies. */
+int pvo_corr_volume_f16_tiled(const void* fmap1, const void* fmap2, void* const* levels_out, const int* slots, int E, int h, int w,
+                              int wpad, int num_levels, void* stream);
 
 /* CorrBlock.__call__ (droid_slam/modules/corr.py:40-50 -> src/correlation_kernels.cu:19-70) on the tiled layout: all four
  *   levels in one launch, radius 3, float16; bit-identical to pvo_corr_lookup_pyramid / the reference kernel on the same volume
- *   values.  levels / level_h / level_w: the tiled level tensors and the plane sizes (h>>l, w>>l); coords (E,h,w,2) float32;
+ *   values.  levels / level_h / level_w: the tiled level tensors and the plane sizes (h>>l, wpad>>l); slots as above; coords (E,h,w,2) float32;
  *   layout / out / out_cstride as pvo_corr_lookup_pyramid.  The window rows are staged per pixel into shared memory with
  *   zero-filling cp.async (out-of-plane pieces are not fetched), one code path for interior, border and outside windows. */
 int pvo_corr_lookup_tiled(const void* const* levels, const int* level_h, const int* level_w, int num_levels,
-                          const float* coords, void* out, int E, int h, int w, int radius, int layout, int out_cstride,
-                          void* stream);
+                          const int* slots, const float* coords, void* out, int E, int h, int w, int radius, int layout,
+                          int out_cstride, void* stream);
 
 /* layout conversion of ONE level between (nplanes, h2, w2) and (nplanes, ceil(h2/4), ceil(w2/8), 4, 8), float16 */
-int pvo_corr_untile(const void* tiled, void* planar, long nplanes, int h2, int w2, void* stream);
-int pvo_corr_tile(const void* planar, void* tiled, long nplanes, int h2, int w2, void* stream);
+int pvo_corr_untile(const void* tiled, void* planar, long nplanes, int h2, int w2, int w2pad, void* stream);
+int pvo_corr_tile(const void* planar, void* tiled, long nplanes, int h2, int w2, int w2pad, void* stream);
 
 /* droid_backends.altcorr_forward(fmap1, fmap2, coords, radius) -> [corr]
  *   src/droid.cpp:240, src/altcorr_kernel.cu:27-149,290-319.

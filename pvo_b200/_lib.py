@@ -20,10 +20,10 @@ _SIGS = {
     'pvo_corr_lookup_pyramid': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     'pvo_corr_volume': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     'pvo_corr_volume_f16': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
-    'pvo_corr_volume_f16_tiled': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
-    'pvo_corr_lookup_tiled': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
-    'pvo_corr_untile': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),
-    'pvo_corr_tile': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),
+    'pvo_corr_volume_f16_tiled': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    'pvo_corr_lookup_tiled': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    'pvo_corr_untile': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p]),
+    'pvo_corr_tile': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p]),
     'pvo_altcorr_forward': (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
     'pvo_altcorr_backward': (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
     'pvo_cvx_upsample': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),

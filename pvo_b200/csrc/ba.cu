@@ -561,7 +561,7 @@ __device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, 
 }
 
 template <bool IN_SMEM>
-__global__ void __launch_bounds__(128) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem, int moba, int bw_hint) {
+__global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem, int moba, int bw_hint) {
   extern __shared__ double smd[];
   __shared__ int s_fail;
   const int n = 6 * P;
@@ -775,10 +775,12 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
     const int comb_blocks = ceil_div(36L * P * P + 12L * P, 2048) < 148 ? (ceil_div(36L * P * P + 12L * P, 2048) < 8 ? 8 : ceil_div(36L * P * P + 12L * P, 2048)) : 148;
     if (phase == 1) { ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P); break; }
     if (solve_in_smem) {
-      ba_solve_kernel<true><<<1, 128, solve_smem, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint);
+      // small windows are latency bound (128 threads); from ~a dozen poses on the trailing updates (dense windows of the frontend: O(n^2) entries
+      // per block column) want the whole SM
+      ba_solve_kernel<true><<<1, P <= 10 ? 128 : 512, solve_smem, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint);
     } else {
       ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);
-      ba_solve_kernel<false><<<1, 128, 200 * 1024, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint);   // band-packed copy in smem when it fits
+      ba_solve_kernel<false><<<1, 512, 200 * 1024, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint);   // band-packed copy in smem when it fits
       ba_zero_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);
     }
     const bool last = it == iterations - 1;

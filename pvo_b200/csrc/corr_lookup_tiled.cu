@@ -29,7 +29,9 @@ namespace {
 struct TLevels {
   const __half* vol[4];
   int tr[4];   // tile rows  = ceil(h2 / 4)
-  int tc[4];   // tile cols  = ceil(w2 / 8)
+  int tc[4];   // tile cols  = ceil(w2 / 8)  (w2 = the padded width the volume was built with)
+  const int* slots;   // edge -> plane block of the level tensors (NULL: identity).  FactorGraph keeps its volumes in a pool so that
+                      // adding / retiring edges never copies them.
 };
 
 constexpr int kSlot = 272;            // bytes per lane slot: 8 window rows x 32 B, +16 so that LDS.128 / STS.128 are conflict free
@@ -87,7 +89,12 @@ __global__ void __launch_bounds__(128, 6) corr_lookup_tiled_kernel(const __grid_
     const int TR = lv.tr[l], TC = lv.tc[l];
     const int wx0 = fx - 3, wy0 = fy - 3;
     const int tcx0 = wx0 >> 3, ox = wx0 & 7;
-    const __half* plane = lv.vol[l] + p * ((long)TR * TC * 32);
+    long pb = p;
+    if (lv.slots) {
+      const long e = p / HW;
+      pb = (long)__ldg(lv.slots + e) * HW + (p - e * HW);
+    }
+    const __half* plane = lv.vol[l] + pb * ((long)TR * TC * 32);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(slot);
     const bool vx0 = (unsigned)tcx0 < (unsigned)TC;
     const bool vx1 = ox != 0 && (unsigned)(tcx0 + 1) < (unsigned)TC;      // a column-aligned window lies in one tile column
@@ -203,13 +210,14 @@ __global__ void tile_kernel(const __half* __restrict__ src, __half* __restrict__
 
 // levels[l]: (E, h*w, ceil(level_h[l]/4), ceil(level_w[l]/8), 32) float16 (see the header); coords (E,h,w,2) float32.
 extern "C" int pvo_corr_lookup_tiled(const void* const* levels, const int* level_h, const int* level_w, int num_levels,
-                                     const float* coords, void* out, int E, int h, int w, int radius, int layout,
+                                     const int* slots, const float* coords, void* out, int E, int h, int w, int radius, int layout,
                                      int out_cstride, void* stream) {
   if (num_levels != 4 || radius != 3) return PVO_ERR_UNSUPPORTED;
   if (E < 0 || h <= 0 || w <= 0) return PVO_ERR_INVALID;
   if (layout == 1 && (out_cstride < 196 || (out_cstride & 1))) return PVO_ERR_INVALID;
   if (E == 0) return PVO_OK;
   TLevels lv;
+  lv.slots = slots;
   for (int i = 0; i < 4; i++) {
     lv.vol[i] = (const __half*)levels[i];
     lv.tr[i] = (level_h[i] + 3) / 4;
@@ -235,18 +243,18 @@ extern "C" int pvo_corr_lookup_tiled(const void* const* levels, const int* level
   return pvo_check_launch();
 }
 
-extern "C" int pvo_corr_untile(const void* tiled, void* planar, long nplanes, int h2, int w2, void* stream) {
-  if (nplanes < 0 || h2 <= 0 || w2 <= 0) return PVO_ERR_INVALID;
+extern "C" int pvo_corr_untile(const void* tiled, void* planar, long nplanes, int h2, int w2, int w2pad, void* stream) {
+  if (nplanes < 0 || h2 <= 0 || w2 <= 0 || w2pad < w2) return PVO_ERR_INVALID;
   if (nplanes == 0) return PVO_OK;
   untile_kernel<<<PVO_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>((const __half*)tiled, (__half*)planar, nplanes, h2, w2, (h2 + 3) / 4,
-                                                                    (w2 + 7) / 8);
+                                                                    (w2pad + 7) / 8);
   return pvo_check_launch();
 }
 
-extern "C" int pvo_corr_tile(const void* planar, void* tiled, long nplanes, int h2, int w2, void* stream) {
-  if (nplanes < 0 || h2 <= 0 || w2 <= 0) return PVO_ERR_INVALID;
+extern "C" int pvo_corr_tile(const void* planar, void* tiled, long nplanes, int h2, int w2, int w2pad, void* stream) {
+  if (nplanes < 0 || h2 <= 0 || w2 <= 0 || w2pad < w2) return PVO_ERR_INVALID;
   if (nplanes == 0) return PVO_OK;
   tile_kernel<<<PVO_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>((const __half*)planar, (__half*)tiled, nplanes, h2, w2, (h2 + 3) / 4,
-                                                                  (w2 + 7) / 8);
+                                                                  (w2pad + 7) / 8);
   return pvo_check_launch();
 }

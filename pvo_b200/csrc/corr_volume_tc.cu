@@ -24,7 +24,9 @@ constexpr int kStagesB = 3;
 struct VolParams {
   CUtensorMap tmA, tmB;
   __half* lvl[4];
-  int E, H, HW, mtiles, items, nchunks;
+  const int* slots;          // TILED: edge e is written to plane block slots[e] of the level tensors (NULL: e)
+  int E, H, HW, HW2, mtiles, items, nchunks;
+  int wt;                    // true width of image 2 (<= W); columns wt..W-1 of the B operand are zero features
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
@@ -34,6 +36,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
 }
 
 __device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 u2h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
 __device__ __forceinline__ __half pool4(__half a, __half b, __half c, __half d) {
   float s = __half2float(a);
@@ -98,8 +101,8 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* sb = smB + stage * kStage;
           mbar_arrive_expect_tx(&full[stage], kStage);
-          tma_load_2d(&p.tmB, &full[stage], sb, 0, e * p.HW + c * N);
-          tma_load_2d(&p.tmB, &full[stage], sb + kBblk, 64, e * p.HW + c * N);
+          tma_load_2d(&p.tmB, &full[stage], sb, 0, e * p.HW2 + c * N);
+          tma_load_2d(&p.tmB, &full[stage], sb + kBblk, 64, e * p.HW2 + c * N);
           if (++stage == kStagesB) { stage = 0; phase ^= 1; }
         }
       }
@@ -138,13 +141,18 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
     int as = 0;
     uint32_t aphase = 0;
     const int H = p.H, H1 = H / 2, H2 = H1 / 2, H3 = H2 / 2;
+    // image 2 narrower than the template width (its feature map was zero padded to W columns): level 0 is exact by itself (zero
+    // features give zero correlations); the pooled levels must end at (wt >> l) like avg_pool2d's floor, so their columns past
+    // that are forced to zero before they are stored or pooled further
+    const bool masked = p.wt != W;
+    const int wt1 = p.wt >> 1, wt2 = p.wt >> 2, wt3 = p.wt >> 3;
     constexpr int TC0 = W / 8, TC1 = (W1 + 7) / 8, TC2 = (W2 + 7) / 8, TC3 = (W3 + 7) / 8;
     const int TR0 = (H + 3) / 4, TR1 = (H1 + 3) / 4, TR2 = (H2 + 3) / 4, TR3 = (H3 + 3) / 4;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int e = item / p.mtiles, mt = item - e * p.mtiles;
       const int p1 = mt * 128 + q * 32 + lane;
       const bool ok = p1 < p.HW;
-      const long rowi = (long)e * p.HW + p1;
+      const long rowi = (long)((TILED && p.slots) ? __ldg(p.slots + e) : e) * p.HW + p1;
       __half* o0 = p.lvl[0] + rowi * (TILED ? (long)TR0 * TC0 * 32 : (long)H * W);
       __half* o1 = p.lvl[1] + rowi * (TILED ? (long)TR1 * TC1 * 32 : (long)H1 * W1);
       __half* o2 = p.lvl[2] + rowi * (TILED ? (long)TR2 * TC2 * 32 : (long)H2 * W2);
@@ -185,6 +193,11 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
             l1cur[2 * j + t] = __halves2half2(pool4(__low2half(pa[2 * t]), __high2half(pa[2 * t]), __low2half(pb[2 * t]), __high2half(pb[2 * t])),
                                               pool4(__low2half(pa[2 * t + 1]), __high2half(pa[2 * t + 1]), __low2half(pb[2 * t + 1]), __high2half(pb[2 * t + 1])));
         }
+        if (masked) {
+#pragma unroll
+          for (int x = 0; x < W1 / 2; x++)
+            l1cur[x] = u2h2(h2u(l1cur[x]) & ((2 * x + 1 < wt1) ? 0xffffffffu : ((2 * x < wt1) ? 0x0000ffffu : 0u)));
+        }
         // the accumulator is drained: hand it back before the (register-only) pooling tail
         fence_before_sync();
         __syncwarp();
@@ -209,6 +222,11 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
           for (int x = 0; x < W2 / 2; x++)
             l2cur[x] = __halves2half2(pool4(__low2half(l1prev[2 * x]), __high2half(l1prev[2 * x]), __low2half(l1cur[2 * x]), __high2half(l1cur[2 * x])),
                                       pool4(__low2half(l1prev[2 * x + 1]), __high2half(l1prev[2 * x + 1]), __low2half(l1cur[2 * x + 1]), __high2half(l1cur[2 * x + 1])));
+          if (masked) {
+#pragma unroll
+            for (int x = 0; x < W2 / 2; x++)
+              l2cur[x] = u2h2(h2u(l2cur[x]) & ((2 * x + 1 < wt2) ? 0xffffffffu : ((2 * x < wt2) ? 0x0000ffffu : 0u)));
+          }
           if (ok && r2 < H2) {
             if (TILED) {
 #pragma unroll
@@ -228,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_volume_tc_kernel(const __gri
                 __half v3[TC3 * 8];
 #pragma unroll
                 for (int x = 0; x < TC3 * 8; x++)
-                  v3[x] = x < W3 ? pool4(__low2half(l2prev[x < W3 ? x : 0]), __high2half(l2prev[x < W3 ? x : 0]), __low2half(l2cur[x < W3 ? x : 0]),
+                  v3[x] = (x < W3 && x < wt3) ? pool4(__low2half(l2prev[x < W3 ? x : 0]), __high2half(l2prev[x < W3 ? x : 0]), __low2half(l2cur[x < W3 ? x : 0]),
                                          __high2half(l2cur[x < W3 ? x : 0]))
                                  : __float2half_rn(0.0f);
 #pragma unroll
@@ -285,41 +303,53 @@ int launch_vol(const VolParams& p, cudaStream_t s) {
 
 }  // namespace
 
-// fmap1, fmap2: (E, h*w, 128) fp16 pixel-major, pre-divided by 4.  levels_out[l]: (E, h, w, h>>l, w>>l) fp16.
-// Supported: num_levels == 4, w in {40, 80} (N = 2w must be a legal UMMA N and pooling stays register resident);
+// fmap1, fmap2: (E, h*w, 128) fp16 pixel-major, pre-divided by 4.  levels_out[l]: (E, h, w, h>>l, w>>l) fp16 (planar) or tiled.
+// Supported: num_levels == 4, h >= 8, template widths {40, 80} (planar and tiled) and {104, 128} (tiled; narrower images are zero
+// padded to the template width: N = 2 * wpad must be a legal UMMA N and the pooling rows stay register resident);
 // anything else returns PVO_ERR_UNSUPPORTED and the caller uses pvo_corr_volume.
-static int corr_volume_f16_impl(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w, int num_levels,
-                                bool tiled, void* stream) {
+static int corr_volume_f16_impl(const void* fmap1, const void* fmap2, void* const* levels_out, const int* slots, int E, int h, int w,
+                                int wpad, int num_levels, bool tiled, void* stream) {
   if (E < 0 || h <= 0 || w <= 0) return PVO_ERR_INVALID;
-  if (num_levels != 4 || (w != 80 && w != 40) || h < 8) return PVO_ERR_UNSUPPORTED;
+  if (num_levels != 4 || h < 8) return PVO_ERR_UNSUPPORTED;
+  if (!(wpad == 40 || wpad == 80 || wpad == 104 || wpad == 128) || w > wpad || (!tiled && w != wpad)) return PVO_ERR_UNSUPPORTED;
   if (E == 0) return PVO_OK;
   VolParams p;
-  const int HW = h * w;
-  const uint64_t dims[2] = {128, (uint64_t)E * HW};
+  const int HW = h * w, HW2 = h * wpad;
+  const uint64_t dimsA[2] = {128, (uint64_t)E * HW}, dimsB[2] = {128, (uint64_t)E * HW2};
   const uint64_t strides[1] = {256};
   const uint32_t boxA[2] = {64, 128};
-  const uint32_t boxB[2] = {64, (uint32_t)(2 * w)};
-  int rc = tc::make_tmap_f16(&p.tmA, fmap1, 2, dims, strides, boxA);
+  const uint32_t boxB[2] = {64, (uint32_t)(2 * wpad)};
+  int rc = tc::make_tmap_f16(&p.tmA, fmap1, 2, dimsA, strides, boxA);
   if (rc != PVO_OK) return rc;
-  rc = tc::make_tmap_f16(&p.tmB, fmap2, 2, dims, strides, boxB);
+  rc = tc::make_tmap_f16(&p.tmB, fmap2, 2, dimsB, strides, boxB);
   if (rc != PVO_OK) return rc;
   for (int l = 0; l < 4; l++) p.lvl[l] = (__half*)levels_out[l];
-  p.E = E; p.H = h; p.HW = HW;
+  p.slots = slots;
+  p.E = E; p.H = h; p.HW = HW; p.HW2 = HW2; p.wt = w;
   p.mtiles = (HW + 127) / 128;
   p.items = E * p.mtiles;
   p.nchunks = (h + 1) / 2;
   cudaStream_t s = (cudaStream_t)stream;
-  if (tiled) return w == 80 ? launch_vol<80, true>(p, s) : launch_vol<40, true>(p, s);
-  return w == 80 ? launch_vol<80, false>(p, s) : launch_vol<40, false>(p, s);
+  if (tiled) {
+    switch (wpad) {
+      case 40: return launch_vol<40, true>(p, s);
+      case 80: return launch_vol<80, true>(p, s);
+      case 104: return launch_vol<104, true>(p, s);
+      default: return launch_vol<128, true>(p, s);
+    }
+  }
+  return wpad == 80 ? launch_vol<80, false>(p, s) : (wpad == 40 ? launch_vol<40, false>(p, s) : PVO_ERR_UNSUPPORTED);
 }
 
 extern "C" int pvo_corr_volume_f16(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w,
                                    int num_levels, void* stream) {
-  return corr_volume_f16_impl(fmap1, fmap2, levels_out, E, h, w, num_levels, false, stream);
+  return corr_volume_f16_impl(fmap1, fmap2, levels_out, nullptr, E, h, w, w, num_levels, false, stream);
 }
 
-// levels_out[l]: (E, h*w, ceil((h>>l)/4), ceil((w>>l)/8), 32) fp16 -- the tiled private layout of corr_lookup_tiled.cu
-extern "C" int pvo_corr_volume_f16_tiled(const void* fmap1, const void* fmap2, void* const* levels_out, int E, int h, int w,
-                                         int num_levels, void* stream) {
-  return corr_volume_f16_impl(fmap1, fmap2, levels_out, E, h, w, num_levels, true, stream);
+// levels_out[l]: (capacity, h*w, ceil((h>>l)/4), ceil((wpad>>l)/8), 32) fp16 -- the tiled private layout of corr_lookup_tiled.cu.
+// fmap1 (E, h*w, 128); fmap2 (E, h*wpad, 128) with zero features in columns w..wpad-1 (wpad in {40, 80, 104, 128}: the UMMA N is
+// 2*wpad).  slots (E ints, or NULL): edge e is written to plane block slots[e] of the level tensors.
+extern "C" int pvo_corr_volume_f16_tiled(const void* fmap1, const void* fmap2, void* const* levels_out, const int* slots, int E,
+                                         int h, int w, int wpad, int num_levels, void* stream) {
+  return corr_volume_f16_impl(fmap1, fmap2, levels_out, slots, E, h, w, wpad, num_levels, true, stream);
 }

@@ -128,9 +128,14 @@ class FactorGraph:
         self._pull_state()
         net = self.video.nets[ii].to(self.device).unsqueeze(0)
         if self.corr_impl == 'volume':
-            corr = CorrBlock(self.video.fmaps[ii].to(self.device).unsqueeze(0),
-                             self.video.fmaps[jj].to(self.device).unsqueeze(0))
-            self.corr = corr if self.corr is None else self.corr.cat(corr)
+            f1, f2 = self.video.fmaps[ii].to(self.device).unsqueeze(0), self.video.fmaps[jj].to(self.device).unsqueeze(0)
+            pooled = hasattr(CorrBlock, 'append')     # (a reference-style CorrBlock substituted for ours has only cat / __getitem__)
+            if self.corr is None:     # volumes live in a slot pool: later edges are built into free slots, retired ones free theirs
+                self.corr = CorrBlock(f1, f2, capacity=2 * self.max_factors if self.max_factors > 0 else None) if pooled else CorrBlock(f1, f2)
+            elif pooled:
+                self.corr.append(f1, f2)
+            else:
+                self.corr = self.corr.cat(CorrBlock(f1, f2))
             inp = self.video.inps[ii].to(self.device).unsqueeze(0)
             self._inp = inp if self._inp is None else torch.cat([self._inp, inp], 1)
         target, _ = self.video.reproject(ii, jj)

@@ -38,40 +38,60 @@ def to_pixel_major(x):
     return out
 
 
+TC_WIDTHS = (40, 80, 104, 128)          # template widths of the tensor-core volume kernel (UMMA N = 2 * width)
+
+
+def pad_width(w):
+    """smallest tensor-core tile width that holds an image row of w pixels, or None"""
+    for t in TC_WIDTHS:
+        if w <= t:
+            return t
+    return None
+
+
 def tc_volume_supported(fmap, num_levels=4):
     N, C, h, w = fmap.shape
-    return fmap.dtype == torch.float16 and C == 128 and w in (40, 80) and h >= 8 and num_levels == 4
+    return fmap.dtype == torch.float16 and C == 128 and pad_width(w) is not None and h >= 8 and num_levels == 4
 
 
-def tiled_shape(N, h, w, l):
-    """shape of level l of the tiled pyramid for N edges of an (h, w) grid"""
-    return (N, h * w, ((h >> l) + 3) // 4, ((w >> l) + 7) // 8, 32)
+def tiled_shape(N, h, w, l, wpad=None):
+    """shape of level l of the tiled pyramid for N plane blocks (edges) of an (h, w) grid built at template width wpad"""
+    wpad = wpad or pad_width(w)
+    return (N, h * w, ((h >> l) + 3) // 4, ((wpad >> l) + 7) // 8, 32)
 
 
-def build_pyramid_tiled(fmap1, fmap2):
-    """fmap1, fmap2: (N,128,h,w) half -> 4 tiled levels (N, h*w, ceil(h_l/4), ceil(w_l/8), 32), one tcgen05 launch"""
+def build_pyramid_tiled(fmap1, fmap2, out=None, slots=None):
+    """fmap1, fmap2: (N,128,h,w) half -> 4 tiled levels (cap, h*w, ceil(h_l/4), ceil(wpad_l/8), 32), one tcgen05 launch.
+    out / slots: write edge e into plane block slots[e] of the given level tensors (a CorrBlock's pool)."""
     _lib.require_cuda(fmap1, fmap2)
     N, C, h, w = fmap1.shape
-    f1, f2 = to_pixel_major(fmap1 / 4.0), to_pixel_major(fmap2 / 4.0)
-    levels = [torch.empty(tiled_shape(N, h, w, l), dtype=torch.float16, device=fmap1.device) for l in range(4)]
-    check(_lib.lib().pvo_corr_volume_f16_tiled(ptr(f1), ptr(f2), _lib.ptr_array(levels), N, h, w, 4, stream()), 'corr_volume_f16_tiled')
+    wpad = pad_width(w)
+    f1 = to_pixel_major(fmap1 / 4.0)
+    f2 = fmap2 / 4.0
+    if wpad != w:                      # zero features in the pad columns: their correlations are exact zeros
+        f2 = torch.nn.functional.pad(f2, (0, wpad - w))
+    f2 = to_pixel_major(f2)
+    levels = out if out is not None else [torch.empty(tiled_shape(N, h, w, l, wpad), dtype=torch.float16, device=fmap1.device) for l in range(4)]
+    check(_lib.lib().pvo_corr_volume_f16_tiled(ptr(f1), ptr(f2), _lib.ptr_array(levels), ptr(slots), N, h, w, wpad, 4, stream()),
+          'corr_volume_f16_tiled')
     return levels
 
 
-def untile(level, h2, w2):
+def untile(level, h2, w2, w2pad=None):
     """(N, HW, TR, TC, 32) -> (N, HW, h2, w2) planar"""
     N, HW = level.shape[:2]
     out = torch.empty(N, HW, h2, w2, dtype=level.dtype, device=level.device)
-    check(_lib.lib().pvo_corr_untile(ptr(level), ptr(out), N * HW, h2, w2, stream()), 'corr_untile')
+    check(_lib.lib().pvo_corr_untile(ptr(level), ptr(out), N * HW, h2, w2, w2pad or w2, stream()), 'corr_untile')
     return out
 
 
-def tile(level):
-    """(..., h2, w2) planar half -> (prod(...), ceil(h2/4), ceil(w2/8), 32) tiled, zero padded"""
+def tile(level, w2pad=None):
+    """(..., h2, w2) planar half -> (prod(...), ceil(h2/4), ceil(w2pad/8), 32) tiled, zero padded"""
     h2, w2 = level.shape[-2:]
+    w2pad = w2pad or w2
     n = level.numel() // (h2 * w2)
-    out = torch.empty(n, (h2 + 3) // 4, (w2 + 7) // 8, 32, dtype=level.dtype, device=level.device)
-    check(_lib.lib().pvo_corr_tile(ptr(level.contiguous()), ptr(out), n, h2, w2, stream()), 'corr_tile')
+    out = torch.empty(n, (h2 + 3) // 4, (w2pad + 7) // 8, 32, dtype=level.dtype, device=level.device)
+    check(_lib.lib().pvo_corr_tile(ptr(level.contiguous()), ptr(out), n, h2, w2, w2pad, stream()), 'corr_tile')
     return out
 
 
@@ -80,7 +100,7 @@ def build_pyramid(fmap1, fmap2, num_levels=4, use_tc=None):
     _lib.require_cuda(fmap1, fmap2)
     N, C, h, w = fmap1.shape
     if use_tc is None:
-        use_tc = fmap1.dtype == torch.float16 and C == 128 and w in (40, 80) and h >= 8 and num_levels == 4
+        use_tc = fmap1.dtype == torch.float16 and C == 128 and w in (40, 80) and h >= 8 and num_levels == 4      # planar: exact widths only
     if use_tc:      # the tensor-core kernel takes the reference's `fmap / 4.0` (a half op, corr.py:66-67) as input
         f1, f2 = to_pixel_major(fmap1 / 4.0), to_pixel_major(fmap2 / 4.0)
     else:           # the CUDA-core kernel applies the same rounding while loading
@@ -96,9 +116,17 @@ def build_pyramid(fmap1, fmap2, num_levels=4, use_tc=None):
 
 
 class CorrBlock:
-    """corr.py:23-71"""
+    """corr.py:23-71.
 
-    def __init__(self, fmap1, fmap2, num_levels=4, radius=3, use_tc=None, tiled=None):
+    Production half path: the pyramid lives in a POOL of tiled plane blocks (one block = the four levels of one edge) addressed
+    through an edge -> slot table.  New edges are built straight into free slots (`append`), retiring edges only drops their table
+    entries (`block[mask]`): the per-frame loop adds and removes a few edges of a 48-edge window every frame, and with the
+    reference's representation (`torch.cat` / boolean indexing of the whole (E, h, w, h, w) tensors, factor_graph.py:128-131,
+    185-187) that copied the entire 1.2 GB volume several times per frame (4.2 ms of 22.5 ms GPU time per frame at the VKITTI
+    shape, tools/prof_loop.py).  Slots are handed out from the tail; when it is exhausted the live blocks are compacted into a
+    pool twice the live size (amortised)."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=3, use_tc=None, tiled=None, capacity=None):
         self.num_levels = num_levels
         self.radius = radius
         batch, num, dim, ht, wd = fmap1.shape
@@ -111,30 +139,77 @@ class CorrBlock:
         if tiled is None:
             tiled = can_tile
         if tiled and not can_tile:
-            raise RuntimeError('CorrBlock: the tiled layout needs half features, 128 channels, w in (40, 80), 4 levels, radius 3')
-        self._tiled = build_pyramid_tiled(f1, f2) if tiled else None
-        self._planar = None if tiled else build_pyramid(f1, f2, num_levels, use_tc)
+            raise RuntimeError('CorrBlock: the tiled layout needs half features, 128 channels, h >= 8, w <= 128, 4 levels, radius 3')
+        self._tiled = self._slots = self._planar = None
+        self._tail = 0
+        if tiled:
+            E = batch * num
+            self.wpad = pad_width(wd)
+            self._alloc_pool(max(E, capacity or 0), fmap1.device)
+            self._slots = torch.arange(E, dtype=torch.int32, device=fmap1.device)
+            self._tail = E
+            build_pyramid_tiled(f1, f2, out=self._tiled, slots=self._slots)
+        else:
+            self._planar = build_pyramid(f1, f2, num_levels, use_tc)
+
+    # ------------------------------------------------------------------ pool
+    def _alloc_pool(self, cap, device):
+        self._cap = cap
+        self._tiled = [torch.empty(tiled_shape(cap, self.ht, self.wd, l, self.wpad), dtype=torch.float16, device=device) for l in range(4)]
+
+    def _reserve(self, k):
+        """make room for k more blocks at the tail: compact the live blocks into a fresh pool when the tail is exhausted"""
+        if self._tail + k <= self._cap:
+            return
+        live = self._slots.long()
+        old = self._tiled
+        n = int(live.shape[0])
+        self._alloc_pool(max(2 * (n + k), 8), old[0].device)
+        for dst, src in zip(self._tiled, old):
+            if n:
+                torch.index_select(src, 0, live, out=dst[:n])
+        self._slots = torch.arange(n, dtype=torch.int32, device=old[0].device)
+        self._tail = n
+
+    def append(self, fmap1, fmap2):
+        """volumes of new edges (fmap1, fmap2: (1,k,128,h,w)) built directly into free slots; returns self"""
+        if self._tiled is None:
+            return self.cat(CorrBlock(fmap1, fmap2, self.num_levels, self.radius, tiled=False))
+        batch, num, dim, ht, wd = fmap1.shape
+        k = batch * num
+        self._reserve(k)
+        new = torch.arange(self._tail, self._tail + k, dtype=torch.int32, device=self._slots.device)
+        build_pyramid_tiled(fmap1.reshape(k, dim, ht, wd).contiguous(), fmap2.reshape(k, dim, ht, wd).contiguous(), out=self._tiled, slots=new)
+        self._slots = torch.cat([self._slots, new])
+        self._tail += k
+        self._planar = None
+        return self
+
+    def _live(self, l):
+        """level l of the live edges, in edge order: (E, HW, TR, TC, 32)"""
+        return torch.index_select(self._tiled[l], 0, self._slots.long())
 
     @property
     def corr_pyramid(self):
         """the reference's attribute (corr.py:29-38): [ (N, h, w, h>>l, w>>l) ]; converted from the tiled store when needed"""
         if self._planar is None:
-            self._planar = [untile(t, self.ht >> l, self.wd >> l).view(t.shape[0], self.ht, self.wd, self.ht >> l, self.wd >> l)
-                            for l, t in enumerate(self._tiled)]
+            self._planar = [untile(self._live(l), self.ht >> l, self.wd >> l, self.wpad >> l).view(-1, self.ht, self.wd, self.ht >> l, self.wd >> l)
+                            for l in range(4)]
         return self._planar
 
     @corr_pyramid.setter
     def corr_pyramid(self, levels):
         self._planar = list(levels)
-        self._tiled = None               # a caller-supplied pyramid is used as is, through the planar kernels
+        self._tiled = self._slots = None               # a caller-supplied pyramid is used as is, through the planar kernels
 
     def _lookup_tiled(self, coords, batch, num, ht, wd, out, layout, out_cstride):
-        t = self._tiled
+        if batch * num != self._slots.shape[0]:
+            raise RuntimeError('CorrBlock: %d coordinate maps for %d edges' % (batch * num, self._slots.shape[0]))
         if out is None:
             out = torch.empty(batch, num, 196, ht, wd, dtype=torch.float16, device=coords.device)
-        check(_lib.lib().pvo_corr_lookup_tiled(_lib.ptr_array(t), _lib.int_array([ht >> l for l in range(4)]),
-                                               _lib.int_array([wd >> l for l in range(4)]), 4, ptr(coords), ptr(out), batch * num, ht, wd,
-                                               3, layout, out_cstride, stream()), 'corr_lookup_tiled')
+        check(_lib.lib().pvo_corr_lookup_tiled(_lib.ptr_array(self._tiled), _lib.int_array([ht >> l for l in range(4)]),
+                                               _lib.int_array([self.wpad >> l for l in range(4)]), 4, ptr(self._slots), ptr(coords),
+                                               ptr(out), batch * num, ht, wd, 3, layout, out_cstride, stream()), 'corr_lookup_tiled')
         return out
 
     def __call__(self, coords, out=None, layout=0, out_cstride=0):
@@ -172,22 +247,26 @@ class CorrBlock:
 
     @property
     def num_edges(self):
-        return (self._tiled or self._planar)[0].shape[0]
+        return self._slots.shape[0] if self._tiled is not None else self._planar[0].shape[0]
 
     def cat(self, other):
-        if (self._tiled is None) != (other._tiled is None):          # mixed stores: fall back to the planar one
-            self.corr_pyramid = self.corr_pyramid
-            other = type('P', (), {'_tiled': None, '_planar': other.corr_pyramid})
-        if self._tiled is not None:
-            self._tiled = [torch.cat([a, b], 0) for a, b in zip(self._tiled, other._tiled)]
+        """reference interface (corr.py:52-56): append the edges of another block (copies the other block's volumes)"""
+        if self._tiled is not None and other._tiled is not None and other.wpad == self.wpad:
+            k = other.num_edges
+            self._reserve(k)
+            for l in range(4):
+                self._tiled[l][self._tail:self._tail + k] = other._live(l)
+            self._slots = torch.cat([self._slots, torch.arange(self._tail, self._tail + k, dtype=torch.int32, device=self._slots.device)])
+            self._tail += k
             self._planar = None
         else:
-            self._planar = [torch.cat([a, b], 0) for a, b in zip(self._planar, other._planar)]
+            self.corr_pyramid = [torch.cat([a, b], 0) for a, b in zip(self.corr_pyramid, other.corr_pyramid)]
         return self
 
     def __getitem__(self, index):
+        """reference interface (corr.py:58-61): keep the edges selected by a mask / index (no volume is moved on the tiled path)"""
         if self._tiled is not None:
-            self._tiled = [t[index].contiguous() for t in self._tiled]
+            self._slots = self._slots[index].contiguous()
             self._planar = None
         else:
             self._planar = [t[index].contiguous() for t in self._planar]

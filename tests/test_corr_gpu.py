@@ -279,6 +279,68 @@ def test_tiled_lookup_equals_planar_lookup_bit_for_bit(hw):
     # edge bookkeeping on the tiled store
     keep = torch.tensor([True, False, True, True, False], device='cuda')
     tb2 = CorrBlock(f1, f2)[keep]
-    assert tb2.num_edges == 3 and torch.equal(tb2(coords[:, keep]).view(torch.int16), a[:, keep].contiguous().view(torch.int16))
+    assert tb2.num_edges == 3 and torch.equal(tb2(coords[:, keep].contiguous()).view(torch.int16), a[:, keep].contiguous().view(torch.int16))
     tb3 = CorrBlock(f1[:, :2], f2[:, :2]).cat(CorrBlock(f1[:, 2:], f2[:, 2:]))
     assert torch.equal(tb3(coords).view(torch.int16), a.view(torch.int16))
+
+
+@pytest.mark.parametrize('hw', [(30, 101), (16, 24), (20, 128), (12, 96), (9, 57)])
+def test_tiled_volume_and_lookup_at_widths_padded_to_the_tensor_core_tile(hw):
+    """image rows that are not 40 / 80 pixels wide (the VKITTI2 grid is 30 x 101) are zero padded to the next tensor-core tile width
+    (40 / 80 / 104 / 128): level 0 within 2 ulp of the CUDA-core build, the pooled levels EXACTLY the avg_pool2d cascade of the
+    kernel's own level 0 with the reference's floor widths (columns past w >> l are zeros, not pooled pad values), every pad element
+    zero, and the lookup bit-identical to the planar kernel on the same values"""
+    from pvo_b200.modules.corr import CorrBlock, build_pyramid, build_pyramid_tiled, pad_width, tile, untile
+    h, w = hw
+    g = torch.Generator().manual_seed(18)
+    E = 3
+    f1 = torch.randn(E, 128, h, w, generator=g).half().cuda()
+    f2 = torch.randn(E, 128, h, w, generator=g).half().cuda()
+    wp = pad_width(w)
+    junk = torch.full((64 << 20,), 7.0, dtype=torch.float16, device='cuda')
+    del junk
+    tiled = build_pyramid_tiled(f1, f2)
+    cc = build_pyramid(f1, f2, 4, use_tc=False)
+    ulp = torch.finfo(torch.float16).eps
+    planar = []
+    for l in range(4):
+        h2, w2 = h >> l, w >> l
+        x = untile(tiled[l], h2, w2, wp >> l)
+        planar.append(x.view(E, h, w, h2, w2))
+        assert torch.equal(tile(x, wp >> l).view(tiled[l].shape).view(torch.int16), tiled[l].view(torch.int16)), 'pad elements of level %d' % l
+    assert (planar[0].float() - cc[0].float()).abs().max().item() <= 2 * ulp * max(1.0, cc[0].float().abs().max().item())
+    for l in range(3):
+        x = planar[l].cpu()
+        pooled = ocorr.avg_pool_level(x.reshape(-1, 1, x.shape[3], x.shape[4])).reshape(planar[l + 1].shape)
+        assert torch.equal(pooled, planar[l + 1].cpu()), l
+    tb = CorrBlock(f1[None], f2[None])
+    assert tb._tiled is not None and tb.wpad == wp
+    pb = CorrBlock(f1[None], f2[None], tiled=False)
+    pb.corr_pyramid = tb.corr_pyramid
+    coords = _coords(E, h, w, 35, spread=6.0, far=True).permute(0, 2, 3, 1)[None].contiguous().cuda()
+    assert torch.equal(tb(coords).view(torch.int16), pb(coords).view(torch.int16))
+
+
+def test_corrblock_slot_pool_append_retire_compact():
+    """edges appended into free slots, retired without moving a volume, compacted when the tail runs out: always the same lookups as
+    a block built from scratch on the surviving edges in the same order"""
+    from pvo_b200.modules.corr import CorrBlock
+    g = torch.Generator().manual_seed(19)
+    h, w, n = 16, 40, 9
+    f1 = torch.randn(1, n, 128, h, w, generator=g).half().cuda()
+    f2 = torch.randn(1, n, 128, h, w, generator=g).half().cuda()
+    coords = _coords(n, h, w, 36, spread=5.0).permute(0, 2, 3, 1)[None].contiguous().cuda()
+    blk = CorrBlock(f1[:, :4], f2[:, :4], capacity=6)
+    order = [0, 1, 2, 3]
+    p0 = blk._tiled[0].data_ptr()
+    blk.append(f1[:, 4:6], f2[:, 4:6]); order += [4, 5]
+    assert blk._tiled[0].data_ptr() == p0 and blk.num_edges == 6                 # fitted into the pool
+    keep = torch.tensor([True, False, True, True, False, True], device='cuda')
+    blk = blk[keep]; order = [o for o, k in zip(order, keep.tolist()) if k]
+    assert blk._tiled[0].data_ptr() == p0                                        # nothing moved
+    blk.append(f1[:, 6:9], f2[:, 6:9]); order += [6, 7, 8]                       # tail exhausted -> compaction into a new pool
+    assert blk._tiled[0].data_ptr() != p0 and blk.num_edges == 7
+    ref = CorrBlock(f1[:, order], f2[:, order])
+    assert torch.equal(blk(coords[:, order]).view(torch.int16), ref(coords[:, order]).view(torch.int16))
+    for a, b in zip(blk.corr_pyramid, ref.corr_pyramid):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
