@@ -742,7 +742,9 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
           (double*)(ws + L.off_sys), (float*)(ws + L.off_dx)};
   cudaStream_t s = (cudaStream_t)stream;
   const int n = 6 * P;
-  if (!(flags & 1)) ba_plan_kernel<<<1, 1024, 0, s>>>(ii, E, nframes, t0, t1, K, pl, bf.sys, n);
+  // flags bit 4: the caller guarantees that the system replicas are already zero (a workspace nobody else uses: every call leaves
+  // them zeroed) -- skips the 2.3 MB single-block clear at P = 63
+  if (!(flags & 1)) ba_plan_kernel<<<1, 1024, 0, s>>>(ii, E, nframes, t0, t1, K, pl, (flags & 16) ? nullptr : bf.sys, n);
   const dim3 grid(ceil_div(HW, kPix), K);
   static bool attr_set = false;
   const int deg_hint = (flags >> 8) & 0xFFF;
@@ -779,7 +781,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
       // per block column) want the whole SM
       ba_solve_kernel<true><<<1, P <= 10 ? 128 : 512, solve_smem, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint);
     } else {
-      ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);
+      if (phase != 2) ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);      // phase 2: phase 1 already folded the replicas
       ba_solve_kernel<false><<<1, 512, 200 * 1024, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint);   // band-packed copy in smem when it fits
       ba_zero_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);
     }

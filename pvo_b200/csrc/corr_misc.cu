@@ -55,47 +55,85 @@ __global__ void __launch_bounds__(128) corr_index_bwd_kernel(const float* __rest
     }
 }
 
-// altcorr: one thread per (b, s, pixel); 8x8 taps, each a C-channel dot product (float4 loads), bilinear splat kept in
-// registers.  First version (SURVEY.md section 8(f) item 3 marks the tiled / tensor-core rewrite as "next").
-__global__ void __launch_bounds__(128) altcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+// altcorr forward (AltCorrBlock, the global-BA path `update_lowmem`): the 8x8 dot products <f1[pixel], f2[tap]> of every pixel, blended
+// bilinearly into the 7x7 outputs (VO_Module/src/altcorr_kernel.cu:27-149).  The reference (and round 1 here) gives every pixel to one
+// thread, which walks 64 taps x C channels with row loads that no two lanes share.  Here a WARP owns a pixel: the lanes split the
+// channels (one float4 each at C = 128), so every tap is one coalesced 512-byte row read; the 64 per-lane partial sums are
+// transpose-reduced across the warp (62 shuffles instead of 64 x 5) so that lane L ends with taps 2L, 2L+1, which go through 256 B of
+// shared memory to the lanes that blend the 49 outputs.  A block is an 8x8 pixel tile of one (batch, sample) plane: neighbouring
+// pixels' windows overlap, so most tap rows of a tile are L1 hits.  float32 throughout (the reference forces .float(), corr.py:120).
+template <int WW, int BIT>
+__device__ __forceinline__ void xr64_step(float* x, int lane) {
+  const bool up = lane & BIT;
+#pragma unroll
+  for (int j = 0; j < WW; j++) {
+    const float send = up ? x[j] : x[j + WW];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, BIT);
+    x[j] = (up ? x[j + WW] : x[j]) + recv;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) altcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                                                           const float* __restrict__ coords, float* __restrict__ out,
-                                                          int B, int S, int H1, int W1, int H2, int W2, int C) {
+                                                          int B, int S, int H1, int W1, int H2, int W2, int C, int tiles_x, int tiles_y) {
+  __shared__ float dots[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long plane = (long)H1 * W1;
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long)B * S * plane) return;
-  const long bs = t / plane;
-  const long pix = t - bs * plane;
+  const int tile = blockIdx.x % (tiles_x * tiles_y);
+  const long bs = blockIdx.x / (tiles_x * tiles_y);
   const int b = (int)(bs / S);
-  const float x2 = coords[t * 2], y2 = coords[t * 2 + 1];
-  const float dx = x2 - floorf(x2), dy = y2 - floorf(y2);
-  const int fx = (int)fminf(fmaxf(floorf(x2), -16777216.f), 16777216.f), fy = (int)fminf(fmaxf(floorf(y2), -16777216.f), 16777216.f);
-  const float* a = f1 + ((long)b * plane + pix) * C;
-  float acc[49];
+  const int y = (tile / tiles_x) * 8 + warp;
+  if (y >= H1) return;
+  for (int k = 0; k < 8; k++) {
+    const int x = (tile % tiles_x) * 8 + k;
+    if (x >= W1) break;                                                  // warp-uniform
+    const long pix = (long)y * W1 + x;
+    const long t = bs * plane + pix;
+    const float x2 = coords[t * 2], y2 = coords[t * 2 + 1];
+    const float dx = x2 - floorf(x2), dy = y2 - floorf(y2);
+    const int fx = (int)fminf(fmaxf(floorf(x2), -16777216.f), 16777216.f), fy = (int)fminf(fmaxf(floorf(y2), -16777216.f), 16777216.f);
+    const float* a = f1 + ((long)b * plane + pix) * C;
+#pragma unroll 1
+    for (int part = 0; part < 4; part++) {                                 // two window rows (16 taps) at a time: 16 partial sums per lane
+      float acc[16];
 #pragma unroll
-  for (int q = 0; q < 49; q++) acc[q] = 0.0f;
+      for (int q = 0; q < 16; q++) acc[q] = 0.0f;
+      for (int c0 = lane * 4; c0 < C; c0 += 128) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(a + c0));
 #pragma unroll
-  for (int iy = 0; iy < 8; iy++) {
+        for (int iy = 0; iy < 2; iy++) {
 #pragma unroll
-    for (int ix = 0; ix < 8; ix++) {
-      const int hh = fy - 3 + iy, ww = fx - 3 + ix;
-      float s = 0.0f;
-      if (inb(hh, ww, H2, W2)) {
-        const float* bb = f2 + (((long)b * H2 + hh) * W2 + ww) * C;
-        for (int c = 0; c < C; c += 4) {
-          const float4 u = __ldg(reinterpret_cast<const float4*>(a + c));
-          const float4 v = __ldg(reinterpret_cast<const float4*>(bb + c));
-          s = fmaf(u.x, v.x, s); s = fmaf(u.y, v.y, s); s = fmaf(u.z, v.z, s); s = fmaf(u.w, v.w, s);
+          for (int ix = 0; ix < 8; ix++) {
+            const int hh = fy - 3 + part * 2 + iy, ww = fx - 3 + ix;
+            const bool v_ok = inb(hh, ww, H2, W2);                         // warp-uniform
+            const float4 v = v_ok ? __ldg(reinterpret_cast<const float4*>(f2 + (((long)b * H2 + hh) * W2 + ww) * C + c0))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            float s = acc[iy * 8 + ix];
+            s = fmaf(u.x, v.x, s); s = fmaf(u.y, v.y, s); s = fmaf(u.z, v.z, s); s = fmaf(u.w, v.w, s);
+            acc[iy * 8 + ix] = s;
+          }
         }
       }
-      if (iy > 0 && ix > 0) acc[(iy - 1) + 7 * (ix - 1)] += s * (dy * dx);
-      if (iy > 0 && ix < 7) acc[(iy - 1) + 7 * ix] += s * (dy * (1 - dx));
-      if (iy < 7 && ix > 0) acc[iy + 7 * (ix - 1)] += s * ((1 - dy) * dx);
-      if (iy < 7 && ix < 7) acc[iy + 7 * ix] += s * ((1 - dy) * (1 - dx));
+      xr64_step<8, 16>(acc, lane);
+      xr64_step<4, 8>(acc, lane);
+      xr64_step<2, 4>(acc, lane);
+      xr64_step<1, 2>(acc, lane);
+      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);                   // lanes 2k, 2k+1 now both hold tap k of this part
+      if (!(lane & 1)) dots[warp][part * 16 + (lane >> 1)] = acc[0];       // tap = iy * 8 + ix, fully summed over the channels
     }
+    __syncwarp();
+    float* o = out + bs * 49 * plane + pix;
+    for (int q = lane; q < 49; q += 32) {
+      const int ox = q / 7, oy = q - ox * 7;                                               // channel = y-offset + 7 * x-offset
+      const float* d = &dots[warp][oy * 8 + ox];
+      float r = d[0] * ((1 - dy) * (1 - dx));
+      r += d[1] * ((1 - dy) * dx);
+      r += d[8] * (dy * (1 - dx));
+      r += d[9] * (dy * dx);
+      o[(long)q * plane] = r;
+    }
+    __syncwarp();                                                          // dots[warp] is rewritten by the next pixel
   }
-  float* o = out + bs * 49 * plane + pix;
-#pragma unroll
-  for (int q = 0; q < 49; q++) o[(long)q * plane] = acc[q];
 }
 
 // altcorr backward (training path): one warp per (b, source pixel), lane <-> 4 channels.  For every sample n and tap (iy, ix) of the
@@ -177,7 +215,9 @@ extern "C" int pvo_altcorr_forward(const float* fmap1, const float* fmap2, const
   if (B < 0 || S < 0 || C % 4) return PVO_ERR_INVALID;
   if (radius != 3) return PVO_ERR_UNSUPPORTED;
   if (B == 0 || S == 0) return PVO_OK;
-  const int grid = ceil_div((long)B * S * H1 * W1, 128);
-  altcorr_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(fmap1, fmap2, coords, out, B, S, H1, W1, H2, W2, C);
+  const int tx = (W1 + 7) / 8, ty = (H1 + 7) / 8;
+  const long blocks = (long)B * S * tx * ty;
+  if (blocks > 0x7fffffffL) return PVO_ERR_UNSUPPORTED;
+  altcorr_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(fmap1, fmap2, coords, out, B, S, H1, W1, H2, W2, C, tx, ty);
   return pvo_check_launch();
 }

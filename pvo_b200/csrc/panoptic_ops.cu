@@ -63,6 +63,28 @@ __global__ void __launch_bounds__(256) paste_masks_kernel(const float* __restric
   reinterpret_cast<unsigned int*>(out + (long)r * H * W)[q] = bits;
 }
 
+// the same paste, one pixel per thread: image widths that are not a multiple of 4 (a packed word would straddle two rows)
+__global__ void __launch_bounds__(256) paste_masks_px_kernel(const float* __restrict__ prob, const float* __restrict__ boxes, int S, int H, int W,
+                                                             float thr, unsigned char* __restrict__ out) {
+  extern __shared__ float P[];
+  const int r = blockIdx.y;
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) P[i] = prob[(long)r * S * S + i];
+  __syncthreads();
+  const float bx0 = boxes[r * 4 + 0], by0 = boxes[r * 4 + 1], bx1 = boxes[r * 4 + 2], by1 = boxes[r * 4 + 3];
+  const float bw = __fsub_rn(bx1, bx0), bh = __fsub_rn(by1, by0);
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= H * W) return;
+  const int y = q / W, x = q - y * W;
+  const float cy = (float)y + 0.5f, cx = (float)x + 0.5f;
+  bool on = false;
+  if (cy >= by0 - 1.0f && cy <= by1 + 1.0f && cx >= bx0 - 1.0f && cx <= bx1 + 1.0f) {
+    const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(cy, by0), bh), 2.0f), 1.0f);
+    const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(cx, bx0), bw), 2.0f), 1.0f);
+    on = paste_px(P, S, gx, gy, thr);
+  }
+  out[(long)r * H * W + q] = on ? 1 : 0;
+}
+
 // ---- merge
 // info_out[n][k] = {segment id, category, isthing, area, instance index}; counts_out[n] = number of segments.
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(1024)
@@ -221,12 +243,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(1024)
 }  // namespace
 
 // paste_masks_in_image for R detections of images of one size: prob (R,S,S) float32 probabilities of the predicted class,
-// boxes (R,4) float32, out (R,H,W) uint8 (0/1).  W % 4 == 0.
+// boxes (R,4) float32, out (R,H,W) uint8 (0/1).  Any width (4 pixels per thread when W % 4 == 0).
 extern "C" int pvo_paste_masks(const float* prob, const float* boxes, int R, int S, int H, int W, float thr, void* out, void* stream) {
   if (R == 0) return PVO_OK;
-  if (W % 4 || S < 1 || S > 64) return PVO_ERR_INVALID;
-  dim3 grid(ceil_div((long)H * W / 4, 256), R);
-  paste_masks_kernel<<<grid, 256, S * S * sizeof(float), (cudaStream_t)stream>>>(prob, boxes, S, H, W, thr, (unsigned char*)out);
+  if (S < 1 || S > 64) return PVO_ERR_INVALID;
+  if (W % 4 == 0) {
+    dim3 grid(ceil_div((long)H * W / 4, 256), R);
+    paste_masks_kernel<<<grid, 256, S * S * sizeof(float), (cudaStream_t)stream>>>(prob, boxes, S, H, W, thr, (unsigned char*)out);
+  } else {
+    dim3 grid(ceil_div((long)H * W, 256), R);
+    paste_masks_px_kernel<<<grid, 256, S * S * sizeof(float), (cudaStream_t)stream>>>(prob, boxes, S, H, W, thr, (unsigned char*)out);
+  }
   return pvo_check_launch();
 }
 

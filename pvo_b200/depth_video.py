@@ -136,7 +136,7 @@ class DepthVideo:
         return d.reshape(N, N) if return_matrix else d
 
     def ba(self, target, weight, eta, ii, jj, t0=1, t1=None, itrs=2, lm=1e-4, ep=0.1, motion_only=False,
-           interleaved=False, reuse_plan=False, max_degree=0, max_span=None):
+           interleaved=False, reuse_plan=False, max_degree=0, max_span=None, workspace=None, sys_clean=False):
         """dense bundle adjustment (depth_video.py:197-214): in place on poses/disps, then disps.clamp_(min=0.001)."""
         with self.get_lock():
             if t1 is None:
@@ -146,6 +146,6 @@ class DepthVideo:
                 eta = 1e-7 * torch.ones([k, self.ht // 8, self.wd // 8], device=self.device)
             out = droid_backends.ba(self.poses, self.disps, self.intrinsics[0].contiguous(), target, weight, eta, ii, jj,
                                     t0, t1, itrs, lm, ep, motion_only, interleaved=interleaved, reuse_plan=reuse_plan,
-                                    max_degree=max_degree, max_span=max_span)
+                                    max_degree=max_degree, max_span=max_span, workspace=workspace, sys_clean=sys_clean)
             check(_lib.lib().pvo_clamp_min(ptr(self.disps), self.disps.numel(), 0.001, stream()), 'clamp_min')
             return out

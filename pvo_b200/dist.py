@@ -89,7 +89,8 @@ def system_view(ws, E, nframes, P, K, HW):
 
 
 def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only,
-               interleaved=False, group=None, workspace=None, max_degree=0, reducer=None, max_span=None):
+               interleaved=False, group=None, workspace=None, max_degree=0, reducer=None, max_span=None, reuse_plan=False,
+               sys_clean=False):
     """droid_backends.ba for a rank's shard of the edges: assemble -> all-reduce -> solve + update, per iteration.
     poses must be identical on all ranks on entry and are identical on exit."""
     E = ii.shape[0]
@@ -102,13 +103,13 @@ def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, 
     L = _lib.lib()
 
     def call(phase, reuse):
-        flags = (1 if reuse else 0) | (phase << 1) | ((int(max_degree) & 0xFFF) << 8) | droid_backends.band_flag(max_span)
+        flags = (1 if reuse else 0) | (phase << 1) | (16 if sys_clean else 0) | ((int(max_degree) & 0xFFF) << 8) | droid_backends.band_flag(max_span)
         check(L.pvo_ba(ptr(poses), ptr(disps), ptr(intrinsics), ptr(targets), ptr(weights), ptr(eta), ptr(ii), ptr(jj), E,
                        nframes, ht, wd, int(t0), int(t1), K, 1, float(lm), float(ep), 1 if motion_only else 0,
                        1 if interleaved else 0, ptr(dx), ptr(dz), ptr(ws), ws.numel(), flags, stream()), 'ba',
               launches=(0 if reuse else 1) + 2)
     for it in range(int(iterations)):
-        call(1, it > 0)
+        call(1, it > 0 or reuse_plan)
         if reducer is not None:
             reducer(sysbuf)
         else:
@@ -124,11 +125,11 @@ def attach(fg, rank, world, frames_per_rank, group=None):
     fg.allreduce_kind = 'one-shot push over NVLink peer memory (own kernel)' if reducer is not None else 'ncclAllReduce'
 
     def ba(target, weight, eta, ii, jj, t0=1, t1=None, itrs=2, lm=1e-4, ep=0.1, motion_only=False, interleaved=False,
-           reuse_plan=False, max_degree=0, max_span=None):
+           reuse_plan=False, max_degree=0, max_span=None, workspace=None, sys_clean=False):
         # max_span arrives already maximised over ranks (fg._span_reduce below, called by FactorGraph when the edge set changes)
         out = ba_sharded(video.poses, video.disps, video.intrinsics[0].contiguous(), target, weight, eta, ii, jj, t0, t1,
                          itrs, lm, ep, motion_only, interleaved=interleaved, group=group, max_degree=max_degree, reducer=reducer,
-                         max_span=max_span)
+                         max_span=max_span, workspace=workspace, reuse_plan=reuse_plan, sys_clean=sys_clean)
         check(_lib.lib().pvo_clamp_min(ptr(video.disps), video.disps.numel(), 0.001, stream()), 'clamp_min')
         return out
     def span_reduce(local_span):

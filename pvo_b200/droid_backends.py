@@ -112,13 +112,15 @@ def band_flag(max_span):
 
 
 def ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iterations, lm, ep, motion_only,
-       interleaved=False, reuse_plan=False, workspace=None, max_degree=0, max_span=None):
+       interleaved=False, reuse_plan=False, workspace=None, max_degree=0, max_span=None, sys_clean=False):
     """src/droid_kernels.cu:1293-1410.  Mutates poses (buf,7) and disps (buf,ht,wd) in place; returns [dx, dz].
 
     targets / weights: (E,2,ht,wd) as the reference passes them (factor_graph.py:297-300), or (E,ht,wd,2) with
     ``interleaved=True`` (saves the permute+contiguous copies).  eta: (K,ht,wd).
     max_span: optional max |ii - jj| over the WHOLE graph (all shards): the pose system then has block bandwidth <= 2 max_span
-    and the solver skips its own sparsity scan."""
+    and the solver skips its own sparsity scan.
+    workspace / sys_clean: a caller-owned workspace (zero-initialised once, used by nobody else) whose system replicas are therefore
+    known to be zero on entry -- every call leaves them zeroed -- so the schedule kernel need not clear them (CUDA-graph replays)."""
     require_cuda(poses, disps, intrinsics, targets, weights, eta, ii, jj)
     if not reuse_plan:
         _ba_plan[0] = None
@@ -134,7 +136,7 @@ def ba(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, iteratio
     check(_lib.lib().pvo_ba(ptr(poses), ptr(disps), ptr(intrinsics), ptr(targets), ptr(weights), ptr(eta), ptr(ii),
                             ptr(jj), E, nframes, ht, wd, int(t0), int(t1), K, int(iterations), float(lm), float(ep),
                             1 if motion_only else 0, 1 if interleaved else 0, ptr(dx), ptr(dz), ptr(ws), ws.numel(),
-                            (1 if reuse_plan else 0) | ((int(max_degree) & 0xFFF) << 8) | band_flag(max_span), stream()), 'ba',
+                            (1 if reuse_plan else 0) | (16 if sys_clean else 0) | ((int(max_degree) & 0xFFF) << 8) | band_flag(max_span), stream()), 'ba',
           launches=(0 if reuse_plan else 1) + int(iterations) * (3 if motion_only else 4))
     if CHECK_BA:
         check_ba_meta(ws, E, nframes, P, K, ht * wd)

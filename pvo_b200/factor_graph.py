@@ -255,10 +255,9 @@ class FactorGraph:
             return self._update(t0, t1, itrs, use_inactive, EP, motion_only)
         # CUDA-graph path: 1st call with a given signature runs eagerly (lazy initialisation, attribute setup; with
         # use_inactive it also builds the inactive slab, the only step with a host synchronisation), 2nd call captures, later
-        # calls replay.  Every launch of the iteration is capture-safe.  The captured iteration always contains the BA
-        # schedule kernel and runs on a workspace this graph holds a reference to, so other BA calls on the device between
-        # replays (another FactorGraph, the backend, a different window) can neither leave a foreign schedule behind nor
-        # free the buffer the graph writes to.
+        # calls replay.  Every launch of the iteration is capture-safe.  The BA of such a graph runs on a private workspace
+        # held by this cache entry (see _iteration), so other BA calls on the device between replays (another FactorGraph, the
+        # backend, a different window) can neither leave a foreign schedule behind nor free the buffer the graph writes to.
         c = self._cache or self._prepare()
         key = (t0, t1, itrs, EP, motion_only, use_inactive)
         entry = c['graphs'].get(key)
@@ -274,10 +273,8 @@ class FactorGraph:
             with torch.cuda.graph(g, capture_error_mode=mode):
                 self._update(t0, t1, itrs, use_inactive, EP, motion_only, capturing=True)
             c['graphs'][key] = g
-            c.setdefault('ws_refs', []).append(droid_backends.current_workspace(self.video.poses.device))
             entry = g
         entry.replay()
-        droid_backends.set_ba_plan_owner(None)          # the replay rewrote the shared schedule
 
     def _inactive_slab(self, c, t0, t1):
         """`use_inactive=True` (every frontend call, droid_frontend.py:49,62,81,87): the BA also sees the stored edges whose
@@ -347,12 +344,12 @@ class FactorGraph:
             self.launch_count = plan.launches
             return
         with _lib.recording(plannable) as rec:
-            self._iteration(c, eng, ia, t0, t1, itrs, EP, motion_only, use_inactive, capturing or plannable)
+            self._iteration(c, eng, ia, t0, t1, itrs, EP, motion_only, use_inactive, capturing or plannable, capturing)
         if rec is not None and rec.calls is not None:
             c['plans'][key] = rec
         self.launch_count = _lib.LAUNCHES[0] - n0
 
-    def _iteration(self, c, eng, ia, t0, t1, itrs, EP, motion_only, use_inactive, fresh_schedule):
+    def _iteration(self, c, eng, ia, t0, t1, itrs, EP, motion_only, use_inactive, fresh_schedule, capturing=False):
         L = _lib.lib()
         E, ht, wd = c['E'], self.ht, self.wd
         v = self.video
@@ -403,14 +400,32 @@ class FactorGraph:
             damping.mul_(.2).add_(EP)
         _lib.torch_op(damp)
         # the BA schedule in the (shared) workspace can be reused iff the last BA call anywhere was this graph's, on this edge set and
-        # window; a captured / recorded iteration always rebuilds it (see update())
+        # window; a recorded iteration always rebuilds it.  A graph that replays as a CUDA graph owns a PRIVATE workspace per
+        # (edges, window): nobody else can leave a foreign schedule there or dirty its system replicas, so the captured iteration
+        # carries neither the schedule kernel nor the clearing of the replicas (43 us per step at P = 63), and growth of the shared
+        # workspace elsewhere cannot free the buffer under the graph.
         token = (id(self), serial, t0, t1, ii.shape[0], motion_only)
-        reuse = (not fresh_schedule) and droid_backends.ba_plan_owner() == token
+        ws, clean = None, False
+        if self.use_cuda_graph:
+            wkey = ('ba_ws', ii.shape[0], t0, t1, kx_ba.shape[0])
+            ws = c.get(wkey)
+            if ws is None:
+                if capturing:
+                    raise RuntimeError('FactorGraph: the private BA workspace must exist before capture')
+                need = _lib.lib().pvo_ba_workspace_bytes(ii.shape[0], v.disps.shape[0], t1 - t0, kx_ba.shape[0], ht * wd)
+                ws = c[wkey] = torch.zeros(int(need) + 1024, dtype=torch.uint8, device=self.device)
+            reuse = c.get(wkey + ('token',)) == token
+            clean = reuse
+        else:
+            reuse = (not fresh_schedule) and droid_backends.ba_plan_owner() == token
         # (5) dense bundle adjustment, in place on video.poses / video.disps
         with T('ba_total'):
             v.ba(target_cam[0], weight[0], damping, ii, jj, t0, t1, itrs=itrs, lm=1e-4, ep=0.1, motion_only=motion_only,
-                 interleaved=True, reuse_plan=reuse, max_degree=max_degree, max_span=max_span)
-        droid_backends.set_ba_plan_owner(token)
+                 interleaved=True, reuse_plan=reuse, max_degree=max_degree, max_span=max_span, workspace=ws, sys_clean=clean)
+        if ws is not None:
+            c[wkey + ('token',)] = token
+        else:
+            droid_backends.set_ba_plan_owner(token)
         age = self.age
         _lib.torch_op(lambda: age.add_(1))
 

@@ -79,18 +79,6 @@ def grid_anchors(h, w, stride, size, device):
     return (shifts.view(-1, 1, 4) + cell.view(1, -1, 4)).reshape(-1, 4)
 
 
-def paste_masks(masks, boxes, img_h, img_w, threshold=0.5):
-    """layers/mask_ops.py:17-152: bilinear resample of the 28x28 probabilities into the box, thresholded -> (R,H,W) bool"""
-    R = masks.shape[0]
-    if R == 0:
-        return torch.zeros(0, img_h, img_w, dtype=torch.bool, device=masks.device)
-    x0, y0, x1, y1 = torch.split(boxes, 1, dim=1)
-    img_y = (torch.arange(0, img_h, dtype=torch.float32, device=masks.device) + 0.5 - y0) / (y1 - y0) * 2 - 1
-    img_x = (torch.arange(0, img_w, dtype=torch.float32, device=masks.device) + 0.5 - x0) / (x1 - x0) * 2 - 1
-    grid = torch.stack([img_x[:, None, :].expand(R, img_h, img_w), img_y[:, :, None].expand(R, img_h, img_w)], dim=3)
-    return F.grid_sample(masks.float(), grid, align_corners=False)[:, 0] >= threshold
-
-
 def segments_for_vo(pan, size=None):
     """In-process hand-off of a panoptic id map to VO_Module (replaces the PNG round trip panoptic_evaluation.py ->
     split_init_segm.py -> evaluation_scripts/test_vo.py:44-50): nearest resize to the VO input size, then nearest 1/8
@@ -462,8 +450,6 @@ class PanopticFPN:
     def paste(self, prob, boxes, H, W, threshold=0.5):
         """paste_masks_in_image (mask_ops.py:74-152): prob (R,1,28,28) probabilities, boxes (R,4) -> (R,H,W) bool"""
         R = prob.shape[0]
-        if W % 4:
-            return paste_masks(prob, boxes, H, W, threshold)
         out = torch.empty(R, H, W, dtype=torch.uint8, device=self.device)
         prob, boxes = prob.float().contiguous(), boxes.float().contiguous()
         check(_lib.lib().pvo_paste_masks(ptr(prob), ptr(boxes), R, prob.shape[-1], H, W, float(threshold), ptr(out), stream()), 'paste_masks')

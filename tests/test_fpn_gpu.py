@@ -178,13 +178,26 @@ def test_roi_align_fpn_matches_torchvision():
         assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max() < 1e-4 * ref.abs().max()
 
 
-def test_paste_masks_matches_grid_sample():
-    """the paste kernel restates mask_ops.py's grid construction + grid_sample operation for operation: same booleans"""
-    from pvo_b200.panoptic_fpn import PanopticFPN, paste_masks
+def paste_masks(masks, boxes, img_h, img_w, threshold=0.5):
+    """layers/mask_ops.py:17-152 restated with torch ops (the test's reference): bilinear resample of the 28x28 probabilities into
+    the box via F.grid_sample, thresholded -> (R,H,W) bool"""
+    R = masks.shape[0]
+    x0, y0, x1, y1 = torch.split(boxes, 1, dim=1)
+    img_y = (torch.arange(0, img_h, dtype=torch.float32, device=masks.device) + 0.5 - y0) / (y1 - y0) * 2 - 1
+    img_x = (torch.arange(0, img_w, dtype=torch.float32, device=masks.device) + 0.5 - x0) / (x1 - x0) * 2 - 1
+    grid = torch.stack([img_x[:, None, :].expand(R, img_h, img_w), img_y[:, :, None].expand(R, img_h, img_w)], dim=3)
+    return torch.nn.functional.grid_sample(masks.float(), grid, align_corners=False)[:, 0] >= threshold
+
+
+@pytest.mark.parametrize('w', [200, 203])
+def test_paste_masks_matches_grid_sample(w):
+    """the paste kernel restates mask_ops.py's grid construction + grid_sample operation for operation: same booleans (4 pixels
+    per thread when 4 | W, one otherwise -- there is no torch fallback)"""
+    from pvo_b200.panoptic_fpn import PanopticFPN
     m = PanopticFPN.__new__(PanopticFPN)
     m.device = torch.device('cuda')
     g = torch.Generator().manual_seed(11)
-    h, w, R = 120, 200, 64
+    h, R = 120, 64
     c = torch.rand(R, 2, generator=g) * torch.tensor([w, h])
     wh = torch.exp(torch.rand(R, 2, generator=g) * 4.5) + 2
     boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
