@@ -271,3 +271,31 @@ def test_inference_end_to_end(setup):
         NOTES.setdefault('detections', []).append([o['instances']['scores'].shape[0], r['instances']['scores'].shape[0]])
         assert agree > 0.9, agree
         assert (o['sem_seg'].argmax(0).cpu() == r['sem_seg'].argmax(0)).float().mean() > 0.97
+
+
+def test_config4_resolution_480x640():
+    """BASELINE configs[3] resolution (one 480x640 image; the bench runs 8): feature pyramid, semantic logits and RPN heads against
+    the fp32 oracle at the stage tolerances of the 128x192 tests, then the composed output by pixel agreement"""
+    from pvo_b200.panoptic_fpn import PanopticFPN
+    sd = ofpn.init_params(0)
+    g = torch.Generator().manual_seed(5)
+    hh, ww = 480, 640
+    img = torch.nn.functional.avg_pool2d(torch.randint(0, 256, (1, 3, hh, ww), generator=g).float(), 7, 1, 3)[0] * 2 - 64
+    dbg = {}
+    ref = ofpn.inference(sd, [img], debug=dbg)
+    m = PanopticFPN(sd, device='cuda')
+    x, sizes = m.preprocess([img])
+    feats = m.backbone(x)
+    for k in ('p2', 'p3', 'p4', 'p5', 'p6'):
+        t, h, w = feats[k]
+        e = rel(nchw(t, 1, h, w), dbg['feats'][k], 'cfg4_' + k)
+        assert e < 2e-2, (k, e)
+    sem = m.sem_seg(feats)
+    assert rel(sem[..., :12].permute(0, 3, 1, 2), dbg['sem'], 'cfg4_sem_logits') < 2e-2
+    assert (sem[..., :12].argmax(-1).cpu() == dbg['sem'].argmax(1)).float().mean() > 0.97
+    out = m.inference([img.cuda()])
+    pan, segs = out[0]['panoptic_seg']
+    assert pan.shape == (hh, ww)
+    agree = ((pan.cpu() // 10000) == (ref[0]['panoptic_seg'][0] // 10000)).float().mean().item()
+    NOTES['cfg4_panoptic_class_agreement'] = agree
+    assert agree > 0.9, agree
