@@ -425,6 +425,17 @@ template <bool BAND> struct SysMat {
   }
 };
 
+// 1 / d for the pivots.  IEEE double division is a ~200-cycle dependent software sequence and sits six times on the critical path of
+// every block column; the hardware reciprocal seed (relative error 2^-23) plus two Newton steps (-> 2^-92, i.e. last-bit accurate) is
+// ~70 cycles.  d > 0 and far from the subnormal range here (the diagonal carries the damping ep + lm d).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(fma(-d, r, 1.0), r, r);
+  r = fma(fma(-d, r, 1.0), r, r);
+  return r;
+}
+
 // 6x6 diagonal block at c0: A_kk = L D L^T in place (unit lower L below the diagonal, d on it), 1/d -> dinv, and the
 // block's share of the forward substitution (y_k <- L_kk^-1 y_k).  One thread: float64 div / sqrt are ~100-cycle software
 // sequences, so the factorisation keeps one reciprocal per column and no square roots.
@@ -443,7 +454,7 @@ __device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int
     for (int t = 0; t < 6; t++) if (t < j) d -= D[j][t] * D[j][t] * D[t][t];
     if (!(d > 0.0)) { bad = true; d = 1.0; }
     D[j][j] = d;
-    iv[j] = 1.0 / d;
+    iv[j] = fast_rcp(d);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
       if (i > j) {
