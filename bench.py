@@ -19,7 +19,13 @@ capture (profiles/ncu_traffic.json); cpu_baseline = the CPU oracle (a port of th
 cores; reference_gpu_path = the reference's own GPU code for the stages that can be had on this box, timed on the same GPU
 (its correlation kernel and its BA kernels compiled into oracle/_ref/, its update operator's module structure on cuDNN).
 --workload vkitti / fpn run BASELINE configs[2] shape / configs[3] (fusion / loop: the video branch of the segmenter, the whole
-per-frame loop); --impl reference = the reference's CPU path.
+per-frame loop); --radius 8 at 8 GPUs = BASELINE configs[4] (64 keyframes, banded-8 graph, 952 edges); --impl reference = the
+reference's CPU path.  Further keys of the line (round 2): use_inactive_step = the frontend's mode (stored edges in the BA) timed the
+same way; roofline_other.corr_lookup / corr_volume = the HBM-bound kernels (the volume build warm, per new edge); parity_gate = the
+benchmarked half path's deviation from float32 next to the reference's own autocast run on the same GPU (a checker leg: it runs the
+staged reference bytecode of oracle/_ref/py through tests/ref_harness.py, outside every timed region; --no-gate skips it);
+multi_gpu_consistency = N > 1 only: pose replicas bitwise equal across ranks and equal to a single-GPU solve of the whole graph,
+asserted during warm-up; numa = CPUs this rank bound itself to before allocating its pinned staging buffers.
 """
 import argparse
 import json

@@ -419,10 +419,11 @@ __global__ void __launch_bounds__(256) ba_combine_kernel(Bufs bf, int P) {
 // row r keeps columns [6*(r/6) - band, r]: exactly the entries the band-limited factorisation touches.
 template <bool BAND> struct SysMat {
   double* p; int ld; int band;
-  __device__ __forceinline__ double& operator()(int r, int c) const {
-    if (BAND) return p[(long)r * ld + c - max(0, 6 * (r / 6) - band)];
-    return p[(long)r * ld + c];
+  __device__ __forceinline__ long off(int r) const {       // element (r, c) lives at p[off(r) + c]
+    if (BAND) return (long)r * ld - max(0, 6 * (r / 6) - band);
+    return (long)r * ld;
   }
+  __device__ __forceinline__ double& operator()(int r, int c) const { return p[off(r) + c]; }
 };
 
 // 1 / d for the pivots.  IEEE double division is a ~200-cycle dependent software sequence and sits six times on the critical path of
@@ -489,25 +490,62 @@ __device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int
 template <class M>
 __device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, int tid, int T, int* s_fail) {
   const int lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_rowoff[1024];                           // row r of the (band-packed or dense) matrix starts at A.p + s_rowoff[r]
+  const bool use_rowoff = n <= 1024 && A.off(n - 1) + n < 0x7fffffffL;
+  if (use_rowoff)
+    for (int r = tid; r < n; r += T) s_rowoff[r] = (int)A.off(r);
   if (tid == 0) ldl_diag_block(A, y, dinv, 0, s_fail);
   __syncthreads();
   for (int kb = 0; kb < P && !*s_fail; kb++) {
     const int c0 = 6 * kb;
     const int rend = min(n, c0 + 6 + band);
-    for (int r = c0 + 6 + tid; r < rend; r += T) {         // panel: L_rk = A_rk L_kk^-T D_k^-1; y_r -= L_rk z_k
-      double x[6];
-      double yr = y[r];
+    if (use_rowoff && c0 + 6 + tid < rend) {                // panel: L_rk = A_rk L_kk^-T D_k^-1; y_r -= L_rk z_k
+      // the factored diagonal block (L_kk d products, 1/d, z_k) once per thread, rows through the row table
+      double ldk[6][6], di[6], zk[6];
 #pragma unroll
       for (int j = 0; j < 6; j++) {
-        double v = A(r, c0 + j);
+        const double* Lj = A.p + s_rowoff[c0 + j] + c0;
+        di[j] = dinv[c0 + j];
+        zk[j] = y[c0 + j];
 #pragma unroll
-        for (int t = 0; t < 6; t++) if (t < j) v -= x[t] * A((c0 + t), c0 + t) * A((c0 + j), c0 + t);
-        x[j] = v * dinv[c0 + j];
-        yr -= x[j] * y[c0 + j];
+        for (int t = 0; t < 6; t++) ldk[j][t] = (t < j) ? Lj[t] : 0.0;
       }
 #pragma unroll
-      for (int j = 0; j < 6; j++) A(r, c0 + j) = x[j];
-      y[r] = yr;
+      for (int j = 0; j < 6; j++)
+#pragma unroll
+        for (int t = 0; t < 6; t++) if (t < j) ldk[j][t] *= A.p[s_rowoff[c0 + t] + c0 + t];       // L_jt d_t
+      for (int r = c0 + 6 + tid; r < rend; r += T) {
+        double* Ar = A.p + s_rowoff[r] + c0;
+        double x[6];
+        double yr = y[r];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          double v = Ar[j];
+#pragma unroll
+          for (int t = 0; t < 6; t++) if (t < j) v = fma(-x[t], ldk[j][t], v);
+          x[j] = v * di[j];
+          yr = fma(-x[j], zk[j], yr);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; j++) Ar[j] = x[j];
+        y[r] = yr;
+      }
+    } else if (!use_rowoff) {
+      for (int r = c0 + 6 + tid; r < rend; r += T) {
+        double x[6];
+        double yr = y[r];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          double v = A(r, c0 + j);
+#pragma unroll
+          for (int t = 0; t < 6; t++) if (t < j) v -= x[t] * A((c0 + t), c0 + t) * A((c0 + j), c0 + t);
+          x[j] = v * dinv[c0 + j];
+          yr -= x[j] * y[c0 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 6; j++) A(r, c0 + j) = x[j];
+        y[r] = yr;
+      }
     }
     __syncthreads();
     const int m = rend - c0 - 6;                           // trailing update (lower triangle): A_ic -= sum_t L_it d_t L_ct
@@ -525,6 +563,37 @@ __device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, 
         }
         __syncwarp();
         if (lane == 0) ldl_diag_block(A, y, dinv, c0 + 6, s_fail);
+      } else if (use_rowoff) {
+        // Measured: with one (i, c) entry per loop trip, located by idx / m and idx % m and fetched through the band accessor, this loop
+        // was INSTRUCTION bound (~300 instructions per entry: 13 k warp-instructions per block column at a 36-row band, the 2 us per
+        // column that made the solve 65 % of the sharded BA).  Now a thread owns (row i, four consecutive columns): the row's six
+        // L_it d_t products stay in registers, row starts come from a table, and the (row, chunk) split is a shift and a mask.
+        double d6[6];
+#pragma unroll
+        for (int t = 0; t < 6; t++) d6[t] = A.p[s_rowoff[c0 + t] + c0 + t];
+        int lg = 0;
+        while ((4 << lg) < m) lg++;                          // chunks per row, rounded up to a power of two
+        const int cpr = 1 << lg;
+        for (int w = tid - 32; w < ((m - 6) << lg); w += T - 32) {
+          const int ir = 6 + (w >> lg), cb = (w & (cpr - 1)) * 4;          // row / first column, relative to c0 + 6
+          if (cb > ir) continue;
+          const double* Li = A.p + s_rowoff[c0 + 6 + ir] + c0;
+          double ld_[6];
+#pragma unroll
+          for (int t = 0; t < 6; t++) ld_[t] = Li[t] * d6[t];
+          double* Ai = A.p + s_rowoff[c0 + 6 + ir] + c0 + 6;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int c = cb + q;
+            if (c <= ir) {
+              const double* Lc = A.p + s_rowoff[c0 + 6 + c] + c0;
+              double v = Ai[c];
+#pragma unroll
+              for (int t = 0; t < 6; t++) v = fma(-ld_[t], Lc[t], v);
+              Ai[c] = v;
+            }
+          }
+        }
       } else {
         for (int idx = tid - 32; idx < m * m; idx += T - 32) {
           const int i = c0 + 6 + idx / m, c = c0 + 6 + idx % m;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs on the GPU box (via gpurun): parity tests in isolated processes (a trapping kernel poisons its CUDA context),
 # smoke, bench, and optional ncu captures.  Everything is logged under gpurun_out/.
-#   tools/gpu_suite.sh [tests] [bench] [launches] [ncufull] [fpn] [fusion] [loop] [dist] [multi]
+#   tools/gpu_suite.sh [tests] [bench] [launches] [ncufull] [fpn] [fusion] [loop] [micro] [dist] [multi]
 set +e
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -27,7 +27,11 @@ tests)
   run t_edge 600 $PT tests/test_edge_cases_gpu.py
   run t_fusion 600 $PT tests/test_video_fusion_gpu.py
   run t_visual 300 $PT tests/test_visual_ops_gpu.py
-  run t_loop 900 $PT -rxX tests/test_zz_slam_loop_gpu.py
+  run t_config2 900 $PT tests/test_config2_gpu.py
+  run t_dropin 600 $PT tests/test_dropin_gpu.py
+  run t_misc 600 $PT tests/test_misc_gpu.py
+  run t_modes 600 $PT tests/test_zy_graph_modes_gpu.py
+  run t_loop 900 $PT tests/test_zz_slam_loop_gpu.py
   run smoke 300 python __graft_entry__.py smoke ;;
 bench)
   run bench_fp16 900 python bench.py --steps 50 --warmup 5
@@ -42,10 +46,15 @@ fpn)
 fusion)
   run t_fusion 600 $PT tests/test_video_fusion_gpu.py
   run bench_fusion 300 python tools/bench_fusion.py ;;
-loop)      # first hardware run of the whole per-frame loop: decisions vs the reference golden, then the config-3 bench
-  run t_modes 600 $PT -rxX --runxfail tests/test_zy_graph_modes_gpu.py
-  run t_loop 900 $PT -rxX --runxfail tests/test_zz_slam_loop_gpu.py tests/test_visual_ops_gpu.py
-  run bench_loop 900 python tools/bench_loop.py ;;
+loop)      # the whole per-frame loop: decisions vs the reference golden, then the config-3 bench and its GPU-time profile
+  run t_modes 600 $PT tests/test_zy_graph_modes_gpu.py
+  run t_loop 900 $PT tests/test_zz_slam_loop_gpu.py tests/test_visual_ops_gpu.py
+  run bench_loop 900 python tools/bench_loop.py
+  run prof_loop 600 python tools/prof_loop.py ;;
+micro)     # HBM-bound kernels next to their reference counterparts
+  run bench_lookup 600 python tools/bench_lookup.py
+  run bench_altcorr 600 python tools/bench_altcorr.py
+  run diag_ba 600 python tools/diag_ba.py 8 16 32 64 ;;
 dist)
   run t_dist 600 $PT tests/test_dist_gpu.py ;;
 multi)
