@@ -494,6 +494,9 @@ __device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, 
   const bool use_rowoff = n <= 1024 && A.off(n - 1) + n < 0x7fffffffL;
   if (use_rowoff)
     for (int r = tid; r < n; r += T) s_rowoff[r] = (int)A.off(r);
+  int bi = 0, bj = lane;                                   // lower-triangle entry of a 6x6 block updated by this lane (lanes < 21)
+  while (bj > bi) { bj -= bi + 1; bi++; }
+  __syncthreads();
   if (tid == 0) ldl_diag_block(A, y, dinv, 0, s_fail);
   __syncthreads();
   for (int kb = 0; kb < P && !*s_fail; kb++) {
@@ -551,18 +554,20 @@ __device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, 
     const int m = rend - c0 - 6;                           // trailing update (lower triangle): A_ic -= sum_t L_it d_t L_ct
     if (m > 0) {
       if (warp == 0) {
-        // the next diagonal block first (21 entries), then its factorisation while the other warps do the rest
+        // the next diagonal block first (21 entries, one per lane), then its factorisation while the other warps do the rest of the
+        // trailing update.  The factorisation stays in ONE thread: a warp-parallel variant (lane <-> lower-triangle entry, pivot column
+        // broadcast by 64-bit shuffles) was measured slower (P = 63: 593 vs 538 us per BA) -- the scalar routine's 384 instructions
+        // (ncu, profiles/r02_solve63_source.csv) have enough ILP to beat six rounds of dependent shuffles.
         if (lane < 21) {
-          int bi = 0, bj = lane;
-          while (bj > bi) { bj -= bi + 1; bi++; }
           const int i = c0 + 6 + bi, c = c0 + 6 + bj;
-          double v = A(i, c);
+          double vn = A(i, c);
 #pragma unroll
-          for (int t = 0; t < 6; t++) v -= A(i, c0 + t) * A((c0 + t), c0 + t) * A(c, c0 + t);
-          A(i, c) = v;
+          for (int t = 0; t < 6; t++) vn -= A(i, c0 + t) * A((c0 + t), c0 + t) * A(c, c0 + t);
+          A(i, c) = vn;
         }
         __syncwarp();
         if (lane == 0) ldl_diag_block(A, y, dinv, c0 + 6, s_fail);
+        __syncwarp();
       } else if (use_rowoff) {
         // Measured: with one (i, c) entry per loop trip, located by idx / m and idx % m and fetched through the band accessor, this loop
         // was INSTRUCTION bound (~300 instructions per entry: 13 k warp-instructions per block column at a 36-row band, the 2 us per

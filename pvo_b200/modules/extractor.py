@@ -46,7 +46,13 @@ class BasicEncoder(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
         self._packed = None
-        self.register_load_state_dict_post_hook(lambda m, k: setattr(m, '_packed', None))
+        self._plans = None
+        self.register_load_state_dict_post_hook(BasicEncoder._forget_packed)
+
+    @staticmethod
+    def _forget_packed(module, incompatible_keys):
+        module._packed = None
+        module._plans = None
 
     def _make_layer(self, dim, stride=1):
         layers = (ResidualBlock(self.in_planes, dim, self.norm_fn, stride=stride), ResidualBlock(dim, dim, self.norm_fn, stride=1))
@@ -64,19 +70,43 @@ class BasicEncoder(nn.Module):
         return self._packed
 
     def forward(self, x):
-        """x (b,n,3,H,W) float -> (b,n,output_dim,H/8,W/8).  Inference only."""
+        """x (b,n,3,H,W) float -> (b,n,output_dim,H/8,W/8).  Inference only.
+
+        The ~45 launches of a forward pass have fixed shapes for a given input size, so the first call per (shape, precision)
+        allocates the activation buffers once and records the launches (`_lib.LaunchPlan`); later calls copy the image into the
+        recorded input buffer and re-issue them -- the per-frame loop calls both encoders on every frame and was host bound."""
         if x.requires_grad:
             raise NotImplementedError('BasicEncoder: inference only')
         b, n, c1, h1, w1 = x.shape
-        N = b * n
         half = x.dtype == torch.float16 or torch.is_autocast_enabled()
+        key = (b * n, c1, h1, w1, half, x.dtype, str(x.device))
+        if self._plans is None:
+            self._plans = {}
+        ent = self._plans.get(key)
+        if ent is None or ent['packed'] is not self._pack(x.device):
+            src = torch.empty(b * n, c1, h1, w1, dtype=x.dtype, device=x.device)
+            src.copy_(x.reshape(b * n, c1, h1, w1))
+            with _lib.recording(True) as plan:
+                res = self._forward_impl(src, half)
+            ent = self._plans[key] = {'src': src, 'res': res, 'plan': plan if plan.calls is not None else None, 'packed': self._pack(x.device)}
+        else:
+            ent['src'].copy_(x.reshape(b * n, c1, h1, w1))
+            if ent['plan'] is not None:
+                ent['plan'].replay()
+            else:
+                ent['res'] = self._forward_impl(ent['src'], half)
+        res = ent['res']
+        return res.clone().view(b, n, res.shape[1], res.shape[2], res.shape[3])
+
+    def _forward_impl(self, x, half):
+        """x (N,3,H,W) -> (N,output_dim,H/8,W/8); every launch goes through the C ABI (recordable)"""
+        N, c1, h1, w1 = x.shape
         dt = torch.float16 if half else torch.float32
         dc = _lib.F16 if half else _lib.F32
         dev = x.device
         pk = self._pack(dev)
         L = _lib.lib()
         inorm = self.norm_fn == 'instance'
-        x = x.reshape(N, c1, h1, w1).contiguous()
         xin = torch.empty(N * h1 * w1, c1, dtype=dt, device=dev)
         check(L.pvo_nchw_to_nhwc(ptr(x), _lib.dtype_code(x), ptr(xin), dc, N, c1, h1 * w1, c1, 0, stream()), 'nchw_to_nhwc')
         scratch = torch.empty(N * 128 * 66 + 16, dtype=torch.float32, device=dev)
@@ -88,6 +118,7 @@ class BasicEncoder(nn.Module):
             cv = pk[name]
             Ho, Wo = osz(H, cv.kh, stride), osz(W, cv.kw, stride)
             out = torch.empty(N * Ho * Wo, cv.cout, dtype=dt, device=dev)
+            _keep.append(out)
             pnn.conv2d(cv, [(src, cin, cin)], N, H, W, dc, out, cv.cout, 0, 1 if relu else 0, aux0=res,
                        aux_stride=cv.cout if res is not None else 0, stride=stride)
             return out, Ho, Wo
@@ -97,6 +128,7 @@ class BasicEncoder(nn.Module):
                   'instance_norm', launches=3)
             return t
 
+        _keep = [xin, scratch]          # conv2d takes raw data_ptr()s of its segments: a recording must keep those tensors alive itself
         y, H, W = conv('conv1', xin, c1, h1, w1, 2, relu=not inorm)
         if inorm:
             inst_norm(y, H * W, DIM, True)
@@ -123,4 +155,7 @@ class BasicEncoder(nn.Module):
         cout = pk['conv2'].cout
         res = torch.empty(N, cout, H, W, dtype=dt, device=dev)
         check(L.pvo_nhwc_to_nchw(ptr(out), dc, cout, 0, ptr(res), dc, N, cout, H * W, stream()), 'nhwc_to_nchw')
-        return res.view(b, n, cout, H, W)
+        rec = _lib._REC[0]
+        if rec is not None:
+            rec.keep.extend(_keep)
+        return res

@@ -5,8 +5,9 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import torch
 from tests.golden import cases
 from pvo_b200 import droid_backends
+RADIUS = int(os.environ.get('DIAG_BA_RADIUS', '3'))          # 8 = BASELINE configs[4] (banded-8 graph)
 for F in ([int(a) for a in sys.argv[1:]] or [8, 16, 32, 64]):
-    c = cases.graph_case(F=F, radius=3, h=60, w=80, seed=1)
+    c = cases.graph_case(F=F, radius=RADIUS, h=60, w=80, seed=1)
     ii, jj = c['ii'].cuda(), c['jj'].cuda()
     own = ii < 8                                    # one rank's shard: the out-edges of its 8 keyframes
     ii, jj = ii[own].contiguous(), jj[own].contiguous()
@@ -20,11 +21,11 @@ for F in ([int(a) for a in sys.argv[1:]] or [8, 16, 32, 64]):
     eta = torch.full((kx.shape[0], 60, 80), 0.02, device='cuda')
     def run():
         p, d = poses.clone(), disps.clone()
-        droid_backends.ba(p, d, intr, tgt, wgt, eta, ii, jj, 1, F, 2, 1e-4, 0.1, False, max_span=3)
+        droid_backends.ba(p, d, intr, tgt, wgt, eta, ii, jj, 1, F, 2, 1e-4, 0.1, False, max_span=RADIUS)
     for _ in range(3): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20): run()
     e1.record(); torch.cuda.synchronize()
-    print('F=%2d  P=%2d  edges on this rank=%3d   2 GN iterations: %.1f us' % (F, F - 1, E, e0.elapsed_time(e1) / 20 * 1e3), flush=True)
+    print('radius %d  F=%2d  P=%2d  edges on this rank=%3d   2 GN iterations: %.1f us' % (RADIUS, F, F - 1, E, e0.elapsed_time(e1) / 20 * 1e3), flush=True)
