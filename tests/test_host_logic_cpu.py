@@ -405,3 +405,46 @@ def test_geom_chol_matches_dense_algebra_and_its_gradient():
     assert torch.allclose(br.grad, ba_.grad, atol=1e-9)
     bad = -torch.eye(4, dtype=torch.float64)[None]
     assert float(chol.CholeskySolver.apply(bad, torch.ones(1, 4, 1, dtype=torch.float64)).abs().max()) == 0.0
+
+
+def test_launch_plan_records_and_replays_host_side():
+    """_lib.LaunchPlan: calls made through the library proxy and torch_op closures while recording are re-issued verbatim by replay();
+    nothing is recorded outside a recording, nested recordings restore the outer one, a failed recording is discarded"""
+    import torch
+    from pvo_b200 import _lib
+    log = []
+
+    class FakeLib:
+        def pvo_fake(self, a, b):
+            log.append((a, b))
+            return 0
+    proxy = _lib._Recording(FakeLib())
+    proxy.pvo_fake(1, 2)                                   # not recording
+    x = torch.zeros(3)
+    with _lib.recording(True) as plan:
+        _lib.check(proxy.pvo_fake(3, 4), 'fake')
+        _lib.torch_op(lambda: x.add_(1))
+        with _lib.recording(False) as inner:               # a disabled nested recording
+            proxy.pvo_fake(5, 6)
+        assert inner is None and _lib._REC[0] is plan
+        keep = torch.ones(2)
+        assert _lib.ptr(keep) == keep.data_ptr() and plan.keep[-1] is keep
+    assert _lib._REC[0] is None and plan.launches == 1 and len(plan.calls) == 2
+    n0 = _lib.LAUNCHES[0]
+    plan.replay()
+    plan.replay()
+    assert log == [(1, 2), (3, 4), (5, 6), (3, 4), (3, 4)] and x.tolist() == [3.0, 3.0, 3.0] and _lib.LAUNCHES[0] == n0 + 2
+    try:
+        with _lib.recording(True) as bad:
+            raise ValueError('boom')
+    except ValueError:
+        pass
+    assert bad.calls is None and _lib._REC[0] is None
+
+
+def test_tiled_volume_geometry():
+    """tensor-core tile widths and the tiled level shapes (csrc/corr_lookup_tiled.cu): 4-row x 8-column tiles, zero padded"""
+    from pvo_b200.modules.corr import pad_width, tiled_shape
+    assert [pad_width(w) for w in (24, 40, 41, 80, 101, 104, 128, 129)] == [40, 40, 80, 80, 104, 104, 128, None]
+    assert tiled_shape(36, 60, 80, 0) == (36, 4800, 15, 10, 32) and tiled_shape(36, 60, 80, 3) == (36, 4800, 2, 2, 32)
+    assert tiled_shape(5, 30, 101, 1) == (5, 3030, 4, 7, 32) and tiled_shape(5, 30, 101, 3) == (5, 3030, 1, 2, 32)
