@@ -70,3 +70,27 @@ def test_allreduced_system_equals_single_device_system(tmp_path):
     c, tgt, wgt, eta = _case()
     full = _system(c, tgt, wgt, eta, torch.ones(c['E'], dtype=torch.bool), 1, 8)
     assert torch.allclose(got, full, rtol=1e-9, atol=1e-9 * full.abs().max())
+
+
+def _span_worker(rank, world, port, out):
+    """dist.attach on a stand-in graph: the bandwidth bound of the pose system must come out as the maximum over ranks, through a
+    collective that every rank issues on every call (a rank-local cache in front of it could hit on one rank and miss on another)"""
+    import types
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    video = types.SimpleNamespace(poses=torch.zeros(4, 7), disps=torch.ones(4, 2, 2), intrinsics=torch.ones(4, 4))
+    fg = types.SimpleNamespace(video=video)
+    pdist.attach(fg, rank, world, 2)
+    assert fg.world == world and fg.rank == rank and fg.allreduce_kind == 'ncclAllReduce'      # no peer memory on CPU
+    seq = [(3, 5), (3, 3), (7, 2), (3, 5)]            # (rank 0's local span, rank 1's): repeats included -- nothing may be cached
+    got = [fg._span_reduce(a if rank == 0 else b) for a, b in seq]
+    if rank == 0:
+        torch.save(torch.tensor(got), out)
+    dist.destroy_process_group()
+
+
+def test_span_bound_is_the_maximum_over_ranks_on_every_call(tmp_path):
+    out = str(tmp_path / 'span.pt')
+    mp.spawn(_span_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.load(out).tolist() == [5, 3, 7, 5]
