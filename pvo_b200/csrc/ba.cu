@@ -418,9 +418,9 @@ __global__ void __launch_bounds__(256) ba_combine_kernel(Bufs bf, int P) {
 // Dense (row-major, leading dimension ld) or band-packed view of the symmetric system's lower triangle.  Band-packed:
 // row r keeps columns [6*(r/6) - band, r]: exactly the entries the band-limited factorisation touches.
 template <bool BAND> struct SysMat {
-  double* p; int ld; int band;
+  double* p; int ld; int band; int r0;                     // r0: first resident row (band-packed windows; 0 otherwise)
   __device__ __forceinline__ long off(int r) const {       // element (r, c) lives at p[off(r) + c]
-    if (BAND) return (long)r * ld - max(0, 6 * (r / 6) - band);
+    if (BAND) return (long)(r - r0) * ld - max(0, 6 * (r / 6) - band);
     return (long)r * ld;
   }
   __device__ __forceinline__ double& operator()(int r, int c) const { return p[off(r) + c]; }
@@ -487,19 +487,22 @@ __device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int
 // path): [panel: L_rk for the band rows + their forward-substitution update] | [trailing update by warps 1.. while warp 0
 // updates, factors and forward-solves the NEXT diagonal block].  The backward substitution runs in warp 0 alone with
 // warp-level reductions (no block barriers at all).
+// Forward elimination of block columns kb0 .. kb1-1 (every row they touch -- up to 6 kb1 + band + 5 -- must be resident in A), then,
+// separately, the D scaling and the backward substitution over a range of block columns: a system whose band does not fit shared
+// memory is processed window by window (ba_solve_kernel), everything else in one call (ldl_solve).
 template <class M>
-__device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, int tid, int T, int* s_fail) {
+__device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int tid, int T, int* s_fail, int* s_rowoff, int kb0, int kb1,
+                            int row_lo, int row_hi) {
   const int lane = tid & 31, warp = tid >> 5;
-  __shared__ int s_rowoff[1024];                           // row r of the (band-packed or dense) matrix starts at A.p + s_rowoff[r]
-  const bool use_rowoff = n <= 1024 && A.off(n - 1) + n < 0x7fffffffL;
-  if (use_rowoff)
-    for (int r = tid; r < n; r += T) s_rowoff[r] = (int)A.off(r);
+  const bool use_rowoff = n <= 1024 && A.off(row_hi - 1) + n < 0x7fffffffL && A.off(row_lo) > -0x7fffffffL;
+  if (use_rowoff)                                          // row r of the (band-packed or dense) matrix starts at A.p + s_rowoff[r]
+    for (int r = row_lo + tid; r < row_hi; r += T) s_rowoff[r] = (int)A.off(r);
   int bi = 0, bj = lane;                                   // lower-triangle entry of a 6x6 block updated by this lane (lanes < 21)
   while (bj > bi) { bj -= bi + 1; bi++; }
   __syncthreads();
-  if (tid == 0) ldl_diag_block(A, y, dinv, 0, s_fail);
+  if (kb0 == 0 && tid == 0) ldl_diag_block(A, y, dinv, 0, s_fail);
   __syncthreads();
-  for (int kb = 0; kb < P && !*s_fail; kb++) {
+  for (int kb = kb0; kb < kb1; kb++) {
     const int c0 = 6 * kb;
     const int rend = min(n, c0 + 6 + band);
     if (use_rowoff && c0 + 6 + tid < rend) {                // panel: L_rk = A_rk L_kk^-T D_k^-1; y_r -= L_rk z_k
@@ -612,11 +615,14 @@ __device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, 
     }
     __syncthreads();
   }
-  if (*s_fail) return;
-  for (int i = tid; i < n; i += T) y[i] *= dinv[i];        // D w = z
-  __syncthreads();
-  if (warp == 0) {                                         // L^T x = w: block rows from the bottom, one warp, no block barriers
-    for (int kb = P - 1; kb >= 0; kb--) {
+}
+
+// L^T x = w for block columns kb_hi down to kb_lo: block rows from the bottom, one warp, no block barriers
+template <class M>
+__device__ void ldl_backward(M A, double* y, int n, int band, int tid, int kb_hi, int kb_lo) {
+  const int lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) {
+    for (int kb = kb_hi; kb >= kb_lo; kb--) {
       const int c0 = 6 * kb;
       const int rlast = min(n, c0 + 6 + band);             // rows below this block with L(r, c0..c0+5) != 0 stay within the band
       double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -643,6 +649,16 @@ __device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, 
     }
   }
   __syncthreads();
+}
+
+template <class M>
+__device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, int tid, int T, int* s_fail) {
+  __shared__ int s_rowoff[1024];
+  ldl_forward(A, y, dinv, n, band, tid, T, s_fail, s_rowoff, 0, P, 0, n);
+  if (*s_fail) return;
+  for (int i = tid; i < n; i += T) y[i] *= dinv[i];        // D w = z
+  __syncthreads();
+  ldl_backward(A, y, n, band, tid, P - 1, 0);
 }
 
 template <bool IN_SMEM>
@@ -697,12 +713,70 @@ __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm,
     }
     for (int i = tid; i < n; i += T) yb[i] = y[i];
     __syncthreads();
-    ldl_solve(SysMat<true>{Ab, W, band}, yb, db, P, n, band, tid, T, &s_fail);
+    ldl_solve(SysMat<true>{Ab, W, band, 0}, yb, db, P, n, band, tid, T, &s_fail);
+    __syncthreads();
+    for (int i = tid; i < n; i += T) y[i] = yb[i];
+    __syncthreads();
+  } else if (!IN_SMEM && n <= 1024 && sizeof(double) * ((size_t)(band + 6) * (band + 18) + 2 * n) <= 190 * 1024) {
+    // The whole band does not fit (BASELINE configs[4]: 63 poses, block bandwidth 16: 378 x 102 doubles = 308 KB), but a WINDOW of
+    // rows does: the elimination of block column k touches rows 6k .. 6k + band + 5 only.  Keep `rows` consecutive band rows resident,
+    // eliminate as many block columns as they cover, write the rows back to the dense system in global memory (its lower band is
+    // the backing store), slide.  The backward substitution walks the windows in reverse.  Measured before this existed: the
+    // factorisation ran out of L2 and the BA of the banded-8 graph took 2.1 ms (of which ~1.6 ms solve).
+    const int W = band + 6;
+    const int cap_rows = (int)((190 * 1024 - sizeof(double) * 2 * n) / (sizeof(double) * W));
+    const int rows = min(n, cap_rows / 6 * 6);                        // resident rows (a multiple of 6, >= band + 12)
+    const int kcount = (rows - band - 6) / 6 + 1;                     // block columns one window can eliminate
+    double* Ab = smd;
+    double* yb = smd + (long)rows * W;
+    double* db = yb + n;
+    __shared__ int s_rowoff_w[1024];
+    for (int i = tid; i < n; i += T) yb[i] = y[i];
+    auto load = [&](int r0) {
+      const int r1 = min(n, r0 + rows);
+      for (long i = tid; i < (long)(r1 - r0) * W; i += T) {
+        const int r = r0 + (int)(i / W), c = (int)(i % W) + max(0, 6 * (r / 6) - band);
+        Ab[i] = c <= r ? A[(long)r * ld + c] : 0.0;
+      }
+    };
+    auto store = [&](int r0) {
+      const int r1 = min(n, r0 + rows);
+      for (long i = tid; i < (long)(r1 - r0) * W; i += T) {
+        const int r = r0 + (int)(i / W), c = (int)(i % W) + max(0, 6 * (r / 6) - band);
+        if (c <= r) A[(long)r * ld + c] = Ab[i];
+      }
+    };
+    int k0 = 0;
+    for (;; k0 += kcount) {                                           // forward, window by window
+      const int r0 = 6 * k0, k1 = min(P, k0 + kcount);
+      __syncthreads();
+      load(r0);
+      __syncthreads();
+      ldl_forward(SysMat<true>{Ab, W, band, r0}, yb, db, n, band, tid, T, &s_fail, s_rowoff_w, k0, k1, r0, min(n, r0 + rows));
+      if (k1 == P) break;
+      __syncthreads();
+      store(r0);
+    }
+    __syncthreads();
+    if (!s_fail) {
+      for (int i = tid; i < n; i += T) yb[i] *= db[i];                // D w = z
+      __syncthreads();
+      for (int kw = k0;; kw -= kcount) {                              // backward: the last window is still resident
+        const int r0 = 6 * kw;
+        if (kw != k0) {
+          __syncthreads();
+          load(r0);
+          __syncthreads();
+        }
+        ldl_backward(SysMat<true>{Ab, W, band, r0}, yb, n, band, tid, min(P, kw + kcount) - 1, kw);
+        if (kw == 0) break;
+      }
+    }
     __syncthreads();
     for (int i = tid; i < n; i += T) y[i] = yb[i];
     __syncthreads();
   } else {
-    ldl_solve(SysMat<false>{A, ld, band}, y, dinv, P, n, band, tid, T, &s_fail);
+    ldl_solve(SysMat<false>{A, ld, band, 0}, y, dinv, P, n, band, tid, T, &s_fail);
   }
   const bool fail = s_fail != 0;
   for (int i = tid; i < n; i += T) bf.dx[i] = fail ? 0.0f : (float)y[i];

@@ -59,7 +59,7 @@ def main():
     import torch
     from oracle import panoptic_fpn as ofpn          # seeded weights only (and the optional CPU baseline leg)
     from pvo_b200 import _lib
-    from pvo_b200.panoptic_fpn import PanopticFPN, paste_masks
+    from pvo_b200.panoptic_fpn import PanopticFPN
     sd = ofpn.init_params(0)
     g = torch.Generator().manual_seed(2)                    # U{0..255}, seed 2
     host = [torch.randint(0, 256, (3, args.height, args.width), generator=g).float().pin_memory() for _ in range(args.batch)]
