@@ -65,7 +65,12 @@ class BasicEncoder(nn.Module):
             sd = {k: v.detach().to(device) for k, v in self.state_dict().items()}
             pk = {'device': str(device)}
             for name in sorted(set(k.rsplit('.', 1)[0] for k in sd)):
-                pk[name] = pnn._Conv(sd[name + '.weight'], sd[name + '.bias'])
+                w = sd[name + '.weight']
+                # stride-1 3x3 layers (10 of the 17 convolutions, ~70 % of the FLOPs) also get the tensor-core packing: in half precision
+                # they run on conv_tc.cu (32-channel layers zero-padded to one 64-channel K block)
+                tc = (w.shape[2] == 3 and w.shape[1] % 8 == 0 and name not in ('layer2.0.conv1', 'layer3.0.conv1')) or name == 'conv2'
+                # (layer{2,3}.0.conv1 have stride 2; conv2 is the 1x1 output projection)
+                pk[name] = pnn._Conv(w, sd[name + '.bias'], tc=bool(tc))
             self._packed = pk
         return self._packed
 
@@ -119,8 +124,12 @@ class BasicEncoder(nn.Module):
             Ho, Wo = osz(H, cv.kh, stride), osz(W, cv.kw, stride)
             out = torch.empty(N * Ho * Wo, cv.cout, dtype=dt, device=dev)
             _keep.append(out)
-            pnn.conv2d(cv, [(src, cin, cin)], N, H, W, dc, out, cv.cout, 0, 1 if relu else 0, aux0=res,
-                       aux_stride=cv.cout if res is not None else 0, stride=stride)
+            if half and stride == 1 and cv.Wh is not None:            # tensor cores (bias / ReLU / residual fused as on the CUDA-core path)
+                pnn.conv2d(cv, [(src, cin, cin)], N, H, W, dc, out, cv.cout, 0, 1 if relu else 0, aux0=res,
+                           aux_stride=cv.cout if res is not None else 0, use_tc=True)
+            else:
+                pnn.conv2d(cv, [(src, cin, cin)], N, H, W, dc, out, cv.cout, 0, 1 if relu else 0, aux0=res,
+                           aux_stride=cv.cout if res is not None else 0, stride=stride)
             return out, Ho, Wo
 
         def inst_norm(t, HW, C, relu, res=None):

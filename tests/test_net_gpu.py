@@ -48,3 +48,24 @@ def test_droid_net_forward_matches_reference_golden():
     assert rel(disp_list[-1].cpu()[:, :, ::4, ::4], gold['disps_up']) < 1e-3
     assert (flow_list[-1].cpu() - gold['flow']).norm(dim=-1).mean().item() < 1e-3
     assert (mask_list[-1].cpu()[:, :, ::4, ::4] - gold['mask']).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize('norm,od', [('instance', 128), ('none', 256)])
+def test_basic_encoder_half_tensor_core_path_tracks_float32(norm, od):
+    """half precision (what the per-frame loop runs under autocast): the stride-1 3x3 layers are on the tcgen05 conv kernel, the
+    strided ones on CUDA cores; against the float32 oracle to half-level tolerance, at the VKITTI2 frame size (odd sizes after /2),
+    and the recorded launch plan of the second call reproduces the first call bit for bit"""
+    from pvo_b200.modules.extractor import BasicEncoder
+    sd = oenc.init_params(od, seed=od)
+    m = BasicEncoder(od, norm).cuda()
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 1, 3, 120, 200, generator=g)
+    with torch.no_grad():
+        ref = oenc.basic_encoder(sd, x, norm)
+        out = m(x.cuda().half())
+        again = m(x.cuda().half())
+    assert out.dtype == torch.float16 and out.shape == ref.shape
+    scale = ref.abs().max().item()
+    assert (out.float().cpu() - ref).abs().max().item() < 2e-2 * scale
+    assert torch.equal(out, again)

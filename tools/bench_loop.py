@@ -71,7 +71,12 @@ def main():
             'frames': a.frames, 'keyframes': droid.video.counter.value, 'frontend_s': round(front_s, 3), 'frontend_update_iterations': front_iters,
             'update_iterations_per_s': round(front_iters / front_s, 1), 'initialisation_s': round(per_frame[args.warmup - 1], 3),
             'steady_ms_per_frame': round(1e3 * sum(steady) / len(steady), 2), 'gpu_launches': launches,
-            'config': {'workload': 'SURVEY 8(d) config 3 shape', 'warmup': args.warmup, 'max_factors': 48, 'timing': 'host clock with a device synchronize per frame'}}
+            'config': {'workload': 'SURVEY 8(d) config 3 shape', 'warmup': args.warmup, 'max_factors': 48, 'timing': 'host clock with a device synchronize per frame'},
+            'roofline_note': 'a frame = motion filter (2 feature encoders + 1 volume + 1 update-operator call) + ~5 new edge volumes + 6 window update '
+                             'iterations (48 active + stored edges) + 12 dense-window BA solves; tools/prof_loop.py (torch.profiler) puts the CUDA time at '
+                             '~13 ms of the frame, the rest is host work between the reference\'s own synchronisation points (.item() on the motion '
+                             'magnitude and the keyframe distance, the proximity matrix to the host); the iterations inside are the config-2 kernels '
+                             '(z|r conv 0.85 of the tensor peak, lookup 0.33 of HBM, bench.py)'}
     if not a.no_backend:
         t0 = time.perf_counter()
         droid.backend(7)
