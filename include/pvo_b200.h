@@ -140,6 +140,11 @@ int pvo_ba(float* poses, float* disps, const float* intrinsics, const float* tar
 /* byte range of {H, b} (float64) inside the workspace -- what pvo_b200/dist.py all-reduces between the two phases
  *   (flags bits 1-2 of pvo_ba: 1 = assemble only, 2 = solve + update only) when edges are sharded over GPUs */
 int pvo_ba_system_range(int E, int nframes, int P, int K, int HW, long* offset, long* bytes);
+/* the range the ranks exchange for a pvo_ba call with these `flags` / `motion_only`: when the flags carry the block bandwidth of the
+ *   pose system (bits 20-27) and the system is too large for the dense shared-memory solve, phase 1 leaves a BAND-PACKED block
+ *   {[6P][band + 6] lower-band rows | b | dA} (P = 63, radius 3: 133 KB instead of 1.1 MB) and phase 2 solves from it; otherwise the
+ *   dense range of pvo_ba_system_range.  The reference has no multi-GPU path; the system is droid_kernels.cu:1096-1198's SparseBlock. */
+int pvo_ba_exchange_range(int E, int nframes, int P, int K, int HW, int flags, int motion_only, long* offset, long* bytes);
 /* copies {K seen on the device, error flag, max out-degree} to the host (synchronises; debugging only) */
 int pvo_ba_read_meta(const void* workspace, int E, int nframes, int P, int K, int HW, int* meta_host3);
 /* DepthVideo.ba's trailing disps.clamp_(min=0.001), depth_video.py:214 */

@@ -34,6 +34,7 @@ _SIGS = {
     'pvo_ba': (c_int, [c_void_p] * 8 + [c_int] * 8 + [c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                                      c_long, c_int, c_void_p]),
     'pvo_ba_system_range': (c_int, [c_int] * 5 + [c_void_p, c_void_p]),
+    'pvo_ba_exchange_range': (c_int, [c_int] * 7 + [c_void_p, c_void_p]),
     'pvo_ba_read_meta': (c_int, [c_void_p] + [c_int] * 5 + [c_void_p]),
     'pvo_clamp_min': (c_int, [c_void_p, c_long, c_float, c_void_p]),
     'pvo_conv2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 9 +

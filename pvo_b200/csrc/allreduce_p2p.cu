@@ -87,7 +87,7 @@ extern "C" int pvo_allreduce_oneshot(double* data, void* const* stage_ptrs, void
     p.stage[i] = i < world ? (double*)stage_ptrs[i] : nullptr;
     p.flags[i] = i < world ? (int*)flag_ptrs[i] : nullptr;
   }
-  int blocks = (int)((n + 2047) / 2048);
+  int blocks = (int)((n + 1023) / 1024);
   blocks = blocks < 1 ? 1 : (blocks > 128 ? 128 : blocks);       // every block must be co-resident with its peers' blocks
   allreduce_oneshot_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(data, p, epochs, rank, world, n, n_max);
   return pvo_check_launch();

@@ -415,6 +415,40 @@ __global__ void __launch_bounds__(256) ba_combine_kernel(Bufs bf, int P) {
   }
 }
 
+// Band-packed exchange (frame graphs with a known block bandwidth): what the factorisation reads is the lower band only -- n (band + 6)
+// doubles instead of n^2 (P = 63, radius 3: 133 KB instead of 1.1 MB).  Folds the replicas' band into `packed` ([n][band + 6] rows in the
+// SysMat<true> layout | b [n] | dA [n]) and clears EVERY entry of every replica (pass 1 / pass 2 write both triangles), so the sharded
+// path all-reduces the packed block and nobody needs ba_zero_kernel afterwards.  An in-band entry is read and cleared by the same
+// thread; out-of-band entries are only written.
+__global__ void __launch_bounds__(256) ba_combine_band_kernel(Bufs bf, double* __restrict__ packed, int P, int band) {
+  const int n = 6 * P, W = band + 6;
+  const long psz = (long)n * n + 2 * n;
+  const long stride = (long)gridDim.x * blockDim.x, t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long i = t0; i < (long)n * W + 2 * n; i += stride) {
+    double s = 0.0;
+    if (i < (long)n * W) {
+      const int r = (int)(i / W), c = (int)(i % W) + max(0, 6 * (r / 6) - band);
+      if (c <= r) {
+        const long d = (long)r * n + c;
+#pragma unroll
+        for (int g = 0; g < kParts; g++) { s += bf.sys[g * psz + d]; bf.sys[g * psz + d] = 0.0; }
+      }
+    } else {
+      const long d = (long)n * n + (i - (long)n * W);
+#pragma unroll
+      for (int g = 0; g < kParts; g++) { s += bf.sys[g * psz + d]; bf.sys[g * psz + d] = 0.0; }
+    }
+    packed[i] = s;
+  }
+  for (long i = t0; i < (long)n * n; i += stride) {
+    const int r = (int)(i / n), c = (int)(i % n);
+    if (c > r || c < 6 * (r / 6) - band) {
+#pragma unroll
+      for (int g = 0; g < kParts; g++) bf.sys[g * psz + i] = 0.0;
+    }
+  }
+}
+
 // Dense (row-major, leading dimension ld) or band-packed view of the symmetric system's lower triangle.  Band-packed:
 // row r keeps columns [6*(r/6) - band, r]: exactly the entries the band-limited factorisation touches.
 template <bool BAND> struct SysMat {
@@ -490,18 +524,24 @@ __device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int
 // Forward elimination of block columns kb0 .. kb1-1 (every row they touch -- up to 6 kb1 + band + 5 -- must be resident in A), then,
 // separately, the D scaling and the backward substitution over a range of block columns: a system whose band does not fit shared
 // memory is processed window by window (ba_solve_kernel), everything else in one call (ldl_solve).
+// A thread GROUP (tid in [0, T), T a multiple of 32, its own named barrier `bar`) runs these: the whole block (bar 0 == __syncthreads) or
+// one half of it when two eliminations proceed side by side (two-sided factorisation in ba_solve_kernel).
+__device__ __forceinline__ void group_sync(int bar, int T) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(T) : "memory"); }
+
+// factor_first: factor the diagonal block of column kb0 on entry (false when the previous call already did, as its "next" block);
+// factor_last: factor the diagonal block after column kb1 - 1 (false when other contributions are still to be added to it).
 template <class M>
 __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int tid, int T, int* s_fail, int* s_rowoff, int kb0, int kb1,
-                            int row_lo, int row_hi) {
+                            int row_lo, int row_hi, int bar = 0, bool factor_first = true, bool factor_last = true) {
   const int lane = tid & 31, warp = tid >> 5;
   const bool use_rowoff = n <= 1024 && A.off(row_hi - 1) + n < 0x7fffffffL && A.off(row_lo) > -0x7fffffffL;
   if (use_rowoff)                                          // row r of the (band-packed or dense) matrix starts at A.p + s_rowoff[r]
     for (int r = row_lo + tid; r < row_hi; r += T) s_rowoff[r] = (int)A.off(r);
   int bi = 0, bj = lane;                                   // lower-triangle entry of a 6x6 block updated by this lane (lanes < 21)
   while (bj > bi) { bj -= bi + 1; bi++; }
-  __syncthreads();
-  if (kb0 == 0 && tid == 0) ldl_diag_block(A, y, dinv, 0, s_fail);
-  __syncthreads();
+  group_sync(bar, T);
+  if (factor_first && tid == 0) ldl_diag_block(A, y, dinv, 6 * kb0, s_fail);
+  group_sync(bar, T);
   for (int kb = kb0; kb < kb1; kb++) {
     const int c0 = 6 * kb;
     const int rend = min(n, c0 + 6 + band);
@@ -553,7 +593,7 @@ __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int t
         y[r] = yr;
       }
     }
-    __syncthreads();
+    group_sync(bar, T);
     const int m = rend - c0 - 6;                           // trailing update (lower triangle): A_ic -= sum_t L_it d_t L_ct
     if (m > 0) {
       if (warp == 0) {
@@ -569,7 +609,7 @@ __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int t
           A(i, c) = vn;
         }
         __syncwarp();
-        if (lane == 0) ldl_diag_block(A, y, dinv, c0 + 6, s_fail);
+        if (lane == 0 && (factor_last || kb + 1 < kb1)) ldl_diag_block(A, y, dinv, c0 + 6, s_fail);
         __syncwarp();
       } else if (use_rowoff) {
         // Measured: with one (i, c) entry per loop trip, located by idx / m and idx % m and fetched through the band accessor, this loop
@@ -613,13 +653,13 @@ __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int t
         }
       }
     }
-    __syncthreads();
+    group_sync(bar, T);
   }
 }
 
 // L^T x = w for block columns kb_hi down to kb_lo: block rows from the bottom, one warp, no block barriers
 template <class M>
-__device__ void ldl_backward(M A, double* y, int n, int band, int tid, int kb_hi, int kb_lo) {
+__device__ void ldl_backward(M A, double* y, int n, int band, int tid, int kb_hi, int kb_lo, int bar = 0, int T = 0) {
   const int lane = tid & 31, warp = tid >> 5;
   if (warp == 0) {
     for (int kb = kb_hi; kb >= kb_lo; kb--) {
@@ -648,7 +688,7 @@ __device__ void ldl_backward(M A, double* y, int n, int band, int tid, int kb_hi
       __syncwarp();
     }
   }
-  __syncthreads();
+  if (T) group_sync(bar, T); else __syncthreads();
 }
 
 template <class M>
@@ -662,13 +702,127 @@ __device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, 
 }
 
 template <bool IN_SMEM>
-__global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem, int moba, int bw_hint) {
+__global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem, int moba, int bw_hint, double* packed) {
   extern __shared__ double smd[];
   __shared__ int s_fail;
   const int n = 6 * P;
   const int tid = threadIdx.x, T = blockDim.x;
   const long psz = (long)n * n + 2 * n;
   const int ld = IN_SMEM ? n + 1 : n;
+  if (!IN_SMEM && packed) {
+    // band-packed system from ba_combine_band_kernel (all-reduced in between on the sharded path): [n][W] | b | dA.  The band is
+    // the caller's (bw_hint >= 0, not the block-diagonal-damped MoBA variant); no dense matrix is touched.
+    const int band = 6 * min(bw_hint, P - 1), W = band + 6;
+    double* pb = packed + (long)n * W;                        // b, then dA
+    if (tid == 0) s_fail = 0;
+    for (int i = tid; i < n; i += T) {                       // LM damping of the diagonal (see damp())
+      double* d = packed + (long)i * W + (i - max(0, 6 * (i / 6) - band));
+      *d += (double)ep + (double)lm * (sem ? pb[n + i] : *d);
+    }
+    __syncthreads();
+    const bool whole = sizeof(double) * ((size_t)n * W + 2 * n) <= 200 * 1024;
+    const int rows = whole ? n : min(n, (int)((190 * 1024 - sizeof(double) * 2 * n) / (sizeof(double) * W)) / 6 * 6);
+    double* Ab = smd;
+    double* yb = smd + (long)rows * W;
+    double* db = yb + n;
+    __shared__ int s_rowoff_p[1024];
+    // Two-sided factorisation.  The 63 block columns of the 8-GPU window are 63 SEQUENTIAL steps of a few hundred dependent
+    // instructions each (profiles/r02_solve63_source.csv: the kernel is the sum of its serial pieces).  A band matrix splits into
+    // top part T | separator S (one band width) | bottom part B with no T-B coupling, so T is eliminated downwards by one half of
+    // the block while the other half eliminates B UPWARDS -- run as the same forward code on the index-reversed matrix -- each adding
+    // its Schur complement into S; then S is factored, and the back substitutions of T and B again run side by side.  Sequential
+    // depth |T| + |S| = 29 + 6 block columns instead of 63.  Every rank executes the same schedule, so replicas stay bitwise equal.
+    const int bwb = band / 6, Tb = (P - bwb + 1) / 2, Bb = P - bwb - Tb;
+    const bool two_sided = whole && T == 512 && Bb >= 2 && n + band <= 1024 &&
+                           sizeof(double) * ((size_t)(n + band) * (W + 2)) <= 200 * 1024;
+    if (two_sided) {
+      const int n1 = 6 * (Tb + bwb), nB = 6 * Bb, n2 = nB + band;      // matrix 1: rows of T and S; matrix 2 (reversed indices): B then S
+      double* A1 = smd;
+      double* A2 = A1 + (long)n1 * W;
+      double* y1 = A2 + (long)n2 * W;
+      double* y2 = y1 + n1;
+      double* d1 = y2 + n2;
+      double* d2 = d1 + n1;
+      for (long i = tid; i < (long)n1 * W; i += T) A1[i] = packed[i];
+      for (int i = tid; i < n1; i += T) y1[i] = pb[i];
+      for (long i = tid; i < (long)n2 * W; i += T) {
+        const int r = (int)(i / W), c = (int)(i % W) + max(0, 6 * (r / 6) - band);
+        double v = 0.0;
+        if (c <= r && !(r >= nB && c >= nB)) {                   // the S x S block of matrix 2 starts at zero: it collects B's Schur complement
+          const int R = n - 1 - c, C = n - 1 - r;                // reversed element (r, c) = original (n-1-c, n-1-r), lower triangle
+          v = packed[(long)R * W + C - max(0, 6 * (R / 6) - band)];
+        }
+        A2[i] = v;
+      }
+      for (int l = tid; l < n2; l += T) y2[l] = l < nB ? pb[n - 1 - l] : 0.0;
+      __syncthreads();
+      const int g = tid >> 8, gt = tid & 255;
+      const SysMat<true> M1{A1, W, band, 0}, M2{A2, W, band, 0};
+      if (g == 0) ldl_forward(M1, y1, d1, n1, band, gt, 256, &s_fail, s_rowoff_p, 0, Tb, 0, n1, 1, true, false);
+      else        ldl_forward(M2, y2, d2, n2, band, gt, 256, &s_fail, s_rowoff_p + n1, 0, Bb, 0, n2, 2, true, false);
+      __syncthreads();
+      for (int idx = tid; idx < band * band; idx += T) {        // S += B's Schur complement (matrix 2 indexes rows in reverse)
+        const int a = idx / band, b = idx % band;
+        if (b <= a) M1(6 * Tb + a, 6 * Tb + b) += M2(n - 1 - (6 * Tb + b), n - 1 - (6 * Tb + a));
+      }
+      for (int a = tid; a < band; a += T) y1[6 * Tb + a] += y2[n - 1 - (6 * Tb + a)];
+      __syncthreads();
+      ldl_forward(M1, y1, d1, n1, band, tid, T, &s_fail, s_rowoff_p, Tb, Tb + bwb, 0, n1, 0, true, true);
+      if (!s_fail) {
+        for (int i = tid; i < n1; i += T) y1[i] *= d1[i];       // D w = z
+        for (int l = tid; l < nB; l += T) y2[l] *= d2[l];
+        __syncthreads();
+        ldl_backward(M1, y1, n1, band, tid, Tb + bwb - 1, Tb);  // x_S
+        for (int l = nB + tid; l < n2; l += T) y2[l] = y1[n - 1 - l];
+        __syncthreads();
+        if (g == 0) ldl_backward(M1, y1, n1, band, gt, Tb - 1, 0, 1, 256);
+        else        ldl_backward(M2, y2, n2, band, gt, Bb - 1, 0, 2, 256);
+      }
+      __syncthreads();
+      const bool failed2 = s_fail != 0;
+      for (int i = tid; i < n; i += T) bf.dx[i] = failed2 ? 0.0f : (float)(i < n1 ? y1[i] : y2[n - 1 - i]);
+      return;
+    }
+    for (int i = tid; i < n; i += T) yb[i] = pb[i];
+    if (whole) {
+      for (long i = tid; i < (long)n * W; i += T) Ab[i] = packed[i];
+      __syncthreads();
+      ldl_solve(SysMat<true>{Ab, W, band, 0}, yb, db, P, n, band, tid, T, &s_fail);
+    } else {
+      // window by window (see the dense-backed variant below); the packed block in global memory is the backing store
+      const int kcount = (rows - band - 6) / 6 + 1;
+      int k0 = 0;
+      for (;; k0 += kcount) {
+        const int r0 = 6 * k0, k1 = min(P, k0 + kcount), r1 = min(n, r0 + rows);
+        __syncthreads();
+        for (long i = tid; i < (long)(r1 - r0) * W; i += T) Ab[i] = packed[(long)r0 * W + i];
+        __syncthreads();
+        ldl_forward(SysMat<true>{Ab, W, band, r0}, yb, db, n, band, tid, T, &s_fail, s_rowoff_p, k0, k1, r0, r1, 0, k0 == 0, true);
+        if (k1 == P) break;
+        __syncthreads();
+        for (long i = tid; i < (long)(r1 - r0) * W; i += T) packed[(long)r0 * W + i] = Ab[i];
+      }
+      __syncthreads();
+      if (!s_fail) {
+        for (int i = tid; i < n; i += T) yb[i] *= db[i];
+        __syncthreads();
+        for (int kw = k0;; kw -= kcount) {
+          const int r0 = 6 * kw, r1 = min(n, r0 + rows);
+          if (kw != k0) {
+            __syncthreads();
+            for (long i = tid; i < (long)(r1 - r0) * W; i += T) Ab[i] = packed[(long)r0 * W + i];
+            __syncthreads();
+          }
+          ldl_backward(SysMat<true>{Ab, W, band, r0}, yb, n, band, tid, min(P, kw + kcount) - 1, kw);
+          if (kw == 0) break;
+        }
+      }
+    }
+    __syncthreads();
+    const bool failed = s_fail != 0;
+    for (int i = tid; i < n; i += T) bf.dx[i] = failed ? 0.0f : (float)yb[i];
+    return;
+  }
   double* A = IN_SMEM ? smd : bf.sys;                      // !IN_SMEM: parts were combined into part 0 beforehand
   double* y = IN_SMEM ? smd + (long)n * ld : bf.sys + (long)n * n;
   double* dA = IN_SMEM ? y + n : bf.sys + (long)n * n + n;
@@ -752,7 +906,7 @@ __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm,
       __syncthreads();
       load(r0);
       __syncthreads();
-      ldl_forward(SysMat<true>{Ab, W, band, r0}, yb, db, n, band, tid, T, &s_fail, s_rowoff_w, k0, k1, r0, min(n, r0 + rows));
+      ldl_forward(SysMat<true>{Ab, W, band, r0}, yb, db, n, band, tid, T, &s_fail, s_rowoff_w, k0, k1, r0, min(n, r0 + rows), 0, k0 == 0, true);
       if (k1 == P) break;
       __syncthreads();
       store(r0);
@@ -852,7 +1006,7 @@ __global__ void clamp_min_kernel(float* x, long n, float lo) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
-  size_t off_frame2k, off_kx, off_ptr, off_idx, off_meta, off_Eij, off_Ei, off_Q, off_w, off_sys, off_dx, total;
+  size_t off_frame2k, off_kx, off_ptr, off_idx, off_meta, off_Eij, off_Ei, off_Q, off_w, off_sys, off_packed, off_dx, total;
 };
 
 Layout make_layout(int E, int nframes, int P, int K, int HW) {
@@ -869,9 +1023,24 @@ Layout make_layout(int E, int nframes, int P, int K, int HW) {
   L.off_Q = take(sizeof(float) * (size_t)K * HW);
   L.off_w = take(sizeof(float) * (size_t)K * HW);
   L.off_sys = take(sizeof(double) * kParts * (36 * (size_t)P * P + 12 * (size_t)P));
+  L.off_packed = take(sizeof(double) * (36 * (size_t)P * P + 12 * (size_t)P));      // band-packed system (<= one dense part)
   L.off_dx = take(sizeof(float) * 6 * (size_t)P);
   L.total = o;
   return L;
+}
+
+// The band-packed exchange applies when the caller states the block bandwidth (flags bits 20-27), the system is too large for the dense
+// shared-memory solve, it is not the MoBA variant (whose damping fills every block), and a band window fits shared memory.
+// Returns the band in scalars (6 x block bandwidth), or -1.
+int packed_band(int P, int flags) {
+  const int n = 6 * P;
+  const int bw_hint = ((flags >> 20) & 0xFF) - 1;
+  if (bw_hint < 0) return -1;
+  if (sizeof(double) * ((size_t)n * (n + 1) + 2 * n) <= 200 * 1024) return -1;        // dense solve in shared memory
+  if (n > 1024) return -1;
+  const int band = 6 * (bw_hint < P - 1 ? bw_hint : P - 1);
+  if (sizeof(double) * ((size_t)(band + 6) * (band + 18) + 2 * n) > 190 * 1024) return -1;
+  return band;
 }
 
 }  // namespace
@@ -926,6 +1095,8 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
   // 2 = solve + back-substitution + retraction only.
   const int phase = (flags >> 1) & 3;
   const int sem = (flags >> 3) & 1;      // 0: droid_backends.ba semantics, 1: geom/ba.py BA()/MoBA() semantics
+  const int pband = (sem && motion_only) ? -1 : packed_band(P, flags);
+  double* packed = (double*)(ws + L.off_packed);
   for (int it = 0; it < iterations; it++) {
     if (phase != 2) {
       ba_pass1_kernel<<<grid, kPix, 0, s>>>(poses, disps, intrinsics, targets, weights, eta, ii, jj, pl, bf, E, HW, wd,
@@ -934,14 +1105,21 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
         ba_pass2_kernel<<<dim3(ceil_div(HW, kPix2), K), 256, pass2_smem, s>>>(jj, pl, bf, HW, t0, P, pass2_smem / 4);
     }
     const int comb_blocks = ceil_div(36L * P * P + 12L * P, 2048) < 148 ? (ceil_div(36L * P * P + 12L * P, 2048) < 8 ? 8 : ceil_div(36L * P * P + 12L * P, 2048)) : 148;
-    if (phase == 1) { ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P); break; }
-    if (solve_in_smem) {
+    if (pband >= 0) {
+      // band-packed: fold + clear -> [all-reduce of the packed block between the phases] -> solve straight from it
+      if (phase != 2) ba_combine_band_kernel<<<comb_blocks, 256, 0, s>>>(bf, packed, P, pband);
+      if (phase == 1) break;
+      ba_solve_kernel<false><<<1, 512, 200 * 1024, s>>>(bf, P, lm, ep, sem, 0, bw_hint, packed);
+    } else if (phase == 1) {
+      ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);
+      break;
+    } else if (solve_in_smem) {
       // small windows are latency bound (128 threads); from ~a dozen poses on the trailing updates (dense windows of the frontend: O(n^2) entries
       // per block column) want the whole SM
-      ba_solve_kernel<true><<<1, P <= 10 ? 128 : 512, solve_smem, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint);
+      ba_solve_kernel<true><<<1, P <= 10 ? 128 : 512, solve_smem, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint, nullptr);
     } else {
       if (phase != 2) ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);      // phase 2: phase 1 already folded the replicas
-      ba_solve_kernel<false><<<1, 512, 200 * 1024, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint);   // band-packed copy in smem when it fits
+      ba_solve_kernel<false><<<1, 512, 200 * 1024, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint, nullptr);   // band-packed copy in smem when it fits
       ba_zero_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);
     }
     const bool last = it == iterations - 1;
@@ -976,6 +1154,19 @@ extern "C" int pvo_ba_system_range(int E, int nframes, int P, int K, int HW, lon
   const Layout L = make_layout(E > 0 ? E : 1, nframes, P, K, HW);
   *offset = (long)L.off_sys;                                  // part 0 (ba_combine_kernel folds the other parts into it)
   *bytes = (long)(sizeof(double) * (36 * (size_t)P * P + 12 * (size_t)P));
+  return PVO_OK;
+}
+
+// What the ranks exchange for a pvo_ba call with these flags / motion_only: the band-packed block {[n][band + 6] | b | dA} when
+// packed_band() applies (P = 63, radius 3: 133 KB), else part 0 of the dense system as pvo_ba_system_range reports it.
+extern "C" int pvo_ba_exchange_range(int E, int nframes, int P, int K, int HW, int flags, int motion_only, long* offset, long* bytes) {
+  if (E < 0 || nframes <= 0 || P <= 0 || K <= 0 || HW <= 0) return PVO_ERR_INVALID;
+  const int sem = (flags >> 3) & 1;
+  const int pband = (sem && motion_only) ? -1 : packed_band(P, flags);
+  if (pband < 0) return pvo_ba_system_range(E, nframes, P, K, HW, offset, bytes);
+  const Layout L = make_layout(E > 0 ? E : 1, nframes, P, K, HW);
+  *offset = (long)L.off_packed;
+  *bytes = (long)(sizeof(double) * ((size_t)6 * P * (pband + 6) + 12 * (size_t)P));
   return PVO_OK;
 }
 

@@ -81,10 +81,12 @@ def make_reducer(device, group=None):
     return red if ok.item() > 0 else None
 
 
-def system_view(ws, E, nframes, P, K, HW):
-    """float64 view of the reduced camera system inside a BA workspace (torch.uint8 tensor)."""
+def system_view(ws, E, nframes, P, K, HW, flags=0, motion_only=False):
+    """float64 view of what the ranks exchange inside a BA workspace (torch.uint8 tensor): the band-packed reduced camera system when
+    `flags` carry the graph's bandwidth and the window is large (pvo_ba_exchange_range), else the dense {H | b | dA} block."""
     off, nb = ctypes.c_long(0), ctypes.c_long(0)
-    check(_lib.lib().pvo_ba_system_range(E, nframes, P, K, HW, ctypes.byref(off), ctypes.byref(nb)), 'ba_system_range', launches=0)
+    check(_lib.lib().pvo_ba_exchange_range(E, nframes, P, K, HW, int(flags), 1 if motion_only else 0, ctypes.byref(off), ctypes.byref(nb)),
+          'ba_exchange_range', launches=0)
     return ws[off.value:off.value + nb.value].view(torch.float64)
 
 
@@ -97,13 +99,14 @@ def ba_sharded(poses, disps, intrinsics, targets, weights, eta, ii, jj, t0, t1, 
     nframes, ht, wd = disps.shape
     K, P = eta.shape[0], t1 - t0
     ws = workspace if workspace is not None else droid_backends.ba_workspace(E, nframes, P, K, ht * wd, poses.device)
-    sysbuf = system_view(ws, E, nframes, P, K, ht * wd)
+    hints = ((int(max_degree) & 0xFFF) << 8) | droid_backends.band_flag(max_span)
+    sysbuf = system_view(ws, E, nframes, P, K, ht * wd, hints, motion_only)
     dx = torch.empty(P, 6, dtype=torch.float32, device=poses.device)
     dz = torch.empty(K, ht * wd, dtype=torch.float32, device=poses.device)
     L = _lib.lib()
 
     def call(phase, reuse):
-        flags = (1 if reuse else 0) | (phase << 1) | (16 if sys_clean else 0) | ((int(max_degree) & 0xFFF) << 8) | droid_backends.band_flag(max_span)
+        flags = (1 if reuse else 0) | (phase << 1) | (16 if sys_clean else 0) | hints
         check(L.pvo_ba(ptr(poses), ptr(disps), ptr(intrinsics), ptr(targets), ptr(weights), ptr(eta), ptr(ii), ptr(jj), E,
                        nframes, ht, wd, int(t0), int(t1), K, 1, float(lm), float(ep), 1 if motion_only else 0,
                        1 if interleaved else 0, ptr(dx), ptr(dz), ptr(ws), ws.numel(), flags, stream()), 'ba',

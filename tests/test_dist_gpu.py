@@ -45,37 +45,39 @@ def _graph(c, ii, jj, dev, rank=None, world=1, fpr=4):
     return v, fg
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, F=8, fpr=4, h=16, w=24):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda:%d' % rank))
     from pvo_b200 import dist as pdist
     dev = 'cuda:%d' % rank
-    c = cases.graph_case(F=8, radius=3, h=16, w=24, seed=6)
-    ii, jj, own = pdist.shard_edges(c['ii'], c['jj'], rank, world, 4)
-    v, fg = _graph(c, ii, jj, dev, rank, world, 4)
+    c = cases.graph_case(F=F, radius=3, h=h, w=w, seed=6)
+    ii, jj, own = pdist.shard_edges(c['ii'], c['jj'], rank, world, fpr)
+    v, fg = _graph(c, ii, jj, dev, rank, world, fpr)
     for _ in range(2):
-        fg.update(t0=1, t1=8, itrs=2)
+        fg.update(t0=1, t1=F, itrs=2)
     torch.cuda.synchronize()
-    torch.save({'poses': v.poses[:8].cpu(), 'disps': v.disps[:8].cpu(), 'flow': fg.full_flow.cpu(), 'own': own}, out % rank)
+    torch.save({'poses': v.poses[:F].cpu(), 'disps': v.disps[:F].cpu(), 'flow': fg.full_flow.cpu(), 'own': own}, out % rank)
     dist.destroy_process_group()
 
 
-def test_sharded_update_matches_single_gpu(tmp_path):
+# F = 32: 31 free poses do not fit the dense shared-memory solve, so the ranks exchange the BAND-PACKED system (pvo_ba_exchange_range)
+@pytest.mark.parametrize('F,fpr,h,w', [(8, 4, 16, 24), (32, 16, 8, 12)])
+def test_sharded_update_matches_single_gpu(tmp_path, F, fpr, h, w):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     out = str(tmp_path / 'r%d.pt')
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    c = cases.graph_case(F=8, radius=3, h=16, w=24, seed=6)
+    mp.spawn(_worker, args=(2, _free_port(), out, F, fpr, h, w), nprocs=2, join=True)
+    c = cases.graph_case(F=F, radius=3, h=h, w=w, seed=6)
     v, fg = _graph(c, c['ii'], c['jj'], 'cuda:0')
     for _ in range(2):
-        fg.update(t0=1, t1=8, itrs=2)
-    ref_p, ref_d, ref_f = v.poses[:8].cpu(), v.disps[:8].cpu(), fg.full_flow.cpu()
+        fg.update(t0=1, t1=F, itrs=2)
+    ref_p, ref_d, ref_f = v.poses[:F].cpu(), v.disps[:F].cpu(), fg.full_flow.cpu()
     r = [torch.load(out % k) for k in range(2)]
     for k in range(2):
         assert (r[k]['poses'] - ref_p).abs().max() < 2e-5, k                       # pose replicas identical to single GPU
-        frames = slice(4 * k, 4 * k + 4)
+        frames = slice(fpr * k, fpr * k + fpr)
         assert (r[k]['disps'][frames] - ref_d[frames]).abs().max() < 2e-5, k      # each rank owns its frames' depth
         assert (r[k]['flow'] - ref_f[:, r[k]['own']]).abs().max() < 2e-4, k
     assert torch.equal(r[0]['poses'], r[1]['poses'])                               # redundant solves are bit-identical

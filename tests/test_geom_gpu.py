@@ -103,6 +103,7 @@ def _rel(a, b):
                                  dict(F=22, radius=2, h=8, w=12, t0=1),      # banded system (bandwidth 4 of 21 blocks): band-limited LDL^T
                                  dict(F=20, radius=3, h=8, w=12, t0=1),      # same, bandwidth found by the solver's own scan
                                  dict(F=34, radius=1, h=8, w=12, t0=2),      # P = 32 > 26: band-packed copy in shared memory
+                                 dict(F=64, radius=3, h=8, w=12, t0=1),      # the 8-GPU window: P = 63, band 36 -> band-packed system (133 KB), one window
                                  dict(F=64, radius=8, h=8, w=12, t0=1),      # BASELINE configs[4] structure: P = 63, block bandwidth 16 -- the band
                                                                              # (308 KB) exceeds shared memory: windowed factorisation
                                  dict(F=50, radius=6, h=8, w=12, t0=3)])     # another windowed case: P = 47, bandwidth 12 (254 KB)

@@ -106,3 +106,24 @@ def test_launch_plan_replay_equals_marshalled_launches(use_inactive):
     assert dt < 2e-3 and ang < 2e-3
     assert (res[1][2] - res[0][2]).abs().max().item() < 0.2
     assert torch.equal(res[1][3], res[0][3])
+
+
+def test_ba_reports_misaligned_damping_rows_when_checked():
+    """eta must have one row per depth frame unique(arange(t0,t1) U ii) (droid_kernels.cu:1311-1319; the reference raises a shape error
+    at `C + eta`).  The schedule kernel records the mismatch on the device; with droid_backends.CHECK_BA the call raises."""
+    from pvo_b200 import droid_backends
+    from tests.test_geom_gpu import _ba_case, _video
+    c, tgt, wgt, g = _ba_case(6, 2, 12, 16, seed=3)
+    ii, jj = c['ii'].cuda(), c['jj'].cuda()
+    v = _video(c, buffer=9)
+    K = torch.unique(torch.cat([torch.arange(1, 6), c['ii']])).numel()     # depth frames of the window t0 = 1, t1 = 6 and the edges
+    eta_short = torch.full((K - 2, 12, 16), 0.01, device='cuda')
+    old = droid_backends.CHECK_BA
+    droid_backends.CHECK_BA = True
+    try:
+        with pytest.raises(RuntimeError, match='depth frames'):
+            droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), tgt.cuda(), wgt.cuda(), eta_short, ii, jj, 1, 6, 2, 1e-4, 0.1, False)
+        eta_ok = torch.full((K, 12, 16), 0.01, device='cuda')
+        droid_backends.ba(v.poses, v.disps, v.intrinsics[0].contiguous(), tgt.cuda(), wgt.cuda(), eta_ok, ii, jj, 1, 6, 2, 1e-4, 0.1, False)
+    finally:
+        droid_backends.CHECK_BA = old
