@@ -472,111 +472,187 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 
 // 6x6 diagonal block at c0: A_kk = L D L^T in place (unit lower L below the diagonal, d on it), 1/d -> dinv, and the
-// block's share of the forward substitution (y_k <- L_kk^-1 y_k).  One thread: float64 div / sqrt are ~100-cycle software
-// sequences, so the factorisation keeps one reciprocal per column and no square roots.
+// block's share of the forward substitution (y_k <- L_kk^-1 y_k).  One thread, RIGHT-looking: column j costs one reciprocal (hardware
+// seed + two Newton steps; float64 div / sqrt are ~100-cycle software sequences), five multiplies and the rank-1 update of what is left --
+// ~100 arithmetic instructions for the block.  What bounds it is the dependent chain pivot -> rcp -> l -> next pivot: ~9 float64
+// operations of ~20 cycles each per pivot (tools/prof_solve.py), so everything that is not on that chain is free: the positivity test
+// does not feed it (a failed factorisation zeroes dx anyway, garbage after a bad pivot is harmless), and the thread also inverts the
+// unit-triangular factor, N = L_kk^-1, in the chain's shadow -- with N the panel rows become independent dot products.
+// (The left-looking form this replaces recomputed every L d L product: 384 instructions, 1 700 cycles per block column.)
+// dk (optional, 48 doubles): what the panel rows need from this block -- N [6][6] | 1/d [6] | z_k [6] -- in one place.
 template <class M>
-__device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int c0, int* s_fail) {
-  double D[6][6], iv[6];
+__device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int c0, int* s_fail, double* dk) {
+  double D[6][6], N[6][6], z[6];
+  double* row0 = A.p + A.off(c0) + c0;                      // rows c0 .. c0+5 share the band start: row i begins i * ld further
 #pragma unroll
-  for (int i = 0; i < 6; i++)
+  for (int i = 0; i < 6; i++) {
+    z[i] = y[c0 + i];
 #pragma unroll
-    for (int j = 0; j < 6; j++) D[i][j] = (j <= i) ? A((c0 + i), c0 + j) : 0.0;
+    for (int j = 0; j < 6; j++) D[i][j] = (j <= i) ? row0[(long)i * A.ld + j] : 0.0;
+  }
   bool bad = false;
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    double d = D[j][j];
+    const double d = D[j][j];
+    bad = bad || !(d > 0.0);
+    const double iv = fast_rcp(d);
+    dinv[c0 + j] = iv;
+    if (dk) dk[36 + j] = iv;
+    double l[6];
 #pragma unroll
-    for (int t = 0; t < 6; t++) if (t < j) d -= D[j][t] * D[j][t] * D[t][t];
-    if (!(d > 0.0)) { bad = true; d = 1.0; }
-    D[j][j] = d;
-    iv[j] = fast_rcp(d);
+    for (int i = 0; i < 6; i++) l[i] = (i > j) ? D[i][j] * iv : 0.0;       // D[i][j] holds L_ij d_j until the end of this step
 #pragma unroll
     for (int i = 0; i < 6; i++) {
       if (i > j) {
-        double v = D[i][j];
+        z[i] = fma(-l[i], z[j], z[i]);
 #pragma unroll
-        for (int t = 0; t < 6; t++) if (t < j) v -= D[i][t] * D[j][t] * D[t][t];
-        D[i][j] = v * iv[j];
+        for (int c = 0; c < 6; c++)
+          if (c > j && c <= i) D[i][c] = fma(-l[i], D[c][j], D[i][c]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+      if (i > j) D[i][j] = l[i];
+    if (dk) {
+      // row j+1 of N = L^-1 needs columns 0..j of L only: N[i][c] = -(L[i][c] + sum_{c<t<i} L[i][t] N[t][c])
+      const int i = j + 1;
+      if (i < 6) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          if (c < i) {
+            double v = D[i][c];
+#pragma unroll
+            for (int t = 0; t < 6; t++) if (t > c && t < i) v = fma(D[i][t], N[t][c], v);
+            N[i][c] = -v;
+          }
+        }
       }
     }
   }
   if (bad) *s_fail = 1;
-  double z[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    dinv[c0 + i] = iv[i];
-    double v = y[c0 + i];
+    y[c0 + i] = z[i];
+    if (dk) {
+      dk[42 + i] = z[i];
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
-      if (j <= i) A((c0 + i), c0 + j) = D[i][j];
-      if (j < i) v -= D[i][j] * z[j];
+      for (int c = 0; c < 6; c++) if (c < i) dk[i * 6 + c] = N[i][c];
     }
-    z[i] = v;
-    y[c0 + i] = v;
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+      if (j <= i) row0[(long)i * A.ld + j] = D[i][j];
   }
 }
 
 // A = L D L^T restricted to the block band, then L z = b, D w = z, L^T x = w in place in y.  dinv: scratch [n].
-// Schedule per 6-wide block column k (two block barriers instead of five, and the serial 6x6 step is off the critical
-// path): [panel: L_rk for the band rows + their forward-substitution update] | [trailing update by warps 1.. while warp 0
-// updates, factors and forward-solves the NEXT diagonal block].  The backward substitution runs in warp 0 alone with
-// warp-level reductions (no block barriers at all).
+// Schedule per 6-wide block column k (two barriers, and the serial 6x6 step overlaps the trailing update):
+//   [panel: L_rk for the band rows + their forward-substitution update] | [trailing update by warps 1.. while warp 0
+//   updates, factors and forward-solves the NEXT diagonal block].
 // Forward elimination of block columns kb0 .. kb1-1 (every row they touch -- up to 6 kb1 + band + 5 -- must be resident in A), then,
 // separately, the D scaling and the backward substitution over a range of block columns: a system whose band does not fit shared
 // memory is processed window by window (ba_solve_kernel), everything else in one call (ldl_solve).
+//
+// Measured on the 8-GPU window (P = 63, band 36; tools/prof_solve.py, cycles of thread 0 per block column): panel 760, next diagonal
+// block 540 + 1 680, and then 1 300 more WAITING for the trailing update -- its loads walked rows four apart in a 42-double-pitch
+// matrix (8-way bank conflicts) and recomputed L d per entry.  Now the panel leaves its two results, L and L d, transposed in a
+// scratch ([6][band] each: consecutive rows in consecutive banks), the trailing update is one lower-triangle entry per thread
+// with lanes along a matrix row, and matrices in shared memory get an odd pitch.
+// Cycle probes for tools/prof_solve.py (a separate build with -DPVO_SOLVE_PROF; never compiled into the product library): thread 0 adds
+// the cycles since its previous probe to slot i, so the slots partition thread 0's time through the solve.
+#ifdef PVO_SOLVE_PROF
+__device__ long long g_solve_prof[32];
+__shared__ long long s_solve_prof[32];                      // accumulated in shared memory (a global read-modify-write would stall thread 0 ~500 cycles per probe)
+#define PROF_DECL long long t_prof = clock64()
+#define PROF(i) do { if (threadIdx.x == 0) { const long long t_now = clock64(); s_solve_prof[i] += t_now - t_prof; t_prof = clock64(); } } while (0)
+#define PROF_BEGIN do { if (threadIdx.x == 0) for (int q = 0; q < 32; q++) s_solve_prof[q] = 0; } while (0)
+#define PROF_END do { if (threadIdx.x == 0) for (int q = 0; q < 32; q++) g_solve_prof[q] += s_solve_prof[q]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_BEGIN
+#define PROF_END
+#endif
+
 // A thread GROUP (tid in [0, T), T a multiple of 32, its own named barrier `bar`) runs these: the whole block (bar 0 == __syncthreads) or
 // one half of it when two eliminations proceed side by side (two-sided factorisation in ba_solve_kernel).
 __device__ __forceinline__ void group_sync(int bar, int T) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(T) : "memory"); }
 
+__host__ __device__ __forceinline__ int ldl_scratch_doubles(int band) { return 12 * band + 48; }
+
+// scratch: ldl_scratch_doubles(band) doubles of shared memory owned by this group (panel L [6][band] | L d [6][band] | diagonal-block
+//   digest [48]), or nullptr: generic accessor-based path (systems that live in global memory).  It carries the digest of the last factored
+//   diagonal block from one call to the next (windowed factorisation).
 // factor_first: factor the diagonal block of column kb0 on entry (false when the previous call already did, as its "next" block);
 // factor_last: factor the diagonal block after column kb1 - 1 (false when other contributions are still to be added to it).
+// Which warps of a group of T threads take the trailing update when warp `fw` factors the diagonal blocks: all the others.  (Warps w and
+// w + 4 share an SM sub-partition; keeping the factoring sub-partition free of trailing work was measured: the single-thread 6x6
+// factorisation got 17 % faster, the trailing update -- then the longer of the two -- 40 % slower; P = 63 solve 82 vs 79.5 us.)
+__device__ __forceinline__ int default_trailing_mask(int T, int fw = 0) { return ((1 << (T >> 5)) - 1) & ~(1 << fw); }
+
+// fw: the group-relative warp that factors the diagonal blocks; tmask: the group-relative warps that do the trailing update (0 = default)
 template <class M>
-__device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int tid, int T, int* s_fail, int* s_rowoff, int kb0, int kb1,
-                            int row_lo, int row_hi, int bar = 0, bool factor_first = true, bool factor_last = true) {
+__device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int tid, int T, int* s_fail, int* s_rowoff, double* scratch,
+                            int kb0, int kb1, int row_lo, int row_hi, int bar = 0, bool factor_first = true, bool factor_last = true,
+                            int fw = 0, int tmask = 0) {
   const int lane = tid & 31, warp = tid >> 5;
-  const bool use_rowoff = n <= 1024 && A.off(row_hi - 1) + n < 0x7fffffffL && A.off(row_lo) > -0x7fffffffL;
-  if (use_rowoff)                                          // row r of the (band-packed or dense) matrix starts at A.p + s_rowoff[r]
+  if (!tmask) tmask = default_trailing_mask(T, fw);
+  const int Tt = 32 * __popc(tmask);                                              // threads on the trailing update
+  const int ttid = ((tmask >> warp) & 1) ? 32 * __popc(tmask & ((1 << warp) - 1)) + lane : -1;      // this thread's rank among them
+  const bool fast = scratch != nullptr && n <= 1024 && A.off(row_hi - 1) + n < 0x7fffffffL && A.off(row_lo) > -0x7fffffffL;
+  const int PS = band;
+  double* Lp = scratch;                                    // [6][PS]: L_rj of the current panel, row-contiguous per j
+  double* LDp = scratch + 6 * PS;                          // [6][PS]: L_rj d_j
+  double* dk = fast ? scratch + 12 * PS : nullptr;
+  if (fast)                                                // row r of the matrix starts at A.p + s_rowoff[r]
     for (int r = row_lo + tid; r < row_hi; r += T) s_rowoff[r] = (int)A.off(r);
   int bi = 0, bj = lane;                                   // lower-triangle entry of a 6x6 block updated by this lane (lanes < 21)
   while (bj > bi) { bj -= bi + 1; bi++; }
   group_sync(bar, T);
-  if (factor_first && tid == 0) ldl_diag_block(A, y, dinv, 6 * kb0, s_fail);
+  if (factor_first && tid == 32 * fw) ldl_diag_block(A, y, dinv, 6 * kb0, s_fail, dk);
   group_sync(bar, T);
+  PROF_DECL;
   for (int kb = kb0; kb < kb1; kb++) {
     const int c0 = 6 * kb;
     const int rend = min(n, c0 + 6 + band);
-    if (use_rowoff && c0 + 6 + tid < rend) {                // panel: L_rk = A_rk L_kk^-T D_k^-1; y_r -= L_rk z_k
-      // the factored diagonal block (L_kk d products, 1/d, z_k) once per thread, rows through the row table
-      double ldk[6][6], di[6], zk[6];
-#pragma unroll
-      for (int j = 0; j < 6; j++) {
-        const double* Lj = A.p + s_rowoff[c0 + j] + c0;
-        di[j] = dinv[c0 + j];
-        zk[j] = y[c0 + j];
-#pragma unroll
-        for (int t = 0; t < 6; t++) ldk[j][t] = (t < j) ? Lj[t] : 0.0;
-      }
-#pragma unroll
-      for (int j = 0; j < 6; j++)
-#pragma unroll
-        for (int t = 0; t < 6; t++) if (t < j) ldk[j][t] *= A.p[s_rowoff[c0 + t] + c0 + t];       // L_jt d_t
-      for (int r = c0 + 6 + tid; r < rend; r += T) {
-        double* Ar = A.p + s_rowoff[r] + c0;
-        double x[6];
-        double yr = y[r];
+    const int m = rend - c0 - 6;                           // band rows below the diagonal block (a multiple of 6)
+    if (fast) {                                            // panel: L_rk = A_rk L_kk^-T D_k^-1; y_r -= L_rk z_k
+      if (tid < m) {
+        // L_rk d = A_rk N^T (N = L_kk^-1 from the diagonal block's digest): six independent dot products per row, no chain from x_0 to x_5
+        double Nk[6][6], di[6], zk[6];
 #pragma unroll
         for (int j = 0; j < 6; j++) {
-          double v = Ar[j];
+          di[j] = dk[36 + j];
+          zk[j] = dk[42 + j];
 #pragma unroll
-          for (int t = 0; t < 6; t++) if (t < j) v = fma(-x[t], ldk[j][t], v);
-          x[j] = v * di[j];
-          yr = fma(-x[j], zk[j], yr);
+          for (int t = 0; t < 6; t++) Nk[j][t] = (t < j) ? dk[j * 6 + t] : 0.0;
         }
+        for (int rr = tid; rr < m; rr += T) {
+          const int r = c0 + 6 + rr;
+          double* Ar = A.p + s_rowoff[r] + c0;
+          double a[6], x[6];
 #pragma unroll
-        for (int j = 0; j < 6; j++) Ar[j] = x[j];
-        y[r] = yr;
+          for (int j = 0; j < 6; j++) a[j] = Ar[j];
+          double ya = y[r], yb2 = 0.0;
+#pragma unroll
+          for (int j = 0; j < 6; j++) {
+            double va = a[j], vb = 0.0;
+#pragma unroll
+            for (int t = 0; t < 6; t++) {
+              if (t < j) {
+                if (t & 1) vb = fma(a[t], Nk[j][t], vb); else va = fma(a[t], Nk[j][t], va);
+              }
+            }
+            const double v = va + vb;
+            LDp[j * PS + rr] = v;
+            x[j] = v * di[j];
+            Lp[j * PS + rr] = x[j];
+            Ar[j] = x[j];
+            if (j & 1) yb2 = fma(x[j], zk[j], yb2); else ya = fma(-x[j], zk[j], ya);
+          }
+          y[r] = ya - yb2;
+        }
       }
-    } else if (!use_rowoff) {
+    } else {
       for (int r = c0 + 6 + tid; r < rend; r += T) {
         double x[6];
         double yr = y[r];
@@ -593,57 +669,59 @@ __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int t
         y[r] = yr;
       }
     }
+    PROF(0);                                                // panel (thread 0's row)
     group_sync(bar, T);
-    const int m = rend - c0 - 6;                           // trailing update (lower triangle): A_ic -= sum_t L_it d_t L_ct
-    if (m > 0) {
-      if (warp == 0) {
+    PROF(1);                                                // wait for the slowest panel row
+    if (m > 0) {                                            // trailing update (lower triangle): A_ic -= sum_t L_it d_t L_ct
+      if (warp == fw) {
         // the next diagonal block first (21 entries, one per lane), then its factorisation while the other warps do the rest of the
         // trailing update.  The factorisation stays in ONE thread: a warp-parallel variant (lane <-> lower-triangle entry, pivot column
-        // broadcast by 64-bit shuffles) was measured slower (P = 63: 593 vs 538 us per BA) -- the scalar routine's 384 instructions
-        // (ncu, profiles/r02_solve63_source.csv) have enough ILP to beat six rounds of dependent shuffles.
+        // broadcast by 64-bit shuffles) was measured slower -- six rounds of dependent shuffles lose to one thread's ILP.
         if (lane < 21) {
-          const int i = c0 + 6 + bi, c = c0 + 6 + bj;
-          double vn = A(i, c);
+          if (fast) {
+            double* Ai = A.p + s_rowoff[c0 + 6 + bi] + c0 + 6;
+            double va = Ai[bj], vb = 0.0;
 #pragma unroll
-          for (int t = 0; t < 6; t++) vn -= A(i, c0 + t) * A((c0 + t), c0 + t) * A(c, c0 + t);
-          A(i, c) = vn;
-        }
-        __syncwarp();
-        if (lane == 0 && (factor_last || kb + 1 < kb1)) ldl_diag_block(A, y, dinv, c0 + 6, s_fail);
-        __syncwarp();
-      } else if (use_rowoff) {
-        // Measured: with one (i, c) entry per loop trip, located by idx / m and idx % m and fetched through the band accessor, this loop
-        // was INSTRUCTION bound (~300 instructions per entry: 13 k warp-instructions per block column at a 36-row band, the 2 us per
-        // column that made the solve 65 % of the sharded BA).  Now a thread owns (row i, four consecutive columns): the row's six
-        // L_it d_t products stay in registers, row starts come from a table, and the (row, chunk) split is a shift and a mask.
-        double d6[6];
-#pragma unroll
-        for (int t = 0; t < 6; t++) d6[t] = A.p[s_rowoff[c0 + t] + c0 + t];
-        int lg = 0;
-        while ((4 << lg) < m) lg++;                          // chunks per row, rounded up to a power of two
-        const int cpr = 1 << lg;
-        for (int w = tid - 32; w < ((m - 6) << lg); w += T - 32) {
-          const int ir = 6 + (w >> lg), cb = (w & (cpr - 1)) * 4;          // row / first column, relative to c0 + 6
-          if (cb > ir) continue;
-          const double* Li = A.p + s_rowoff[c0 + 6 + ir] + c0;
-          double ld_[6];
-#pragma unroll
-          for (int t = 0; t < 6; t++) ld_[t] = Li[t] * d6[t];
-          double* Ai = A.p + s_rowoff[c0 + 6 + ir] + c0 + 6;
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int c = cb + q;
-            if (c <= ir) {
-              const double* Lc = A.p + s_rowoff[c0 + 6 + c] + c0;
-              double v = Ai[c];
-#pragma unroll
-              for (int t = 0; t < 6; t++) v = fma(-ld_[t], Lc[t], v);
-              Ai[c] = v;
+            for (int t = 0; t < 3; t++) {
+              va = fma(-LDp[t * PS + bi], Lp[t * PS + bj], va);
+              vb = fma(LDp[(t + 3) * PS + bi], Lp[(t + 3) * PS + bj], vb);
             }
+            Ai[bj] = va - vb;
+          } else {
+            const int i = c0 + 6 + bi, c = c0 + 6 + bj;
+            double vn = A(i, c);
+#pragma unroll
+            for (int t = 0; t < 6; t++) vn -= A(i, c0 + t) * A((c0 + t), c0 + t) * A(c, c0 + t);
+            A(i, c) = vn;
           }
         }
-      } else {
-        for (int idx = tid - 32; idx < m * m; idx += T - 32) {
+        __syncwarp();
+        PROF(2);                                            // next diagonal block: 21-entry update
+        if (lane == 0 && (factor_last || kb + 1 < kb1)) ldl_diag_block(A, y, dinv, c0 + 6, s_fail, dk);
+        PROF(3);                                            // its factorisation
+        __syncwarp();
+      } else if (fast && ttid >= 0) {
+        // rows 6 .. m-1 of the trailing block (the first six belong to warp 0), lower triangle: row 6+p (7+p entries) and row m-1-p
+        // (m-p entries) together always hold m+7 entries, so R/2 row pairs x (m+7) entries enumerate the triangle without idle lanes
+        const int R = m - 6, width = m + 7, total = (R >> 1) * width;
+        int idx = ttid;
+        int p = idx / width, k = idx - p * width;
+        for (; idx < total; idx += Tt) {
+          const bool first = k <= 6 + p;
+          const int i = first ? 6 + p : m - 1 - p, c = first ? k : k - 7 - p;
+          double* Ai = A.p + s_rowoff[c0 + 6 + i] + c0 + 6;
+          double va = Ai[c], vb = 0.0;
+#pragma unroll
+          for (int t = 0; t < 3; t++) {
+            va = fma(-LDp[t * PS + i], Lp[t * PS + c], va);
+            vb = fma(LDp[(t + 3) * PS + i], Lp[(t + 3) * PS + c], vb);
+          }
+          Ai[c] = va - vb;
+          k += Tt;
+          while (k >= width) { k -= width; p++; }
+        }
+      } else if (!fast && ttid >= 0) {
+        for (int idx = ttid; idx < m * m; idx += Tt) {
           const int i = c0 + 6 + idx / m, c = c0 + 6 + idx % m;
           if (c > i || i < c0 + 12) continue;              // rows of the next diagonal block belong to warp 0
           double v = A(i, c);
@@ -654,37 +732,64 @@ __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int t
       }
     }
     group_sync(bar, T);
+    PROF(4);                                                // wait for the trailing update
   }
 }
 
-// L^T x = w for block columns kb_hi down to kb_lo: block rows from the bottom, one warp, no block barriers
+// L^T x = w for block columns kb_hi down to kb_lo, right-looking, one warp, no block barriers: once x_k is known it is pushed into the
+// right-hand side of the band columns to its left (lanes along a matrix row: no reductions, no bank conflicts).  The rows below the
+// range -- solved by an earlier call: the separator, or the previous window -- are pushed first.  A column outside [kb_lo, kb_hi] is
+// never written, so every (row block, column) contribution is applied by exactly one call.
 template <class M>
-__device__ void ldl_backward(M A, double* y, int n, int band, int tid, int kb_hi, int kb_lo, int bar = 0, int T = 0) {
+__device__ void ldl_backward(M A, double* y, int n, int band, int tid, int kb_hi, int kb_lo, int bar = 0, int T = 0, int fw = 0) {
   const int lane = tid & 31, warp = tid >> 5;
-  if (warp == 0) {
+  if (warp == fw && kb_hi >= kb_lo) {
+    const int clo = 6 * kb_lo;
+    auto push = [&](int rb, int cb) {                      // y_c -= sum_j L(rb + j, c) x_{rb + j} for columns max(clo, rb - band) <= c < cb
+      const double* row0 = A.p + A.off(rb);                // the six rows of a block share the band start: row j begins j * ld further
+      double x[6];
+#pragma unroll
+      for (int j = 0; j < 6; j++) x[j] = y[rb + j];
+      for (int c = max(clo, rb - band) + lane; c < cb; c += 64) {      // two columns per trip: their loads overlap
+        const int c2 = c + 32;
+        const bool two = c2 < cb;
+        double va = y[c], vb = 0.0, wa = two ? y[c2] : 0.0, wb = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          va = fma(-row0[(long)j * A.ld + c], x[j], va);
+          vb = fma(row0[(long)(j + 3) * A.ld + c], x[j + 3], vb);
+          if (two) {
+            wa = fma(-row0[(long)j * A.ld + c2], x[j], wa);
+            wb = fma(row0[(long)(j + 3) * A.ld + c2], x[j + 3], wb);
+          }
+        }
+        y[c] = va - vb;
+        if (two) y[c2] = wa - wb;
+      }
+    };
+    const int ctop = 6 * (kb_hi + 1), rtop = min(n, ctop + band);
+    for (int rb = ctop; rb < rtop; rb += 6) { push(rb, ctop); __syncwarp(); }
     for (int kb = kb_hi; kb >= kb_lo; kb--) {
       const int c0 = 6 * kb;
-      const int rlast = min(n, c0 + 6 + band);             // rows below this block with L(r, c0..c0+5) != 0 stay within the band
-      double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int r = c0 + 6 + lane; r < rlast; r += 32) {
-        const double yr = y[r];
-#pragma unroll
-        for (int j = 0; j < 6; j++) acc[j] += A(r, c0 + j) * yr;
-      }
-#pragma unroll
-      for (int j = 0; j < 6; j++) acc[j] = warp_sum_d(acc[j]);
       if (lane == 0) {                                     // unit upper-triangular 6x6 (L_kk^T) by back substitution
-        double x[6];
+        const double* r0p = A.p + A.off(c0) + c0;
+        double x[6], l[6][6];
+#pragma unroll
+        for (int t = 0; t < 6; t++)
+#pragma unroll
+          for (int j = 0; j < 6; j++) l[t][j] = (t > j) ? r0p[(long)t * A.ld + j] : 0.0;
 #pragma unroll
         for (int j = 5; j >= 0; j--) {
-          double v = y[c0 + j] - acc[j];
+          double v = y[c0 + j];
 #pragma unroll
-          for (int t = 0; t < 6; t++) if (t > j) v -= A((c0 + t), c0 + j) * x[t];
+          for (int t = 0; t < 6; t++) if (t > j) v = fma(-l[t][j], x[t], v);
           x[j] = v;
         }
 #pragma unroll
         for (int j = 0; j < 6; j++) y[c0 + j] = x[j];
       }
+      __syncwarp();
+      push(c0, c0);
       __syncwarp();
     }
   }
@@ -692,40 +797,62 @@ __device__ void ldl_backward(M A, double* y, int n, int band, int tid, int kb_hi
 }
 
 template <class M>
-__device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, int tid, int T, int* s_fail) {
-  __shared__ int s_rowoff[1024];
-  ldl_forward(A, y, dinv, n, band, tid, T, s_fail, s_rowoff, 0, P, 0, n);
+__device__ void ldl_solve(M A, double* y, double* dinv, int P, int n, int band, int tid, int T, int* s_fail, int* s_rowoff, double* scratch) {
+  ldl_forward(A, y, dinv, n, band, tid, T, s_fail, s_rowoff, scratch, 0, P, 0, n);
   if (*s_fail) return;
   for (int i = tid; i < n; i += T) y[i] *= dinv[i];        // D w = z
   __syncthreads();
   ldl_backward(A, y, n, band, tid, P - 1, 0);
 }
 
+constexpr int kSolveSmem = 208 * 1024;      // dynamic shared memory of ba_solve_kernel<false>
+constexpr int kWindowBytes = 190 * 1024;    // ... of which a sliding window of band rows + y + 1/d may take this much (the rest: panel scratch)
+
+// Can a window of band rows (odd pitch band + 7) plus y and 1/d live in shared memory?  Shared by the kernel and by packed_band().
+__host__ __device__ __forceinline__ bool window_fits(int n, int band) {
+  return sizeof(double) * ((size_t)(band + 7) * (band + 18) + 2 * (size_t)n) <= (size_t)kWindowBytes;
+}
+
+// f(i, src[i]) for i in [i0, i1), eight loads in flight per thread: a dependent-latency copy loop (one L2 round trip per element and
+// thread) was 16 us of the P = 63 solve
+template <class F>
+__device__ __forceinline__ void for_each_loaded(const double* __restrict__ src, long i0, long i1, int tid, int T, F f) {
+  for (long base = i0; base < i1; base += 8L * T) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const long i = base + (long)u * T + tid;
+      v[u] = i < i1 ? __ldg(src + i) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const long i = base + (long)u * T + tid;
+      if (i < i1) f(i, v[u]);
+    }
+  }
+}
+
 template <bool IN_SMEM>
 __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm, float ep, int sem, int moba, int bw_hint, double* packed) {
   extern __shared__ double smd[];
   __shared__ int s_fail;
+  __shared__ int s_rowoff[1024];
   const int n = 6 * P;
   const int tid = threadIdx.x, T = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = T >> 5;
   const long psz = (long)n * n + 2 * n;
   const int ld = IN_SMEM ? n + 1 : n;
   if (!IN_SMEM && packed) {
     // band-packed system from ba_combine_band_kernel (all-reduced in between on the sharded path): [n][W] | b | dA.  The band is
-    // the caller's (bw_hint >= 0, not the block-diagonal-damped MoBA variant); no dense matrix is touched.
-    const int band = 6 * min(bw_hint, P - 1), W = band + 6;
-    double* pb = packed + (long)n * W;                        // b, then dA
+    // the caller's (bw_hint >= 0, not the block-diagonal-damped MoBA variant); no dense matrix is touched.  In shared memory the rows
+    // get the odd pitch Ws: threads that walk down a column (panel rows, the back substitution) then hit distinct banks.
+    const int band = 6 * min(bw_hint, P - 1), W = band + 6, Ws = W + 1, SCR = ldl_scratch_doubles(band);
+    const double* pb = packed + (long)n * W;                  // b, then dA
+    PROF_BEGIN;
+    PROF_DECL;
     if (tid == 0) s_fail = 0;
-    for (int i = tid; i < n; i += T) {                       // LM damping of the diagonal (see damp())
-      double* d = packed + (long)i * W + (i - max(0, 6 * (i / 6) - band));
-      *d += (double)ep + (double)lm * (sem ? pb[n + i] : *d);
-    }
-    __syncthreads();
-    const bool whole = sizeof(double) * ((size_t)n * W + 2 * n) <= 200 * 1024;
-    const int rows = whole ? n : min(n, (int)((190 * 1024 - sizeof(double) * 2 * n) / (sizeof(double) * W)) / 6 * 6);
-    double* Ab = smd;
-    double* yb = smd + (long)rows * W;
-    double* db = yb + n;
-    __shared__ int s_rowoff_p[1024];
+    auto damped = [&](double v, int r) { return v + (double)ep + (double)lm * (sem ? pb[n + r] : v); };     // LM damping of a diagonal entry (see damp())
+    const bool whole = sizeof(double) * ((size_t)n * Ws + 2 * n + SCR) <= (size_t)kSolveSmem;
     // Two-sided factorisation.  The 63 block columns of the 8-GPU window are 63 SEQUENTIAL steps of a few hundred dependent
     // instructions each (profiles/r02_solve63_source.csv: the kernel is the sum of its serial pieces).  A band matrix splits into
     // top part T | separator S (one band width) | bottom part B with no T-B coupling, so T is eliminated downwards by one half of
@@ -734,40 +861,51 @@ __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm,
     // depth |T| + |S| = 29 + 6 block columns instead of 63.  Every rank executes the same schedule, so replicas stay bitwise equal.
     const int bwb = band / 6, Tb = (P - bwb + 1) / 2, Bb = P - bwb - Tb;
     const bool two_sided = whole && T == 512 && Bb >= 2 && n + band <= 1024 &&
-                           sizeof(double) * ((size_t)(n + band) * (W + 2)) <= 200 * 1024;
+                           sizeof(double) * ((size_t)(n + band) * (Ws + 2) + 2 * SCR) <= (size_t)kSolveSmem;
     if (two_sided) {
       const int n1 = 6 * (Tb + bwb), nB = 6 * Bb, n2 = nB + band;      // matrix 1: rows of T and S; matrix 2 (reversed indices): B then S
       double* A1 = smd;
-      double* A2 = A1 + (long)n1 * W;
-      double* y1 = A2 + (long)n2 * W;
+      double* A2 = A1 + (long)n1 * Ws;
+      double* y1 = A2 + (long)n2 * Ws;
       double* y2 = y1 + n1;
       double* d1 = y2 + n2;
       double* d2 = d1 + n1;
-      for (long i = tid; i < (long)n1 * W; i += T) A1[i] = packed[i];
+      double* sc1 = d2 + n2;
+      double* sc2 = sc1 + SCR;
+      for (long i = tid; i < (long)n2 * Ws; i += T) A2[i] = 0.0;       // upper triangle, pad column and the S x S block (it collects B's Schur complement)
       for (int i = tid; i < n1; i += T) y1[i] = pb[i];
-      for (long i = tid; i < (long)n2 * W; i += T) {
-        const int r = (int)(i / W), c = (int)(i % W) + max(0, 6 * (r / 6) - band);
-        double v = 0.0;
-        if (c <= r && !(r >= nB && c >= nB)) {                   // the S x S block of matrix 2 starts at zero: it collects B's Schur complement
-          const int R = n - 1 - c, C = n - 1 - r;                // reversed element (r, c) = original (n-1-c, n-1-r), lower triangle
-          v = packed[(long)R * W + C - max(0, 6 * (R / 6) - band)];
-        }
-        A2[i] = v;
-      }
       for (int l = tid; l < n2; l += T) y2[l] = l < nB ? pb[n - 1 - l] : 0.0;
+      for_each_loaded(packed, 0, (long)n1 * W, tid, T, [&](long i, double v) {        // matrix 1 = the first n1 packed rows (damped diagonal)
+        const int r = (int)(i / W), cc = (int)(i - (long)r * W);
+        if (max(0, 6 * (r / 6) - band) + cc == r) v = damped(v, r);
+        A1[(long)r * Ws + cc] = v;
+      });
       __syncthreads();
+      for_each_loaded(packed, (long)(6 * Tb + band) * W, (long)n * W, tid, T, [&](long i, double v) {      // matrix 2: element (R, C) of the rows of B lands at (n-1-C, n-1-R)
+        const int R = (int)(i / W), C = max(0, 6 * (R / 6) - band) + (int)(i - (long)R * W);
+        if (C > R) return;
+        if (C == R) v = damped(v, R);
+        const int r = n - 1 - C, c = n - 1 - R;
+        A2[(long)r * Ws + c - max(0, 6 * (r / 6) - band)] = v;
+      });
+      __syncthreads();
+      PROF(9);                                                  // load of both halves
       const int g = tid >> 8, gt = tid & 255;
-      const SysMat<true> M1{A1, W, band, 0}, M2{A2, W, band, 0};
-      if (g == 0) ldl_forward(M1, y1, d1, n1, band, gt, 256, &s_fail, s_rowoff_p, 0, Tb, 0, n1, 1, true, false);
-      else        ldl_forward(M2, y2, d2, n2, band, gt, 256, &s_fail, s_rowoff_p + n1, 0, Bb, 0, n2, 2, true, false);
+      const SysMat<true> M1{A1, Ws, band, 0}, M2{A2, Ws, band, 0};
+      // warps 0 (top half) and 9 (bottom half) factor: different SM sub-partitions
+      if (g == 0) ldl_forward(M1, y1, d1, n1, band, gt, 256, &s_fail, s_rowoff, sc1, 0, Tb, 0, n1, 1, true, false, 0);
+      else        ldl_forward(M2, y2, d2, n2, band, gt, 256, &s_fail, s_rowoff + n1, sc2, 0, Bb, 0, n2, 2, true, false, 1);
       __syncthreads();
+      PROF(10);                                                 // both eliminations
       for (int idx = tid; idx < band * band; idx += T) {        // S += B's Schur complement (matrix 2 indexes rows in reverse)
         const int a = idx / band, b = idx % band;
         if (b <= a) M1(6 * Tb + a, 6 * Tb + b) += M2(n - 1 - (6 * Tb + b), n - 1 - (6 * Tb + a));
       }
       for (int a = tid; a < band; a += T) y1[6 * Tb + a] += y2[n - 1 - (6 * Tb + a)];
       __syncthreads();
-      ldl_forward(M1, y1, d1, n1, band, tid, T, &s_fail, s_rowoff_p, Tb, Tb + bwb, 0, n1, 0, true, true);
+      PROF(11);                                                 // merge
+      ldl_forward(M1, y1, d1, n1, band, tid, T, &s_fail, s_rowoff, sc1, Tb, Tb + bwb, 0, n1, 0, true, true);
+      PROF(12);                                                 // separator
       if (!s_fail) {
         for (int i = tid; i < n1; i += T) y1[i] *= d1[i];       // D w = z
         for (int l = tid; l < nB; l += T) y2[l] *= d2[l];
@@ -776,46 +914,77 @@ __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm,
         for (int l = nB + tid; l < n2; l += T) y2[l] = y1[n - 1 - l];
         __syncthreads();
         if (g == 0) ldl_backward(M1, y1, n1, band, gt, Tb - 1, 0, 1, 256);
-        else        ldl_backward(M2, y2, n2, band, gt, Bb - 1, 0, 2, 256);
+        else        ldl_backward(M2, y2, n2, band, gt, Bb - 1, 0, 2, 256, 1);
       }
       __syncthreads();
+      PROF(13);                                                 // back substitution
+      PROF_END;
       const bool failed2 = s_fail != 0;
       for (int i = tid; i < n; i += T) bf.dx[i] = failed2 ? 0.0f : (float)(i < n1 ? y1[i] : y2[n - 1 - i]);
       return;
     }
-    for (int i = tid; i < n; i += T) yb[i] = pb[i];
     if (whole) {
-      for (long i = tid; i < (long)n * W; i += T) Ab[i] = packed[i];
+      double* Ab = smd;
+      double* yb = smd + (long)n * Ws;
+      double* db = yb + n;
+      for (int i = tid; i < n; i += T) yb[i] = pb[i];
+      for_each_loaded(packed, 0, (long)n * W, tid, T, [&](long i, double v) {
+        const int r = (int)(i / W), cc = (int)(i - (long)r * W);
+        if (max(0, 6 * (r / 6) - band) + cc == r) v = damped(v, r);
+        Ab[(long)r * Ws + cc] = v;
+      });
       __syncthreads();
-      ldl_solve(SysMat<true>{Ab, W, band, 0}, yb, db, P, n, band, tid, T, &s_fail);
-    } else {
-      // window by window (see the dense-backed variant below); the packed block in global memory is the backing store
-      const int kcount = (rows - band - 6) / 6 + 1;
-      int k0 = 0;
-      for (;; k0 += kcount) {
-        const int r0 = 6 * k0, k1 = min(P, k0 + kcount), r1 = min(n, r0 + rows);
-        __syncthreads();
-        for (long i = tid; i < (long)(r1 - r0) * W; i += T) Ab[i] = packed[(long)r0 * W + i];
-        __syncthreads();
-        ldl_forward(SysMat<true>{Ab, W, band, r0}, yb, db, n, band, tid, T, &s_fail, s_rowoff_p, k0, k1, r0, r1, 0, k0 == 0, true);
-        if (k1 == P) break;
-        __syncthreads();
-        for (long i = tid; i < (long)(r1 - r0) * W; i += T) packed[(long)r0 * W + i] = Ab[i];
-      }
+      ldl_solve(SysMat<true>{Ab, Ws, band, 0}, yb, db, P, n, band, tid, T, &s_fail, s_rowoff, db + n);
       __syncthreads();
-      if (!s_fail) {
-        for (int i = tid; i < n; i += T) yb[i] *= db[i];
-        __syncthreads();
-        for (int kw = k0;; kw -= kcount) {
-          const int r0 = 6 * kw, r1 = min(n, r0 + rows);
-          if (kw != k0) {
-            __syncthreads();
-            for (long i = tid; i < (long)(r1 - r0) * W; i += T) Ab[i] = packed[(long)r0 * W + i];
-            __syncthreads();
-          }
-          ldl_backward(SysMat<true>{Ab, W, band, r0}, yb, n, band, tid, min(P, kw + kcount) - 1, kw);
-          if (kw == 0) break;
+      const bool failed = s_fail != 0;
+      for (int i = tid; i < n; i += T) bf.dx[i] = failed ? 0.0f : (float)yb[i];
+      return;
+    }
+    // The whole band does not fit (BASELINE configs[4]: 63 poses, block bandwidth 16: 378 x 102 doubles = 308 KB), but a WINDOW of
+    // rows does: the elimination of block column k touches rows 6k .. 6k + band + 5 only.  Keep `rows` consecutive band rows resident,
+    // eliminate as many block columns as they cover, write the rows back (the packed block in global memory is the backing store),
+    // slide.  The backward substitution walks the windows in reverse.  Measured before this existed: the factorisation ran out of L2
+    // and the BA of the banded-8 graph took 2.1 ms (of which ~1.6 ms solve).
+    for (int i = tid; i < n; i += T) {                         // rows are re-read after they were factored: damp in place, once
+      double* d = packed + (long)i * W + (i - max(0, 6 * (i / 6) - band));
+      *d = damped(*d, i);
+    }
+    const int rows = min(n, (int)((kWindowBytes - sizeof(double) * 2 * n) / (sizeof(double) * Ws)) / 6 * 6);    // resident rows (>= band + 12)
+    const int kcount = (rows - band - 6) / 6 + 1;              // block columns one window can eliminate
+    double* Ab = smd;
+    double* yb = smd + (long)rows * Ws;
+    double* db = yb + n;
+    double* scratch = smd + kWindowBytes / sizeof(double);
+    for (int i = tid; i < n; i += T) yb[i] = pb[i];
+    auto load = [&](int r0, int r1) {
+      for (int r = r0 + warp; r < r1; r += nw)
+        for (int cc = lane; cc < W; cc += 32) Ab[(long)(r - r0) * Ws + cc] = packed[(long)r * W + cc];
+    };
+    int k0 = 0;
+    for (;; k0 += kcount) {                                    // forward, window by window
+      const int r0 = 6 * k0, k1 = min(P, k0 + kcount), r1 = min(n, r0 + rows);
+      __syncthreads();
+      load(r0, r1);
+      __syncthreads();
+      ldl_forward(SysMat<true>{Ab, Ws, band, r0}, yb, db, n, band, tid, T, &s_fail, s_rowoff, scratch, k0, k1, r0, r1, 0, k0 == 0, true);
+      if (k1 == P) break;
+      __syncthreads();
+      for (int r = r0 + warp; r < r1; r += nw)
+        for (int cc = lane; cc < W; cc += 32) packed[(long)r * W + cc] = Ab[(long)(r - r0) * Ws + cc];
+    }
+    __syncthreads();
+    if (!s_fail) {
+      for (int i = tid; i < n; i += T) yb[i] *= db[i];         // D w = z
+      __syncthreads();
+      for (int kw = k0;; kw -= kcount) {                       // backward: the last window is still resident
+        const int r0 = 6 * kw, r1 = min(n, r0 + rows);
+        if (kw != k0) {
+          __syncthreads();
+          load(r0, r1);
+          __syncthreads();
         }
+        ldl_backward(SysMat<true>{Ab, Ws, band, r0}, yb, n, band, tid, min(P, kw + kcount) - 1, kw);
+        if (kw == 0) break;
       }
     }
     __syncthreads();
@@ -823,16 +992,18 @@ __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm,
     for (int i = tid; i < n; i += T) bf.dx[i] = failed ? 0.0f : (float)yb[i];
     return;
   }
-  double* A = IN_SMEM ? smd : bf.sys;                      // !IN_SMEM: parts were combined into part 0 beforehand
+  // ---- dense system: in shared memory (IN_SMEM: up to 26 poses) or, without a caller-supplied bandwidth / for the MoBA variant, in
+  // global memory (parts folded into part 0 by ba_combine_kernel beforehand)
+  double* A = IN_SMEM ? smd : bf.sys;
   double* y = IN_SMEM ? smd + (long)n * ld : bf.sys + (long)n * n;
   double* dA = IN_SMEM ? y + n : bf.sys + (long)n * n + n;
   if (IN_SMEM) {
-    for (long i = tid; i < (long)n * n + 2 * n; i += T) {
-      double v = 0.0;
-#pragma unroll
-      for (int g = 0; g < kParts; g++) v += bf.sys[g * psz + i];
+    static_assert(kParts == 2, "the in-shared-memory solve folds exactly two replicas");
+    const double* part1 = bf.sys + psz;
+    for_each_loaded(bf.sys, 0, psz, tid, T, [&](long i, double v) {
+      v += __ldcg(part1 + i);
       if (i < (long)n * n) A[(i / n) * ld + (i % n)] = v; else y[i - (long)n * n] = v;      // y | dA are contiguous
-    }
+    });
   }
   if (tid == 0) s_fail = 0;
   __syncthreads();
@@ -854,83 +1025,30 @@ __global__ void __launch_bounds__(512) ba_solve_kernel(Bufs bf, int P, float lm,
   }
   __syncthreads();
   const int band = 6 * s_bw;
+  const int SCR = ldl_scratch_doubles(band);
   double* dinv = dA;                                       // dA is dead after damp(): reuse it for 1/d_j
-  if (!IN_SMEM && sizeof(double) * ((size_t)n * (band + 6) + 2 * n) <= 200 * 1024) {
-    // too large for a dense copy, but the band fits: pack it into shared memory (8 GPUs x 8 keyframes: n = 378, band 36)
-    const int W = band + 6;
+  if (IN_SMEM) {
+    ldl_solve(SysMat<false>{A, ld, band, 0}, y, dinv, P, n, band, tid, T, &s_fail, s_rowoff, dA + n);      // the host sized the scratch for band = n
+  } else if (sizeof(double) * ((size_t)n * (band + 7) + 2 * n + SCR) <= (size_t)kSolveSmem) {
+    // too large for a dense copy, but the band (found by the scan) fits: pack it into shared memory
+    const int Ws = band + 7;
     double* Ab = smd;
-    double* yb = smd + (long)n * W;
+    double* yb = smd + (long)n * Ws;
     double* db = yb + n;
-    for (long i = tid; i < (long)n * W; i += T) {
-      const int r = (int)(i / W), c = (int)(i % W) + max(0, 6 * (r / 6) - band);
-      Ab[i] = c <= r ? A[(long)r * ld + c] : 0.0;
+    for (int r = warp; r < n; r += nw) {
+      const int cs = max(0, 6 * (r / 6) - band);
+      for (int cc = lane; cc < Ws; cc += 32) Ab[(long)r * Ws + cc] = (cs + cc <= r) ? A[(long)r * ld + cs + cc] : 0.0;
     }
     for (int i = tid; i < n; i += T) yb[i] = y[i];
     __syncthreads();
-    ldl_solve(SysMat<true>{Ab, W, band, 0}, yb, db, P, n, band, tid, T, &s_fail);
-    __syncthreads();
-    for (int i = tid; i < n; i += T) y[i] = yb[i];
-    __syncthreads();
-  } else if (!IN_SMEM && n <= 1024 && sizeof(double) * ((size_t)(band + 6) * (band + 18) + 2 * n) <= 190 * 1024) {
-    // The whole band does not fit (BASELINE configs[4]: 63 poses, block bandwidth 16: 378 x 102 doubles = 308 KB), but a WINDOW of
-    // rows does: the elimination of block column k touches rows 6k .. 6k + band + 5 only.  Keep `rows` consecutive band rows resident,
-    // eliminate as many block columns as they cover, write the rows back to the dense system in global memory (its lower band is
-    // the backing store), slide.  The backward substitution walks the windows in reverse.  Measured before this existed: the
-    // factorisation ran out of L2 and the BA of the banded-8 graph took 2.1 ms (of which ~1.6 ms solve).
-    const int W = band + 6;
-    const int cap_rows = (int)((190 * 1024 - sizeof(double) * 2 * n) / (sizeof(double) * W));
-    const int rows = min(n, cap_rows / 6 * 6);                        // resident rows (a multiple of 6, >= band + 12)
-    const int kcount = (rows - band - 6) / 6 + 1;                     // block columns one window can eliminate
-    double* Ab = smd;
-    double* yb = smd + (long)rows * W;
-    double* db = yb + n;
-    __shared__ int s_rowoff_w[1024];
-    for (int i = tid; i < n; i += T) yb[i] = y[i];
-    auto load = [&](int r0) {
-      const int r1 = min(n, r0 + rows);
-      for (long i = tid; i < (long)(r1 - r0) * W; i += T) {
-        const int r = r0 + (int)(i / W), c = (int)(i % W) + max(0, 6 * (r / 6) - band);
-        Ab[i] = c <= r ? A[(long)r * ld + c] : 0.0;
-      }
-    };
-    auto store = [&](int r0) {
-      const int r1 = min(n, r0 + rows);
-      for (long i = tid; i < (long)(r1 - r0) * W; i += T) {
-        const int r = r0 + (int)(i / W), c = (int)(i % W) + max(0, 6 * (r / 6) - band);
-        if (c <= r) A[(long)r * ld + c] = Ab[i];
-      }
-    };
-    int k0 = 0;
-    for (;; k0 += kcount) {                                           // forward, window by window
-      const int r0 = 6 * k0, k1 = min(P, k0 + kcount);
-      __syncthreads();
-      load(r0);
-      __syncthreads();
-      ldl_forward(SysMat<true>{Ab, W, band, r0}, yb, db, n, band, tid, T, &s_fail, s_rowoff_w, k0, k1, r0, min(n, r0 + rows), 0, k0 == 0, true);
-      if (k1 == P) break;
-      __syncthreads();
-      store(r0);
-    }
-    __syncthreads();
-    if (!s_fail) {
-      for (int i = tid; i < n; i += T) yb[i] *= db[i];                // D w = z
-      __syncthreads();
-      for (int kw = k0;; kw -= kcount) {                              // backward: the last window is still resident
-        const int r0 = 6 * kw;
-        if (kw != k0) {
-          __syncthreads();
-          load(r0);
-          __syncthreads();
-        }
-        ldl_backward(SysMat<true>{Ab, W, band, r0}, yb, n, band, tid, min(P, kw + kcount) - 1, kw);
-        if (kw == 0) break;
-      }
-    }
+    ldl_solve(SysMat<true>{Ab, Ws, band, 0}, yb, db, P, n, band, tid, T, &s_fail, s_rowoff, db + n);
     __syncthreads();
     for (int i = tid; i < n; i += T) y[i] = yb[i];
     __syncthreads();
   } else {
-    ldl_solve(SysMat<false>{A, ld, band, 0}, y, dinv, P, n, band, tid, T, &s_fail);
+    // wide or unknown structure in global memory (rare: the MoBA variant of a large window): generic path, panel scratch when it fits
+    ldl_solve(SysMat<false>{A, ld, band, 0}, y, dinv, P, n, band, tid, T, &s_fail, s_rowoff,
+              (n <= 1024 && sizeof(double) * SCR <= (size_t)kSolveSmem) ? smd : nullptr);
   }
   const bool fail = s_fail != 0;
   for (int i = tid; i < n; i += T) bf.dx[i] = fail ? 0.0f : (float)y[i];
@@ -1039,7 +1157,7 @@ int packed_band(int P, int flags) {
   if (sizeof(double) * ((size_t)n * (n + 1) + 2 * n) <= 200 * 1024) return -1;        // dense solve in shared memory
   if (n > 1024) return -1;
   const int band = 6 * (bw_hint < P - 1 ? bw_hint : P - 1);
-  if (sizeof(double) * ((size_t)(band + 6) * (band + 18) + 2 * n) > 190 * 1024) return -1;
+  if (!window_fits(n, band)) return -1;
   return band;
 }
 
@@ -1082,12 +1200,12 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
     const long need = 4L * (128L * (6 * (deg_hint + 1) + 2) + ((deg_hint + 1 + 3) & ~3)) + 64;
     if (need < pass2_smem) pass2_smem = (int)need;
   }
-  const size_t solve_smem = sizeof(double) * ((size_t)n * (n + 1) + 2 * n);
-  const bool solve_in_smem = solve_smem <= 200 * 1024;
+  const bool solve_in_smem = sizeof(double) * ((size_t)n * (n + 1) + 2 * n) <= 200 * 1024;
+  const size_t solve_smem = sizeof(double) * ((size_t)n * (n + 1) + 2 * n + ldl_scratch_doubles(n));     // + panel scratch for any band
   if (!attr_set) {
     cudaFuncSetAttribute(ba_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(ba_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(ba_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(ba_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSolveSmem);
     attr_set = true;
   }
   // flags bits 1-2 select a phase for the multi-GPU path (pvo_b200/dist.py): 0 = whole iteration(s),
@@ -1109,7 +1227,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
       // band-packed: fold + clear -> [all-reduce of the packed block between the phases] -> solve straight from it
       if (phase != 2) ba_combine_band_kernel<<<comb_blocks, 256, 0, s>>>(bf, packed, P, pband);
       if (phase == 1) break;
-      ba_solve_kernel<false><<<1, 512, 200 * 1024, s>>>(bf, P, lm, ep, sem, 0, bw_hint, packed);
+      ba_solve_kernel<false><<<1, 512, kSolveSmem, s>>>(bf, P, lm, ep, sem, 0, bw_hint, packed);
     } else if (phase == 1) {
       ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);
       break;
@@ -1119,7 +1237,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
       ba_solve_kernel<true><<<1, P <= 10 ? 128 : 512, solve_smem, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint, nullptr);
     } else {
       if (phase != 2) ba_combine_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);      // phase 2: phase 1 already folded the replicas
-      ba_solve_kernel<false><<<1, 512, 200 * 1024, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint, nullptr);   // band-packed copy in smem when it fits
+      ba_solve_kernel<false><<<1, 512, kSolveSmem, s>>>(bf, P, lm, ep, sem, sem && motion_only, bw_hint, nullptr);   // band-packed copy in smem when it fits
       ba_zero_kernel<<<comb_blocks, 256, 0, s>>>(bf, P);
     }
     const bool last = it == iterations - 1;
@@ -1169,6 +1287,14 @@ extern "C" int pvo_ba_exchange_range(int E, int nframes, int P, int K, int HW, i
   *bytes = (long)(sizeof(double) * ((size_t)6 * P * (pband + 6) + 12 * (size_t)P));
   return PVO_OK;
 }
+
+#ifdef PVO_SOLVE_PROF
+extern "C" int pvo_solve_prof_read(long long* host32, int reset) {
+  if (cudaMemcpyFromSymbol(host32, g_solve_prof, sizeof(long long) * 32) != cudaSuccess) return PVO_ERR_CUDA;
+  if (reset) { long long z[32] = {}; cudaMemcpyToSymbol(g_solve_prof, z, sizeof(z)); }
+  return PVO_OK;
+}
+#endif
 
 extern "C" int pvo_ba_read_meta(const void* workspace, int E, int nframes, int P, int K, int HW, int* meta_host3) {
   const Layout L = make_layout(E, nframes, P, K, HW);

@@ -29,3 +29,10 @@ for F in ([int(a) for a in sys.argv[1:]] or [8, 16, 32, 64]):
     for _ in range(20): run()
     e1.record(); torch.cuda.synchronize()
     print('radius %d  F=%2d  P=%2d  edges on this rank=%3d   2 GN iterations: %.1f us' % (RADIUS, F, F - 1, E, e0.elapsed_time(e1) / 20 * 1e3), flush=True)
+    if os.environ.get('DIAG_BA_KERNELS'):           # per-kernel GPU time of one call (torch.profiler / CUPTI)
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(5): run()
+            torch.cuda.synchronize()
+        for ev in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:12]:
+            print('      %-90s n=%3d  avg %.1f us' % (ev.key[:90], ev.count, ev.device_time_total / ev.count), flush=True)
