@@ -298,8 +298,13 @@ __global__ void __launch_bounds__(kPix) ba_pass1_kernel(
 // (exactly the pair enumeration of schur_block :1236-1251), b -= sum_pix Q w Erow.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kPix2 = 128;      // pixels per block in the Schur pass (more, smaller blocks: 2+ resident per SM)
-__global__ void __launch_bounds__(256) ba_pass2_kernel(const long* __restrict__ jj, Plan pl, Bufs bf, int HW, int t0,
-                                                       int P, int smem_floats) {
+// Register-tiled: a task is one 6x6 pose block (row ra, row rb <= ra) of the frame's Gram matrix, held as 36 accumulators by each
+// of 8 lanes that split the pixels (lane q takes pixels q, q+8, ...: consecutive shared-memory rows, no bank conflicts); three
+// shuffle rounds fold the 8 partial blocks and the lanes share out the float64 atomics.  One shared-memory read per three
+// multiply-adds -- the scalar-pair version this replaces (one (a, b) entry per thread: three reads per multiply-add, 10.7 k load
+// wavefronts per block) was the largest kernel of the BA at 38 us.  Products are formed exactly as before, (E_a Q) E_b in float32.
+__global__ void __launch_bounds__(256, 3) ba_pass2_kernel(const long* __restrict__ jj, Plan pl, Bufs bf, int HW, int t0,
+                                                          int P, int smem_floats) {       // 3 blocks per SM: the 304 blocks of config 2 in one wave
   extern __shared__ float sm[];
   const int K = pl.meta[0];
   const int k = blockIdx.y;
@@ -309,15 +314,15 @@ __global__ void __launch_bounds__(256) ba_pass2_kernel(const long* __restrict__ 
   const int deg = pl.src_ptr[k + 1] - pl.src_ptr[k];
   if (deg == 0) return;                              // no out-edges here (e.g. a frame another rank owns): E_k = 0, nothing to eliminate
   const int R = deg + 1, R6 = 6 * R;                 // row 0 = self, rows 1.. = out-edges (CSR order)
-  // smem: rowpose[R] ints | Qs[PC] | QWs[PC] | tile[PC][R6]
+  // smem: rowpose[R] ints | Wt[PC] | tile E [PC][R6] | tile E Q [PC][R6]
   int* rowpose = reinterpret_cast<int*>(sm);
   const int hdr = (R + 3) & ~3;
-  int PC = (smem_floats - hdr) / (R6 + 2);
-  PC = min(kPix2, PC & ~31);
+  int PC = (smem_floats - hdr) / (2 * R6 + 2);
+  PC = min(kPix2, PC & ~7);
   if (PC <= 0) { if (tid == 0) pl.meta[1] = 2; return; }
-  float* Qs = sm + hdr;
-  float* QWs = Qs + PC;
-  float* tile = QWs + PC;
+  float* Wt = sm + hdr;
+  float* tile = Wt + ((PC + 1) & ~1);                // 8-byte aligned rows (R6 is even)
+  float* tileq = tile + PC * R6;
   for (int r = tid; r < R; r += 256) {
     const int pose = (r == 0) ? f - t0 : (int)jj[pl.src_idx[pl.src_ptr[k] + r - 1]] - t0;
     rowpose[r] = (pose >= 0 && pose < P) ? pose : -1;
@@ -326,61 +331,104 @@ __global__ void __launch_bounds__(256) ba_pass2_kernel(const long* __restrict__ 
   double* Hp = bf.sys + (long)(blockIdx.x % kParts) * ((long)n * n + 2 * n);
   double* bp = Hp + (long)n * n;
   const int pix0 = blockIdx.x * kPix2;
+  const int q = tid & 7, ntask = R * (R + 1) / 2;
   for (int c0 = 0; c0 < kPix2; c0 += PC) {
     __syncthreads();
     const int np = min(PC, HW - pix0 - c0);
     if (np <= 0) break;
-    // load tile (coalesced along pixels), rows outside the window are zero
-    for (int idx = tid; idx < R6 * PC; idx += 256) {
-      const int row = idx / PC, p = idx - row * PC;
+    // load both tiles (coalesced along pixels); rows outside the window and pixels past the end are zero
+    // warp per tile row, lanes along the pixels, four loads of E and four of Q in flight per lane (a one-element-per-trip copy loop
+    // pays one L2 round trip per element: 21 trips per thread at config 2)
+    const float* Qk = bf.Q + (long)k * HW + pix0 + c0;
+    for (int row = tid >> 5; row < R6; row += 8) {
       const int r = row / 6, m = row - 6 * r;
-      float v = 0.f;
-      if (p < np && rowpose[r] >= 0) {
-        const long px = pix0 + c0 + p;
-        v = (r == 0) ? bf.Ei[((long)k * 6 + m) * HW + px]
-                     : bf.Eij[((long)pl.src_idx[pl.src_ptr[k] + r - 1] * 6 + m) * HW + px];
+      const float* src = (r == 0) ? bf.Ei + ((long)k * 6 + m) * HW : bf.Eij + ((long)pl.src_idx[pl.src_ptr[k] + r - 1] * 6 + m) * HW;
+      src += pix0 + c0;
+      const bool live = rowpose[r] >= 0;
+      for (int pb0 = 0; pb0 < PC; pb0 += 128) {
+        float v[4], qv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int p = pb0 + 32 * u + (tid & 31);
+          const bool ok = live && p < np;
+          v[u] = ok ? __ldg(src + p) : 0.f;
+          qv[u] = ok ? __ldg(Qk + p) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int p = pb0 + 32 * u + (tid & 31);
+          if (p < PC) {
+            tile[p * R6 + row] = v[u];
+            tileq[p * R6 + row] = v[u] * qv[u];
+          }
+        }
       }
-      tile[p * R6 + row] = v;
     }
-    for (int p = tid; p < PC; p += 256) {
-      const bool ok = p < np;
-      const float q = ok ? bf.Q[(long)k * HW + pix0 + c0 + p] : 0.f;
-      Qs[p] = q;
-      QWs[p] = ok ? q * bf.w[(long)k * HW + pix0 + c0 + p] : 0.f;
-    }
+    for (int p = tid; p < PC; p += 256) Wt[p] = p < np ? bf.w[(long)k * HW + pix0 + c0 + p] : 0.f;
     __syncthreads();
-    // S is symmetric: enumerate a <= b only (903 of 1764 entries at config 2) and mirror
-    for (int idx = tid; idx < R6 * (R6 + 1) / 2; idx += 256) {
-      int a = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);          // idx = a(a+1)/2 + b, b <= a  (then swap roles)
-      while (a * (a + 1) / 2 > idx) a--;
-      while ((a + 1) * (a + 2) / 2 <= idx) a++;
-      const int b = idx - a * (a + 1) / 2;                               // b <= a
-      const int pa = rowpose[a / 6], pb = rowpose[b / 6];
-      if (pa < 0 || pb < 0) continue;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // 4 independent chains (tile rows past np are zero)
-      for (int p = 0; p < PC; p += 4) {
-        s0 = fmaf(tile[p * R6 + a] * Qs[p], tile[p * R6 + b], s0);
-        s1 = fmaf(tile[(p + 1) * R6 + a] * Qs[p + 1], tile[(p + 1) * R6 + b], s1);
-        s2 = fmaf(tile[(p + 2) * R6 + a] * Qs[p + 2], tile[(p + 2) * R6 + b], s2);
-        s3 = fmaf(tile[(p + 3) * R6 + a] * Qs[p + 3], tile[(p + 3) * R6 + b], s3);
+    for (int task = tid >> 3; task < ntask; task += 32) {              // all 8 lanes of a task stay together (ntask is block-uniform)
+      int ra = (int)((sqrtf(8.0f * task + 1.0f) - 1.0f) * 0.5f);       // task = ra (ra + 1) / 2 + rb, rb <= ra
+      while (ra * (ra + 1) / 2 > task) ra--;
+      while ((ra + 1) * (ra + 2) / 2 <= task) ra++;
+      const int rb = task - ra * (ra + 1) / 2;
+      const int pa = rowpose[ra], pb = rowpose[rb];
+      if (pa < 0 || pb < 0) continue;                                  // uniform over the 8 lanes
+      float acc[6][6], bw[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        bw[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; j++) acc[i][j] = 0.f;
       }
-      const float s = (s0 + s1) + (s2 + s3);
-      const long i = 6 * pa + a % 6, j = 6 * pb + b % 6;
-      if (a == b) {
-        atomicAdd(&Hp[i * n + j], -(double)s);
-      } else if (i == j) {                                               // two rows of the same pose (duplicate edges)
-        atomicAdd(&Hp[i * n + j], -2.0 * (double)s);
-      } else {
-        atomicAdd(&Hp[i * n + j], -(double)s);
-        atomicAdd(&Hp[j * n + i], -(double)s);
+      const bool diag = ra == rb;
+      for (int p = q; p < PC; p += 8) {
+        const float2* ea = reinterpret_cast<const float2*>(tileq + p * R6 + 6 * ra);
+        const float2* eb = reinterpret_cast<const float2*>(tile + p * R6 + 6 * rb);
+        const float2 a0 = ea[0], a1 = ea[1], a2 = ea[2], b0 = eb[0], b1 = eb[1], b2 = eb[2];
+        const float a[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y}, b[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+          for (int j = 0; j < 6; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        if (diag) {
+          const float wv = Wt[p];
+#pragma unroll
+          for (int i = 0; i < 6; i++) bw[i] = fmaf(wv, a[i], bw[i]);
+        }
       }
-    }
-    for (int a = tid; a < R6; a += 256) {
-      const int pa = rowpose[a / 6];
-      if (pa < 0) continue;
-      float s = 0.f;
-      for (int p = 0; p < np; p++) s += QWs[p] * tile[p * R6 + a];
-      atomicAdd(&bp[6 * pa + a % 6], -(double)s);
+      const unsigned gmask = 0xFFu << (tid & 24);                      // the task's 8 lanes: tasks of one warp may diverge (skipped rows, loop tail)
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          bw[i] += __shfl_xor_sync(gmask, bw[i], o);
+#pragma unroll
+          for (int j = 0; j < 6; j++) acc[i][j] += __shfl_xor_sync(gmask, acc[i][j], o);
+        }
+      }
+      // every lane holds the block; lane q emits entries q, q + 8, ...  (i, j) = system indices of (row a, row b), a >= b as scalars
+#pragma unroll
+      for (int e = 0; e < 36; e++) {
+        if ((e & 7) != q) continue;
+        const int ma = e / 6, mb = e % 6;
+        if (diag && mb > ma) continue;
+        const double sv = -(double)acc[ma][mb];
+        const long i = 6 * pa + ma, j = 6 * pb + mb;
+        if (diag && ma == mb) {
+          atomicAdd(&Hp[i * n + j], sv);
+        } else if (i == j) {                                           // two rows of the same pose (duplicate edges)
+          atomicAdd(&Hp[i * n + j], 2.0 * sv);
+        } else {
+          atomicAdd(&Hp[i * n + j], sv);
+          atomicAdd(&Hp[j * n + i], sv);
+        }
+      }
+      if (diag && q < 6) {
+        float bsel = bw[0];
+#pragma unroll
+        for (int i = 1; i < 6; i++) if (q == i) bsel = bw[i];
+        atomicAdd(&bp[6 * pa + q], -(double)bsel);
+      }
     }
   }
 }
@@ -1196,8 +1244,8 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
   const int deg_hint = (flags >> 8) & 0xFFF;
   const int bw_hint = ((flags >> 20) & 0xFF) - 1;          // bits 20-27: 1 + block bandwidth of the pose system (0 = unknown: scan)
   int pass2_smem = 160 * 1024;
-  if (deg_hint > 0) {        // tile [256][6(deg+1)] + Q + QW + row table; smaller request => several blocks per SM, one wave
-    const long need = 4L * (128L * (6 * (deg_hint + 1) + 2) + ((deg_hint + 1 + 3) & ~3)) + 64;
+  if (deg_hint > 0) {        // two tiles [128][6(deg+1)] + w + row table; smaller request => several blocks per SM, one wave
+    const long need = 4L * (128L * (12 * (deg_hint + 1) + 2) + ((deg_hint + 1 + 3) & ~3)) + 64;
     if (need < pass2_smem) pass2_smem = (int)need;
   }
   const bool solve_in_smem = sizeof(double) * ((size_t)n * (n + 1) + 2 * n) <= 200 * 1024;
