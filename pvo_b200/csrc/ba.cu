@@ -520,17 +520,12 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 
 // 6x6 diagonal block at c0: A_kk = L D L^T in place (unit lower L below the diagonal, d on it), 1/d -> dinv, and the
-// block's share of the forward substitution (y_k <- L_kk^-1 y_k).  One thread, RIGHT-looking: column j costs one reciprocal (hardware
-// seed + two Newton steps; float64 div / sqrt are ~100-cycle software sequences), five multiplies and the rank-1 update of what is left --
-// ~100 arithmetic instructions for the block.  What bounds it is the dependent chain pivot -> rcp -> l -> next pivot: ~9 float64
-// operations of ~20 cycles each per pivot (tools/prof_solve.py), so everything that is not on that chain is free: the positivity test
-// does not feed it (a failed factorisation zeroes dx anyway, garbage after a bad pivot is harmless), and the thread also inverts the
-// unit-triangular factor, N = L_kk^-1, in the chain's shadow -- with N the panel rows become independent dot products.
-// (The left-looking form this replaces recomputed every L d L product: 384 instructions, 1 700 cycles per block column.)
-// dk (optional, 48 doubles): what the panel rows need from this block -- N [6][6] | 1/d [6] | z_k [6] -- in one place.
+// block's share of the forward substitution (y_k <- L_kk^-1 y_k).  One thread, right-looking: column j costs one reciprocal (hardware
+// seed + two Newton steps; float64 div / sqrt are ~100-cycle software sequences), five multiplies and the rank-1 update of what is left.
+// Used by the generic path (systems that stay in global memory); shared-memory systems use the warp form below.
 template <class M>
-__device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int c0, int* s_fail, double* dk) {
-  double D[6][6], N[6][6], z[6];
+__device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int c0, int* s_fail) {
+  double D[6][6], z[6];
   double* row0 = A.p + A.off(c0) + c0;                      // rows c0 .. c0+5 share the band start: row i begins i * ld further
 #pragma unroll
   for (int i = 0; i < 6; i++) {
@@ -542,10 +537,9 @@ __device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int
 #pragma unroll
   for (int j = 0; j < 6; j++) {
     const double d = D[j][j];
-    bad = bad || !(d > 0.0);
+    bad = bad || !(d > 0.0);                                // does not feed the chain: a failed factorisation zeroes dx, garbage after it is harmless
     const double iv = fast_rcp(d);
     dinv[c0 + j] = iv;
-    if (dk) dk[36 + j] = iv;
     double l[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) l[i] = (i > j) ? D[i][j] * iv : 0.0;       // D[i][j] holds L_ij d_j until the end of this step
@@ -561,34 +555,55 @@ __device__ __forceinline__ void ldl_diag_block(M A, double* y, double* dinv, int
 #pragma unroll
     for (int i = 0; i < 6; i++)
       if (i > j) D[i][j] = l[i];
-    if (dk) {
-      // row j+1 of N = L^-1 needs columns 0..j of L only: N[i][c] = -(L[i][c] + sum_{c<t<i} L[i][t] N[t][c])
-      const int i = j + 1;
-      if (i < 6) {
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-          if (c < i) {
-            double v = D[i][c];
-#pragma unroll
-            for (int t = 0; t < 6; t++) if (t > c && t < i) v = fma(D[i][t], N[t][c], v);
-            N[i][c] = -v;
-          }
-        }
-      }
-    }
   }
   if (bad) *s_fail = 1;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     y[c0 + i] = z[i];
-    if (dk) {
-      dk[42 + i] = z[i];
-#pragma unroll
-      for (int c = 0; c < 6; c++) if (c < i) dk[i * 6 + c] = N[i][c];
-    }
 #pragma unroll
     for (int j = 0; j < 6; j++)
       if (j <= i) row0[(long)i * A.ld + j] = D[i][j];
+  }
+}
+
+// The same 6x6 step by ONE WARP: lane <-> one entry of the block's lower triangle (lanes 0..20, row-major) or of its right-hand side
+// (lanes 21..26, treated as a seventh matrix row: the forward substitution is the same elimination).  `v` is the lane's entry, already
+// holding every update from earlier block columns -- it comes straight from the trailing-update registers.  Per pivot: broadcast d,
+// one reciprocal (all lanes), two lane-indexed shuffles, one multiply, one FMA: ~14 instructions instead of ~60 in the single-thread
+// form, whose ~370 instructions per block ran at 3-4 cycles each on the serial warp (section 4d of DESIGN.md); the dependent chain
+// (shuffle, rcp, mul, fma per pivot) is ~90 cycles.  dk receives what the panel rows need: L_jt d_t [6][6] | 1/d [6] | z_k [6].
+template <class M>
+__device__ __forceinline__ void ldl_diag_block_warp(M A, double* y, double* dinv, int c0, int* s_fail, double* dk, int lane, int bi, int bj,
+                                                    double v) {
+  const bool tri = lane < 21, rhs = lane >= 21 && lane < 27;
+  const int i = tri ? bi : 6, c = tri ? bj : (rhs ? lane - 21 : 7);        // c = 7: idle lane (never updated, never stored)
+  const int baseA = tri ? bi * (bi + 1) / 2 : 21, baseB = (c < 6) ? c * (c + 1) / 2 : 0;
+  double myiv = 0.0;
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const double d = __shfl_sync(0xffffffffu, v, j * (j + 1) / 2 + j);
+    bad = bad || !(d > 0.0);
+    const double iv = fast_rcp(d);
+    const double va = __shfl_sync(0xffffffffu, v, min(baseA + j, 31));      // entry (i, j), still L_ij d_j
+    const double vb = __shfl_sync(0xffffffffu, v, min(baseB + j, 31));      // entry (c, j)
+    if (c == j) myiv = iv;
+    if (c > j && c < 6) v = fma(-(va * iv), vb, v);
+  }
+  if (bad && lane == 0) *s_fail = 1;
+  if (tri) {
+    double* e = A.p + A.off(c0) + (long)i * A.ld + c0 + c;
+    if (i == c) {
+      *e = v;                                              // d_i
+      dinv[c0 + i] = myiv;
+      dk[36 + i] = myiv;
+    } else {
+      dk[i * 6 + c] = v;                                   // L_ic d_c for the panel recurrence
+      *e = v * myiv;                                       // L_ic
+    }
+  } else if (rhs) {
+    y[c0 + c] = v;
+    dk[42 + c] = v;
   }
 }
 
@@ -656,7 +671,17 @@ __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int t
   int bi = 0, bj = lane;                                   // lower-triangle entry of a 6x6 block updated by this lane (lanes < 21)
   while (bj > bi) { bj -= bi + 1; bi++; }
   group_sync(bar, T);
-  if (factor_first && tid == 32 * fw) ldl_diag_block(A, y, dinv, 6 * kb0, s_fail, dk);
+  if (factor_first && warp == fw) {
+    if (fast) {
+      const int f0 = 6 * kb0;
+      double v = 0.0;
+      if (lane < 21) v = A.p[s_rowoff[f0 + bi] + f0 + bj];
+      else if (lane < 27) v = y[f0 + lane - 21];
+      ldl_diag_block_warp(A, y, dinv, f0, s_fail, dk, lane, bi, bj, v);
+    } else if (lane == 0) {
+      ldl_diag_block(A, y, dinv, 6 * kb0, s_fail);
+    }
+  }
   group_sync(bar, T);
   PROF_DECL;
   for (int kb = kb0; kb < kb1; kb++) {
@@ -665,14 +690,13 @@ __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int t
     const int m = rend - c0 - 6;                           // band rows below the diagonal block (a multiple of 6)
     if (fast) {                                            // panel: L_rk = A_rk L_kk^-T D_k^-1; y_r -= L_rk z_k
       if (tid < m) {
-        // L_rk d = A_rk N^T (N = L_kk^-1 from the diagonal block's digest): six independent dot products per row, no chain from x_0 to x_5
-        double Nk[6][6], di[6], zk[6];
+        double ldk[6][6], di[6], zk[6];                    // the diagonal block's digest: L_jt d_t, 1/d_j, z_k
 #pragma unroll
         for (int j = 0; j < 6; j++) {
           di[j] = dk[36 + j];
           zk[j] = dk[42 + j];
 #pragma unroll
-          for (int t = 0; t < 6; t++) Nk[j][t] = (t < j) ? dk[j * 6 + t] : 0.0;
+          for (int t = 0; t < 6; t++) ldk[j][t] = (t < j) ? dk[j * 6 + t] : 0.0;
         }
         for (int rr = tid; rr < m; rr += T) {
           const int r = c0 + 6 + rr;
@@ -683,14 +707,9 @@ __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int t
           double ya = y[r], yb2 = 0.0;
 #pragma unroll
           for (int j = 0; j < 6; j++) {
-            double va = a[j], vb = 0.0;
+            double v = a[j];                               // L_rj d_j = A_rj - sum_{t<j} L_rt (d_t L_jt)
 #pragma unroll
-            for (int t = 0; t < 6; t++) {
-              if (t < j) {
-                if (t & 1) vb = fma(a[t], Nk[j][t], vb); else va = fma(a[t], Nk[j][t], va);
-              }
-            }
-            const double v = va + vb;
+            for (int t = 0; t < 6; t++) if (t < j) v = fma(-x[t], ldk[j][t], v);
             LDp[j * PS + rr] = v;
             x[j] = v * di[j];
             Lp[j * PS + rr] = x[j];
@@ -722,11 +741,12 @@ __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int t
     PROF(1);                                                // wait for the slowest panel row
     if (m > 0) {                                            // trailing update (lower triangle): A_ic -= sum_t L_it d_t L_ct
       if (warp == fw) {
-        // the next diagonal block first (21 entries, one per lane), then its factorisation while the other warps do the rest of the
-        // trailing update.  The factorisation stays in ONE thread: a warp-parallel variant (lane <-> lower-triangle entry, pivot column
-        // broadcast by 64-bit shuffles) was measured slower -- six rounds of dependent shuffles lose to one thread's ILP.
-        if (lane < 21) {
-          if (fast) {
+        // the next diagonal block first (21 entries, one per lane), then its factorisation -- same lanes, the entries stay in
+        // registers -- while the other warps do the rest of the trailing update
+        const bool factor_next = factor_last || kb + 1 < kb1;
+        if (fast) {
+          double v = 0.0;
+          if (lane < 21) {
             double* Ai = A.p + s_rowoff[c0 + 6 + bi] + c0 + 6;
             double va = Ai[bj], vb = 0.0;
 #pragma unroll
@@ -734,20 +754,26 @@ __device__ void ldl_forward(M A, double* y, double* dinv, int n, int band, int t
               va = fma(-LDp[t * PS + bi], Lp[t * PS + bj], va);
               vb = fma(LDp[(t + 3) * PS + bi], Lp[(t + 3) * PS + bj], vb);
             }
-            Ai[bj] = va - vb;
-          } else {
+            v = va - vb;
+            if (!factor_next) Ai[bj] = v;
+          } else if (lane < 27) {
+            v = y[c0 + 6 + lane - 21];
+          }
+          PROF(2);                                          // next diagonal block: 21-entry update
+          if (factor_next) ldl_diag_block_warp(A, y, dinv, c0 + 6, s_fail, dk, lane, bi, bj, v);     // the updated entries never leave the registers
+          PROF(3);                                          // its factorisation
+        } else {
+          if (lane < 21) {
             const int i = c0 + 6 + bi, c = c0 + 6 + bj;
             double vn = A(i, c);
 #pragma unroll
             for (int t = 0; t < 6; t++) vn -= A(i, c0 + t) * A((c0 + t), c0 + t) * A(c, c0 + t);
             A(i, c) = vn;
           }
+          __syncwarp();
+          if (lane == 0 && factor_next) ldl_diag_block(A, y, dinv, c0 + 6, s_fail);
+          __syncwarp();
         }
-        __syncwarp();
-        PROF(2);                                            // next diagonal block: 21-entry update
-        if (lane == 0 && (factor_last || kb + 1 < kb1)) ldl_diag_block(A, y, dinv, c0 + 6, s_fail, dk);
-        PROF(3);                                            // its factorisation
-        __syncwarp();
       } else if (fast && ttid >= 0) {
         // rows 6 .. m-1 of the trailing block (the first six belong to warp 0), lower triangle: row 6+p (7+p entries) and row m-1-p
         // (m-p entries) together always hold m+7 entries, so R/2 row pairs x (m+7) entries enumerate the triangle without idle lanes
