@@ -74,3 +74,27 @@ def test_ba_workspace_size_is_monotone():
     b = L.pvo_ba_workspace_bytes(72, 1024, 7, 8, 4800)
     assert 0 < a < b
     assert L.pvo_ba_workspace_bytes(36, 1024, 0, 8, 4800) == -1
+
+
+def test_ba_exchange_range_is_the_band_for_large_windows():
+    """What the ranks all-reduce (host arithmetic only, no GPU): the dense {H | b | dA} block for windows that are solved densely in
+    shared memory, for an unknown bandwidth and for the MoBA variant; the band-packed block [6P][12r+6] | b | dA otherwise."""
+    import ctypes
+    from pvo_b200 import _lib, droid_backends
+    L = _lib.lib()
+
+    def rng(P, flags, motion_only=0):
+        off, nb = ctypes.c_long(0), ctypes.c_long(0)
+        assert L.pvo_ba_exchange_range(42, 64, P, 8, 4800, flags, motion_only, ctypes.byref(off), ctypes.byref(nb)) == 0
+        return off.value, nb.value
+
+    dense = lambda P: 8 * (36 * P * P + 12 * P)
+    band3 = droid_backends.band_flag(3)                        # radius 3 -> block bandwidth 6
+    assert rng(7, band3)[1] == dense(7)                        # 7 poses: dense shared-memory solve
+    assert rng(63, 0)[1] == dense(63)                          # bandwidth unknown
+    assert rng(63, band3)[1] == 8 * (378 * 42 + 2 * 378)       # 133 KB instead of 1.1 MB
+    assert rng(63, band3)[0] != rng(63, 0)[0]                  # its own block of the workspace
+    assert rng(63, band3 | (1 << 3), motion_only=1)[1] == dense(63)      # geom/ba.py MoBA damps every block: stays dense
+    assert rng(63, droid_backends.band_flag(8))[1] == 8 * (378 * 102 + 2 * 378)   # config 5: windowed factorisation, packed all the same
+    off, nb = rng(63, band3)
+    assert off + nb <= L.pvo_ba_workspace_bytes(42, 64, 63, 8, 4800)

@@ -54,7 +54,9 @@ loop)      # the whole per-frame loop: decisions vs the reference golden, then t
 micro)     # HBM-bound kernels next to their reference counterparts
   run bench_lookup 600 python tools/bench_lookup.py
   run bench_altcorr 600 python tools/bench_altcorr.py
-  run diag_ba 600 python tools/diag_ba.py 8 16 32 64 ;;
+  run diag_ba 600 env DIAG_BA_KERNELS=1 python tools/diag_ba.py 8 16 32 64
+  run prof_solve 300 python tools/prof_solve.py 64        # needs tools/_prof/libpvo_ba_prof.so (python tools/prof_solve.py build, here)
+  run ubench_fp64 120 python -c "import ctypes; ctypes.CDLL('tools/_prof/libubench.so').ubench_run()" ;;
 dist)
   run t_dist 600 $PT tests/test_dist_gpu.py ;;
 multi)
