@@ -298,7 +298,6 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm) conv_tc_kernel(
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    constexpr uint32_t idesc = idesc_f16(kBM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -306,6 +305,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm) conv_tc_kernel(
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[as], aphase ^ 1);
       fence_after_sync();
+      const uint32_t idesc = idesc_f16(kBM, min(BN, (p.Cout - (tile % p.n_tiles) * BN + 15) & ~15));     // narrow last N tile: see conv_tc_halo_kernel
       const uint32_t tmem_d = tmem_base + as * BN;
       for (int kb0 = 0; kb0 < nkb; kb0 += C::kG) {
         const int g = min(C::kG, nkb - kb0);
@@ -509,12 +509,14 @@ __global__ void __launch_bounds__(kThreads, HCfg<BN, MT>::kCtasPerSm) conv_tc_ha
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    constexpr uint32_t idesc = idesc_f16(kBM, BN);
     int sa = 0, sb = 0, as = 0;
     uint32_t pa = 0, pb = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[as], aphase ^ 1);
       fence_after_sync();
+      // the last N tile of a layer whose width is not a multiple of BN multiplies only the columns that exist (heads: 640 = 256 + 256
+      // + 128): UMMA N is a field of the instruction descriptor, the weight rows past Cout are TMA zero fill that nobody reads
+      const uint32_t idesc = idesc_f16(kBM, min(BN, (p.Cout - (tile % p.n_tiles) * BN + 15) & ~15));
       const uint32_t tmem_d = tmem_base + as * C::kAccCols;
       for (int cbg = 0; cbg < ncb; cbg++) {
         mbar_wait(&afull[sa], pa);
