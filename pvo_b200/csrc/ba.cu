@@ -1269,7 +1269,7 @@ extern "C" int pvo_ba(float* poses, float* disps, const float* intrinsics, const
   static bool attr_set = false;
   const int deg_hint = (flags >> 8) & 0xFFF;
   const int bw_hint = ((flags >> 20) & 0xFF) - 1;          // bits 20-27: 1 + block bandwidth of the pose system (0 = unknown: scan)
-  int pass2_smem = 160 * 1024;
+  int pass2_smem = 96 * 1024;   // out-degree unknown (the reference's own FactorGraph passes no hint): two blocks per SM; frames of higher degree take several pixel chunks
   if (deg_hint > 0) {        // two tiles [128][6(deg+1)] + w + row table; smaller request => several blocks per SM, one wave
     const long need = 4L * (128L * (12 * (deg_hint + 1) + 2) + ((deg_hint + 1 + 3) & ~3)) + 64;
     if (need < pass2_smem) pass2_smem = (int)need;
