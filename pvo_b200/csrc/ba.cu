@@ -17,8 +17,9 @@
 // out-edges, so C, w and the self-row Ei are complete in registers without any cross-block accumulation, the
 // per-edge 12x12 Hessian is reduced with warp shuffles, and the grid is K * ceil(HW/256) blocks (152 at config 2).
 // The reduced camera system (6P x 6P) is accumulated in float64 with atomics straight into one dense matrix, the
-// Schur products are formed per frame from an smem tile, and a single-block float64 Cholesky solves it on the
-// device.  No host synchronisation anywhere: the whole call is CUDA-graph capturable.
+// Schur products are formed per frame from an smem tile (6x6 pose blocks in registers), and a single-block float64 band
+// LDL^T solves it on the device -- from both ends at once when the window is large (ba_solve_kernel).  No host
+// synchronisation anywhere: the whole call is CUDA-graph capturable.
 // Algorithmic HBM bytes per GN iteration: 76 B * HW * E -> latency-bound at config 2.
 #include "se3.cuh"
 
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(256, 3) ba_pass2_kernel(const long* __restrict
 
 // ---------------------------------------------------------------------------------------------------
 // solve: sum the kParts replicas, LM damping, blocked (6x6 = one pose) right-looking LDL^T + blocked triangular
-// solves in float64 (SPD test: every pivot d_j > 0, same acceptance as the reference's LLT).  One block; 7P block-level barriers (49 at P = 7) instead of ~7n.
+// solves in float64 (SPD test: every pivot d_j > 0, same acceptance as the reference's LLT).  One block; two barriers per block column.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void damp(double* A, int ld, const double* dA, int P, float lm, float ep, int sem, int moba, int tid, int T) {
   const int n = 6 * P;
